@@ -1,0 +1,172 @@
+// Input re-layout kernels: the AdaMML data_layer (reference models/adamml.py:42-67) and
+// weight / weight-gradient re-packing between torch's OIHW parameters and the OHWI
+// operand layout of the convolution engines.
+#include "common.cuh"
+
+namespace {
+
+inline int ew_blocks(long long total) {
+  long long b = (total + 255) / 256;
+  long long cap = 148LL * 64;
+  return (int)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+// x: NCHW fp32 [N, S*F*C, H, W]  ->  out: NHWC [(s*N+n)*F+f, H, W, Cpad]   (adamml.py:53,65)
+template <typename T>
+__global__ void pack_frames_kernel(const float* __restrict__ x, T* __restrict__ out, int N, int S, int F, int C,
+                                   int H, int W, int Cpad) {
+  long long total = (long long)S * N * F * H * W;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int w = (int)(idx % W);
+    int h = (int)((idx / W) % H);
+    long long img = idx / ((long long)W * H);
+    int f = (int)(img % F);
+    int n = (int)((img / F) % N);
+    int s = (int)(img / ((long long)F * N));
+    const float* src = x + (((long long)n * S * F * C + ((long long)s * F + f) * C) * H + h) * W + w;
+    T* dst = out + idx * Cpad;
+    for (int c = 0; c < C; ++c) dst[c] = from_f32<T>(src[(long long)c * H * W]);
+    for (int c = C; c < Cpad; ++c) dst[c] = from_f32<T>(0.f);
+  }
+}
+
+// bilinear, align_corners=False, no antialias (F.interpolate at adamml.py:59), keeping
+// frames 0, fstep, 2*fstep, ... of each segment (adamml.py:60-62).
+template <typename T>
+__global__ void resize_frames_kernel(const float* __restrict__ x, T* __restrict__ out, int N, int S, int F, int C,
+                                     int H, int W, int OH, int OW, int fstep, int Fk, int Cpad) {
+  const float sh = (float)H / (float)OH;
+  const float sw = (float)W / (float)OW;
+  long long total = (long long)S * N * Fk * OH * OW;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int ow = (int)(idx % OW);
+    int oh = (int)((idx / OW) % OH);
+    long long img = idx / ((long long)OW * OH);
+    int fk = (int)(img % Fk);
+    int n = (int)((img / Fk) % N);
+    int s = (int)(img / ((long long)Fk * N));
+    int f = fk * fstep;
+    float hr = sh * ((float)oh + 0.5f) - 0.5f;
+    if (hr < 0.f) hr = 0.f;
+    float wr = sw * ((float)ow + 0.5f) - 0.5f;
+    if (wr < 0.f) wr = 0.f;
+    int h0 = (int)hr; if (h0 > H - 1) h0 = H - 1;
+    int w0 = (int)wr; if (w0 > W - 1) w0 = W - 1;
+    int hp = h0 < H - 1 ? 1 : 0;
+    int wp = w0 < W - 1 ? 1 : 0;
+    float lh1 = fminf(fmaxf(hr - (float)h0, 0.f), 1.f), lh0 = 1.f - lh1;
+    float lw1 = fminf(fmaxf(wr - (float)w0, 0.f), 1.f), lw0 = 1.f - lw1;
+    const float* src = x + ((long long)n * S * F * C + ((long long)s * F + f) * C) * H * W;
+    T* dst = out + idx * Cpad;
+    for (int c = 0; c < C; ++c) {
+      const float* pl = src + (long long)c * H * W;
+      float p00 = pl[(long long)h0 * W + w0];
+      float p01 = pl[(long long)h0 * W + w0 + wp];
+      float p10 = pl[(long long)(h0 + hp) * W + w0];
+      float p11 = pl[(long long)(h0 + hp) * W + w0 + wp];
+      float v = lh0 * (lw0 * p00 + lw1 * p01) + lh1 * (lw0 * p10 + lw1 * p11);
+      dst[c] = from_f32<T>(v);
+    }
+    for (int c = C; c < Cpad; ++c) dst[c] = from_f32<T>(0.f);
+  }
+}
+
+// OIHW fp32 -> OHWI T
+template <typename T>
+__global__ void pack_weight_kernel(const float* __restrict__ src, T* __restrict__ dst, int Cout, int Cin, int R,
+                                   int S, int CinPad) {
+  long long total = (long long)Cout * R * S * CinPad;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int ci = (int)(idx % CinPad);
+    int s = (int)((idx / CinPad) % S);
+    int r = (int)((idx / ((long long)CinPad * S)) % R);
+    int co = (int)(idx / ((long long)CinPad * S * R));
+    float v = ci < Cin ? src[(((long long)co * Cin + ci) * R + r) * S + s] : 0.f;
+    dst[idx] = from_f32<T>(v);
+  }
+}
+
+// OHWI fp32 (CinPad channels) -> OIHW fp32 ; dst = (accumulate ? dst : 0) + src
+__global__ void unpack_wgrad_kernel(const float* __restrict__ src, float* __restrict__ dst, int Cout, int Cin, int R,
+                                    int S, int CinPad, int accumulate) {
+  long long total = (long long)Cout * Cin * R * S;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int s = (int)(idx % S);
+    int r = (int)((idx / S) % R);
+    int ci = (int)((idx / ((long long)S * R)) % Cin);
+    int co = (int)(idx / ((long long)S * R * Cin));
+    float v = src[(((long long)co * R + r) * S + s) * CinPad + ci];
+    dst[idx] = accumulate ? dst[idx] + v : v;
+  }
+}
+
+template <typename TI, typename TO>
+__global__ void cast_kernel(const TI* __restrict__ src, TO* __restrict__ dst, long long total) {
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x)
+    dst[idx] = from_f32<TO>(to_f32(src[idx]));
+}
+
+}  // namespace
+
+extern "C" {
+
+int adamml_pack_frames(const float* x, void* out, int N, int S, int F, int C, int H, int W, int Cpad, int dtype,
+                       cudaStream_t stream) {
+  ADAMML_REQUIRE(N > 0 && S > 0 && F > 0 && C > 0 && H > 0 && W > 0 && Cpad >= C, "pack_frames: bad dims");
+  long long total = (long long)S * N * F * H * W;
+  ADAMML_DISPATCH_DTYPE(dtype, T,
+    pack_frames_kernel<T><<<ew_blocks(total), 256, 0, stream>>>(x, (T*)out, N, S, F, C, H, W, Cpad));
+  return adamml_check_launch("pack_frames");
+}
+
+int adamml_resize_frames(const float* x, void* out, int N, int S, int F, int C, int H, int W, int OH, int OW,
+                         int fstep, int Cpad, int dtype, cudaStream_t stream) {
+  ADAMML_REQUIRE(N > 0 && S > 0 && F > 0 && C > 0 && H > 0 && W > 0 && OH > 0 && OW > 0 && fstep > 0 && Cpad >= C,
+                 "resize_frames: bad dims");
+  int Fk = (F + fstep - 1) / fstep;
+  long long total = (long long)S * N * Fk * OH * OW;
+  ADAMML_DISPATCH_DTYPE(dtype, T,
+    resize_frames_kernel<T><<<ew_blocks(total), 256, 0, stream>>>(x, (T*)out, N, S, F, C, H, W, OH, OW, fstep, Fk, Cpad));
+  return adamml_check_launch("resize_frames");
+}
+
+int adamml_pack_weight(const float* w_oihw, void* w_ohwi, int Cout, int Cin, int R, int S, int CinPad, int dtype,
+                       cudaStream_t stream) {
+  ADAMML_REQUIRE(Cout > 0 && Cin > 0 && R > 0 && S > 0 && CinPad >= Cin, "pack_weight: bad dims");
+  long long total = (long long)Cout * R * S * CinPad;
+  ADAMML_DISPATCH_DTYPE(dtype, T,
+    pack_weight_kernel<T><<<ew_blocks(total), 256, 0, stream>>>(w_oihw, (T*)w_ohwi, Cout, Cin, R, S, CinPad));
+  return adamml_check_launch("pack_weight");
+}
+
+int adamml_unpack_wgrad(const float* dw_ohwi, float* dw_oihw, int Cout, int Cin, int R, int S, int CinPad,
+                        int accumulate, cudaStream_t stream) {
+  ADAMML_REQUIRE(Cout > 0 && Cin > 0 && R > 0 && S > 0 && CinPad >= Cin, "unpack_wgrad: bad dims");
+  long long total = (long long)Cout * Cin * R * S;
+  unpack_wgrad_kernel<<<ew_blocks(total), 256, 0, stream>>>(dw_ohwi, dw_oihw, Cout, Cin, R, S, CinPad, accumulate);
+  return adamml_check_launch("unpack_wgrad");
+}
+
+// dtype codes for src/dst
+int adamml_cast(const void* src, void* dst, long long total, int src_dtype, int dst_dtype, cudaStream_t stream) {
+  ADAMML_REQUIRE(total >= 0, "cast: negative size");
+  if (total == 0) return ADAMML_OK;
+  if (src_dtype == ADAMML_F32 && dst_dtype == ADAMML_BF16)
+    cast_kernel<float, bf16><<<ew_blocks(total), 256, 0, stream>>>((const float*)src, (bf16*)dst, total);
+  else if (src_dtype == ADAMML_BF16 && dst_dtype == ADAMML_F32)
+    cast_kernel<bf16, float><<<ew_blocks(total), 256, 0, stream>>>((const bf16*)src, (float*)dst, total);
+  else if (src_dtype == ADAMML_F32 && dst_dtype == ADAMML_F32)
+    cast_kernel<float, float><<<ew_blocks(total), 256, 0, stream>>>((const float*)src, (float*)dst, total);
+  else {
+    adamml_set_error("cast: unsupported dtype pair %d -> %d", src_dtype, dst_dtype);
+    return ADAMML_ERR_ARG;
+  }
+  return adamml_check_launch("cast");
+}
+
+}  // extern "C"

@@ -1,0 +1,297 @@
+"""Execution engine: runs a backbone as a flat sequence of fused CUDA ops with a manual tape.
+
+A backbone (ResNet / sound MobileNetV2 / policy MobileNetV2) is executed for ALL segments
+of ALL videos in one batched pass (images ordered segment-major, one BatchNorm group per
+segment, see csrc/bn.cu) instead of the reference's Python loop over segments
+(models/adamml.py:84-86, models/policy_net.py:323-326).  Forward pushes records on a tape,
+backward pops them; both only call the C-ABI (adamml_b200.ops).  torch is used for memory,
+streams, autograd plumbing and (sync-BN) torch.distributed collectives.
+"""
+import torch
+import torch.distributed as dist
+
+from . import ops
+from .ops import ACT_NONE, ACT_RELU, ACT_RELU6
+
+
+class Exec:
+    """State of one backbone pass."""
+
+    def __init__(self, dtype, training, groups, save, param_needs_grad=True):
+        self.dtype = dtype
+        self.training = training
+        self.G = groups
+        self.save = save
+        self.param_needs_grad = param_needs_grad
+        self.tape = []
+        self.grads = {}  # parameter -> gradient tensor (filled by bwd)
+
+    # ------------------------------------------------------------------ helpers
+    def _acc(self, p, g):
+        if p is None or not p.requires_grad:
+            return
+        if p in self.grads:
+            self.grads[p] = self.grads[p] + g
+        else:
+            self.grads[p] = g
+
+    @staticmethod
+    def _sync_group(bn):
+        if isinstance(bn, torch.nn.SyncBatchNorm) and dist.is_available() and dist.is_initialized():
+            pg = bn.process_group if bn.process_group is not None else dist.group.WORLD
+            if dist.get_world_size(pg) > 1:
+                return pg
+        return None
+
+    # ------------------------------------------------------------------ conv + BN + act (+ residual)
+    def cba(self, x, conv, bn, act, res=None, res_rec=None):
+        """out = act(bn(conv(x)) [+ res] [+ bn_ds(z_ds) from res_rec]).
+
+        res_rec: record returned by `conv_bn_stats` for the downsample branch (resnet.py:164-167).
+        """
+        rec = self.conv_bn_stats(x, conv, bn)
+        out = ops.bn_apply(rec["z"], rec["ss"], self.G, act, res=res,
+                           res_z=res_rec["z"] if res_rec else None, res_ss=res_rec["ss"] if res_rec else None)
+        rec["ss"] = None
+        if res_rec:
+            res_rec["ss"] = None
+        if self.save:
+            rec.update(out=out, act=act, has_res=res is not None, res_rec=res_rec)
+            self.tape.append(rec)
+        return out
+
+    def conv_bn_stats(self, x, conv, bn):
+        """z = conv(x); BN statistics (train) or folded running stats (eval) -> record with z, mi, ss."""
+        G = self.G
+        w = conv.weight
+        Cout, Cin_g, R, S = w.shape
+        stride, pad = conv.stride[0], conv.padding[0]
+        depthwise = conv.groups > 1
+        sums = None
+        fused = False
+        if depthwise:
+            assert conv.groups == conv.in_channels == Cout and R == 3 and pad == 1
+            wp = w.detach()
+            z = ops.dwconv_fwd(x, wp, stride)
+        else:
+            wp = ops.pack_weight(w.detach(), self.dtype)
+            if self.training:
+                sums = torch.empty((G, Cout, 2), device=x.device, dtype=torch.float64)
+            rows = x.shape[0] * ((x.shape[1] + 2 * pad - R) // stride + 1) * ((x.shape[2] + 2 * pad - S) // stride + 1)
+            z, fused = ops.conv_fwd(x, wp, stride, pad, stats=sums, rows_per_group=rows // G)
+        C = z.shape[-1]
+        count = z.numel() // C // G
+        pg = None
+        if self.training:
+            if not fused:
+                sums = ops.bn_stats(z, G)
+            pg = self._sync_group(bn)
+            if pg is not None:
+                dist.all_reduce(sums, group=pg)
+                count = count * dist.get_world_size(pg)
+            mi, ss = ops.bn_finalize(sums, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var,
+                                     count, bn.momentum if bn.momentum is not None else 0.1, bn.eps, C, G, True,
+                                     bn.track_running_stats)
+            if bn.num_batches_tracked is not None:
+                bn.num_batches_tracked += G
+        else:
+            mi, ss = ops.bn_finalize(None, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, 1,
+                                     0.1, bn.eps, C, G, False, False)
+        return dict(x=x, z=z, mi=mi, ss=ss, w=wp, conv=conv, bn=bn, count=count, pg=pg, depthwise=depthwise)
+
+    def cba_bwd(self, dout, need_dx=True, addend=None):
+        """Pops one cba record.  Returns (dx or None, dres or None)."""
+        rec = self.tape.pop()
+        return self._bn_conv_bwd(rec, dout, rec["out"], rec["act"], need_dx, addend,
+                                 want_dres=rec["has_res"] and rec["act"] != ACT_NONE)
+
+    def _bn_conv_bwd(self, rec, dout, out, act, need_dx, addend, want_dres):
+        G = self.G
+        conv, bn, z, mi = rec["conv"], rec["bn"], rec["z"], rec["mi"]
+        C = z.shape[-1]
+        sums = ops.bn_bwd_reduce(dout, out, z, mi, G, act)
+        if bn.weight.requires_grad or bn.bias.requires_grad:
+            dgamma, dbeta = ops.bn_param_grad(sums, C, G)
+            self._acc(bn.weight, dgamma)
+            self._acc(bn.bias, dbeta)
+        if rec["pg"] is not None:
+            dist.all_reduce(sums, group=rec["pg"])
+        need_w = conv.weight.requires_grad
+        dz, dres = ops.bn_bwd_apply(dout, out, z, mi, bn.weight.detach(), sums, G, rec["count"], act, self.training,
+                                    want_dz=(need_w or need_dx), want_dres=want_dres)
+        dx = None
+        x = rec["x"]
+        stride, pad = conv.stride[0], conv.padding[0]
+        if rec["depthwise"]:
+            if need_w:
+                self._acc(conv.weight, ops.dwconv_wgrad(x, dz, stride))
+            if need_dx:
+                dx = ops.dwconv_dgrad(dz, rec["w"], tuple(x.shape), stride, addend=addend)
+        else:
+            w = rec["w"]
+            if need_w:
+                dw = ops.conv_wgrad(x, dz, tuple(w.shape), stride, pad)
+                self._acc(conv.weight, ops.unpack_wgrad(dw, conv.weight.shape[1]))
+            if need_dx:
+                w_t = None
+                if (addend is None and self.dtype == torch.bfloat16 and w.shape[1] == 1 and w.shape[2] == 1
+                        and stride == 1 and ops.TC_MODE == "auto"):
+                    w_t = w.view(w.shape[0], w.shape[3]).t().contiguous()
+                dx = ops.conv_dgrad(dz, w, tuple(x.shape), stride, pad, addend=addend, w_t=w_t)
+        return dx, dres
+
+    # ------------------------------------------------------------------ ResNet blocks
+    def bottleneck(self, x, blk):
+        """resnet.py:93-113."""
+        a = self.cba(x, blk.conv1, blk.bn1, ACT_RELU)
+        a = self.cba(a, blk.conv2, blk.bn2, ACT_RELU)
+        if blk.downsample is not None:
+            ds = self.conv_bn_stats(x, blk.downsample[0], blk.downsample[1])
+            return self.cba(a, blk.conv3, blk.bn3, ACT_RELU, res_rec=ds)
+        return self.cba(a, blk.conv3, blk.bn3, ACT_RELU, res=x)
+
+    def bottleneck_bwd(self, dout, need_dx=True):
+        rec3 = self.tape[-1]
+        ds = rec3["res_rec"]
+        d_id = None
+        dx_ds = None
+        if ds is not None:
+            # downsample branch shares (dout, out, act mask) with bn3
+            dx_ds, _ = self._bn_conv_bwd(ds, dout, rec3["out"], rec3["act"], need_dx, None, want_dres=False)
+        da, d_id = self.cba_bwd(dout)          # conv3/bn3 (+identity grad)
+        da, _ = self.cba_bwd(da)               # conv2/bn2
+        addend = dx_ds if ds is not None else d_id
+        dx, _ = self.cba_bwd(da, need_dx=need_dx, addend=addend if need_dx else None)  # conv1/bn1
+        return dx
+
+    def basicblock(self, x, blk):
+        """resnet.py:59-74."""
+        a = self.cba(x, blk.conv1, blk.bn1, ACT_RELU)
+        if blk.downsample is not None:
+            ds = self.conv_bn_stats(x, blk.downsample[0], blk.downsample[1])
+            return self.cba(a, blk.conv2, blk.bn2, ACT_RELU, res_rec=ds)
+        return self.cba(a, blk.conv2, blk.bn2, ACT_RELU, res=x)
+
+    def basicblock_bwd(self, dout, need_dx=True):
+        rec2 = self.tape[-1]
+        ds = rec2["res_rec"]
+        dx_ds = None
+        if ds is not None:
+            dx_ds, _ = self._bn_conv_bwd(ds, dout, rec2["out"], rec2["act"], need_dx, None, want_dres=False)
+        da, d_id = self.cba_bwd(dout)
+        addend = dx_ds if ds is not None else d_id
+        dx, _ = self.cba_bwd(da, need_dx=need_dx, addend=addend if need_dx else None)
+        return dx
+
+    # ------------------------------------------------------------------ MobileNetV2 block
+    def inverted_residual(self, x, layers, use_res):
+        """layers: list of (conv, bn, act) triples: [pw] + dw + pw-linear
+        (sound_mobilenet_v2.py:52-69, policy_net.py:63-95)."""
+        a = x
+        for i, (conv, bn, act) in enumerate(layers):
+            last = i == len(layers) - 1
+            a = self.cba(a, conv, bn, act, res=x if (last and use_res) else None)
+        if self.save:
+            self.tape.append(dict(kind="ir", n=len(layers), use_res=use_res))
+        return a
+
+    def inverted_residual_bwd(self, dout, need_dx=True):
+        meta = self.tape.pop()
+        n, use_res = meta["n"], meta["use_res"]
+        d = dout
+        for i in range(n):
+            first = i == n - 1
+            addend = dout if (first and use_res) else None  # linear bottleneck: d(res) = dout itself
+            d, _ = self.cba_bwd(d, need_dx=(need_dx or not first), addend=addend if (need_dx or not first) else None)
+        return d
+
+    # ------------------------------------------------------------------ pools
+    def maxpool(self, x):
+        y = ops.maxpool_fwd(x)
+        if self.save:
+            self.tape.append(dict(x=x))
+        return y
+
+    def maxpool_bwd(self, dy):
+        rec = self.tape.pop()
+        return ops.maxpool_bwd(rec["x"], dy)
+
+    def tpool(self, x, frames, mode_avg=False):
+        y = ops.tpool_fwd(x, frames, mode_avg)
+        if self.save:
+            self.tape.append(dict(x=x, frames=frames, avg=mode_avg))
+        return y
+
+    def tpool_bwd(self, dy):
+        rec = self.tape.pop()
+        return ops.tpool_bwd(rec["x"], dy, rec["frames"], rec["avg"])
+
+    # ------------------------------------------------------------------ heads
+    def avgpool(self, x):
+        y = ops.avgpool_fwd(x)
+        if self.save:
+            self.tape.append(dict(shape=tuple(x.shape)))
+        return y
+
+    def avgpool_bwd(self, dy):
+        rec = self.tape.pop()
+        return ops.avgpool_bwd(dy, rec["shape"], self.dtype)
+
+    def classifier(self, feat, fc, drop_mask, frames):
+        """Dropout (mask supplied by the caller, torch-RNG order) + Linear + mean over the remaining
+        frames (resnet.py:214-221, sound_mobilenet_v2.py:157)."""
+        xin = ops.mul(feat, drop_mask) if drop_mask is not None else feat
+        y = ops.linear_fwd(xin, fc.weight.detach())
+        ops.bias_act_(y, fc.bias.detach() if fc.bias is not None else None, ACT_NONE)
+        if frames > 1:
+            y = ops.frame_mean(y, frames)
+        if self.save:
+            self.tape.append(dict(xin=xin, fc=fc, mask=drop_mask, frames=frames))
+        return y
+
+    def classifier_bwd(self, dy):
+        rec = self.tape.pop()
+        fc = rec["fc"]
+        if rec["frames"] > 1:
+            dy = ops.frame_mean_bwd(dy, rec["frames"])
+        if fc.weight.requires_grad:
+            self._acc(fc.weight, ops.linear_wgrad(rec["xin"], dy))
+        if fc.bias is not None and fc.bias.requires_grad:
+            self._acc(fc.bias, ops.colsum(dy))
+        dx = ops.linear_dgrad(dy, fc.weight.detach())
+        if rec["mask"] is not None:
+            dx = ops.mul(dx, rec["mask"])
+        return dx
+
+
+class BackboneFunction(torch.autograd.Function):
+    """autograd bridge: (x_nhwc, *params) -> head output; backward replays the tape in reverse."""
+
+    @staticmethod
+    def forward(ctx, net, x, groups, extra, *params):
+        need = bool(extra.get("_save")) and any(ctx.needs_input_grad[4:])
+        ex = Exec(net.compute_dtype, net.training, groups, save=need)
+        y = net.run_forward(ex, x, extra)
+        ctx.ex = ex if need else None
+        ctx.net = net
+        ctx.params = params
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        ex = ctx.ex
+        if ex is None:
+            return (None,) * (4 + len(ctx.params))
+        dy = dy.contiguous()
+        ctx.net.run_backward(ex, dy)
+        grads = tuple(ex.grads.get(p) if need else None for p, need in zip(ctx.params, ctx.needs_input_grad[4:]))
+        ctx.ex = None
+        return (None, None, None, None) + grads
+
+
+def run_backbone(net, x, groups, extra=None):
+    params = tuple(net.parameters())
+    extra = dict(extra or {})
+    # grad mode is invisible inside Function.forward, so capture it here
+    extra["_save"] = torch.is_grad_enabled()
+    return BackboneFunction.apply(net, x, groups, extra, *params)

@@ -1,0 +1,140 @@
+"""AdaMML wrapper (drop-in for reference models/adamml.py): data layer -> policy -> gated main
+nets -> late fusion, with the segment x modality loop packed into batched launches."""
+import torch
+import torch.nn as nn
+
+from .. import ops
+from .joint_resnet_mobilenetv2 import joint_resnet_mobilenetv2
+from .policy_net import p_joint_mobilenet
+from .resnet import default_compute_dtype
+
+
+class AdaMML(nn.Module):
+    def __init__(self, policy_net, main_net, num_frames, num_segments, modality, rng_policy, rng_threshold,
+                 num_classes, compute_dtype=None):
+        super().__init__()
+        self.rng_policy = rng_policy
+        self.policy_net = policy_net
+        self.main_net = main_net
+        self.num_segments = num_segments
+        self.num_frames = num_frames * num_segments
+        self.num_frames_per_segment = num_frames
+        self.modality = modality
+        self.num_modality = len(modality) - 1 if ("rgbdiff" in modality and "flow" in modality) else len(modality)
+        self.p_data_idx = [modality.index(x) for x in policy_net.modality]
+        self.m_data_idx = [modality.index(x) for x in main_net.modality]
+        self.rng_threshold = rng_threshold
+        self.decay_ratio = 0.965
+        self.update_policy_net = True
+        self.update_main_net = True
+        self.compute_dtype = compute_dtype or default_compute_dtype()
+        if rng_policy:
+            self.freeze_policy_net()
+            del self.policy_net.fcs
+
+    # ------------------------------------------------------------------ data layer (adamml.py:42-67)
+    def data_layer(self, x, num_segments, p_rgb_size=(160, 160)):
+        """-> (p_x, m_x): NHWC image batches ordered (segment, video, frame) in the compute dtype."""
+        p_x, m_x = [], []
+        S, F = num_segments, self.num_frames_per_segment
+        dt = self.compute_dtype
+        for idx, (x_, m) in enumerate(zip(x, self.modality)):
+            x_ = x_.float()
+            if m == "sound":
+                if x_.size(-1) != x_.size(-2):  # segments stacked along the last dim
+                    x_ = torch.stack(x_.chunk(S, dim=-1), dim=1).reshape(x_.size(0), -1, x_.size(-2),
+                                                                         x_.size(-1) // S)
+                x_ = x_.reshape(x_.size(0), -1, x_.size(-2), x_.size(-1)).contiguous()
+                c = x_.size(1) // S
+                t = ops.pack_frames(x_, S, 1, c, dt)
+                p_x.append(t)
+                m_x.append(t)
+                continue
+            x_ = x_.contiguous()
+            c = x_.size(1) // (S * F)
+            if idx in self.p_data_idx:
+                p_x.append(ops.resize_frames(x_, S, F, c, p_rgb_size[0], p_rgb_size[1], 2, dt))
+            if idx in self.m_data_idx:
+                m_x.append(ops.pack_frames(x_, S, F, c, dt))
+        return p_x, m_x, S
+
+    def forward(self, x, num_segments=None, noise=None):
+        """x: list over modalities of [N, S*F*C, H, W] (sound: [N, S, 256, 256]).
+        -> (logits [N, classes], decisions [N, S, M]).  `noise` (tests only): dict(expo=[S,M*N,2],
+        drop=[per main modality [S*N*T', feat]]) replacing the torch RNG draws."""
+        S = num_segments if num_segments else self.num_segments
+        N = x[0].size(0)
+        p_x, m_x, S = self.data_layer(x, S)
+        dev = x[0].device
+        expo = noise["expo"] if noise else None
+        if not self.rng_policy:
+            if expo is None:  # drawn first, like the reference (policy runs before the main nets)
+                expo = self.policy_net.draw_gumbel_noise(S, N, dev)
+            decisions, _ = self.policy_net(p_x, S, N, expo=expo)
+        else:  # adamml.py:76-78
+            decisions = (torch.rand((S, self.num_modality, N), dtype=torch.float32, device=dev)
+                         > self.rng_threshold).float()
+        del p_x
+        logits = self.main_net(m_x, decisions, S, N, drop_masks=noise.get("drop") if noise else None)
+        return logits, decisions.permute(2, 0, 1)
+
+    def mean(self, modality="rgb"):
+        return [0.485, 0.456, 0.406] if modality in ("rgb", "rgbdiff") else [0.5]
+
+    def std(self, modality="rgb"):
+        return [0.229, 0.224, 0.225] if modality in ("rgb", "rgbdiff") else [sum([0.229, 0.224, 0.225]) / 3]
+
+    @property
+    def network_name(self):
+        name = "adamml"
+        if self.rng_policy:
+            name += "-rng-{:.1f}".format(self.rng_threshold)
+        else:
+            name += "-{}".format(self.policy_net.network_name)
+        return name + "-{}".format(self.main_net.network_name)
+
+    def decay_temperature(self, decay_ratio=None):
+        self.policy_net.decay_temperature(decay_ratio if decay_ratio else self.decay_ratio)
+
+    def _set_grad(self, net, flag):
+        for p in net.parameters():
+            p.requires_grad = flag
+
+    def freeze_policy_net(self):
+        self.update_policy_net = False
+        self._set_grad(self.policy_net, False)
+
+    def unfreeze_policy_net(self):
+        self.update_policy_net = True
+        self._set_grad(self.policy_net, True)
+
+    def freeze_main_net(self):
+        self.update_main_net = False
+        self._set_grad(self.main_net, False)
+
+    def unfreeze_main_net(self):
+        self.update_main_net = True
+        self._set_grad(self.main_net, True)
+
+
+def adamml(groups, modality, input_channels, num_segments, rng_policy, rng_threshold, causality_modeling,
+           num_classes, depth, without_t_stride, dropout, pooling_method, fusion_point, unimodality_pretrained,
+           learnable_lf_weights, **kwargs):
+    """Factory with the reference's kwargs (adamml.py:134-171)."""
+    cd = kwargs.get("compute_dtype")
+    if "rgbdiff" in modality and "flow" in modality:
+        p_mod = [m for m in modality if m != "flow"]
+        m_mod = [m for m in modality if m != "rgbdiff"]
+        p_ch = [c for c, m in zip(input_channels, modality) if m != "flow"]
+        m_ch = [c for c, m in zip(input_channels, modality) if m != "rgbdiff"]
+    else:
+        p_mod, m_mod, p_ch, m_ch = modality, modality, input_channels, input_channels
+    policy_net = p_joint_mobilenet(num_frames=max(1, groups // 2), modality=p_mod, input_channels=p_ch,
+                                   causality_modeling=causality_modeling, compute_dtype=cd)
+    main_net = joint_resnet_mobilenetv2(depth=depth, num_classes=num_classes, without_t_stride=without_t_stride,
+                                        groups=groups, dropout=dropout, pooling_method=pooling_method,
+                                        input_channels=m_ch, fusion_point=fusion_point, modality=m_mod,
+                                        unimodality_pretrained=unimodality_pretrained,
+                                        learnable_lf_weights=learnable_lf_weights, compute_dtype=cd)
+    return AdaMML(policy_net, main_net, num_frames=groups, num_segments=num_segments, modality=modality,
+                  rng_policy=rng_policy, rng_threshold=rng_threshold, num_classes=num_classes, compute_dtype=cd)

@@ -1,0 +1,333 @@
+"""Tensor-level wrappers over the C-ABI (include/adamml_b200.h).
+
+Every function takes/returns torch CUDA tensors whose storage comes from torch's caching
+allocator; all arithmetic happens inside libadamml_b200.so.  Activations are NHWC
+`[IMGS, H, W, C]` tensors (fp32 or bf16); weights for the dense engines are OHWI.
+"""
+import torch
+
+from . import _lib
+from ._lib import ACT_NONE, ACT_RELU, ACT_RELU6, call, dtype_code  # noqa: F401
+
+# Engine selection for bf16 dense GEMM-shaped convs: "auto" = tcgen05 when the shape fits,
+# "simt" = always the exact CUDA-core engine.
+TC_MODE = "auto"
+
+
+def _chk(t, dtype=None):
+    assert t.is_cuda and t.is_contiguous(), "adamml_b200 ops need contiguous CUDA tensors"
+    if dtype is not None:
+        assert t.dtype == dtype, f"expected {dtype}, got {t.dtype}"
+    return t
+
+
+def conv_out_hw(H, W, R, S, stride, pad):
+    return (H + 2 * pad - R) // stride + 1, (W + 2 * pad - S) // stride + 1
+
+
+# ---------------------------------------------------------------- data layer
+def pack_frames(x, S, F, C, dtype, cpad=None):
+    """x NCHW fp32 [N, S*F*C, H, W] -> NHWC [(s*N+n)*F+f, H, W, cpad]."""
+    _chk(x, torch.float32)
+    N, SFC, H, W = x.shape
+    assert SFC == S * F * C, (x.shape, S, F, C)
+    cpad = cpad or C
+    out = torch.empty((S * N * F, H, W, cpad), device=x.device, dtype=dtype)
+    call("pack_frames", x, out, N, S, F, C, H, W, cpad, dtype_code(dtype))
+    return out
+
+
+def resize_frames(x, S, F, C, OH, OW, fstep, dtype, cpad=None):
+    _chk(x, torch.float32)
+    N, SFC, H, W = x.shape
+    assert SFC == S * F * C
+    cpad = cpad or C
+    Fk = (F + fstep - 1) // fstep
+    out = torch.empty((S * N * Fk, OH, OW, cpad), device=x.device, dtype=dtype)
+    call("resize_frames", x, out, N, S, F, C, H, W, OH, OW, fstep, cpad, dtype_code(dtype))
+    return out
+
+
+def pack_weight(w, dtype, cin_pad=None):
+    """OIHW fp32 parameter -> OHWI operand [Cout, R, S, cin_pad] in `dtype`."""
+    _chk(w, torch.float32)
+    Cout, Cin, R, S = w.shape
+    cin_pad = cin_pad or Cin
+    if R == 1 and S == 1 and cin_pad == Cin and dtype == torch.float32:
+        return w.view(Cout, 1, 1, Cin)
+    out = torch.empty((Cout, R, S, cin_pad), device=w.device, dtype=dtype)
+    call("pack_weight", w, out, Cout, Cin, R, S, cin_pad, dtype_code(dtype))
+    return out
+
+
+def unpack_wgrad(dw_ohwi, Cin):
+    Cout, R, S, cin_pad = dw_ohwi.shape
+    _chk(dw_ohwi, torch.float32)
+    if R == 1 and S == 1 and cin_pad == Cin:
+        return dw_ohwi.view(Cout, Cin, 1, 1)
+    out = torch.empty((Cout, Cin, R, S), device=dw_ohwi.device, dtype=torch.float32)
+    call("unpack_wgrad", dw_ohwi, out, Cout, Cin, R, S, cin_pad, 0)
+    return out
+
+
+def cast(x, dtype):
+    _chk(x)
+    out = torch.empty_like(x, dtype=dtype)
+    call("cast", x, out, x.numel(), dtype_code(x.dtype), dtype_code(dtype))
+    return out
+
+
+# ---------------------------------------------------------------- dense conv
+def _tc_ok(x, Cin, Cout, R, S, stride, pad):
+    return (TC_MODE == "auto" and x.dtype == torch.bfloat16 and R == 1 and S == 1 and stride == 1 and pad == 0
+            and Cin % 8 == 0 and Cout % 8 == 0)
+
+
+def conv_fwd(x, w, stride, pad, out=None, stats=None, rows_per_group=0):
+    """x [IMGS,H,W,Cin], w OHWI [Cout,R,S,Cin] -> y [IMGS,Ho,Wo,Cout].
+
+    If `stats` (double [G,Cout,2]) is given and the tcgen05 engine takes the layer, the BN
+    batch statistics are produced by the GEMM epilogue and True is returned as second value.
+    """
+    _chk(x); _chk(w, x.dtype)
+    IMGS, H, W, Cin = x.shape
+    Cout, R, S, Cw = w.shape
+    assert Cw == Cin, (w.shape, x.shape)
+    Ho, Wo = conv_out_hw(H, W, R, S, stride, pad)
+    if out is None:
+        out = torch.empty((IMGS, Ho, Wo, Cout), device=x.device, dtype=x.dtype)
+    if _tc_ok(x, Cin, Cout, R, S, stride, pad):
+        call("tc_gemm_bf16", x, w, out, IMGS * H * W, Cout, Cin, 0, 0, 0, _lib.BF16, stats, rows_per_group)
+        return out, stats is not None
+    call("simt_conv_fwd", x, w, out, IMGS, H, W, Cin, Cout, R, S, stride, pad, Ho, Wo, 0, 0, 0, dtype_code(x.dtype))
+    return out, False
+
+
+def conv_dgrad(dy, w, x_shape, stride, pad, addend=None, w_t=None):
+    """dx = conv_transpose(dy, w) (+ addend).  w_t: optional [Cin, Cout] transposed 1x1 weight (bf16)."""
+    _chk(dy); _chk(w, dy.dtype)
+    IMGS, H, W, Cin = x_shape
+    Cout, R, S, _ = w.shape
+    Ho, Wo = dy.shape[1], dy.shape[2]
+    dx = torch.empty(x_shape, device=dy.device, dtype=dy.dtype)
+    if addend is None and w_t is not None and _tc_ok(dy, Cout, Cin, R, S, stride, pad):
+        call("tc_gemm_bf16", dy, w_t, dx, IMGS * H * W, Cin, Cout, 0, 0, 0, _lib.BF16, None, 0)
+        return dx
+    call("simt_conv_dgrad", dy, w, dx, addend, IMGS, H, W, Cin, Cout, R, S, stride, pad, Ho, Wo, 0, 0, 0,
+         dtype_code(dy.dtype))
+    return dx
+
+
+def conv_wgrad(x, dy, w_shape, stride, pad):
+    """-> dw fp32 OHWI [Cout,R,S,Cin]."""
+    _chk(x); _chk(dy, x.dtype)
+    IMGS, H, W, Cin = x.shape
+    Cout, R, S, _ = w_shape
+    Ho, Wo = dy.shape[1], dy.shape[2]
+    dw = torch.empty((Cout, R, S, Cin), device=x.device, dtype=torch.float32)
+    call("simt_conv_wgrad", x, dy, dw, IMGS, H, W, Cin, Cout, R, S, stride, pad, Ho, Wo, 0, 0, 0,
+         dtype_code(x.dtype))
+    return dw
+
+
+# ---------------------------------------------------------------- fp32 linear algebra (H=W=1 convs)
+def linear_fwd(x, w, out=None, x_ld=0, y_ld=0, w_ld=0, K=None):
+    """y[rows, Nout] = x[rows, :K] . w[Nout, :K]^T   (fp32, strided)."""
+    rows = x.shape[0]
+    Nout = w.shape[0]
+    K = K or w.shape[1]
+    if out is None:
+        out = torch.empty((rows, Nout), device=x.device, dtype=torch.float32)
+    call("simt_conv_fwd", x, w, out, rows, 1, 1, K, Nout, 1, 1, 1, 0, 1, 1, x_ld or x.stride(0), y_ld or out.stride(0),
+         w_ld or w.stride(0), _lib.F32)
+    return out
+
+
+def linear_dgrad(dy, w, K=None, out=None, w_ld=0, x_ld=0, y_ld=0):
+    """dx[rows, K] = dy[rows, Nout] . w[Nout, :K]."""
+    rows, Nout = dy.shape[0], w.shape[0]
+    K = K or w.shape[1]
+    if out is None:
+        out = torch.empty((rows, K), device=dy.device, dtype=torch.float32)
+    call("simt_conv_dgrad", dy, w, out, None, rows, 1, 1, K, Nout, 1, 1, 1, 0, 1, 1, x_ld or out.stride(0),
+         y_ld or dy.stride(0), w_ld or w.stride(0), _lib.F32)
+    return out
+
+
+def linear_wgrad(x, dy, K=None, x_ld=0, y_ld=0):
+    """dw[Nout, K] = dy[rows, Nout]^T . x[rows, :K]."""
+    rows, Nout = dy.shape
+    K = K or x.shape[1]
+    dw = torch.empty((Nout, K), device=x.device, dtype=torch.float32)
+    call("simt_conv_wgrad", x, dy, dw, rows, 1, 1, K, Nout, 1, 1, 1, 0, 1, 1, x_ld or x.stride(0),
+         y_ld or dy.stride(0), 0, _lib.F32)
+    return dw
+
+
+# ---------------------------------------------------------------- depthwise
+def dwconv_fwd(x, w, stride):
+    _chk(x); _chk(w, torch.float32)
+    IMGS, H, W, C = x.shape
+    Ho, Wo = conv_out_hw(H, W, 3, 3, stride, 1)
+    y = torch.empty((IMGS, Ho, Wo, C), device=x.device, dtype=x.dtype)
+    call("dwconv_fwd", x, w, y, IMGS, H, W, C, stride, Ho, Wo, dtype_code(x.dtype))
+    return y
+
+
+def dwconv_dgrad(dy, w, x_shape, stride, addend=None):
+    IMGS, H, W, C = x_shape
+    dx = torch.empty(x_shape, device=dy.device, dtype=dy.dtype)
+    call("dwconv_dgrad", dy, w, dx, addend, IMGS, H, W, C, stride, dy.shape[1], dy.shape[2], dtype_code(dy.dtype))
+    return dx
+
+
+def dwconv_wgrad(x, dy, stride):
+    IMGS, H, W, C = x.shape
+    dw = torch.empty((C, 1, 3, 3), device=x.device, dtype=torch.float32)
+    call("dwconv_wgrad", x, dy, dw, IMGS, H, W, C, stride, dy.shape[1], dy.shape[2], dtype_code(x.dtype))
+    return dw
+
+
+# ---------------------------------------------------------------- batch norm
+def bn_stats(z, G):
+    C = z.shape[-1]
+    rows = z.numel() // C
+    sums = torch.empty((G, C, 2), device=z.device, dtype=torch.float64)
+    call("bn_stats", z, sums, rows // G, C, G, dtype_code(z.dtype))
+    return sums
+
+
+def bn_finalize(sums, gamma, beta, running_mean, running_var, count, momentum, eps, C, G, training, update_running):
+    dev = gamma.device
+    mean_invstd = torch.empty((G, C, 2), device=dev, dtype=torch.float32)
+    scale_shift = torch.empty((G, C, 2), device=dev, dtype=torch.float32)
+    call("bn_finalize", sums, gamma, beta, running_mean, running_var, mean_invstd, scale_shift, float(count),
+         float(momentum), float(eps), C, G, int(training), int(update_running))
+    return mean_invstd, scale_shift
+
+
+def bn_apply(z, scale_shift, G, act, res=None, res_z=None, res_ss=None, out=None):
+    C = z.shape[-1]
+    rows = z.numel() // C
+    if out is None:
+        out = torch.empty_like(z)
+    call("bn_apply", z, scale_shift, res, res_z, res_ss, out, rows // G, C, G, act, dtype_code(z.dtype))
+    return out
+
+
+def bn_bwd_reduce(dout, out, z, mean_invstd, G, act):
+    C = z.shape[-1]
+    rows = z.numel() // C
+    sums = torch.empty((G, C, 2), device=z.device, dtype=torch.float64)
+    call("bn_bwd_reduce", dout, out, z, mean_invstd, sums, rows // G, C, G, act, dtype_code(z.dtype))
+    return sums
+
+
+def bn_bwd_apply(dout, out, z, mean_invstd, gamma, sums, G, count, act, training, want_dz=True, want_dres=False):
+    C = dout.shape[-1]
+    rows = dout.numel() // C
+    dz = torch.empty_like(dout) if want_dz else None
+    dres = torch.empty_like(dout) if want_dres else None
+    call("bn_bwd_apply", dout, out, z, mean_invstd, gamma, sums, dz, dres, rows // G, C, G, float(count), act,
+         int(training), dtype_code(dout.dtype))
+    return dz, dres
+
+
+def bn_param_grad(sums, C, G):
+    dgamma = torch.empty(C, device=sums.device, dtype=torch.float32)
+    dbeta = torch.empty(C, device=sums.device, dtype=torch.float32)
+    call("bn_param_grad", sums, dgamma, dbeta, C, G, 0)
+    return dgamma, dbeta
+
+
+# ---------------------------------------------------------------- pools
+def maxpool_fwd(x):
+    IMGS, H, W, C = x.shape
+    Ho, Wo = conv_out_hw(H, W, 3, 3, 2, 1)
+    y = torch.empty((IMGS, Ho, Wo, C), device=x.device, dtype=x.dtype)
+    call("maxpool3x3s2_fwd", x, y, IMGS, H, W, C, Ho, Wo, dtype_code(x.dtype))
+    return y
+
+
+def maxpool_bwd(x, dy):
+    IMGS, H, W, C = x.shape
+    dx = torch.empty_like(x)
+    call("maxpool3x3s2_bwd", x, dy, dx, IMGS, H, W, C, dy.shape[1], dy.shape[2], dtype_code(x.dtype))
+    return dx
+
+
+def tpool_fwd(x, T, mode_avg=False):
+    IMGS, H, W, C = x.shape
+    V = IMGS // T
+    To = (T + 2 - 3) // 2 + 1
+    y = torch.empty((V * To, H, W, C), device=x.device, dtype=x.dtype)
+    call("tpool_fwd", x, y, V, T, H * W * C, int(mode_avg), dtype_code(x.dtype))
+    return y
+
+
+def tpool_bwd(x, dy, T, mode_avg=False):
+    IMGS, H, W, C = x.shape
+    dx = torch.empty_like(x)
+    call("tpool_bwd", x, dy, dx, IMGS // T, T, H * W * C, int(mode_avg), dtype_code(x.dtype))
+    return dx
+
+
+def avgpool_fwd(x, out=None, out_ld=0):
+    IMGS, H, W, C = x.shape
+    if out is None:
+        out = torch.empty((IMGS, C), device=x.device, dtype=torch.float32)
+    call("avgpool_fwd", x, out, IMGS, H * W, C, out_ld or out.stride(0), dtype_code(x.dtype))
+    return out
+
+
+def avgpool_bwd(dy, x_shape, dtype, dy_ld=0):
+    IMGS, H, W, C = x_shape
+    dx = torch.empty(x_shape, device=dy.device, dtype=dtype)
+    call("avgpool_bwd", dy, dx, IMGS, H * W, C, dy_ld or dy.stride(0), dtype_code(dtype))
+    return dx
+
+
+def frame_mean(x, T, out=None, out_ld=0):
+    rows, C = x.shape
+    V = rows // T
+    if out is None:
+        out = torch.empty((V, C), device=x.device, dtype=torch.float32)
+    call("frame_mean", x, out, V, T, C, out_ld or out.stride(0))
+    return out
+
+
+def frame_mean_bwd(dy, T, dy_ld=0):
+    V, C = dy.shape
+    dx = torch.empty((V * T, C), device=dy.device, dtype=torch.float32)
+    call("frame_mean_bwd", dy, dx, V, T, C, dy_ld or dy.stride(0))
+    return dx
+
+
+# ---------------------------------------------------------------- small fp32 helpers
+def bias_act_(y, bias, act, rows=None, cols=None, ld=0):
+    rows = rows if rows is not None else y.shape[0]
+    cols = cols if cols is not None else y.shape[1]
+    call("bias_act", y, bias, rows, cols, ld or y.stride(0), act)
+    return y
+
+
+def act_bwd(dy, y, act, rows=None, cols=None, ld_dy=0, ld_y=0):
+    rows = rows if rows is not None else dy.shape[0]
+    cols = cols if cols is not None else dy.shape[1]
+    dz = torch.empty((rows, cols), device=dy.device, dtype=torch.float32)
+    call("act_bwd", dy, y, dz, rows, cols, ld_dy or dy.stride(0), ld_y or y.stride(0), cols, act)
+    return dz
+
+
+def colsum(x, rows=None, cols=None, ld=0):
+    rows = rows if rows is not None else x.shape[0]
+    cols = cols if cols is not None else x.shape[1]
+    out = torch.empty(cols, device=x.device, dtype=torch.float32)
+    call("colsum", x, out, rows, cols, ld or x.stride(0), 0)
+    return out
+
+
+def mul(a, b):
+    out = torch.empty_like(a)
+    call("mul", a, b, out, a.numel())
+    return out

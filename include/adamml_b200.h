@@ -1,0 +1,170 @@
+/* adamml_b200.h — C-ABI of libadamml_b200.so (sm_100a CUDA kernels of the AdaMML hot path).
+ *
+ * The reference (IBM/AdaMML) has no FFI: every operator below replaces a torch.nn call site
+ * inside reference models/*.py (cited per entry point).  The drop-in boundary above this ABI
+ * is the Python package adamml_b200.models (build_model / MODEL_TABLE / AdaMML.forward), which
+ * binds these symbols with ctypes (adamml_b200/_lib.py; INTEGRATION.md shows the stub).
+ *
+ * Conventions:
+ *  - every pointer is a DEVICE pointer owned by the caller (torch's caching allocator);
+ *    the library never allocates, frees or retains memory;
+ *  - every call is asynchronous on the caller-supplied `stream`; no hidden synchronisation;
+ *  - return value 0 = success; non-zero = error, message via adamml_last_error() (thread local);
+ *  - activations are NHWC ("channels last"), images ordered segment-major:
+ *        img = (segment * N + video) * frames + frame ;  BN group = segment;
+ *  - `dtype` selects the activation type: ADAMML_F32 (0) or ADAMML_BF16 (1); all
+ *    accumulation, BN statistics and the whole policy head are fp32/fp64;
+ *  - dense conv weights are OHWI ([Cout][R][S][Cin], row stride w_ld) in the activation dtype,
+ *    produced from torch's OIHW fp32 parameters by adamml_pack_weight;
+ *  - *_ld arguments are element strides between consecutive pixels/rows; pass 0 for "dense".
+ */
+#ifndef ADAMML_B200_H_
+#define ADAMML_B200_H_
+
+#include <cuda_runtime_api.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ADAMML_F32 0
+#define ADAMML_BF16 1
+#define ADAMML_ACT_NONE 0
+#define ADAMML_ACT_RELU 1
+#define ADAMML_ACT_RELU6 2
+
+/* ---- library ---- */
+const char* adamml_last_error(void);
+int adamml_abi_version(void);
+unsigned long long adamml_launch_count(void); /* kernels launched by this process so far */
+
+/* ---- data layer: models/adamml.py:42-67 (AdaMML.data_layer) ---- */
+/* x NCHW fp32 [N, S*F*C, H, W] -> NHWC [(s*N+n)*F+f, H, W, Cpad]  (adamml.py:53,65) */
+int adamml_pack_frames(const float* x, void* out, int N, int S, int F, int C, int H, int W, int Cpad, int dtype,
+                       cudaStream_t stream);
+/* F.interpolate(bilinear, align_corners=False) to OHxOW + keep frames 0,fstep,.. (adamml.py:59-62) */
+int adamml_resize_frames(const float* x, void* out, int N, int S, int F, int C, int H, int W, int OH, int OW,
+                         int fstep, int Cpad, int dtype, cudaStream_t stream);
+/* nn.Conv2d.weight OIHW fp32 -> OHWI operand (CinPad >= Cin, zero filled) */
+int adamml_pack_weight(const float* w_oihw, void* w_ohwi, int Cout, int Cin, int R, int S, int CinPad, int dtype,
+                       cudaStream_t stream);
+/* OHWI fp32 weight gradient -> OIHW fp32 .grad layout */
+int adamml_unpack_wgrad(const float* dw_ohwi, float* dw_oihw, int Cout, int Cin, int R, int S, int CinPad,
+                        int accumulate, cudaStream_t stream);
+int adamml_cast(const void* src, void* dst, long long total, int src_dtype, int dst_dtype, cudaStream_t stream);
+
+/* ---- dense convolution / linear, exact fp32-math engine (CUDA cores) ----
+ * nn.Conv2d at models/resnet.py:35-43,138 ; sound_mobilenet_v2.py:36,61 ; policy_net.py:40,49,66-84
+ * nn.Linear at resnet.py:159 ; sound_mobilenet_v2.py:134 ; policy_net.py:229-230,278-279 (H=W=1) */
+int adamml_simt_conv_fwd(const void* x, const void* w, void* y, int IMGS, int H, int W, int Cin, int Cout, int R,
+                         int S, int stride, int pad, int Ho, int Wo, long long x_ld, long long y_ld, long long w_ld,
+                         int dtype, cudaStream_t stream);
+/* dx = conv_transpose(dy, w) (+ addend) */
+int adamml_simt_conv_dgrad(const void* dy, const void* w, void* dx, const void* addend, int IMGS, int H, int W,
+                           int Cin, int Cout, int R, int S, int stride, int pad, int Ho, int Wo, long long x_ld,
+                           long long y_ld, long long w_ld, int dtype, cudaStream_t stream);
+/* dw (fp32, OHWI, overwritten) = sum_pixels dy (x) x */
+int adamml_simt_conv_wgrad(const void* x, const void* dy, float* dw, int IMGS, int H, int W, int Cin, int Cout,
+                           int R, int S, int stride, int pad, int Ho, int Wo, long long x_ld, long long y_ld,
+                           long long w_ld, int dtype, cudaStream_t stream);
+
+/* ---- dense convolution, tcgen05 tensor-core engine (bf16 operands, fp32 TMEM accumulators) ----
+ * Same call sites as above.  GEMM view  D[M, Ncols] = A[M, K] . B[Ncols, K]^T  with A and B both
+ * K-major bf16 (row strides lda/ldb elements, multiples of 8), D bf16 or fp32 row-major (ldd).
+ * Used for 1x1 convolutions forward (A = activations, B = weights) and dgrad (A = dy, B = w^T).
+ * Optional fused epilogue: per-(group, column) sum / sum-of-squares of the fp32 accumulators
+ * (train-mode BatchNorm statistics, resnet.py:97,101,105) accumulated into `stats` [G][Ncols][2]
+ * (double), rows_per_group rows per BN group.  Returns ADAMML_ERR_UNSUPPORTED (3) for shapes
+ * outside its envelope so that the caller can route to the exact engine. */
+int adamml_tc_gemm_bf16(const void* A, const void* B, void* D, long long M, int Ncols, int K, long long lda,
+                        long long ldb, long long ldd, int d_dtype, double* stats, long long rows_per_group,
+                        cudaStream_t stream);
+int adamml_tc_supported(long long M, int Ncols, int K, long long lda, long long ldb, long long ldd);
+
+/* ---- depthwise 3x3 conv, pad 1, stride 1|2; weights fp32 [C][3][3] (= torch [C,1,3,3]) ----
+ * sound_mobilenet_v2.py:58 ; policy_net.py:66,80 */
+int adamml_dwconv_fwd(const void* x, const float* w, void* y, int IMGS, int H, int W, int C, int stride, int Ho,
+                      int Wo, int dtype, cudaStream_t stream);
+int adamml_dwconv_dgrad(const void* dy, const float* w, void* dx, const void* addend, int IMGS, int H, int W, int C,
+                        int stride, int Ho, int Wo, int dtype, cudaStream_t stream);
+int adamml_dwconv_wgrad(const void* x, const void* dy, float* dw, int IMGS, int H, int W, int C, int stride, int Ho,
+                        int Wo, int dtype, cudaStream_t stream);
+
+/* ---- BatchNorm2d (+ReLU/ReLU6, + residual) with per-segment groups ----
+ * nn.BatchNorm2d at resnet.py:50,53,82-86,139,166 ; sound_mobilenet_v2.py:37,62 ; policy_net.py:41,50,67-85
+ * sums: double [G][C][2]; mean_invstd / scale_shift: float [G][C][2] */
+int adamml_bn_stats(const void* z, double* sums, long long rows_per_group, int C, int G, int dtype,
+                    cudaStream_t stream);
+int adamml_bn_finalize(const double* sums, const float* gamma, const float* beta, float* running_mean,
+                       float* running_var, float* mean_invstd, float* scale_shift, double count, float momentum,
+                       float eps, int C, int G, int training, int update_running, cudaStream_t stream);
+/* out = act(z*scale+shift [+ res] [+ res_z*res_scale+res_shift])  (resnet.py:104-111 residual + ReLU) */
+int adamml_bn_apply(const void* z, const float* scale_shift, const void* res, const void* res_z,
+                    const float* res_scale_shift, void* out, long long rows_per_group, int C, int G, int act,
+                    int dtype, cudaStream_t stream);
+int adamml_bn_bwd_reduce(const void* dout, const void* out, const void* z, const float* mean_invstd, double* sums,
+                         long long rows_per_group, int C, int G, int act, int dtype, cudaStream_t stream);
+int adamml_bn_bwd_apply(const void* dout, const void* out, const void* z, const float* mean_invstd,
+                        const float* gamma, const double* sums, void* dz, void* dres, long long rows_per_group, int C,
+                        int G, double count, int act, int training, int dtype, cudaStream_t stream);
+int adamml_bn_param_grad(const double* sums, float* dgamma, float* dbeta, int C, int G, int accumulate,
+                         cudaStream_t stream);
+
+/* ---- pooling ---- */
+/* nn.MaxPool2d(3,2,1): resnet.py:141,202 */
+int adamml_maxpool3x3s2_fwd(const void* x, void* y, int IMGS, int H, int W, int C, int Ho, int Wo, int dtype,
+                            cudaStream_t stream);
+int adamml_maxpool3x3s2_bwd(const void* x, const void* dy, void* dx, int IMGS, int H, int W, int C, int Ho, int Wo,
+                            int dtype, cudaStream_t stream);
+/* TemporalPooling k3 s2 p1 over frames: common.py:4-33 ; x [V videos][Tn frames][E = H*W*C] */
+int adamml_tpool_fwd(const void* x, void* y, long long V, int Tn, long long E, int mode_avg, int dtype,
+                     cudaStream_t stream);
+int adamml_tpool_bwd(const void* x, const void* dy, void* dx, long long V, int Tn, long long E, int mode_avg,
+                     int dtype, cudaStream_t stream);
+/* nn.AdaptiveAvgPool2d(1): resnet.py:157,212 ; sound_mobilenet_v2.py:156 ; policy_net.py:136,146 */
+int adamml_avgpool_fwd(const void* x, float* y, int IMGS, int HW, int C, long long y_ld, int dtype,
+                       cudaStream_t stream);
+int adamml_avgpool_bwd(const float* dy, void* dx, int IMGS, int HW, int C, long long dy_ld, int dtype,
+                       cudaStream_t stream);
+/* torch.mean over the remaining frames of a video: resnet.py:218-221 */
+int adamml_frame_mean(const float* x, float* out, long long V, int Tn, int C, long long out_ld, cudaStream_t stream);
+int adamml_frame_mean_bwd(const float* dy, float* dx, long long V, int Tn, int C, long long dy_ld,
+                          cudaStream_t stream);
+
+/* ---- fp32 helpers for nn.Linear bias / ReLU / Dropout-mask ---- */
+int adamml_bias_act(float* y, const float* bias, long long rows, int cols, long long ld, int act,
+                    cudaStream_t stream);
+int adamml_act_bwd(const float* dy, const float* y, float* dz, long long rows, int cols, long long ld_dy,
+                   long long ld_y, long long ld_dz, int act, cudaStream_t stream);
+int adamml_colsum(const float* x, float* out, long long rows, int cols, long long ld, int accumulate,
+                  cudaStream_t stream);
+int adamml_mul(const float* a, const float* b, float* out, long long total, cudaStream_t stream);
+
+/* ---- policy head: LSTMCell + Linear(256,2) x M + hard Gumbel-softmax, one segment step ----
+ * policy_net.py:283-290 (wrapper_gumbel_softmax), :345-365 (LSTM loop).
+ * gx [N,4Hd] = W_ih[:, :Fdim] . feat (hoisted GEMM); prev_logits/logits/ysoft [M][N][2];
+ * expo = Exp(1) samples [M*N][2] in torch's draw order; dec [M][N] in {0,1}. */
+int adamml_policy_step_fwd(const float* gx, const float* prev_logits, const float* h_prev, const float* c_prev,
+                           const float* w_ih, long long w_ih_ld, int Fdim, const float* w_hh, const float* b_ih,
+                           const float* b_hh, const float* fc_w, const float* fc_b, const float* expo, float tau,
+                           float* gates_out, float* h_out, float* c_out, float* logits_out, float* ysoft_out,
+                           float* dec_out, float* xin_tail, long long xin_ld, int N, int M, int Hd,
+                           cudaStream_t stream);
+int adamml_policy_step_bwd(const float* d_dec, const float* d_logits_fb, const float* dh_next, const float* dc_next,
+                           const float* gates, const float* c_cur, const float* c_prev, const float* ysoft,
+                           const float* w_ih, long long w_ih_ld, int Fdim, const float* w_hh, const float* fc_w,
+                           float tau, float* dl_out, long long dl_ms, float* dgates_out, float* dh_prev,
+                           float* dc_prev, float* d_prev_logits, int N, int M, int Hd, cudaStream_t stream);
+
+/* ---- gate x logits, late-fusion weights, sum over modalities, mean over segments ----
+ * joint_resnet_mobilenetv2.py:92-97,112-127 ; adamml.py:88.
+ * logits [M][S][N][C]; dec [S][M][N] (NULL = ungated); lf [M-1] (NULL = plain mean); out [N][C] */
+int adamml_fuse_fwd(const float* logits, const float* dec, const float* lf, float* out, int M, int S, int N, int C,
+                    cudaStream_t stream);
+int adamml_fuse_bwd(const float* g, const float* logits, const float* dec, const float* lf, float* dlogits,
+                    float* ddec, float* dlf, int M, int S, int N, int C, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADAMML_B200_H_ */

@@ -1,0 +1,185 @@
+"""GPU parity: the CUDA path (through the C-ABI) against the golden vectors recorded from the
+reference and against the CPU oracle run live on the same seeded inputs.
+
+Tolerance (BASELINE.json north_star): logits within 1e-3 relative (max|a-b| / max|b|) in the
+fp32 parity mode, policy selections bit-exact under a fixed seed.  The bf16 speed mode is
+checked separately with its own (stated) tolerance.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from util import O, fingerprint, load_golden, namespace, noise_for_model, rel
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["resnet50_rgb_b2", "adamml_rgb_sound_eval", "adamml_rgb_flow_train", "adamml_rgb_sound_flow_train",
+         "adamml_rgb_sound_train"]
+LOGIT_TOL = 1e-3
+
+
+def build(case, dtype, cuda):
+    from adamml_b200.models import build_model
+    model, arch = build_model(namespace(case, compute_dtype=dtype))
+    shapes = {k: v.shape for k, v in model.state_dict().items()}
+    model.load_state_dict(O.fill_state_dict(shapes, seed=0), strict=True)
+    return model.to(cuda), arch
+
+
+def run_product(model, case, g_seed, cuda):
+    cfg = O.make_cfg(case["modality"], num_segments=case["S"])
+    N, S_run, training = case["N"], case.get("S_run", case["S"]), case["training"]
+    xs, y = O.make_inputs(cfg, N, S_run, hw=case["hw"])
+    xs = [x.to(cuda) for x in xs]
+    y = y.to(cuda)
+    model.train(training)
+    if case["kind"] == "resnet":
+        gen = torch.Generator(); gen.manual_seed(g_seed)
+        mask = torch.empty(N, 2048).bernoulli_(0.5, generator=gen).div_(0.5).to(cuda)
+        logits = model(xs[0], drop_mask=mask)
+        return logits, None, F.cross_entropy(logits, y)
+    noise = noise_for_model(O.draw_noise(g_seed, cfg, N, S_run, training), cuda)
+    with torch.set_grad_enabled(training):
+        logits, dec = model(xs, num_segments=S_run, noise=noise)
+    loss = F.cross_entropy(logits, y)
+    if training:  # utils/utils.py:362,380-382 — the loss tail stays in torch
+        correct = (logits.detach().argmax(-1) == y).float()
+        sel = dec.mean(1) ** 2
+        pl = sum(1.0 * torch.mean(correct * c) for c in sel.chunk(sel.shape[-1], dim=-1))
+        loss = loss + pl + torch.mean((1 - correct) * 10.0)
+    return logits, dec, loss
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_fp32_mode_matches_reference_golden(cuda, name):
+    g = load_golden(name)
+    case = g["case"]
+    model, arch = build(case, torch.float32, cuda)
+    assert arch == g["arch"]
+    logits, dec, loss = run_product(model, case, g["seed"], cuda)
+    assert rel(logits, g["logits"]) < LOGIT_TOL
+    if dec is not None:
+        assert torch.equal(dec.detach().cpu(), g["decisions"]), "policy selections must be bit-exact"
+    assert abs(loss.item() - g["loss"].item()) < 1e-3 * max(1.0, abs(g["loss"].item()))
+    if not case["training"]:
+        return
+    loss.backward()
+    torch.cuda.synchronize()
+    grads = {k: p.grad for k, p in model.named_parameters() if p.grad is not None}
+    assert set(g["grad_fp"]) <= set(grads), sorted(set(g["grad_fp"]) - set(grads))[:5]
+    worst = 0.0
+    for k, ref in g["grad_small"].items():
+        e = rel(grads[k], ref)
+        worst = max(worst, e)
+        assert e < 2e-2, (k, e)
+    for k, fp in g["grad_fp"].items():
+        e = rel(fingerprint(grads[k])[1], fp[1])  # sum |g|
+        assert e < 5e-3, (k, e)
+    sd = model.state_dict()
+    for k, fp in g["running_fp"].items():
+        assert rel(fingerprint(sd[k])[1], fp[1]) < 1e-4, k
+    for k, v in g["num_batches_tracked"].items():
+        assert int(sd[k]) == v, k
+    print(f"{name}: logits rel {rel(logits, g['logits']):.2e}, worst small-grad rel {worst:.2e}")
+
+
+def test_fp32_mode_matches_live_oracle_all_grads(cuda):
+    """Every parameter gradient, element-wise, against the oracle run here on CPU."""
+    case = dict(kind="adamml", modality=["rgb", "sound"], N=2, S=3, hw=64, training=True)
+    model, _ = build(case, torch.float32, cuda)
+    logits, dec, loss = run_product(model, case, 5, cuda)
+    loss.backward()
+    cfg = O.make_cfg(case["modality"], num_segments=case["S"])
+    shapes = {k: v.shape for k, v in model.state_dict().items()}
+    sd = O.clone_sd(O.fill_state_dict(shapes, seed=0))
+    xs, y = O.make_inputs(cfg, 2, 3, hw=64)
+    noise = O.draw_noise(5, cfg, 2, 3, True)
+    o_logits, o_dec = O.adamml_forward(sd, xs, cfg, True, noise)
+    o_loss = F.cross_entropy(o_logits, y) + O.policy_loss(o_dec, [1.0, 1.0], 10.0, o_logits, y)
+    o_loss.backward()
+    assert rel(logits, o_logits) < LOGIT_TOL
+    assert torch.equal(dec.detach().cpu(), o_dec.detach())
+    bad = []
+    for k, p in model.named_parameters():
+        og = sd[k].grad
+        if og is None:
+            assert p.grad is None or p.grad.abs().max() == 0, k
+            continue
+        e = rel(p.grad, og)
+        if e > 2e-2:
+            bad.append((k, e))
+    assert not bad, bad[:10]
+    new = model.state_dict()
+    for k in new:
+        if k.endswith(("running_mean", "running_var")):
+            assert rel(new[k], sd[k]) < 1e-4, k
+
+
+def test_frozen_phases(cuda):
+    """Warm-up / policy phases (train_adamml.py:344-345,410-411): frozen halves get no grads, the
+    other half's grads are unchanged."""
+    case = dict(kind="adamml", modality=["rgb", "sound"], N=1, S=2, hw=64, training=True)
+    model, _ = build(case, torch.float32, cuda)
+    _, _, loss = run_product(model, case, 7, cuda)
+    loss.backward()
+    ref = {k: p.grad.clone() for k, p in model.named_parameters()}
+    model.zero_grad(set_to_none=True)
+    sd0 = O.fill_state_dict({k: v.shape for k, v in model.state_dict().items()}, seed=0)
+    for phase in ("policy_frozen", "main_frozen"):
+        model.load_state_dict(sd0)
+        model.unfreeze_policy_net(); model.unfreeze_main_net()
+        (model.freeze_policy_net if phase == "policy_frozen" else model.freeze_main_net)()
+        _, _, loss = run_product(model, case, 7, cuda)
+        loss.backward()
+        for k, p in model.named_parameters():
+            frozen = k.startswith("policy_net." if phase == "policy_frozen" else "main_net.")
+            if frozen:
+                assert p.grad is None, k
+            else:
+                assert rel(p.grad, ref[k]) < 1e-4, (phase, k)
+        model.zero_grad(set_to_none=True)
+
+
+def test_bf16_mode_close_to_oracle(cuda):
+    """Speed mode: bf16 activations/operands (tcgen05 where the shape fits), fp32 accumulate + fp32 BN
+    statistics + fp32 policy head.  Tolerance 5e-2 on logits (bf16 has 8 mantissa bits; 53 conv layers);
+    selections may differ only where the fp32 decision margin is tiny, so we bound the mismatch rate."""
+    case = dict(kind="adamml", modality=["rgb", "sound"], N=2, S=2, hw=96, training=True)
+    model, _ = build(case, torch.bfloat16, cuda)
+    logits, dec, loss = run_product(model, case, 5, cuda)
+    loss.backward()
+    torch.cuda.synchronize()
+    cfg = O.make_cfg(case["modality"], num_segments=2)
+    sd = O.clone_sd(O.fill_state_dict({k: v.shape for k, v in model.state_dict().items()}, seed=0), False)
+    xs, _ = O.make_inputs(cfg, 2, 2, hw=96)
+    with torch.no_grad():
+        o_logits, o_dec = O.adamml_forward(sd, xs, cfg, True, O.draw_noise(5, cfg, 2, 2, True))
+    assert torch.isfinite(logits).all()
+    assert (dec.detach().cpu() != o_dec).float().mean() <= 0.25
+    if torch.equal(dec.detach().cpu(), o_dec):
+        assert rel(logits, o_logits) < 5e-2
+    for k, p in model.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), k
+
+
+def test_unimodal_sound_mobilenet_matches_oracle(cuda):
+    from adamml_b200.models import build_model
+    ns = namespace(dict(kind="resnet", modality=["sound"], S=1), backbone_net="sound_mobilenet_v2", modality="sound",
+                   input_channels=1, compute_dtype=torch.float32)
+    model, arch = build_model(ns)
+    assert arch.startswith("kinetics-sounds-sound-sound_mobilenet_v2")
+    shapes = {k: v.shape for k, v in model.state_dict().items()}
+    sd0 = O.fill_state_dict(shapes, seed=0)
+    model.load_state_dict(sd0)
+    model = model.to(cuda).train()
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(3, 1, 128, 128, generator=g)
+    mask = torch.empty(3, 1280).bernoulli_(0.5, generator=g).div_(0.5)
+    y = model(x.to(cuda), drop_mask=mask.to(cuda))
+    y.sum().backward()
+    sd = O.clone_sd(sd0)
+    yo = O.sound_mobilenet_forward(sd, "", x, True, mask)
+    yo.sum().backward()
+    assert rel(y, yo) < LOGIT_TOL
+    for k, p in model.named_parameters():
+        assert rel(p.grad, sd[k].grad) < 2e-2, k
