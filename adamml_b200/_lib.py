@@ -93,12 +93,24 @@ def _conv(a):
     return a
 
 
+# bench.py sets this to a list to time every call with CUDA events on the launching stream:
+# entries are (name, start_event, end_event, scalar_args)
+PROFILE = None
+
+
 def call(name, *args, allow_unsupported=False):
     """Call `adamml_<name>` with torch tensors / scalars; the current CUDA stream is appended."""
     L = lib()
     fn = getattr(L.cdll, "adamml_" + name)
     stream = torch.cuda.current_stream().cuda_stream
-    rc = fn(*[_conv(a) for a in args], stream)
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*[_conv(a) for a in args], stream)
+        e1.record()
+        PROFILE.append((name, e0, e1, tuple(None if isinstance(a, torch.Tensor) else a for a in args)))
+    else:
+        rc = fn(*[_conv(a) for a in args], stream)
     if rc != 0:
         if allow_unsupported and rc == ERR_UNSUPPORTED:
             return rc

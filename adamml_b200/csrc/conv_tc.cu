@@ -17,86 +17,25 @@
 //                                sum of squares, reduced with warp shuffles, fp64 atomics)
 // Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
 // Ragged M / Ncols / K edges are handled by TMA out-of-bounds zero fill + masked stores.
-#include "common.cuh"
-#include <cuda.h>
+#include "tc_common.cuh"
 
 namespace {
+using namespace tc;
 
-constexpr int BLOCK_M = 128;
-constexpr int BLOCK_K = 64;   // 64 bf16 = one 128-byte swizzle row
-constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 192;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t addr = smem_u32(bar);
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P1;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-      "@P1 bra DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "DONE:\n\t"
-      "}" ::"r"(addr), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(x), "r"(y)
-      : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row atoms 1024 bytes apart.
-__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);       // start address, bits [0,14)
-  d |= (uint64_t)0 << 16;                            // leading byte offset (unused: one atom along K)
-  d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset between 8-row atoms
-  d |= (uint64_t)1 << 46;                            // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;                            // layout type SWIZZLE_128B
-  return d;
-}
-__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
+// Implicit-GEMM geometry: the 128 rows of an M tile are a BW x BH x BI box of output pixels; every filter
+// tap is one shifted 4D TMA box {64 channels, BW, BH, BI} of the (sub-lattice of the) NHWC input.
+constexpr int MAX_TAPS = 49;
+struct ConvGeom {
+  int ntaps, cin, kb_per_tap;
+  int BW, BH, BI;
+  int tiles_w, tiles_h, tiles_i;
+  int Ho, Wo, IMGS;
+  int imgs_per_group;
+  signed char tap_map[MAX_TAPS], tap_dh[MAX_TAPS], tap_dw[MAX_TAPS];
+};
+struct ConvMaps {
+  CUtensorMap m[4];
+};
 
 template <int BLOCK_N>
 struct TcCfg {
@@ -108,11 +47,12 @@ struct TcCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BLOCK_N, bool D_F32>
+template <int BLOCK_N, bool D_F32, bool CONV>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               void* __restrict__ Dptr, long long M, int Ncols, int K, long long ldd, double* __restrict__ stats,
-               long long rows_per_group) {
+               const __grid_constant__ ConvMaps cmaps, const __grid_constant__ ConvGeom geo,
+               void* __restrict__ Dptr, const bf16* __restrict__ addend, long long M, int Ncols, int K, long long ldd,
+               double* __restrict__ stats, long long rows_per_group) {
   using Cfg = TcCfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -125,10 +65,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int num_m_blks = (int)((M + BLOCK_M - 1) / BLOCK_M);
+  const int num_m_blks = CONV ? geo.tiles_w * geo.tiles_h * geo.tiles_i : (int)((M + BLOCK_M - 1) / BLOCK_M);
   const int num_n_blks = (Ncols + BLOCK_N - 1) / BLOCK_N;
   const long long num_tiles = (long long)num_m_blks * num_n_blks;
-  const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+  const int num_kb = CONV ? geo.ntaps * geo.kb_per_tap : (K + BLOCK_K - 1) / BLOCK_K;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < Cfg::STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
@@ -149,20 +89,34 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+      if (!CONV) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
       int stage = 0;
       uint32_t phase = 0;
       for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int n_blk = (int)(tile % num_n_blks);
         const int m_blk = (int)(tile / num_n_blks);
+        int w0 = 0, h0 = 0, i0 = 0;
+        if (CONV) {
+          w0 = (m_blk % geo.tiles_w) * geo.BW;
+          h0 = ((m_blk / geo.tiles_w) % geo.tiles_h) * geo.BH;
+          i0 = (m_blk / (geo.tiles_w * geo.tiles_h)) * geo.BI;
+        }
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
           mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-          tma_load_2d(sa, &tmA, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
-          tma_load_2d(sb, &tmB, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);
+          if (CONV) {
+            const int tap = kb / geo.kb_per_tap;
+            const int c0 = (kb - tap * geo.kb_per_tap) * BLOCK_K;
+            tma_load_4d(sa, &cmaps.m[geo.tap_map[tap]], &full_bar[stage], c0, w0 + geo.tap_dw[tap],
+                        h0 + geo.tap_dh[tap], i0);
+            tma_load_2d(sb, &tmB, &full_bar[stage], tap * geo.cin + c0, n_blk * BLOCK_N);
+          } else {
+            tma_load_2d(sa, &tmA, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
+            tma_load_2d(sb, &tmB, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);
+          }
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -211,17 +165,34 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int m_blk = (int)(tile / num_n_blks);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const long long row = (long long)m_blk * BLOCK_M + q * 32 + lane;
-      const bool row_ok = row < M;
-      // BN groups touched by this warp's 32 rows
-      long long g_lo = 0, g_hi = 0;
-      if (stats) {
-        long long r0 = (long long)m_blk * BLOCK_M + q * 32;
-        long long r1 = r0 + 31 < M - 1 ? r0 + 31 : M - 1;
-        g_lo = r0 / rows_per_group;
-        g_hi = r1 / rows_per_group;
+      long long row;
+      bool row_ok;
+      long long g_lo = 0, g_hi = 0, my_g = 0;
+      if (CONV) {
+        const int ml = q * 32 + lane;
+        const int ow = (m_blk % geo.tiles_w) * geo.BW + ml % geo.BW;
+        const int oh = ((m_blk / geo.tiles_w) % geo.tiles_h) * geo.BH + (ml / geo.BW) % geo.BH;
+        const int img = (m_blk / (geo.tiles_w * geo.tiles_h)) * geo.BI + ml / (geo.BW * geo.BH);
+        row_ok = ow < geo.Wo && oh < geo.Ho && img < geo.IMGS;
+        row = ((long long)img * geo.Ho + oh) * geo.Wo + ow;
+        if (stats) {
+          const int gi = row_ok ? img / geo.imgs_per_group : -1;
+          my_g = gi;
+          g_hi = __reduce_max_sync(0xffffffffu, gi);
+          g_lo = __reduce_min_sync(0xffffffffu, row_ok ? gi : 0x7fffffff);
+        }
+      } else {
+        row = (long long)m_blk * BLOCK_M + q * 32 + lane;
+        row_ok = row < M;
+        // BN groups touched by this warp's 32 rows
+        if (stats) {
+          long long r0 = (long long)m_blk * BLOCK_M + q * 32;
+          long long r1 = r0 + 31 < M - 1 ? r0 + 31 : M - 1;
+          g_lo = r0 / rows_per_group;
+          g_hi = r1 / rows_per_group;
+          my_g = row_ok ? row / rows_per_group : -1;
+        }
       }
-      const long long my_g = stats ? (row_ok ? row / rows_per_group : -1) : 0;
 #pragma unroll 1
       for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
         const int col0 = n_blk * BLOCK_N + chunk * 32;
@@ -231,6 +202,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (addend != nullptr && row_ok) {
+          const bf16* ap = addend + row * ldd + col0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            if (col0 + j < Ncols) {
+              uint4 pk = *reinterpret_cast<const uint4*>(ap + j);
+              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&pk);
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                float2 f = __bfloat1622float2(h2[t]);
+                v[j + 2 * t] += f.x;
+                v[j + 2 * t + 1] += f.y;
+              }
+            }
+          }
+        }
         if (!D_F32) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
@@ -310,21 +297,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ---- host side ---------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
-    if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  return fn;
-}
-
 // 2D bf16 row-major [rows, cols] with row stride ld (elements); box = [box_rows, 64 cols], 128B swizzle
 int make_map_2d(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld, int box_rows) {
   EncodeTiledFn enc = get_encode_fn();
@@ -343,12 +315,13 @@ int make_map_2d(CUtensorMap* map, const void* ptr, long long rows, long long col
   return ADAMML_OK;
 }
 
-template <int BLOCK_N, bool D_F32>
-int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, void* D, long long M, int Ncols, int K, long long ldd,
-              double* stats, long long rpg, cudaStream_t stream) {
+template <int BLOCK_N, bool D_F32, bool CONV>
+int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvMaps& cm, const ConvGeom& geo, void* D,
+              const void* addend, long long M, int Ncols, int K, long long ldd, double* stats, long long rpg,
+              cudaStream_t stream) {
   using Cfg = TcCfg<BLOCK_N>;
   static bool configured = false;
-  auto kern = tc_gemm_kernel<BLOCK_N, D_F32>;
+  auto kern = tc_gemm_kernel<BLOCK_N, D_F32, CONV>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) {
@@ -357,13 +330,29 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, void* D, long long
     }
     configured = true;
   }
-  long long tiles = ((M + BLOCK_M - 1) / BLOCK_M) * ((Ncols + BLOCK_N - 1) / BLOCK_N);
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  long long m_blks = CONV ? (long long)geo.tiles_w * geo.tiles_h * geo.tiles_i : (M + BLOCK_M - 1) / BLOCK_M;
+  long long tiles = m_blks * ((Ncols + BLOCK_N - 1) / BLOCK_N);
+  const int sms = num_sms();
   int grid = (int)(tiles < sms ? tiles : sms);
-  kern<<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, D, M, Ncols, K, ldd, stats, rpg);
-  return adamml_check_launch("tc_gemm");
+  kern<<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, cm, geo, D, (const bf16*)addend, M, Ncols, K, ldd,
+                                                        stats, rpg);
+  return adamml_check_launch(CONV ? "tc_conv" : "tc_gemm");
+}
+
+template <bool CONV>
+int dispatch_tc(int block_n, bool f32, const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvMaps& cm,
+                const ConvGeom& geo, void* D, const void* addend, long long M, int Ncols, int K, long long ldd,
+                double* stats, long long rpg, cudaStream_t stream) {
+#define ADAMML_TC_CASE(BN)                                                                                      \
+  if (block_n == BN)                                                                                            \
+    return f32 ? launch_tc<BN, true, CONV>(tmA, tmB, cm, geo, D, addend, M, Ncols, K, ldd, stats, rpg, stream)  \
+               : launch_tc<BN, false, CONV>(tmA, tmB, cm, geo, D, addend, M, Ncols, K, ldd, stats, rpg, stream);
+  ADAMML_TC_CASE(64)
+  ADAMML_TC_CASE(128)
+  ADAMML_TC_CASE(256)
+#undef ADAMML_TC_CASE
+  adamml_set_error("tc: bad block_n %d", block_n);
+  return ADAMML_ERR_ARG;
 }
 
 }  // namespace
@@ -407,14 +396,81 @@ int adamml_tc_gemm_bf16(const void* A, const void* B, void* D, long long M, int 
     cudaMemsetAsync(stats, 0, sizeof(double) * (size_t)G * Ncols * 2, stream);
   }
   const bool f32 = d_dtype == ADAMML_F32;
-  if (block_n == 64)
-    return f32 ? launch_tc<64, true>(tmA, tmB, D, M, Ncols, K, ldd, stats, rows_per_group, stream)
-               : launch_tc<64, false>(tmA, tmB, D, M, Ncols, K, ldd, stats, rows_per_group, stream);
-  if (block_n == 128)
-    return f32 ? launch_tc<128, true>(tmA, tmB, D, M, Ncols, K, ldd, stats, rows_per_group, stream)
-               : launch_tc<128, false>(tmA, tmB, D, M, Ncols, K, ldd, stats, rows_per_group, stream);
-  return f32 ? launch_tc<256, true>(tmA, tmB, D, M, Ncols, K, ldd, stats, rows_per_group, stream)
-             : launch_tc<256, false>(tmA, tmB, D, M, Ncols, K, ldd, stats, rows_per_group, stream);
+  ConvMaps cm;
+  ConvGeom geo;
+  memset(&cm, 0, sizeof(cm));
+  memset(&geo, 0, sizeof(geo));
+  return dispatch_tc<false>(block_n, f32, tmA, tmB, cm, geo, D, nullptr, M, Ncols, K, ldd, stats, rows_per_group,
+                            stream);
+}
+
+int adamml_tc_conv_supported(int Cin, int Cout, int R, int S, int stride) {
+  if (Cin % 8 || Cout % 8) return 0;
+  if (R * S > MAX_TAPS || R < 1 || S < 1) return 0;
+  if (stride != 1 && stride != 2) return 0;
+  return 1;
+}
+
+int adamml_tc_conv_bf16(const void* x, const void* w, void* y, const void* addend, int IMGS, int H, int W, int Cin,
+                        int Cout, int R, int S, int stride, int pad, int Ho, int Wo, double* stats,
+                        int imgs_per_group, cudaStream_t stream) {
+  if (!adamml_tc_conv_supported(Cin, Cout, R, S, stride)) {
+    adamml_set_error("tc_conv: Cin=%d Cout=%d R=%d S=%d stride=%d outside the tcgen05 envelope", Cin, Cout, R, S,
+                     stride);
+    return ADAMML_ERR_UNSUPPORTED;
+  }
+  ADAMML_REQUIRE(Ho == (H + 2 * pad - R) / stride + 1 && Wo == (W + 2 * pad - S) / stride + 1,
+                 "tc_conv: Ho/Wo inconsistent with H/W/R/S/stride/pad");
+  ADAMML_REQUIRE(((uintptr_t)x % 16) == 0 && ((uintptr_t)w % 16) == 0 && ((uintptr_t)y % 16) == 0 &&
+                     ((uintptr_t)addend % 16) == 0,
+                 "tc_conv: operands must be 16-byte aligned");
+  ADAMML_REQUIRE(!stats || imgs_per_group > 0, "tc_conv: stats need imgs_per_group");
+  ConvGeom geo;
+  memset(&geo, 0, sizeof(geo));
+  geo.ntaps = R * S;
+  geo.cin = Cin;
+  geo.kb_per_tap = (Cin + BLOCK_K - 1) / BLOCK_K;
+  pick_box(Wo, Ho, IMGS, 128, &geo.BW, &geo.BH, &geo.BI);
+  geo.tiles_w = (Wo + geo.BW - 1) / geo.BW;
+  geo.tiles_h = (Ho + geo.BH - 1) / geo.BH;
+  geo.tiles_i = (IMGS + geo.BI - 1) / geo.BI;
+  geo.Ho = Ho; geo.Wo = Wo; geo.IMGS = IMGS;
+  geo.imgs_per_group = imgs_per_group > 0 ? imgs_per_group : IMGS;
+  // taps: input coordinate = stride*o + (r - pad) = stride*(o + d) + parity
+  bool used[4] = {false, false, false, false};
+  for (int r = 0; r < R; ++r)
+    for (int s_ = 0; s_ < S; ++s_) {
+      int th = r - pad, tw = s_ - pad;
+      int ph = ((th % stride) + stride) % stride, pw = ((tw % stride) + stride) % stride;
+      int t = r * S + s_;
+      geo.tap_map[t] = (signed char)(ph * stride + pw);
+      geo.tap_dh[t] = (signed char)((th - ph) / stride);
+      geo.tap_dw[t] = (signed char)((tw - pw) / stride);
+      used[ph * stride + pw] = true;
+    }
+  ConvMaps cm;
+  memset(&cm, 0, sizeof(cm));
+  const bf16* xb = (const bf16*)x;
+  for (int ph = 0; ph < stride; ++ph)
+    for (int pw = 0; pw < stride; ++pw) {
+      int id = ph * stride + pw;
+      if (!used[id]) continue;
+      int Wd = (W - pw + stride - 1) / stride, Hd = (H - ph + stride - 1) / stride;
+      if (Wd <= 0 || Hd <= 0) { Wd = Wd > 0 ? Wd : 1; Hd = Hd > 0 ? Hd : 1; }
+      int rc = make_map_4d(&cm.m[id], xb + ((long long)ph * W + pw) * Cin, Cin, Wd, Hd, IMGS, (long long)stride * Cin,
+                           (long long)stride * W * Cin, (long long)H * W * Cin, geo.BW, geo.BH, geo.BI);
+      if (rc) return rc;
+    }
+  const int block_n = Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 256);
+  CUtensorMap tmB;
+  int rc = make_map_2d(&tmB, w, Cout, (long long)R * S * Cin, (long long)R * S * Cin, block_n);
+  if (rc) return rc;
+  if (stats) {
+    int G = (IMGS + geo.imgs_per_group - 1) / geo.imgs_per_group;
+    cudaMemsetAsync(stats, 0, sizeof(double) * (size_t)G * Cout * 2, stream);
+  }
+  return dispatch_tc<true>(block_n, false, tmB, tmB, cm, geo, y, addend, (long long)IMGS * Ho * Wo, Cout,
+                           R * S * Cin, Cout, stats, 0, stream);
 }
 
 }  // extern "C"

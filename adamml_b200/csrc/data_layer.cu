@@ -89,6 +89,22 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, T* __restrict_
   }
 }
 
+// OIHW fp32 -> dgrad operand [Cin][R][S][Cout] with the filter rotated by 180 degrees:
+// dst[ci][r][s][co] = src[co][ci][R-1-r][S-1-s]   (dx = conv(dy, dst, pad = R-1-pad) for stride 1)
+template <typename T>
+__global__ void pack_weight_dgrad_kernel(const float* __restrict__ src, T* __restrict__ dst, int Cout, int Cin, int R,
+                                         int S) {
+  long long total = (long long)Cin * R * S * Cout;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int co = (int)(idx % Cout);
+    int s = (int)((idx / Cout) % S);
+    int r = (int)((idx / ((long long)Cout * S)) % R);
+    int ci = (int)(idx / ((long long)Cout * S * R));
+    dst[idx] = from_f32<T>(src[(((long long)co * Cin + ci) * R + (R - 1 - r)) * S + (S - 1 - s)]);
+  }
+}
+
 // OHWI fp32 (CinPad channels) -> OIHW fp32 ; dst = (accumulate ? dst : 0) + src
 __global__ void unpack_wgrad_kernel(const float* __restrict__ src, float* __restrict__ dst, int Cout, int Cin, int R,
                                     int S, int CinPad, int accumulate) {
@@ -142,6 +158,15 @@ int adamml_pack_weight(const float* w_oihw, void* w_ohwi, int Cout, int Cin, int
   ADAMML_DISPATCH_DTYPE(dtype, T,
     pack_weight_kernel<T><<<ew_blocks(total), 256, 0, stream>>>(w_oihw, (T*)w_ohwi, Cout, Cin, R, S, CinPad));
   return adamml_check_launch("pack_weight");
+}
+
+int adamml_pack_weight_dgrad(const float* w_oihw, void* w_ihwo, int Cout, int Cin, int R, int S, int dtype,
+                             cudaStream_t stream) {
+  ADAMML_REQUIRE(Cout > 0 && Cin > 0 && R > 0 && S > 0, "pack_weight_dgrad: bad dims");
+  long long total = (long long)Cout * R * S * Cin;
+  ADAMML_DISPATCH_DTYPE(dtype, T,
+    pack_weight_dgrad_kernel<T><<<ew_blocks(total), 256, 0, stream>>>(w_oihw, (T*)w_ihwo, Cout, Cin, R, S));
+  return adamml_check_launch("pack_weight_dgrad");
 }
 
 int adamml_unpack_wgrad(const float* dw_ohwi, float* dw_oihw, int Cout, int Cin, int R, int S, int CinPad,

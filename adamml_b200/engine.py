@@ -133,11 +133,11 @@ class Exec:
                 dw = ops.conv_wgrad(x, dz, tuple(w.shape), stride, pad)
                 self._acc(conv.weight, ops.unpack_wgrad(dw, conv.weight.shape[1]))
             if need_dx:
-                w_t = None
-                if (addend is None and self.dtype == torch.bfloat16 and w.shape[1] == 1 and w.shape[2] == 1
-                        and stride == 1 and ops.TC_MODE == "auto"):
-                    w_t = w.view(w.shape[0], w.shape[3]).t().contiguous()
-                dx = ops.conv_dgrad(dz, w, tuple(x.shape), stride, pad, addend=addend, w_t=w_t)
+                w_rot = None
+                if (self.dtype == torch.bfloat16 and stride == 1 and ops.TC_MODE == "auto"
+                        and w.shape[0] % 8 == 0 and w.shape[3] % 8 == 0 and w.shape[0] >= 32):
+                    w_rot = ops.pack_weight_dgrad(conv.weight.detach(), self.dtype)
+                dx = ops.conv_dgrad(dz, w, tuple(x.shape), stride, pad, addend=addend, w_rot=w_rot)
         return dx, dres
 
     # ------------------------------------------------------------------ ResNet blocks

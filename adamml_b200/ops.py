@@ -60,6 +60,15 @@ def pack_weight(w, dtype, cin_pad=None):
     return out
 
 
+def pack_weight_dgrad(w, dtype):
+    """OIHW fp32 parameter -> rotated dgrad operand [Cin, R, S, Cout] in `dtype`."""
+    _chk(w, torch.float32)
+    Cout, Cin, R, S = w.shape
+    out = torch.empty((Cin, R, S, Cout), device=w.device, dtype=dtype)
+    call("pack_weight_dgrad", w, out, Cout, Cin, R, S, dtype_code(dtype))
+    return out
+
+
 def unpack_wgrad(dw_ohwi, Cin):
     Cout, R, S, cin_pad = dw_ohwi.shape
     _chk(dw_ohwi, torch.float32)
@@ -79,8 +88,16 @@ def cast(x, dtype):
 
 # ---------------------------------------------------------------- dense conv
 def _tc_ok(x, Cin, Cout, R, S, stride, pad):
+    """plain tcgen05 GEMM: 1x1, stride 1"""
     return (TC_MODE == "auto" and x.dtype == torch.bfloat16 and R == 1 and S == 1 and stride == 1 and pad == 0
             and Cin % 8 == 0 and Cout % 8 == 0)
+
+
+def _tc_conv_ok(x, Cin, Cout, R, S, stride):
+    """tcgen05 implicit GEMM (4D TMA taps): any RxS <= 49 taps, stride 1|2.  Cin >= 32 keeps the 64-wide K
+    block at least half full (the 3-channel stem stays on the exact engine)."""
+    return (TC_MODE == "auto" and x.dtype == torch.bfloat16 and Cin % 8 == 0 and Cout % 8 == 0 and Cin >= 32
+            and R * S <= 49 and stride in (1, 2))
 
 
 def conv_fwd(x, w, stride, pad, out=None, stats=None, rows_per_group=0):
@@ -99,19 +116,27 @@ def conv_fwd(x, w, stride, pad, out=None, stats=None, rows_per_group=0):
     if _tc_ok(x, Cin, Cout, R, S, stride, pad):
         call("tc_gemm_bf16", x, w, out, IMGS * H * W, Cout, Cin, 0, 0, 0, _lib.BF16, stats, rows_per_group)
         return out, stats is not None
+    if _tc_conv_ok(x, Cin, Cout, R, S, stride):
+        ipg = rows_per_group // (Ho * Wo) if stats is not None else 0
+        call("tc_conv_bf16", x, w, out, None, IMGS, H, W, Cin, Cout, R, S, stride, pad, Ho, Wo, stats, ipg)
+        return out, stats is not None
     call("simt_conv_fwd", x, w, out, IMGS, H, W, Cin, Cout, R, S, stride, pad, Ho, Wo, 0, 0, 0, dtype_code(x.dtype))
     return out, False
 
 
-def conv_dgrad(dy, w, x_shape, stride, pad, addend=None, w_t=None):
-    """dx = conv_transpose(dy, w) (+ addend).  w_t: optional [Cin, Cout] transposed 1x1 weight (bf16)."""
+def conv_dgrad(dy, w, x_shape, stride, pad, addend=None, w_rot=None):
+    """dx = conv_transpose(dy, w) (+ addend).  w_rot: optional rotated operand [Cin, R, S, Cout] from
+    pack_weight_dgrad (bf16): stride-1 layers then run as a forward conv of dy on the tcgen05 engine."""
     _chk(dy); _chk(w, dy.dtype)
     IMGS, H, W, Cin = x_shape
     Cout, R, S, _ = w.shape
     Ho, Wo = dy.shape[1], dy.shape[2]
     dx = torch.empty(x_shape, device=dy.device, dtype=dy.dtype)
-    if addend is None and w_t is not None and _tc_ok(dy, Cout, Cin, R, S, stride, pad):
-        call("tc_gemm_bf16", dy, w_t, dx, IMGS * H * W, Cin, Cout, 0, 0, 0, _lib.BF16, None, 0)
+    if w_rot is not None and stride == 1 and _tc_conv_ok(dy, Cout, Cin, R, S, 1):
+        if addend is None and R == 1 and S == 1:
+            call("tc_gemm_bf16", dy, w_rot, dx, IMGS * H * W, Cin, Cout, 0, 0, 0, _lib.BF16, None, 0)
+        else:
+            call("tc_conv_bf16", dy, w_rot, dx, addend, IMGS, Ho, Wo, Cout, Cin, R, S, 1, R - 1 - pad, H, W, None, 0)
         return dx
     call("simt_conv_dgrad", dy, w, dx, addend, IMGS, H, W, Cin, Cout, R, S, stride, pad, Ho, Wo, 0, 0, 0,
          dtype_code(dy.dtype))
@@ -125,6 +150,10 @@ def conv_wgrad(x, dy, w_shape, stride, pad):
     Cout, R, S, _ = w_shape
     Ho, Wo = dy.shape[1], dy.shape[2]
     dw = torch.empty((Cout, R, S, Cin), device=x.device, dtype=torch.float32)
+    if (TC_MODE == "auto" and x.dtype == torch.bfloat16 and Cin % 8 == 0 and Cout % 8 == 0 and R * S <= 49
+            and stride in (1, 2)):
+        call("tc_wgrad_bf16", x, dy, dw, IMGS, H, W, Cin, Cout, R, S, stride, pad, Ho, Wo)
+        return dw
     call("simt_conv_wgrad", x, dy, dw, IMGS, H, W, Cin, Cout, R, S, stride, pad, Ho, Wo, 0, 0, 0,
          dtype_code(x.dtype))
     return dw

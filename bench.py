@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""bench.py — clips/sec of the AdaMML training step (RGB + Audio, 5 segments x 8 frames, 224^2).
+
+    python bench.py --gpus N --steps K --warmup W                  # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K --warmup W  # CPU arm: the reference's algorithm
+                                                                    # (oracle port) on the host cores
+
+A step = data_layer + policy + gated main nets + fusion + CE/policy loss + backward + the two
+optimizers (Adam on the policy net, SGD on the main net; train_adamml.py:250-257).  A clip = one
+video sample = 5 segments x 8 frames at 224^2 plus its 5 spectrograms.  Rank 0
+prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.nn.functional as F  # noqa: E402
+
+METRIC = "clips/sec (fwd+bwd) RGB+Audio 5seg x 8 x 4 224^2"
+# forward MACs per clip for RGB+Audio (SURVEY.md §8d / BASELINE.md §2); fwd+bwd = 3x forward
+FWD_MAC_PER_CLIP = 76_434_066_560
+FLOP_PER_CLIP = 2 * 3 * FWD_MAC_PER_CLIP
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return dict(hbm=float(d["hbm_gbs"]), tf=float(d["bf16_tflops"]),
+                        tf_sus=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), src="measured")
+        except Exception:
+            pass
+    return dict(hbm=6650.0, tf=1590.0, tf_sus=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        rows = [r for r in self.rows if len(r) >= 6 and r[0].isdigit()]
+        if not rows:
+            return None
+        sm = sorted(int(r[0]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in rows)]
+        return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=int(rows[0][1]), reasons=reasons, samples=len(rows))
+
+
+def policy_loss(selection, cost_weights, gammas, logits, targets):
+    """utils/utils.py:166-184 'blockdrop' (kept in torch like the reference's train step)."""
+    correct = (logits.detach().argmax(-1) == targets).type_as(logits)
+    sel = selection.mean(1) ** 2
+    loss = logits.new_zeros(())
+    for w, pl in zip(cost_weights, sel.chunk(sel.shape[-1], dim=-1)):
+        loss = loss + w * torch.mean(correct * pl)
+    return loss + torch.mean((1 - correct) * gammas)
+
+
+def namespace(modality, S, precision):
+    from types import SimpleNamespace
+    ch = {"rgb": 3, "flow": 10, "rgbdiff": 15, "sound": 1}
+    return SimpleNamespace(
+        backbone_net="adamml", modality=modality, input_channels=[ch[m] for m in modality], groups=8,
+        frames_per_group=4, num_segments=S, depth=50, num_classes=31, dropout=0.5, pooling_method="max",
+        without_t_stride=False, fusion_point="logits", learnable_lf_weights=True, causality_modeling="lstm",
+        rng_policy=False, rng_threshold=0.5, unimodality_pretrained=[], imagenet_pretrained=False,
+        dataset="kinetics-sounds", dense_sampling=False, lr_scheduler="cosine", sync_bn=False, batch_size=72,
+        prefix="", epochs=1, compute_dtype={"bf16": torch.bfloat16, "fp32": torch.float32}[precision])
+
+
+def synth_inputs(modality, N, S, seed, device, pin=False):
+    g = torch.Generator().manual_seed(seed)
+    ch = {"rgb": 3, "flow": 10, "rgbdiff": 15}
+    xs = []
+    for m in modality:
+        shape = (N, S, 256, 256) if m == "sound" else (N, S * 8 * ch[m], 224, 224)
+        t = torch.empty(shape, pin_memory=pin)
+        # chunked fill keeps the host RNG temporary small
+        for i in range(N):
+            t[i] = torch.randn(shape[1:], generator=g)
+        xs.append(t)
+    y = torch.randint(0, 31, (N,), generator=g)
+    if pin:
+        y = y.pin_memory()
+    return xs, y
+
+
+# ------------------------------------------------------------------------------------------- CPU arm
+def cpu_step_time(modality, S, n_clips, steps, warmup):
+    """The reference's algorithm (oracle port, identical to the reference bit-for-bit on CPU, see
+    tests/golden) timed on all host cores: fwd + loss + bwd on a bounded sample of n_clips clips."""
+    from oracle import adamml_oracle as O
+    from adamml_b200.models import build_model
+    torch.set_num_threads(os.cpu_count())
+    cfg = O.make_cfg(modality, num_segments=S)
+    model, _ = build_model(namespace(modality, S, "fp32"))
+    shapes = {k: v.shape for k, v in model.state_dict().items()}
+    del model
+    sd = O.clone_sd(O.fill_state_dict(shapes, seed=0))
+    xs, y = O.make_inputs(cfg, n_clips, S)
+    times = []
+    for it in range(warmup + steps):
+        noise = O.draw_noise(it, cfg, n_clips, S, True)
+        t0 = time.perf_counter()
+        logits, dec = O.adamml_forward(sd, xs, cfg, True, noise)
+        loss = F.cross_entropy(logits, y) + O.policy_loss(dec, [1.0] * dec.shape[-1], 10.0, logits, y)
+        loss.backward()
+        for v in sd.values():
+            v.grad = None
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    return sum(times) / len(times)
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_clips = 2
+    modality = a.modality.split(",")
+    t = cpu_step_time(modality, a.segments, n_clips, a.steps, a.warmup)
+    val = n_clips / t
+    out = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "clips/s", "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"AdaMML {'+'.join(modality)} S={a.segments} F=8 224^2, fwd+loss+bwd, CPU",
+                   "clips_per_step": n_clips},
+        "cpu_baseline": {"value": val, "unit": "clips/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"{n_clips} clips per step (of the 72-clip batch), {a.steps} steps"},
+        "e2e": {"value": val, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+# ------------------------------------------------------------------------------------------- GPU arm
+def kernel_flops(name, args):
+    """Algorithmic FLOPs of one C-ABI call from its scalar arguments (dense GEMM-shaped ops only)."""
+    if name == "tc_gemm_bf16":
+        M, N, K = args[3], args[4], args[5]
+        return 2.0 * M * N * K
+    if name in ("simt_conv_fwd", "simt_conv_wgrad"):
+        IMGS, H, W, Cin, Cout, R, S, st, pad, Ho, Wo = args[3:14]
+        return 2.0 * IMGS * Ho * Wo * Cout * R * S * Cin
+    if name == "simt_conv_dgrad":
+        IMGS, H, W, Cin, Cout, R, S, st, pad, Ho, Wo = args[4:15]
+        return 2.0 * IMGS * Ho * Wo * Cout * R * S * Cin
+    return 0.0
+
+
+def run_gpu_arm(a):
+    import torch.distributed as dist
+    from adamml_b200 import _lib
+    from adamml_b200.models import build_model
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — adamml_b200 has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    modality = a.modality.split(",")
+    S, N = a.segments, a.batch
+    torch.manual_seed(0)
+    model, _ = build_model(namespace(modality, S, a.precision))
+    model = model.to(dev).train()
+    net = model
+    sync_bn = world > 1 and not a.no_sync_bn
+    if world > 1:
+        if sync_bn:  # train_adamml.py:125-127
+            model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=True)
+    p_opt = torch.optim.Adam(model.policy_net.parameters(), 0.01, weight_decay=1e-4)
+    opt = torch.optim.SGD(model.main_net.parameters(), 0.01, momentum=0.9, weight_decay=1e-4)
+    cost_weights = [1.0] * model.num_modality
+
+    hx, hy = synth_inputs(modality, N, S, 123 + rank, dev, pin=True)
+    dx = [t.to(dev) for t in hx]
+    dy = hy.to(dev)
+    h2d = sum(t.numel() * t.element_size() for t in hx) + hy.numel() * hy.element_size()
+
+    def step(xs, y):
+        out, sel = net(xs)
+        loss = F.cross_entropy(out, y) + policy_loss(sel, cost_weights, 10.0, out, y)
+        loss.backward()
+        p_opt.step()
+        opt.step()
+        p_opt.zero_grad(set_to_none=True)
+        opt.zero_grad(set_to_none=True)
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    for _ in range(a.warmup):
+        step(dx, dy)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n0 = _lib.launch_count()
+    ms = timed(lambda: step(dx, dy), a.steps)
+    launches = (_lib.launch_count() - n0) // a.steps
+    clocks = sampler.stop() if rank == 0 else None
+    peak_mem = torch.cuda.max_memory_allocated() / 2 ** 30
+
+    # ---- end-to-end: host (pinned) inputs -> H2D -> step -> D2H of the loss, every step ----
+    def e2e_step():
+        xs = [t.to(dev, non_blocking=True) for t in hx]
+        y = hy.to(dev, non_blocking=True)
+        return step(xs, y).item()
+
+    e2e_step()
+    ms_e2e = timed(e2e_step, a.steps)
+
+    # ---- per-kernel device time of one extra step (CUDA events around every C-ABI call) ----
+    prof = None
+    if rank == 0:
+        _lib.PROFILE = []
+        step(dx, dy)
+        torch.cuda.synchronize()
+        agg = {}
+        for name, e0, e1, args in _lib.PROFILE:
+            d = agg.setdefault(name, [0.0, 0, 0.0])
+            d[0] += e0.elapsed_time(e1)
+            d[1] += 1
+            d[2] += kernel_flops(name, args)
+        _lib.PROFILE = None
+        prof = sorted(agg.items(), key=lambda kv: -kv[1][0])
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    clips = N * world * a.steps
+    value = clips / (ms / 1e3)
+    out = {
+        "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": a.precision, "data": "synthetic",
+        "config": {"workload": f"AdaMML {'+'.join(modality)} S={S} F=8 224^2, batch {N}/GPU, "
+                               f"fwd+loss+bwd+Adam(policy)+SGD(main)", "batch_per_gpu": N, "segments": S,
+                   "sync_bn": sync_bn, "parallelism": f"dp{world}",
+                   "l2": "inputs (1.8 GB/step) and activations exceed the 126 MB L2; no explicit flush",
+                   "peak_mem_gib": round(peak_mem, 1)},
+        "e2e": {"value": clips / (ms_e2e / 1e3), "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "step_tflops": FLOP_PER_CLIP * N / (ms / a.steps / 1e3) / 1e12 if modality == ["rgb", "sound"] else None,
+    }
+    if prof:
+        total = sum(v[0] for _, v in prof)
+        name, (t_ms, cnt, fl) = next(((n, v) for n, v in prof if v[2] > 0), prof[0])
+        ach = fl / (t_ms / 1e3) / 1e12 if t_ms > 0 else 0.0
+        out["roofline"] = {"bound": "tensor", "kernel": name, "achieved": ach, "peak": pk["tf_sus"], "unit": "TFLOP/s",
+                           "frac": ach / pk["tf_sus"], "traffic": None, "peak_source": pk["src"] + " (sustained)",
+                           "launches_per_step": cnt, "share_of_step": t_ms / total}
+        out["kernel_breakdown_ms"] = {n: round(v[0], 2) for n, v in prof[:12]}
+    if world == 1 and not a.no_cpu_baseline:
+        n_clips = 2
+        t = cpu_step_time(modality, S, n_clips, 2, 1)
+        out["cpu_baseline"] = {"value": n_clips / t, "unit": "clips/s", "cores": torch.get_num_threads(), "kind": "port",
+                               "sample": f"{n_clips} clips per step (of the {N}-clip batch), 1 warm-up + 2 timed steps"}
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=72, help="clips per GPU (BASELINE config: 72)")
+    ap.add_argument("--segments", type=int, default=5)
+    ap.add_argument("--modality", default="rgb,sound")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-sync-bn", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    if a.warmup < 3 and a.impl == "ours":
+        a.warmup = 3
+    if a.impl == "reference":
+        run_reference_arm(a)
+    else:
+        run_gpu_arm(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -48,6 +48,10 @@ int adamml_resize_frames(const float* x, void* out, int N, int S, int F, int C, 
 /* nn.Conv2d.weight OIHW fp32 -> OHWI operand (CinPad >= Cin, zero filled) */
 int adamml_pack_weight(const float* w_oihw, void* w_ohwi, int Cout, int Cin, int R, int S, int CinPad, int dtype,
                        cudaStream_t stream);
+/* nn.Conv2d.weight OIHW fp32 -> [Cin][R][S][Cout] rotated by 180 degrees: the operand that turns the
+ * stride-1 data gradient into a forward convolution of dy (pad' = R-1-pad) on the tcgen05 engine */
+int adamml_pack_weight_dgrad(const float* w_oihw, void* w_ihwo, int Cout, int Cin, int R, int S, int dtype,
+                             cudaStream_t stream);
 /* OHWI fp32 weight gradient -> OIHW fp32 .grad layout */
 int adamml_unpack_wgrad(const float* dw_ohwi, float* dw_oihw, int Cout, int Cin, int R, int S, int CinPad,
                         int accumulate, cudaStream_t stream);
@@ -80,6 +84,24 @@ int adamml_tc_gemm_bf16(const void* A, const void* B, void* D, long long M, int 
                         long long ldb, long long ldd, int d_dtype, double* stats, long long rows_per_group,
                         cudaStream_t stream);
 int adamml_tc_supported(long long M, int Ncols, int K, long long lda, long long ldb, long long ldd);
+/* Implicit-GEMM convolution on the same tcgen05 pipeline (no im2col buffer): the 128 rows of an M tile are
+ * a BWxBHxBI box of output pixels and every filter tap (r,s) is ONE shifted 4D TMA box
+ * {64 channels, BW, BH, BI} of the NHWC input (zero padding = TMA out-of-bounds fill; stride 2 = four
+ * parity sub-lattice tensor maps).  Call sites: resnet.py:35-38,100 (3x3 conv2 of every Bottleneck, stride
+ * 1|2) and :164-167 (strided 1x1 downsample); the stride-1 data gradient runs through the same entry point
+ * with adamml_pack_weight_dgrad weights and `addend` = the residual-branch gradient.
+ * x [IMGS,H,W,Cin] bf16, w [Cout][R][S][Cin] bf16, y/addend [IMGS,Ho,Wo,Cout] bf16, stats double
+ * [G][Cout][2] (optional fused BN statistics, G = IMGS / imgs_per_group). */
+int adamml_tc_conv_bf16(const void* x, const void* w, void* y, const void* addend, int IMGS, int H, int W, int Cin,
+                        int Cout, int R, int S, int stride, int pad, int Ho, int Wo, double* stats,
+                        int imgs_per_group, cudaStream_t stream);
+int adamml_tc_conv_supported(int Cin, int Cout, int R, int S, int stride);
+/* Weight gradient on tcgen05: implicit GEMM whose reduction axis is the pixel axis, both operands MN-major
+ * (64-channel x 64-pixel 4D TMA boxes of x and dy), split-K over pixel ranges with fp32 atomics.
+ * dw fp32 [Cout][R][S][Cin] is overwritten.  Same call sites as adamml_simt_conv_wgrad. */
+int adamml_tc_wgrad_bf16(const void* x, const void* dy, float* dw, int IMGS, int H, int W, int Cin, int Cout, int R,
+                         int S, int stride, int pad, int Ho, int Wo, cudaStream_t stream);
+int adamml_tc_wgrad_supported(int Cin, int Cout, int R, int S, int stride);
 
 /* ---- depthwise 3x3 conv, pad 1, stride 1|2; weights fp32 [C][3][3] (= torch [C,1,3,3]) ----
  * sound_mobilenet_v2.py:58 ; policy_net.py:66,80 */

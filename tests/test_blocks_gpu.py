@@ -1,0 +1,155 @@
+"""Composite blocks of the engine (Bottleneck, BasicBlock, InvertedResidual, stem + pools) against torch
+autograd on the GPU, at batch sizes where BatchNorm is well conditioned (tight tolerances)."""
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def nchw(x):
+    return x.permute(0, 3, 1, 2).contiguous()
+
+
+def relerr(a, b):
+    return ((a.float() - b.float()).abs().max() / b.float().abs().max().clamp_min(1e-30)).item()
+
+
+def randomize(mod, g):
+    with torch.no_grad():
+        for m in mod.modules():
+            if isinstance(m, nn.BatchNorm2d):
+                m.weight.copy_(torch.rand(m.weight.shape, generator=g) + 0.5)
+                m.bias.copy_(torch.randn(m.bias.shape, generator=g) * 0.3)
+
+
+def torch_block(blk, x, G):
+    """Reference forward of a _Block with per-group BN (one call per segment group)."""
+    outs = []
+    for xs in x.chunk(G):
+        idn = xs
+        if blk.bottleneck:
+            o = F.relu(blk.bn1(blk.conv1(xs)))
+            o = F.relu(blk.bn2(blk.conv2(o)))
+            o = blk.bn3(blk.conv3(o))
+        else:
+            o = F.relu(blk.bn1(blk.conv1(xs)))
+            o = blk.bn2(blk.conv2(o))
+        if blk.downsample is not None:
+            idn = blk.downsample(xs)
+        outs.append(F.relu(o + idn))
+    return torch.cat(outs)
+
+
+@pytest.mark.parametrize("cfg", [(64, 16, 1, True, True), (64, 16, 1, True, False), (32, 16, 2, True, True),
+                                 (32, 32, 1, False, False), (32, 64, 2, False, True)])
+def test_resnet_block(cuda, cfg):
+    from adamml_b200.engine import Exec
+    import importlib
+    _Block = importlib.import_module("adamml_b200.models.resnet")._Block
+    inpl, planes, stride, bott, ds = cfg
+    if not ds:
+        inpl = planes * (4 if bott else 1)
+    g = torch.Generator().manual_seed(0)
+    blk = _Block(inpl, planes, stride, bott, ds)
+    randomize(blk, g)
+    blk = blk.to(cuda).train()
+    G, ipg, H = 2, 6, 12
+    x = torch.randn(G * ipg, inpl, H, H, generator=g).to(cuda).requires_grad_(True)
+    ref = torch_block(blk, x, G)
+    dy = torch.randn(ref.shape, generator=g).to(cuda)
+    ref.backward(dy)
+    want = {k: p.grad.clone() for k, p in blk.named_parameters()}
+    dx_want = x.grad.clone()
+    blk.zero_grad()
+    ex = Exec(torch.float32, True, G, save=True)
+    out = ex.bottleneck(nhwc(x.detach()), blk) if bott else ex.basicblock(nhwc(x.detach()), blk)
+    assert relerr(nchw(out), ref) < 1e-5
+    dx = ex.bottleneck_bwd(nhwc(dy)) if bott else ex.basicblock_bwd(nhwc(dy))
+    assert not ex.tape
+    assert relerr(nchw(dx), dx_want) < 2e-4
+    for k, p in blk.named_parameters():
+        assert relerr(ex.grads[p], want[k]) < 2e-4, k
+
+
+@pytest.mark.parametrize("variant", ["sound", "policy"])
+@pytest.mark.parametrize("cfg", [(16, 16, 1, 6), (16, 24, 2, 6), (32, 16, 1, 1), (24, 24, 1, 6)])
+def test_inverted_residual(cuda, variant, cfg):
+    from adamml_b200.engine import Exec
+    import importlib
+    policy_net = importlib.import_module("adamml_b200.models.policy_net")
+    sound_mobilenet_v2 = importlib.import_module("adamml_b200.models.sound_mobilenet_v2")
+    inp, oup, stride, t = cfg
+    g = torch.Generator().manual_seed(1)
+    blk = (sound_mobilenet_v2._InvertedResidual if variant == "sound" else policy_net._InvertedResidual)(inp, oup,
+                                                                                                      stride, t)
+    randomize(blk, g)
+    blk = blk.to(cuda).train()
+    use_res = blk.use_res_connect if variant == "sound" else blk.identity
+    G, ipg, H = 2, 5, 10
+    x = torch.randn(G * ipg, inp, H, H, generator=g).to(cuda).requires_grad_(True)
+    ref = torch.cat([(xs + blk.conv(xs)) if use_res else blk.conv(xs) for xs in x.chunk(G)])
+    dy = torch.randn(ref.shape, generator=g).to(cuda)
+    ref.backward(dy)
+    want = {k: p.grad.clone() for k, p in blk.named_parameters()}
+    ex = Exec(torch.float32, True, G, save=True)
+    out = ex.inverted_residual(nhwc(x.detach()), blk.layers(), use_res)
+    assert relerr(nchw(out), ref) < 1e-5
+    dx = ex.inverted_residual_bwd(nhwc(dy))
+    assert not ex.tape
+    assert relerr(nchw(dx), x.grad) < 2e-4
+    for k, p in blk.named_parameters():
+        assert relerr(ex.grads[p], want[k]) < 2e-4, k
+
+
+def test_small_resnet_end_to_end(cuda):
+    """ResNet-18-style net (BasicBlocks, 3 temporal pools, head) fwd+bwd vs torch, 12 videos x 8 frames.
+    Layer4 sees only 48 values per BN channel, so gradients are judged against a float64 torch run with the
+    "as good as torch fp32" criterion of tests/util.py."""
+    import copy
+    import importlib
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from util import assert_grads_as_good_as_reference
+    ResNet = importlib.import_module("adamml_b200.models.resnet").ResNet
+    g = torch.Generator().manual_seed(2)
+    net = ResNet(18, 8, num_classes=31, dropout=0.5, input_channels=3, compute_dtype=torch.float32)
+    randomize(net, g)
+    net = net.to(cuda).train()
+    N = 12
+    x = torch.randn(N, 24, 64, 64, generator=g).to(cuda)
+    mask = torch.empty(N, 512).bernoulli_(0.5, generator=g).div_(0.5).to(cuda)
+    dy = torch.randn(N, 31, generator=g).to(cuda)
+
+    def tp(t, frames):
+        nt, c, h, w = t.shape
+        v = t.view(-1, frames, c, h, w).transpose(1, 2)
+        v = F.max_pool3d(v, (3, 1, 1), (2, 1, 1), (1, 0, 0))
+        return v.transpose(1, 2).contiguous().view(-1, c, h, w)
+
+    def torch_run(dt):
+        m = copy.deepcopy(net).to(dt)
+        a = x.to(dt).view(N * 8, 3, 64, 64)
+        a = F.max_pool2d(F.relu(m.bn1(m.conv1(a))), 3, 2, 1)
+        frames = 8
+        for li in range(4):
+            for blk in getattr(m, f"layer{li + 1}"):
+                a = torch_block(blk, a, 1)
+            if li < 3:
+                a = tp(a, frames)
+                frames //= 2
+        ref = F.linear(a.mean((2, 3)) * mask.to(dt), m.fc.weight, m.fc.bias)
+        ref.backward(dy.to(dt))
+        return ref.detach(), {k: p.grad for k, p in m.named_parameters()}
+
+    ref32, g32 = torch_run(torch.float32)
+    _, g64 = torch_run(torch.float64)
+    y = net(x, drop_mask=mask)
+    y.backward(dy)
+    assert relerr(y, ref32) < 1e-4
+    assert_grads_as_good_as_reference({k: p.grad for k, p in net.named_parameters()}, g32, g64)

@@ -345,3 +345,84 @@ def test_linear_helpers(cuda):
     assert relerr(ops.frame_mean(xm, 4), xm.view(3, 4, 31).mean(1)) < 1e-6
     dm = torch.randn(3, 31, generator=g).to(cuda)
     assert relerr(ops.frame_mean_bwd(dm, 4), (dm / 4)[:, None, :].expand(3, 4, 31).reshape(12, 31)) < 1e-6
+
+
+TC_CONV_CASES = [
+    # IMGS,H,W,Cin,Cout,R,stride,pad
+    (4, 56, 56, 64, 64, 3, 1, 1),
+    (8, 28, 28, 128, 128, 3, 1, 1),
+    (32, 14, 14, 256, 256, 3, 1, 1),
+    (20, 7, 7, 512, 512, 3, 1, 1),
+    (3, 56, 56, 128, 128, 3, 2, 1),
+    (5, 28, 28, 256, 256, 3, 2, 1),
+    (6, 14, 14, 512, 512, 3, 2, 1),
+    (3, 56, 56, 256, 512, 1, 2, 0),
+    (5, 14, 14, 1024, 2048, 1, 2, 0),
+    (3, 13, 17, 40, 72, 3, 1, 1),
+    (2, 30, 30, 32, 64, 5, 2, 2),
+    (2, 24, 24, 64, 64, 7, 2, 3),
+]
+
+
+@pytest.mark.parametrize("case", TC_CONV_CASES)
+def test_tc_conv_fwd_stats_dgrad(cuda, case):
+    """tcgen05 implicit-GEMM conv (4D TMA taps) vs F.conv2d; fused BN stats; stride-1 dgrad with addend."""
+    from adamml_b200 import _lib, ops
+    IMGS, H, W, Cin, Cout, R, stride, pad = case
+    g = torch.Generator(device="cpu").manual_seed(11)
+    x = torch.randn(IMGS, Cin, H, W, generator=g).to(cuda).bfloat16().float()
+    w = (torch.randn(Cout, Cin, R, R, generator=g) / (Cin * R * R) ** 0.5).to(cuda).bfloat16().float()
+    x.requires_grad_(True)
+    y_ref = F.conv2d(x, w, None, stride, pad)
+    xn = nhwc(x.detach()).bfloat16()
+    wp = ops.pack_weight(w.contiguous(), torch.bfloat16)
+    Ho, Wo = y_ref.shape[2], y_ref.shape[3]
+    G = 1 if IMGS % 2 else 2
+    y = torch.full((IMGS, Ho, Wo, Cout), float("nan"), device=cuda, dtype=torch.bfloat16)
+    stats = torch.full((G, Cout, 2), float("nan"), device=cuda, dtype=torch.float64)
+    _lib.call("tc_conv_bf16", xn, wp, y, None, IMGS, H, W, Cin, Cout, R, R, stride, pad, Ho, Wo, stats, IMGS // G)
+    torch.cuda.synchronize()
+    assert torch.isfinite(y.float()).all()
+    assert relerr(nchw(y), y_ref) < 1e-2
+    yd = y.double().view(G, -1, Cout)
+    ref_stats = torch.stack([yd.sum(1), (yd * yd).sum(1)], -1)
+    assert relerr(stats, ref_stats) < 1e-5
+    if stride != 1:
+        return
+    dy = torch.randn(y_ref.shape, generator=g).to(cuda).bfloat16().float()
+    y_ref.backward(dy)
+    add = torch.randn(xn.shape, generator=g).to(cuda).bfloat16()
+    w_rot = ops.pack_weight_dgrad(w.contiguous(), torch.bfloat16)
+    dx = ops.conv_dgrad(nhwc(dy).bfloat16(), wp, tuple(xn.shape), 1, pad, addend=None, w_rot=w_rot)
+    assert relerr(nchw(dx), x.grad) < 1e-2
+    dx2 = ops.conv_dgrad(nhwc(dy).bfloat16(), wp, tuple(xn.shape), 1, pad, addend=add, w_rot=w_rot)
+    assert relerr(nchw(dx2), x.grad + nchw(add).float()) < 1e-2
+
+
+TC_WGRAD_CASES = TC_CONV_CASES + [
+    (6, 20, 20, 16, 96, 1, 1, 0),
+    (4, 16, 16, 96, 24, 1, 1, 0),
+    (10, 8, 8, 960, 160, 1, 1, 0),
+    (3, 10, 10, 320, 1280, 1, 1, 0),
+    (64, 56, 56, 64, 256, 1, 1, 0),
+]
+
+
+@pytest.mark.parametrize("case", TC_WGRAD_CASES)
+def test_tc_wgrad(cuda, case):
+    """tcgen05 MN-major split-K weight gradient vs torch autograd."""
+    from adamml_b200 import _lib, ops
+    IMGS, H, W, Cin, Cout, R, stride, pad = case
+    g = torch.Generator(device="cpu").manual_seed(12)
+    x = torch.randn(IMGS, Cin, H, W, generator=g).to(cuda).bfloat16().float()
+    w = (torch.randn(Cout, Cin, R, R, generator=g) / (Cin * R * R) ** 0.5).to(cuda).requires_grad_(True)
+    y_ref = F.conv2d(x, w, None, stride, pad)
+    dy = torch.randn(y_ref.shape, generator=g).to(cuda).bfloat16().float()
+    y_ref.backward(dy)
+    Ho, Wo = y_ref.shape[2], y_ref.shape[3]
+    dw = torch.full((Cout, R, R, Cin), float("nan"), device=cuda, dtype=torch.float32)
+    _lib.call("tc_wgrad_bf16", nhwc(x).bfloat16(), nhwc(dy).bfloat16(), dw, IMGS, H, W, Cin, Cout, R, R, stride, pad,
+              Ho, Wo)
+    torch.cuda.synchronize()
+    assert torch.isfinite(dw).all()
+    assert relerr(ops.unpack_wgrad(dw, Cin), w.grad) < 1e-3
