@@ -275,6 +275,11 @@ def run_gpu_arm(a):
             d[0] += e0.elapsed_time(e1)
             d[1] += 1
             d[2] += kernel_flops(name, args)
+        if a.dump_calls:
+            with open(a.dump_calls, "w") as f:
+                for name, e0, e1, args in _lib.PROFILE:
+                    f.write(json.dumps({"op": name, "ms": round(e0.elapsed_time(e1), 4),
+                                        "args": [x for x in args if x is not None]}) + "\n")
         _lib.PROFILE = None
         prof = sorted(agg.items(), key=lambda kv: -kv[1][0])
 
@@ -329,6 +334,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-sync-bn", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dump-calls", default=None, help="write one JSON line per C-ABI call of one step (op, ms, args)")
     a = ap.parse_args()
     if a.warmup < 3 and a.impl == "ours":
         a.warmup = 3
