@@ -193,78 +193,200 @@ __global__ void bn_param_grad_kernel(const double* __restrict__ sums, float* __r
 
 
 // ---------------------------------------------------------------------------------------------------
-// 16-byte vectorised versions (C % VEC == 0): thread = (channel vector, row lane)
-constexpr int VROWS_PER_THREAD = 32;
+// Row-streaming kernels (C % VEC == 0, 16-byte aligned): the [rows, C] NHWC matrix is contiguous, a block
+// of cpb*k threads walks it so that every thread keeps ONE channel vector (VEC = 8 bf16 / 4 fp32 channels)
+// for its whole life: per-channel coefficients live in registers, there is no index arithmetic in the
+// loop, and consecutive threads touch consecutive 16-byte vectors (fully coalesced).  The kernels are
+// pure HBM streams: algorithmic bytes = (tensors read + tensors written) x rows x C x sizeof(T).
+constexpr int EW_THREADS = 256;
+constexpr int EW_UNROLL = 4;
 template <typename T> struct AccT { typedef float type; };
 template <> struct AccT<float> { typedef double type; };
 
-// MODE 0: sum z, sum z^2.   MODE 1: sum gm, sum gm*xhat (gm = dout * mask(out)).
-template <typename T, int MODE>
-__global__ void __launch_bounds__(256)
-bn_reduce_vec_kernel(const T* __restrict__ a /*z | dout*/, const T* __restrict__ out, const T* __restrict__ z,
-                     const float* __restrict__ mean_invstd, double* __restrict__ sums, long long rows_per_group,
-                     int C, int blocks_per_group, int rows_per_block, int act) {
+struct RowGeom {
+  int cpb;      // channel vectors per block
+  int k;        // row lanes per block
+  int threads;  // cpb * k
+  int cchunks;  // blocks along the channel axis
+};
+template <typename T>
+inline RowGeom row_geom(int C) {
+  const int V = VecIO<T>::N;
+  RowGeom g;
+  int cvecs = C / V;
+  g.cchunks = (cvecs + EW_THREADS - 1) / EW_THREADS;
+  g.cpb = (cvecs + g.cchunks - 1) / g.cchunks;
+  g.k = EW_THREADS / g.cpb;
+  if (g.k < 1) g.k = 1;
+  g.threads = g.cpb * g.k;
+  return g;
+}
+inline int num_sms_ew() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+// out = act( z*scale+shift  [+ res]  [+ res_z*res_scale+res_shift] )
+template <typename T>
+__global__ void __launch_bounds__(EW_THREADS)
+bn_apply_rows_kernel(const T* __restrict__ z, const float* __restrict__ ss, const T* __restrict__ res,
+                     const T* __restrict__ res_z, const float* __restrict__ res_ss, T* __restrict__ out,
+                     long long rows_per_group, int C, int cpb, int k, int rows_per_block, int blocks_per_group,
+                     int act) {
   constexpr int V = VecIO<T>::N;
-  extern __shared__ double shd[];
-  const int TX = blockDim.x, TY = blockDim.y;
+  const int cl = threadIdx.x % cpb, rl = threadIdx.x / cpb;
+  const int c0 = (blockIdx.y * cpb + cl) * V;
+  if (c0 >= C) return;
   const int g = blockIdx.x / blocks_per_group;
   const int bg = blockIdx.x % blocks_per_group;
-  const int cv = blockIdx.y * TX + threadIdx.x;
-  const int c0 = cv * V;
-  const bool ok = c0 < C;
-  long long r0 = (long long)bg * rows_per_block;
+  const long long r0 = (long long)bg * rows_per_block;
   long long r1 = r0 + rows_per_block;
   if (r1 > rows_per_group) r1 = rows_per_group;
-  // fp32 (parity) mode accumulates in double per thread; bf16 mode in float over <= 32 rows per thread
-  typedef typename AccT<T>::type acc_t;
-  acc_t s[V], q[V];
+  float sc[V], sh[V], rsc[V], rsh[V];
 #pragma unroll
-  for (int i = 0; i < V; ++i) { s[i] = 0; q[i] = 0; }
-  if (ok) {
-    float mean[V], invstd[V];
-    if (MODE == 1) {
+  for (int i = 0; i < V; ++i) {
+    const float2 p = *reinterpret_cast<const float2*>(ss + ((long long)g * C + c0 + i) * 2);
+    sc[i] = p.x; sh[i] = p.y;
+    rsc[i] = 0.f; rsh[i] = 0.f;
+  }
+  if (res_z) {
 #pragma unroll
-      for (int i = 0; i < V; ++i) {
-        mean[i] = mean_invstd[((long long)g * C + c0 + i) * 2 + 0];
-        invstd[i] = mean_invstd[((long long)g * C + c0 + i) * 2 + 1];
+    for (int i = 0; i < V; ++i) {
+      const float2 p = *reinterpret_cast<const float2*>(res_ss + ((long long)g * C + c0 + i) * 2);
+      rsc[i] = p.x; rsh[i] = p.y;
+    }
+  }
+  const long long base = (long long)g * rows_per_group * C + c0;
+  for (long long r = r0 + rl; r < r1; r += (long long)k * EW_UNROLL) {
+    typename VecIO<T>::raw qz[EW_UNROLL], qr[EW_UNROLL];
+#pragma unroll
+    for (int u = 0; u < EW_UNROLL; ++u) {
+      const long long rr = r + (long long)u * k;
+      if (rr < r1) {
+        qz[u] = VecIO<T>::load_raw(z + base + rr * C);
+        if (res) qr[u] = VecIO<T>::load_raw(res + base + rr * C);
+        else if (res_z) qr[u] = VecIO<T>::load_raw(res_z + base + rr * C);
       }
     }
-    const long long base = (long long)g * rows_per_group * C + c0;
-    for (long long r = r0 + threadIdx.y; r < r1; r += TY) {
-      const long long off = base + r * C;
-      float va[V];
-      VecIO<T>::load(a + off, va);
-      if (MODE == 0) {
 #pragma unroll
-        for (int i = 0; i < V; ++i) { s[i] += (acc_t)va[i]; q[i] += (acc_t)va[i] * (acc_t)va[i]; }
-      } else {
-        float vz[V];
-        VecIO<T>::load(z + off, vz);
-        if (act != ADAMML_ACT_NONE) {
-          float vo[V];
-          VecIO<T>::load(out + off, vo);
-#pragma unroll
-          for (int i = 0; i < V; ++i) if (!act_pass(vo[i], act)) va[i] = 0.f;
-        }
+    for (int u = 0; u < EW_UNROLL; ++u) {
+      const long long rr = r + (long long)u * k;
+      if (rr < r1) {
+        float vo[V], vz[V], vr[V];
+        VecIO<T>::unpack(qz[u], vz);
+        if (res || res_z) VecIO<T>::unpack(qr[u], vr);
 #pragma unroll
         for (int i = 0; i < V; ++i) {
-          s[i] += (acc_t)va[i];
-          q[i] += (acc_t)va[i] * (acc_t)((vz[i] - mean[i]) * invstd[i]);
+          float v = fmaf(vz[i], sc[i], sh[i]);
+          if (res) v += vr[i];
+          else if (res_z) v += fmaf(vr[i], rsc[i], rsh[i]);
+          vo[i] = act_apply(v, act);
         }
+        VecIO<T>::store(out + base + rr * C, vo);
       }
     }
   }
-  // block reduce over TY in double
-  double* sh = shd + ((size_t)threadIdx.y * TX + threadIdx.x) * (2 * V);
+}
+
+// MODE 0: sum z, sum z^2.   MODE 1: sum gm, sum gm*xhat (gm = dout * mask(out)).
+// Persistent over row chunks: block b of a group handles chunks b, b+bpg, ...; per-thread partial sums
+// in fp32 over <= 16 rows are flushed into wide accumulators, one smem reduction + 2 atomics per
+// (block, channel) at the end.
+template <typename T, int MODE>
+__global__ void __launch_bounds__(EW_THREADS)
+bn_reduce_rows_kernel(const T* __restrict__ a /*z | dout*/, const T* __restrict__ out, const T* __restrict__ z,
+                      const float* __restrict__ mean_invstd, double* __restrict__ sums, long long rows_per_group,
+                      int C, int cpb, int k, int blocks_per_group, int act) {
+  constexpr int V = VecIO<T>::N;
+  constexpr int CH = 4;  // row iterations per flush (x EW_UNROLL rows)
+  extern __shared__ double shd[];
+  const int cl = threadIdx.x % cpb, rl = threadIdx.x / cpb;
+  const int c0 = (blockIdx.y * cpb + cl) * V;
+  const bool ok = c0 < C;
+  const int g = blockIdx.x / blocks_per_group;
+  const int bg = blockIdx.x % blocks_per_group;
+  typedef typename AccT<T>::type acc_t;
+  double S[V], Q[V];
 #pragma unroll
-  for (int i = 0; i < V; ++i) { sh[i] = (double)s[i]; sh[V + i] = (double)q[i]; }
+  for (int i = 0; i < V; ++i) { S[i] = 0.0; Q[i] = 0.0; }
+  if (ok) {
+    float mean[V], invstd[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) { mean[i] = 0.f; invstd[i] = 1.f; }
+    if (MODE == 1) {
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const float2 p = *reinterpret_cast<const float2*>(mean_invstd + ((long long)g * C + c0 + i) * 2);
+        mean[i] = p.x; invstd[i] = p.y;
+      }
+    }
+    const long long base = (long long)g * rows_per_group * C + c0;
+    const long long chunk_rows = (long long)k * EW_UNROLL * CH;
+    for (long long rc = (long long)bg * chunk_rows; rc < rows_per_group; rc += (long long)blocks_per_group * chunk_rows) {
+      long long r1 = rc + chunk_rows;
+      if (r1 > rows_per_group) r1 = rows_per_group;
+      acc_t s[V], q[V];
+#pragma unroll
+      for (int i = 0; i < V; ++i) { s[i] = 0; q[i] = 0; }
+      for (long long r = rc + rl; r < r1; r += (long long)k * EW_UNROLL) {
+        typename VecIO<T>::raw qa[EW_UNROLL], qz[EW_UNROLL], qo[EW_UNROLL];
+#pragma unroll
+        for (int u = 0; u < EW_UNROLL; ++u) {
+          const long long rr = r + (long long)u * k;
+          if (rr < r1) {
+            qa[u] = VecIO<T>::load_raw(a + base + rr * C);
+            if (MODE == 1) {
+              qz[u] = VecIO<T>::load_raw(z + base + rr * C);
+              if (act != ADAMML_ACT_NONE) qo[u] = VecIO<T>::load_raw(out + base + rr * C);
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < EW_UNROLL; ++u) {
+          const long long rr = r + (long long)u * k;
+          if (rr < r1) {
+            float va[V], vz[V], vo[V];
+            VecIO<T>::unpack(qa[u], va);
+            if (MODE == 1) {
+              VecIO<T>::unpack(qz[u], vz);
+              if (act != ADAMML_ACT_NONE) VecIO<T>::unpack(qo[u], vo);
+            }
+#pragma unroll
+            for (int i = 0; i < V; ++i) {
+              if (MODE == 0) {
+                s[i] += (acc_t)va[i];
+                q[i] += (acc_t)va[i] * (acc_t)va[i];
+              } else {
+                float gm = va[i];
+                if (act != ADAMML_ACT_NONE && !act_pass(vo[i], act)) gm = 0.f;
+                s[i] += (acc_t)gm;
+                q[i] += (acc_t)gm * (acc_t)((vz[i] - mean[i]) * invstd[i]);
+              }
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < V; ++i) { S[i] += (double)s[i]; Q[i] += (double)q[i]; }
+    }
+  }
+  // block reduce over the k row lanes
+  double* sh = shd + (size_t)threadIdx.x * (2 * V);
+#pragma unroll
+  for (int i = 0; i < V; ++i) { sh[i] = S[i]; sh[V + i] = Q[i]; }
   __syncthreads();
-  if (threadIdx.y == 0 && ok) {
+  if (rl == 0 && ok) {
 #pragma unroll
     for (int i = 0; i < V; ++i) {
       double ds = 0.0, dq = 0.0;
-      for (int y = 0; y < TY; ++y) {
-        const double* o = shd + ((size_t)y * TX + threadIdx.x) * (2 * V);
+      for (int y = 0; y < k; ++y) {
+        const double* o = shd + ((size_t)y * cpb + cl) * (2 * V);
         ds += o[i];
         dq += o[V + i];
       }
@@ -274,88 +396,78 @@ bn_reduce_vec_kernel(const T* __restrict__ a /*z | dout*/, const T* __restrict__
   }
 }
 
+// training: dz = gamma*invstd*(gm - sum_g/cnt - xhat*sum_gx/cnt);  eval: dz = gamma*invstd*gm ; dres = gm
 template <typename T>
-__global__ void __launch_bounds__(256)
-bn_apply_vec_kernel(const T* __restrict__ z, const float* __restrict__ ss, const T* __restrict__ res,
-                    const T* __restrict__ res_z, const float* __restrict__ res_ss, T* __restrict__ out,
-                    long long total_vec, long long elems_per_group, int C, int act) {
+__global__ void __launch_bounds__(EW_THREADS)
+bn_bwd_apply_rows_kernel(const T* __restrict__ dout, const T* __restrict__ out, const T* __restrict__ z,
+                         const float* __restrict__ mean_invstd, const float* __restrict__ gamma,
+                         const double* __restrict__ sums, T* __restrict__ dz, T* __restrict__ dres,
+                         long long rows_per_group, int C, int cpb, int k, int rows_per_block, int blocks_per_group,
+                         double count, int act, int training) {
   constexpr int V = VecIO<T>::N;
-  for (long long iv = (long long)blockIdx.x * blockDim.x + threadIdx.x; iv < total_vec;
-       iv += (long long)gridDim.x * blockDim.x) {
-    const long long idx = iv * V;
-    const int c0 = (int)(idx % C);
-    const int g = (int)(idx / elems_per_group);
-    const float* s = ss + ((long long)g * C + c0) * 2;
-    float vz[V], vo[V];
-    VecIO<T>::load(z + idx, vz);
-#pragma unroll
-    for (int i = 0; i < V; ++i) vo[i] = fmaf(vz[i], s[2 * i], s[2 * i + 1]);
-    if (res) {
-      float vr[V];
-      VecIO<T>::load(res + idx, vr);
-#pragma unroll
-      for (int i = 0; i < V; ++i) vo[i] += vr[i];
-    }
-    if (res_z) {
-      const float* rs = res_ss + ((long long)g * C + c0) * 2;
-      float vr[V];
-      VecIO<T>::load(res_z + idx, vr);
-#pragma unroll
-      for (int i = 0; i < V; ++i) vo[i] += fmaf(vr[i], rs[2 * i], rs[2 * i + 1]);
-    }
-#pragma unroll
-    for (int i = 0; i < V; ++i) vo[i] = act_apply(vo[i], act);
-    VecIO<T>::store(out + idx, vo);
-  }
-}
-
-template <typename T>
-__global__ void __launch_bounds__(256)
-bn_bwd_apply_vec_kernel(const T* __restrict__ dout, const T* __restrict__ out, const T* __restrict__ z,
-                        const float* __restrict__ mean_invstd, const float* __restrict__ gamma,
-                        const double* __restrict__ sums, T* __restrict__ dz, T* __restrict__ dres,
-                        long long total_vec, long long elems_per_group, int C, double count, int act, int training) {
-  constexpr int V = VecIO<T>::N;
+  const int cl = threadIdx.x % cpb, rl = threadIdx.x / cpb;
+  const int c0 = (blockIdx.y * cpb + cl) * V;
+  if (c0 >= C) return;
+  const int g = blockIdx.x / blocks_per_group;
+  const int bg = blockIdx.x % blocks_per_group;
+  const long long r0 = (long long)bg * rows_per_block;
+  long long r1 = r0 + rows_per_block;
+  if (r1 > rows_per_group) r1 = rows_per_group;
   const float inv_count = (float)(1.0 / count);
-  for (long long iv = (long long)blockIdx.x * blockDim.x + threadIdx.x; iv < total_vec;
-       iv += (long long)gridDim.x * blockDim.x) {
-    const long long idx = iv * V;
-    const int c0 = (int)(idx % C);
-    const int g = (int)(idx / elems_per_group);
-    const long long gc = (long long)g * C + c0;
-    float gm[V];
-    VecIO<T>::load(dout + idx, gm);
-    if (act != ADAMML_ACT_NONE) {
-      float vo[V];
-      VecIO<T>::load(out + idx, vo);
+  float mean[V], invstd[V], A[V], m1[V], m2[V];
 #pragma unroll
-      for (int i = 0; i < V; ++i) if (!act_pass(vo[i], act)) gm[i] = 0.f;
+  for (int i = 0; i < V; ++i) {
+    const long long gc = (long long)g * C + c0 + i;
+    const float2 p = *reinterpret_cast<const float2*>(mean_invstd + gc * 2);
+    mean[i] = p.x; invstd[i] = p.y;
+    A[i] = (gamma ? gamma[c0 + i] : 1.f) * p.y;
+    m1[i] = 0.f; m2[i] = 0.f;
+    if (training && dz) {
+      m1[i] = (float)sums[gc * 2 + 0] * inv_count;
+      m2[i] = (float)sums[gc * 2 + 1] * inv_count;
     }
-    if (dres) VecIO<T>::store(dres + idx, gm);
-    if (dz) {
-      float v[V];
-      if (training) {
-        float vz[V];
-        VecIO<T>::load(z + idx, vz);
+  }
+  const long long base = (long long)g * rows_per_group * C + c0;
+  const bool need_z = training && dz;
+  for (long long r = r0 + rl; r < r1; r += (long long)k * EW_UNROLL) {
+    typename VecIO<T>::raw qg[EW_UNROLL], qz[EW_UNROLL], qo[EW_UNROLL];
 #pragma unroll
-        for (int i = 0; i < V; ++i) {
-          const float mean = mean_invstd[(gc + i) * 2 + 0];
-          const float invstd = mean_invstd[(gc + i) * 2 + 1];
-          const float ga = gamma ? gamma[c0 + i] : 1.f;
-          const float m1 = (float)sums[(gc + i) * 2 + 0] * inv_count;
-          const float m2 = (float)sums[(gc + i) * 2 + 1] * inv_count;
-          const float xhat = (vz[i] - mean) * invstd;
-          v[i] = ga * invstd * (gm[i] - m1 - xhat * m2);
+    for (int u = 0; u < EW_UNROLL; ++u) {
+      const long long rr = r + (long long)u * k;
+      if (rr < r1) {
+        qg[u] = VecIO<T>::load_raw(dout + base + rr * C);
+        if (act != ADAMML_ACT_NONE) qo[u] = VecIO<T>::load_raw(out + base + rr * C);
+        if (need_z) qz[u] = VecIO<T>::load_raw(z + base + rr * C);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < EW_UNROLL; ++u) {
+      const long long rr = r + (long long)u * k;
+      if (rr < r1) {
+        float gm[V], vz[V], vo[V];
+        VecIO<T>::unpack(qg[u], gm);
+        if (need_z) VecIO<T>::unpack(qz[u], vz);
+        if (act != ADAMML_ACT_NONE) {
+          VecIO<T>::unpack(qo[u], vo);
+#pragma unroll
+          for (int i = 0; i < V; ++i) if (!act_pass(vo[i], act)) gm[i] = 0.f;
         }
-      } else {
+        if (dres) VecIO<T>::store(dres + base + rr * C, gm);
+        if (dz) {
+          float v[V];
+          if (training) {
 #pragma unroll
-        for (int i = 0; i < V; ++i) {
-          const float invstd = mean_invstd[(gc + i) * 2 + 1];
-          const float ga = gamma ? gamma[c0 + i] : 1.f;
-          v[i] = ga * invstd * gm[i];
+            for (int i = 0; i < V; ++i) {
+              const float xhat = (vz[i] - mean[i]) * invstd[i];
+              v[i] = A[i] * (gm[i] - m1[i] - xhat * m2[i]);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < V; ++i) v[i] = A[i] * gm[i];
+          }
+          VecIO<T>::store(dz + base + rr * C, v);
         }
       }
-      VecIO<T>::store(dz + idx, v);
     }
   }
 }
@@ -370,20 +482,19 @@ inline bool vec_ok(int C, const void* a, const void* b = nullptr, const void* c 
   return true;
 }
 
-// launch geometry of the vectorised reductions
-template <typename T>
-inline void reduce_geom(long long rows_per_group, int C, dim3* block, int* cgrid, int* rows_per_block, int* bpg,
-                        size_t* smem) {
-  const int V = VecIO<T>::N;
-  int cvecs = C / V;
-  int tx = 1;
-  while (tx < cvecs && tx < 32) tx *= 2;
-  int ty = 256 / tx;
-  *block = dim3(tx, ty);
-  *cgrid = (cvecs + tx - 1) / tx;
-  *rows_per_block = ty * VROWS_PER_THREAD;
-  *bpg = (int)((rows_per_group + *rows_per_block - 1) / *rows_per_block);
-  *smem = sizeof(double) * 256 * 2 * V;
+// streaming launch: ~32 vector iterations per thread
+inline void stream_geom(const RowGeom& rg, long long rows_per_group, int* rows_per_block, int* bpg) {
+  long long rpb = (long long)rg.k * EW_UNROLL * 8;
+  *bpg = (int)((rows_per_group + rpb - 1) / rpb);
+  *rows_per_block = (int)rpb;
+}
+// persistent reduction launch: ~4 blocks per SM in total
+inline int reduce_bpg(const RowGeom& rg, long long rows_per_group, int G) {
+  long long chunk_rows = (long long)rg.k * EW_UNROLL * 4;
+  long long chunks = (rows_per_group + chunk_rows - 1) / chunk_rows;
+  long long want = (4LL * num_sms_ew() + (long long)G * rg.cchunks - 1) / ((long long)G * rg.cchunks);
+  if (want < 1) want = 1;
+  return (int)(chunks < want ? chunks : want);
 }
 
 inline int ew_blocks(long long total) {
@@ -403,13 +514,12 @@ int adamml_bn_stats(const void* z, double* sums, long long rows_per_group, int C
   cudaMemsetAsync(sums, 0, sizeof(double) * (size_t)G * C * 2, stream);
   ADAMML_DISPATCH_DTYPE(dtype, T, {
     if (vec_ok<T>(C, z)) {
-      dim3 vb; int cg, rpb, vbpg; size_t sm;
-      reduce_geom<T>(rows_per_group, C, &vb, &cg, &rpb, &vbpg, &sm);
-      static bool cfgd = false;
-      if (!cfgd) { cudaFuncSetAttribute(bn_reduce_vec_kernel<T, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536); cfgd = true; }
-      dim3 vg((unsigned)(vbpg * (long long)G), cg);
-      bn_reduce_vec_kernel<T, 0><<<vg, vb, sm, stream>>>((const T*)z, nullptr, nullptr, nullptr, sums, rows_per_group,
-                                                         C, vbpg, rpb, 0);
+      const RowGeom rg = row_geom<T>(C);
+      const int bpg = reduce_bpg(rg, rows_per_group, G);
+      const size_t sm = sizeof(double) * rg.threads * 2 * VecIO<T>::N;
+      dim3 vg((unsigned)(bpg * (long long)G), rg.cchunks);
+      bn_reduce_rows_kernel<T, 0><<<vg, rg.threads, sm, stream>>>((const T*)z, nullptr, nullptr, nullptr, sums,
+                                                                  rows_per_group, C, rg.cpb, rg.k, bpg, 0);
     } else {
       int bpg = ceil_div(rows_per_group, ROWS_PER_BLOCK);
       dim3 grid((unsigned)(bpg * (long long)G), ceil_div(C, 32));
@@ -441,10 +551,13 @@ int adamml_bn_apply(const void* z, const float* scale_shift, const void* res, co
   long long total = epg * G;
   ADAMML_DISPATCH_DTYPE(dtype, T, {
     if (vec_ok<T>(C, z, res, res_z, out)) {
-      long long tv = total / VecIO<T>::N;
-      bn_apply_vec_kernel<T><<<ew_blocks(tv), 256, 0, stream>>>((const T*)z, scale_shift, (const T*)res,
-                                                                (const T*)res_z, res_scale_shift, (T*)out, tv, epg, C,
-                                                                act);
+      const RowGeom rg = row_geom<T>(C);
+      int rpb, bpg;
+      stream_geom(rg, rows_per_group, &rpb, &bpg);
+      dim3 vg((unsigned)(bpg * (long long)G), rg.cchunks);
+      bn_apply_rows_kernel<T><<<vg, rg.threads, 0, stream>>>((const T*)z, scale_shift, (const T*)res, (const T*)res_z,
+                                                             res_scale_shift, (T*)out, rows_per_group, C, rg.cpb, rg.k,
+                                                             rpb, bpg, act);
     } else {
       bn_apply_kernel<T><<<ew_blocks(total), 256, 0, stream>>>((const T*)z, scale_shift, (const T*)res,
                                                               (const T*)res_z, res_scale_shift, (T*)out, total, epg, C,
@@ -461,13 +574,13 @@ int adamml_bn_bwd_reduce(const void* dout, const void* out, const void* z, const
   cudaMemsetAsync(sums, 0, sizeof(double) * (size_t)G * C * 2, stream);
   ADAMML_DISPATCH_DTYPE(dtype, T, {
     if (vec_ok<T>(C, dout, out, z)) {
-      dim3 vb; int cg, rpb, vbpg; size_t sm;
-      reduce_geom<T>(rows_per_group, C, &vb, &cg, &rpb, &vbpg, &sm);
-      static bool cfgd = false;
-      if (!cfgd) { cudaFuncSetAttribute(bn_reduce_vec_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536); cfgd = true; }
-      dim3 vg((unsigned)(vbpg * (long long)G), cg);
-      bn_reduce_vec_kernel<T, 1><<<vg, vb, sm, stream>>>((const T*)dout, (const T*)out, (const T*)z, mean_invstd, sums,
-                                                         rows_per_group, C, vbpg, rpb, act);
+      const RowGeom rg = row_geom<T>(C);
+      const int bpg = reduce_bpg(rg, rows_per_group, G);
+      const size_t sm = sizeof(double) * rg.threads * 2 * VecIO<T>::N;
+      dim3 vg((unsigned)(bpg * (long long)G), rg.cchunks);
+      bn_reduce_rows_kernel<T, 1><<<vg, rg.threads, sm, stream>>>((const T*)dout, (const T*)out, (const T*)z,
+                                                                  mean_invstd, sums, rows_per_group, C, rg.cpb, rg.k,
+                                                                  bpg, act);
     } else {
       int bpg = ceil_div(rows_per_group, ROWS_PER_BLOCK);
       dim3 grid((unsigned)(bpg * (long long)G), ceil_div(C, 32));
@@ -488,10 +601,14 @@ int adamml_bn_bwd_apply(const void* dout, const void* out, const void* z, const 
   long long total = epg * G;
   ADAMML_DISPATCH_DTYPE(dtype, T, {
     if (vec_ok<T>(C, dout, out, z, dz, dres)) {
-      long long tv = total / VecIO<T>::N;
-      bn_bwd_apply_vec_kernel<T><<<ew_blocks(tv), 256, 0, stream>>>((const T*)dout, (const T*)out, (const T*)z,
-                                                                    mean_invstd, gamma, sums, (T*)dz, (T*)dres, tv, epg,
-                                                                    C, count, act, training);
+      const RowGeom rg = row_geom<T>(C);
+      int rpb, bpg;
+      stream_geom(rg, rows_per_group, &rpb, &bpg);
+      dim3 vg((unsigned)(bpg * (long long)G), rg.cchunks);
+      bn_bwd_apply_rows_kernel<T><<<vg, rg.threads, 0, stream>>>((const T*)dout, (const T*)out, (const T*)z,
+                                                                 mean_invstd, gamma, sums, (T*)dz, (T*)dres,
+                                                                 rows_per_group, C, rg.cpb, rg.k, rpb, bpg, count, act,
+                                                                 training);
     } else {
       bn_bwd_apply_kernel<T><<<ew_blocks(total), 256, 0, stream>>>((const T*)dout, (const T*)out, (const T*)z,
                                                                   mean_invstd, gamma, sums, (T*)dz, (T*)dres, total,

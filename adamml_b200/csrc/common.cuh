@@ -19,6 +19,13 @@
 
 void adamml_set_error(const char* fmt, ...);
 int adamml_check_launch(const char* what);
+// conv_simt.cu: scalar depthwise fallbacks used by dwconv.cu for ragged channel counts
+int adamml_dwconv_fwd_scalar(const void* x, const float* w, void* y, int IMGS, int H, int W, int C, int stride, int Ho,
+                             int Wo, int dtype, cudaStream_t stream);
+int adamml_dwconv_dgrad_scalar(const void* dy, const float* w, void* dx, const void* addend, int IMGS, int H, int W,
+                               int C, int stride, int Ho, int Wo, int dtype, cudaStream_t stream);
+int adamml_dwconv_wgrad_scalar(const void* x, const void* dy, float* dw, int IMGS, int H, int W, int C, int stride,
+                               int Ho, int Wo, int dtype, cudaStream_t stream);
 
 #define ADAMML_REQUIRE(cond, ...)                 \
   do {                                            \
@@ -63,6 +70,11 @@ static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) 
 template <typename T> struct VecIO;
 template <> struct VecIO<float> {
   static constexpr int N = 4;
+  typedef float4 raw;
+  __device__ __forceinline__ static raw load_raw(const float* p) { return *reinterpret_cast<const float4*>(p); }
+  __device__ __forceinline__ static void unpack(const raw& t, float (&v)[4]) {
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
   __device__ __forceinline__ static void load(const float* p, float (&v)[4]) {
     float4 t = *reinterpret_cast<const float4*>(p);
     v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
@@ -73,6 +85,16 @@ template <> struct VecIO<float> {
 };
 template <> struct VecIO<bf16> {
   static constexpr int N = 8;
+  typedef uint4 raw;
+  __device__ __forceinline__ static raw load_raw(const bf16* p) { return *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ static void unpack(const raw& t, float (&v)[8]) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 f = __bfloat1622float2(h[i]);
+      v[2 * i] = f.x; v[2 * i + 1] = f.y;
+    }
+  }
   __device__ __forceinline__ static void load(const bf16* p, float (&v)[8]) {
     uint4 t = *reinterpret_cast<const uint4*>(p);
     const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);

@@ -394,7 +394,10 @@ int adamml_simt_conv_wgrad(const void* x, const void* dy, float* dw, int IMGS, i
   return adamml_check_launch("simt_conv_wgrad");
 }
 
-int adamml_dwconv_fwd(const void* x, const float* w, void* y, int IMGS, int H, int W, int C, int stride, int Ho,
+}  // extern "C"
+
+// scalar fallbacks (C not a multiple of the 16-byte vector); the C-ABI entry points live in dwconv.cu
+int adamml_dwconv_fwd_scalar(const void* x, const float* w, void* y, int IMGS, int H, int W, int C, int stride, int Ho,
                       int Wo, int dtype, cudaStream_t stream) {
   ADAMML_REQUIRE(stride == 1 || stride == 2, "dwconv: stride must be 1 or 2");
   ADAMML_REQUIRE(Ho == (H + 2 - 3) / stride + 1 && Wo == (W + 2 - 3) / stride + 1, "dwconv: bad Ho/Wo");
@@ -402,20 +405,20 @@ int adamml_dwconv_fwd(const void* x, const float* w, void* y, int IMGS, int H, i
   int blocks = (int)((total + 255) / 256 < 148LL * 32 ? (total + 255) / 256 : 148LL * 32);
   ADAMML_DISPATCH_DTYPE(dtype, T,
     dw_fwd_kernel<T><<<blocks, 256, 0, stream>>>((const T*)x, w, (T*)y, IMGS, H, W, C, stride, Ho, Wo));
-  return adamml_check_launch("dwconv_fwd");
+  return adamml_check_launch("dwconv_fwd_scalar");
 }
 
-int adamml_dwconv_dgrad(const void* dy, const float* w, void* dx, const void* addend, int IMGS, int H, int W, int C,
+int adamml_dwconv_dgrad_scalar(const void* dy, const float* w, void* dx, const void* addend, int IMGS, int H, int W, int C,
                         int stride, int Ho, int Wo, int dtype, cudaStream_t stream) {
   ADAMML_REQUIRE(stride == 1 || stride == 2, "dwconv: stride must be 1 or 2");
   long long total = (long long)IMGS * H * W * C;
   int blocks = (int)((total + 255) / 256 < 148LL * 32 ? (total + 255) / 256 : 148LL * 32);
   ADAMML_DISPATCH_DTYPE(dtype, T,
     dw_dgrad_kernel<T><<<blocks, 256, 0, stream>>>((const T*)dy, w, (T*)dx, (const T*)addend, IMGS, H, W, C, stride, Ho, Wo));
-  return adamml_check_launch("dwconv_dgrad");
+  return adamml_check_launch("dwconv_dgrad_scalar");
 }
 
-int adamml_dwconv_wgrad(const void* x, const void* dy, float* dw, int IMGS, int H, int W, int C, int stride, int Ho,
+int adamml_dwconv_wgrad_scalar(const void* x, const void* dy, float* dw, int IMGS, int H, int W, int C, int stride, int Ho,
                         int Wo, int dtype, cudaStream_t stream) {
   ADAMML_REQUIRE(stride == 1 || stride == 2, "dwconv: stride must be 1 or 2");
   cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)C * 9, stream);
@@ -424,7 +427,5 @@ int adamml_dwconv_wgrad(const void* x, const void* dy, float* dw, int IMGS, int 
   dim3 block(128, 2);
   ADAMML_DISPATCH_DTYPE(dtype, T,
     dw_wgrad_kernel<T><<<grid, block, 0, stream>>>((const T*)x, (const T*)dy, dw, IMGS, H, W, C, stride, Ho, Wo));
-  return adamml_check_launch("dwconv_wgrad");
+  return adamml_check_launch("dwconv_wgrad_scalar");
 }
-
-}  // extern "C"

@@ -31,6 +31,13 @@ struct ConvGeom {
   int tiles_w, tiles_h, tiles_i;
   int Ho, Wo, IMGS;
   int imgs_per_group;
+  // output lattice: pixel (img, oh, ow) of this launch is stored at (img, oh*out_s + out_ph, ow*out_s + out_pw)
+  // of an [IMGS, out_H, out_W, ldd] tensor (the 4 parity classes of a stride-2 data gradient)
+  int out_H, out_W, out_s, out_ph, out_pw;
+  // addend_sub == 2: `addend` is the compact [IMGS, ceil(Ho/2), ceil(Wo/2), ldd] gradient of a stride-2 1x1
+  // branch, added at even (oh, ow) only
+  int addend_sub, add_H, add_W;
+  int tap_koff[MAX_TAPS];  // K offset of the tap's weight slice inside a row of B
   signed char tap_map[MAX_TAPS], tap_dh[MAX_TAPS], tap_dw[MAX_TAPS];
 };
 struct ConvMaps {
@@ -112,7 +119,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int c0 = (kb - tap * geo.kb_per_tap) * BLOCK_K;
             tma_load_4d(sa, &cmaps.m[geo.tap_map[tap]], &full_bar[stage], c0, w0 + geo.tap_dw[tap],
                         h0 + geo.tap_dh[tap], i0);
-            tma_load_2d(sb, &tmB, &full_bar[stage], tap * geo.cin + c0, n_blk * BLOCK_N);
+            tma_load_2d(sb, &tmB, &full_bar[stage], geo.tap_koff[tap] + c0, n_blk * BLOCK_N);
           } else {
             tma_load_2d(sa, &tmA, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
             tma_load_2d(sb, &tmB, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);
@@ -165,8 +172,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int m_blk = (int)(tile / num_n_blks);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      long long row;
-      bool row_ok;
+      long long row, arow = 0;
+      bool row_ok, add_ok = addend != nullptr;
       long long g_lo = 0, g_hi = 0, my_g = 0;
       if (CONV) {
         const int ml = q * 32 + lane;
@@ -174,7 +181,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int oh = ((m_blk / geo.tiles_w) % geo.tiles_h) * geo.BH + (ml / geo.BW) % geo.BH;
         const int img = (m_blk / (geo.tiles_w * geo.tiles_h)) * geo.BI + ml / (geo.BW * geo.BH);
         row_ok = ow < geo.Wo && oh < geo.Ho && img < geo.IMGS;
-        row = ((long long)img * geo.Ho + oh) * geo.Wo + ow;
+        row = ((long long)img * geo.out_H + oh * geo.out_s + geo.out_ph) * geo.out_W + ow * geo.out_s + geo.out_pw;
+        arow = row;
+        if (geo.addend_sub == 2) {
+          add_ok = add_ok && !((oh | ow) & 1);
+          arow = ((long long)img * geo.add_H + (oh >> 1)) * geo.add_W + (ow >> 1);
+        }
         if (stats) {
           const int gi = row_ok ? img / geo.imgs_per_group : -1;
           my_g = gi;
@@ -183,6 +195,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       } else {
         row = (long long)m_blk * BLOCK_M + q * 32 + lane;
+        arow = row;
         row_ok = row < M;
         // BN groups touched by this warp's 32 rows
         if (stats) {
@@ -202,8 +215,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (addend != nullptr && row_ok) {
-          const bf16* ap = addend + row * ldd + col0;
+        if (add_ok && row_ok) {
+          const bf16* ap = addend + arow * ldd + col0;
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
             if (col0 + j < Ncols) {
@@ -355,6 +368,30 @@ int dispatch_tc(int block_n, bool f32, const CUtensorMap& tmA, const CUtensorMap
   return ADAMML_ERR_ARG;
 }
 
+
+void set_tiles(ConvGeom& geo, int Wo, int Ho, int IMGS) {
+  pick_box(Wo, Ho, IMGS, 128, &geo.BW, &geo.BH, &geo.BI);
+  geo.tiles_w = (Wo + geo.BW - 1) / geo.BW;
+  geo.tiles_h = (Ho + geo.BH - 1) / geo.BH;
+  geo.tiles_i = (IMGS + geo.BI - 1) / geo.BI;
+  geo.Ho = Ho; geo.Wo = Wo; geo.IMGS = IMGS;
+}
+
+// launches the implicit-GEMM kernel for a prepared geometry; w is [Cout][w_ld] bf16, y/addend rows have Cout columns
+int run_conv(const ConvGeom& geo, const ConvMaps& cm, const void* w, long long w_ld, void* y, const void* addend,
+             int Cout, double* stats, cudaStream_t stream) {
+  const int block_n = Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 256);
+  CUtensorMap tmB;
+  int rc = make_map_2d(&tmB, w, Cout, w_ld, w_ld, block_n);
+  if (rc) return rc;
+  if (stats) {
+    int G = (geo.IMGS + geo.imgs_per_group - 1) / geo.imgs_per_group;
+    cudaMemsetAsync(stats, 0, sizeof(double) * (size_t)G * Cout * 2, stream);
+  }
+  return dispatch_tc<true>(block_n, false, tmB, tmB, cm, geo, y, addend, (long long)geo.IMGS * geo.Ho * geo.Wo, Cout,
+                           geo.ntaps * geo.kb_per_tap * BLOCK_K, Cout, stats, 0, stream);
+}
+
 }  // namespace
 
 extern "C" {
@@ -413,7 +450,7 @@ int adamml_tc_conv_supported(int Cin, int Cout, int R, int S, int stride) {
 
 int adamml_tc_conv_bf16(const void* x, const void* w, void* y, const void* addend, int IMGS, int H, int W, int Cin,
                         int Cout, int R, int S, int stride, int pad, int Ho, int Wo, double* stats,
-                        int imgs_per_group, cudaStream_t stream) {
+                        int imgs_per_group, int addend_sub, cudaStream_t stream) {
   if (!adamml_tc_conv_supported(Cin, Cout, R, S, stride)) {
     adamml_set_error("tc_conv: Cin=%d Cout=%d R=%d S=%d stride=%d outside the tcgen05 envelope", Cin, Cout, R, S,
                      stride);
@@ -425,16 +462,15 @@ int adamml_tc_conv_bf16(const void* x, const void* w, void* y, const void* adden
                      ((uintptr_t)addend % 16) == 0,
                  "tc_conv: operands must be 16-byte aligned");
   ADAMML_REQUIRE(!stats || imgs_per_group > 0, "tc_conv: stats need imgs_per_group");
+  ADAMML_REQUIRE(addend_sub == 0 || addend_sub == 1 || addend_sub == 2, "tc_conv: addend_sub must be 0, 1 or 2");
   ConvGeom geo;
   memset(&geo, 0, sizeof(geo));
   geo.ntaps = R * S;
   geo.cin = Cin;
   geo.kb_per_tap = (Cin + BLOCK_K - 1) / BLOCK_K;
-  pick_box(Wo, Ho, IMGS, 128, &geo.BW, &geo.BH, &geo.BI);
-  geo.tiles_w = (Wo + geo.BW - 1) / geo.BW;
-  geo.tiles_h = (Ho + geo.BH - 1) / geo.BH;
-  geo.tiles_i = (IMGS + geo.BI - 1) / geo.BI;
-  geo.Ho = Ho; geo.Wo = Wo; geo.IMGS = IMGS;
+  set_tiles(geo, Wo, Ho, IMGS);
+  geo.out_H = Ho; geo.out_W = Wo; geo.out_s = 1;
+  if (addend && addend_sub == 2) { geo.addend_sub = 2; geo.add_H = (Ho + 1) / 2; geo.add_W = (Wo + 1) / 2; }
   geo.imgs_per_group = imgs_per_group > 0 ? imgs_per_group : IMGS;
   // taps: input coordinate = stride*o + (r - pad) = stride*(o + d) + parity
   bool used[4] = {false, false, false, false};
@@ -443,6 +479,7 @@ int adamml_tc_conv_bf16(const void* x, const void* w, void* y, const void* adden
       int th = r - pad, tw = s_ - pad;
       int ph = ((th % stride) + stride) % stride, pw = ((tw % stride) + stride) % stride;
       int t = r * S + s_;
+      geo.tap_koff[t] = t * Cin;
       geo.tap_map[t] = (signed char)(ph * stride + pw);
       geo.tap_dh[t] = (signed char)((th - ph) / stride);
       geo.tap_dw[t] = (signed char)((tw - pw) / stride);
@@ -461,16 +498,100 @@ int adamml_tc_conv_bf16(const void* x, const void* w, void* y, const void* adden
                            (long long)stride * W * Cin, (long long)H * W * Cin, geo.BW, geo.BH, geo.BI);
       if (rc) return rc;
     }
-  const int block_n = Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 256);
-  CUtensorMap tmB;
-  int rc = make_map_2d(&tmB, w, Cout, (long long)R * S * Cin, (long long)R * S * Cin, block_n);
-  if (rc) return rc;
-  if (stats) {
-    int G = (IMGS + geo.imgs_per_group - 1) / geo.imgs_per_group;
-    cudaMemsetAsync(stats, 0, sizeof(double) * (size_t)G * Cout * 2, stream);
+  return run_conv(geo, cm, w, (long long)R * S * Cin, y, addend, Cout, stats, stream);
+}
+
+/* Data gradient of a stride-2 convolution (resnet.py:100 conv2 of the first Bottleneck of layer2-4) as four
+ * stride-1 implicit GEMMs, one per parity class (ph, pw) of the input pixel grid: class outputs
+ * dx[2a+ph, 2b+pw] = sum over the taps (r, s) with (ph+pad-r), (pw+pad-s) even of
+ * dy[a + (ph+pad-r)/2, b + (pw+pad-s)/2] . w[r, s]; every MAC of the forward pass is issued exactly once.
+ * w_rot = adamml_pack_weight_dgrad operand [Cin][R][S][Cout] (tap (r,s) of w sits at (R-1-r, S-1-s)). */
+int adamml_tc_dgrad_s2_bf16(const void* dy, const void* w_rot, void* dx, int IMGS, int H, int W, int Cin, int Cout,
+                            int R, int S, int pad, int Ho, int Wo, cudaStream_t stream) {
+  if (Cin % 8 || Cout % 8 || R * S > MAX_TAPS || R < 2 || S < 2) {
+    adamml_set_error("tc_dgrad_s2: Cin=%d Cout=%d R=%d S=%d outside the tcgen05 envelope", Cin, Cout, R, S);
+    return ADAMML_ERR_UNSUPPORTED;
   }
-  return dispatch_tc<true>(block_n, false, tmB, tmB, cm, geo, y, addend, (long long)IMGS * Ho * Wo, Cout,
-                           R * S * Cin, Cout, stats, 0, stream);
+  ADAMML_REQUIRE(Ho == (H + 2 * pad - R) / 2 + 1 && Wo == (W + 2 * pad - S) / 2 + 1,
+                 "tc_dgrad_s2: Ho/Wo inconsistent with H/W/R/S/pad");
+  ADAMML_REQUIRE(((uintptr_t)dy % 16) == 0 && ((uintptr_t)w_rot % 16) == 0 && ((uintptr_t)dx % 16) == 0,
+                 "tc_dgrad_s2: operands must be 16-byte aligned");
+  for (int ph = 0; ph < 2; ++ph)
+    for (int pw = 0; pw < 2; ++pw) {
+      const int Hc = (H - ph + 1) / 2, Wc = (W - pw + 1) / 2;
+      if (Hc <= 0 || Wc <= 0) continue;
+      ConvGeom geo;
+      memset(&geo, 0, sizeof(geo));
+      geo.cin = Cout;  // reduction channels of the gradient GEMM
+      geo.kb_per_tap = (Cout + BLOCK_K - 1) / BLOCK_K;
+      int nt = 0;
+      for (int r = 0; r < R; ++r) {
+        if ((ph + pad - r) & 1) continue;
+        for (int s_ = 0; s_ < S; ++s_) {
+          if ((pw + pad - s_) & 1) continue;
+          geo.tap_koff[nt] = ((R - 1 - r) * S + (S - 1 - s_)) * Cout;
+          geo.tap_map[nt] = 0;
+          // arithmetic shift == floor division by 2 (numerator is even here)
+          geo.tap_dh[nt] = (signed char)((ph + pad - r) / 2);
+          geo.tap_dw[nt] = (signed char)((pw + pad - s_) / 2);
+          ++nt;
+        }
+      }
+      ADAMML_REQUIRE(nt > 0, "tc_dgrad_s2: parity class (%d,%d) has no taps (R=%d S=%d pad=%d)", ph, pw, R, S, pad);
+      geo.ntaps = nt;
+      set_tiles(geo, Wc, Hc, IMGS);
+      geo.out_H = H; geo.out_W = W; geo.out_s = 2; geo.out_ph = ph; geo.out_pw = pw;
+      geo.imgs_per_group = IMGS;
+      ConvMaps cm;
+      memset(&cm, 0, sizeof(cm));
+      int rc = make_map_4d(&cm.m[0], dy, Cout, Wo, Ho, IMGS, Cout, (long long)Wo * Cout, (long long)Ho * Wo * Cout,
+                           geo.BW, geo.BH, geo.BI);
+      if (rc) return rc;
+      rc = run_conv(geo, cm, w_rot, (long long)R * S * Cout, dx, nullptr, Cin, nullptr, stream);
+      if (rc) return rc;
+    }
+  return ADAMML_OK;
+}
+
+/* 7x7 / stride 2 / pad 3 ResNet stem (resnet.py:138,199) on the space-to-depth input written by
+ * adamml_pack_frames_s2d: xs [IMGS, Hs, Wp, Cs] bf16 (Hs = H/2 rows, Wp = W/2 + 4 columns of which the first two
+ * and the last two are zeros, Cs = 4*C padded to a multiple of 16).  In that layout the stem is a 4-tap
+ * (dh = -2..1) stride-1 convolution whose "pixel" is the 4*Cs-wide window of four consecutive s2d columns:
+ * that window is CONTIGUOUS in memory, so it is one TMA box of a tensor map whose W stride (Cs elements) is
+ * smaller than its innermost extent (4*Cs elements) — an overlapping, im2col-free view.  K = 16*Cs.
+ * w: adamml_pack_weight_stem operand [Cout][4][4*Cs] bf16. */
+int adamml_tc_stem_conv_bf16(const void* xs, const void* w, void* y, int IMGS, int Hs, int Wp, int Cs, int Cout,
+                             int Ho, int Wo, double* stats, int imgs_per_group, cudaStream_t stream) {
+  if (Cs % 16 || Cout % 8 || Cs > 64) {
+    adamml_set_error("tc_stem_conv: Cs=%d Cout=%d outside the tcgen05 envelope", Cs, Cout);
+    return ADAMML_ERR_UNSUPPORTED;
+  }
+  ADAMML_REQUIRE(Ho == Hs && Wo + 4 <= Wp + 1, "tc_stem_conv: geometry (Ho == Hs, Wp >= Wo + 3)");
+  ADAMML_REQUIRE(((uintptr_t)xs % 16) == 0 && ((uintptr_t)w % 16) == 0 && ((uintptr_t)y % 16) == 0,
+                 "tc_stem_conv: operands must be 16-byte aligned");
+  ADAMML_REQUIRE(!stats || imgs_per_group > 0, "tc_stem_conv: stats need imgs_per_group");
+  const int VC = 4 * Cs;  // virtual channels per position
+  ConvGeom geo;
+  memset(&geo, 0, sizeof(geo));
+  geo.ntaps = 4;
+  geo.cin = VC;
+  geo.kb_per_tap = (VC + BLOCK_K - 1) / BLOCK_K;
+  for (int t = 0; t < 4; ++t) {
+    geo.tap_koff[t] = t * VC;
+    geo.tap_map[t] = 0;
+    geo.tap_dh[t] = (signed char)(t - 2);
+    geo.tap_dw[t] = 0;
+  }
+  set_tiles(geo, Wo, Ho, IMGS);
+  geo.out_H = Ho; geo.out_W = Wo; geo.out_s = 1;
+  geo.imgs_per_group = imgs_per_group > 0 ? imgs_per_group : IMGS;
+  ConvMaps cm;
+  memset(&cm, 0, sizeof(cm));
+  // positions 0..Wp-4: position p covers stored columns p..p+3
+  int rc = make_map_4d(&cm.m[0], xs, VC, Wp - 3, Hs, IMGS, Cs, (long long)Wp * Cs, (long long)Hs * Wp * Cs, geo.BW,
+                       geo.BH, geo.BI);
+  if (rc) return rc;
+  return run_conv(geo, cm, w, 4LL * VC, y, nullptr, Cout, stats, stream);
 }
 
 }  // extern "C"

@@ -1,0 +1,394 @@
+// Depthwise 3x3 convolution (pad 1, stride 1|2) for NHWC activations: forward, data gradient, weight
+// gradient.  Reference call sites: the 3x3 `groups=hidden_dim` convolutions of every InvertedResidual in
+// models/sound_mobilenet_v2.py:58 and models/policy_net.py:66,80 (+ their autograd).
+//
+// These layers carry 0.6 % of the MACs but stream the 6x-expanded MobileNetV2 tensors, so they are pure
+// HBM streams: algorithmic bytes = (|x| + |y|) x sizeof(T) forward and data gradient, (|x| + |dy|) for the
+// weight gradient.  Every thread owns ONE 16-byte channel vector (8 bf16 / 4 fp32 channels) with its 3x3
+// weights in registers and walks a strip of output pixels along W, so each input vector is loaded once
+// per strip (L1 serves the 3-row overlap) and all global accesses are full 16-byte vectors.
+#include "common.cuh"
+
+namespace {
+
+constexpr int DW_THREADS = 128;
+
+template <typename T>
+__device__ __forceinline__ void load_w9(const float* __restrict__ w, int c0, float (&wr)[9][VecIO<T>::N]) {
+  constexpr int V = VecIO<T>::N;
+#pragma unroll
+  for (int i = 0; i < V; ++i)
+#pragma unroll
+    for (int t = 0; t < 9; ++t) wr[t][i] = w[(c0 + i) * 9 + t];
+}
+
+// Stride-1 stencil shared by forward (FLIP = false) and data gradient (FLIP = true: 180-degree rotated
+// weights, + optional addend).  Strip of SW outputs along W.
+template <typename T, bool FLIP, int SW>
+__global__ void __launch_bounds__(DW_THREADS)
+dw_s1_kernel(const T* __restrict__ x, const float* __restrict__ w, T* __restrict__ y, const T* __restrict__ addend,
+             int IMGS, int H, int W, int C, int strips) {
+  constexpr int V = VecIO<T>::N;
+  const int cvecs = C / V;
+  const long long total = (long long)IMGS * H * strips * cvecs;
+  const long long iv = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (iv >= total) return;
+  const int cv = (int)(iv % cvecs);
+  long long rest = iv / cvecs;
+  const int w0 = (int)(rest % strips) * SW;
+  rest /= strips;
+  const int ho = (int)(rest % H);
+  const long long img = rest / H;
+  const int c0 = cv * V;
+  float wr[9][V];
+  load_w9<T>(w, c0, wr);
+  float acc[SW][V];
+#pragma unroll
+  for (int j = 0; j < SW; ++j)
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc[j][i] = 0.f;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const int hi = ho + r - 1;
+    if (hi < 0 || hi >= H) continue;
+    const T* row = x + ((img * H + hi) * W) * C + c0;
+    typename VecIO<T>::raw q[SW + 2];
+#pragma unroll
+    for (int j = 0; j < SW + 2; ++j) {
+      const int wi = w0 + j - 1;
+      if (wi >= 0 && wi < W) q[j] = VecIO<T>::load_raw(row + (long long)wi * C);
+    }
+#pragma unroll
+    for (int j = 0; j < SW + 2; ++j) {
+      const int wi = w0 + j - 1;
+      if (wi < 0 || wi >= W) continue;
+      float v[V];
+      VecIO<T>::unpack(q[j], v);
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int o = j - s;  // output index inside the strip fed by this column through tap s
+        if (o < 0 || o >= SW) continue;
+        const int t = FLIP ? (2 - r) * 3 + (2 - s) : r * 3 + s;
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc[o][i] = fmaf(v[i], wr[t][i], acc[o][i]);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < SW; ++j) {
+    const int wo = w0 + j;
+    if (wo >= W) continue;
+    const long long o = ((img * H + ho) * W + wo) * C + c0;
+    if (addend) {
+      float a[V];
+      VecIO<T>::load(addend + o, a);
+#pragma unroll
+      for (int i = 0; i < V; ++i) acc[j][i] += a[i];
+    }
+    VecIO<T>::store(y + o, acc[j]);
+  }
+}
+
+// Stride-2 forward: strip of SW outputs needs 2*SW+1 input columns per row.
+template <typename T, int SW>
+__global__ void __launch_bounds__(DW_THREADS)
+dw_s2_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w, T* __restrict__ y, int IMGS, int H, int W,
+                 int C, int Ho, int Wo, int strips) {
+  constexpr int V = VecIO<T>::N;
+  const int cvecs = C / V;
+  const long long total = (long long)IMGS * Ho * strips * cvecs;
+  const long long iv = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (iv >= total) return;
+  const int cv = (int)(iv % cvecs);
+  long long rest = iv / cvecs;
+  const int w0 = (int)(rest % strips) * SW;
+  rest /= strips;
+  const int ho = (int)(rest % Ho);
+  const long long img = rest / Ho;
+  const int c0 = cv * V;
+  float wr[9][V];
+  load_w9<T>(w, c0, wr);
+  float acc[SW][V];
+#pragma unroll
+  for (int j = 0; j < SW; ++j)
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc[j][i] = 0.f;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const int hi = ho * 2 + r - 1;
+    if (hi < 0 || hi >= H) continue;
+    const T* row = x + ((img * H + hi) * W) * C + c0;
+    typename VecIO<T>::raw q[2 * SW + 1];
+#pragma unroll
+    for (int j = 0; j < 2 * SW + 1; ++j) {
+      const int wi = w0 * 2 + j - 1;
+      if (wi >= 0 && wi < W) q[j] = VecIO<T>::load_raw(row + (long long)wi * C);
+    }
+#pragma unroll
+    for (int j = 0; j < 2 * SW + 1; ++j) {
+      const int wi = w0 * 2 + j - 1;
+      if (wi < 0 || wi >= W) continue;
+      float v[V];
+      VecIO<T>::unpack(q[j], v);
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        if ((j - s) & 1) continue;
+        const int o = (j - s) / 2;
+        if (j - s < 0 || o >= SW) continue;
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc[o][i] = fmaf(v[i], wr[r * 3 + s][i], acc[o][i]);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < SW; ++j) {
+    const int wo = w0 + j;
+    if (wo >= Wo) continue;
+    VecIO<T>::store(y + ((img * Ho + ho) * Wo + wo) * C + c0, acc[j]);
+  }
+}
+
+// Stride-2 data gradient: one thread per 2x2 input quad (rows 2m, 2m+1; cols 2n, 2n+1) and channel vector;
+// the quad needs dy[m..m+1][n..n+1] only.
+template <typename T>
+__global__ void __launch_bounds__(DW_THREADS)
+dw_s2_dgrad_kernel(const T* __restrict__ dy, const float* __restrict__ w, T* __restrict__ dx,
+                   const T* __restrict__ addend, int IMGS, int H, int W, int C, int Ho, int Wo) {
+  constexpr int V = VecIO<T>::N;
+  const int cvecs = C / V;
+  const int QH = (H + 1) / 2, QW = (W + 1) / 2;
+  const long long total = (long long)IMGS * QH * QW * cvecs;
+  const long long iv = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (iv >= total) return;
+  const int cv = (int)(iv % cvecs);
+  long long rest = iv / cvecs;
+  const int n = (int)(rest % QW);
+  rest /= QW;
+  const int m = (int)(rest % QH);
+  const long long img = rest / QH;
+  const int c0 = cv * V;
+  float wr[9][V];
+  load_w9<T>(w, c0, wr);
+  float g[2][2][V];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const bool ok = (m + a) < Ho && (n + b) < Wo;
+      if (ok) VecIO<T>::load(dy + ((img * Ho + m + a) * Wo + n + b) * C + c0, g[a][b]);
+      else {
+#pragma unroll
+        for (int i = 0; i < V; ++i) g[a][b][i] = 0.f;
+      }
+    }
+  // dx[2m+p][2n+q]: row taps r with (2m+p+1-r) even: p=0 -> r=1 (ho=m); p=1 -> r=0 (ho=m+1), r=2 (ho=m)
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+    const int hi = 2 * m + p;
+    if (hi >= H) continue;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int wi = 2 * n + q;
+      if (wi >= W) continue;
+      float acc[V];
+#pragma unroll
+      for (int i = 0; i < V; ++i) acc[i] = 0.f;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        if ((p + 1 - r) & 1) continue;
+        const int a = (p + 1 - r) / 2;  // 0 or 1 (p=1,r=0 -> 1)
+        if (p + 1 - r < 0) continue;
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+          if ((q + 1 - s) & 1) continue;
+          if (q + 1 - s < 0) continue;
+          const int b = (q + 1 - s) / 2;
+#pragma unroll
+          for (int i = 0; i < V; ++i) acc[i] = fmaf(g[a][b][i], wr[r * 3 + s][i], acc[i]);
+        }
+      }
+      const long long o = ((img * H + hi) * W + wi) * C + c0;
+      if (addend) {
+        float ad[V];
+        VecIO<T>::load(addend + o, ad);
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc[i] += ad[i];
+      }
+      VecIO<T>::store(dx + o, acc);
+    }
+  }
+}
+
+// Weight gradient: thread = (channel vector, item lane); items = (img, ho, strip of SW outputs) dealt
+// round-robin over a persistent grid; 9 x V fp32 accumulators per thread, block reduction through smem,
+// one atomic per (block, channel, tap).
+template <typename T, int STRIDE, int SW>
+__global__ void __launch_bounds__(256)
+dw_wgrad_vec_kernel(const T* __restrict__ x, const T* __restrict__ dy, float* __restrict__ dw, int IMGS, int H, int W,
+                    int C, int Ho, int Wo, int strips, int cpb, int k) {
+  constexpr int V = VecIO<T>::N;
+  constexpr int NC = STRIDE * SW + (3 - STRIDE);  // input columns per strip row: s1 -> SW+2, s2 -> 2*SW+1
+  __shared__ float sh[256][V + 1];
+  const int cl = threadIdx.x % cpb, rl = threadIdx.x / cpb;
+  const int c0 = (blockIdx.y * cpb + cl) * V;
+  const bool ok = c0 < C;
+  float acc[9][V];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc[t][i] = 0.f;
+  const long long items = (long long)IMGS * Ho * strips;
+  if (ok) {
+    for (long long it = (long long)blockIdx.x * k + rl; it < items; it += (long long)gridDim.x * k) {
+      const int w0 = (int)(it % strips) * SW;
+      const long long rest = it / strips;
+      const int ho = (int)(rest % Ho);
+      const long long img = rest / Ho;
+      float g[SW][V];
+#pragma unroll
+      for (int j = 0; j < SW; ++j) {
+        if (w0 + j < Wo) VecIO<T>::load(dy + ((img * Ho + ho) * Wo + w0 + j) * C + c0, g[j]);
+        else {
+#pragma unroll
+          for (int i = 0; i < V; ++i) g[j][i] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const int hi = ho * STRIDE + r - 1;
+        if (hi < 0 || hi >= H) continue;
+        const T* row = x + ((img * H + hi) * W) * C + c0;
+        typename VecIO<T>::raw q[NC];
+#pragma unroll
+        for (int j = 0; j < NC; ++j) {
+          const int wi = w0 * STRIDE + j - 1;
+          if (wi >= 0 && wi < W) q[j] = VecIO<T>::load_raw(row + (long long)wi * C);
+        }
+#pragma unroll
+        for (int j = 0; j < NC; ++j) {
+          const int wi = w0 * STRIDE + j - 1;
+          if (wi < 0 || wi >= W) continue;
+          float v[V];
+          VecIO<T>::unpack(q[j], v);
+#pragma unroll
+          for (int s = 0; s < 3; ++s) {
+            if (j - s < 0 || ((j - s) % STRIDE) != 0) continue;
+            const int o = (j - s) / STRIDE;
+            if (o >= SW) continue;
+#pragma unroll
+            for (int i = 0; i < V; ++i) acc[r * 3 + s][i] = fmaf(g[o][i], v[i], acc[r * 3 + s][i]);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll 1
+  for (int t = 0; t < 9; ++t) {
+#pragma unroll
+    for (int i = 0; i < V; ++i) sh[threadIdx.x][i] = acc[t][i];
+    __syncthreads();
+    if (rl == 0 && ok) {
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        float s = 0.f;
+        for (int y = 0; y < k; ++y) s += sh[y * cpb + cl][i];
+        atomicAdd(&dw[(c0 + i) * 9 + t], s);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <typename T>
+inline bool dw_vec_ok(int C, const void* a, const void* b, const void* c = nullptr, const void* d = nullptr) {
+  if (C % VecIO<T>::N) return false;
+  const void* ps[4] = {a, b, c, d};
+  for (int i = 0; i < 4; ++i)
+    if (ps[i] && ((uintptr_t)ps[i] % 16)) return false;
+  return true;
+}
+
+inline unsigned blocks_for(long long total, int threads) { return (unsigned)((total + threads - 1) / threads); }
+
+}  // namespace
+
+extern "C" {
+
+int adamml_dwconv_fwd(const void* x, const float* w, void* y, int IMGS, int H, int W, int C, int stride, int Ho,
+                      int Wo, int dtype, cudaStream_t stream) {
+  ADAMML_REQUIRE(stride == 1 || stride == 2, "dwconv: stride must be 1 or 2");
+  ADAMML_REQUIRE(Ho == (H + 2 - 3) / stride + 1 && Wo == (W + 2 - 3) / stride + 1, "dwconv: bad Ho/Wo");
+  ADAMML_DISPATCH_DTYPE(dtype, T, {
+    if (!dw_vec_ok<T>(C, x, y))
+      return adamml_dwconv_fwd_scalar(x, w, y, IMGS, H, W, C, stride, Ho, Wo, dtype, stream);
+    const int cvecs = C / VecIO<T>::N;
+    if (stride == 1) {
+      constexpr int SW = 4;
+      const int strips = (W + SW - 1) / SW;
+      const long long total = (long long)IMGS * H * strips * cvecs;
+      dw_s1_kernel<T, false, SW><<<blocks_for(total, DW_THREADS), DW_THREADS, 0, stream>>>(
+          (const T*)x, w, (T*)y, nullptr, IMGS, H, W, C, strips);
+    } else {
+      constexpr int SW = 2;
+      const int strips = (Wo + SW - 1) / SW;
+      const long long total = (long long)IMGS * Ho * strips * cvecs;
+      dw_s2_fwd_kernel<T, SW><<<blocks_for(total, DW_THREADS), DW_THREADS, 0, stream>>>((const T*)x, w, (T*)y, IMGS,
+                                                                                         H, W, C, Ho, Wo, strips);
+    }
+  });
+  return adamml_check_launch("dwconv_fwd");
+}
+
+int adamml_dwconv_dgrad(const void* dy, const float* w, void* dx, const void* addend, int IMGS, int H, int W, int C,
+                        int stride, int Ho, int Wo, int dtype, cudaStream_t stream) {
+  ADAMML_REQUIRE(stride == 1 || stride == 2, "dwconv: stride must be 1 or 2");
+  ADAMML_REQUIRE(Ho == (H + 2 - 3) / stride + 1 && Wo == (W + 2 - 3) / stride + 1, "dwconv: bad Ho/Wo");
+  ADAMML_DISPATCH_DTYPE(dtype, T, {
+    if (!dw_vec_ok<T>(C, dy, dx, addend))
+      return adamml_dwconv_dgrad_scalar(dy, w, dx, addend, IMGS, H, W, C, stride, Ho, Wo, dtype, stream);
+    const int cvecs = C / VecIO<T>::N;
+    if (stride == 1) {
+      constexpr int SW = 4;
+      const int strips = (W + SW - 1) / SW;
+      const long long total = (long long)IMGS * H * strips * cvecs;
+      dw_s1_kernel<T, true, SW><<<blocks_for(total, DW_THREADS), DW_THREADS, 0, stream>>>(
+          (const T*)dy, w, (T*)dx, (const T*)addend, IMGS, H, W, C, strips);
+    } else {
+      const long long total = (long long)IMGS * ((H + 1) / 2) * ((W + 1) / 2) * cvecs;
+      dw_s2_dgrad_kernel<T><<<blocks_for(total, DW_THREADS), DW_THREADS, 0, stream>>>(
+          (const T*)dy, w, (T*)dx, (const T*)addend, IMGS, H, W, C, Ho, Wo);
+    }
+  });
+  return adamml_check_launch("dwconv_dgrad");
+}
+
+int adamml_dwconv_wgrad(const void* x, const void* dy, float* dw, int IMGS, int H, int W, int C, int stride, int Ho,
+                        int Wo, int dtype, cudaStream_t stream) {
+  ADAMML_REQUIRE(stride == 1 || stride == 2, "dwconv: stride must be 1 or 2");
+  ADAMML_REQUIRE(Ho == (H + 2 - 3) / stride + 1 && Wo == (W + 2 - 3) / stride + 1, "dwconv: bad Ho/Wo");
+  ADAMML_DISPATCH_DTYPE(dtype, T, {
+    if (!dw_vec_ok<T>(C, x, dy))
+      return adamml_dwconv_wgrad_scalar(x, dy, dw, IMGS, H, W, C, stride, Ho, Wo, dtype, stream);
+    cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)C * 9, stream);
+    const int cvecs = C / VecIO<T>::N;
+    const int cchunks = (cvecs + 255) / 256;
+    const int cpb = (cvecs + cchunks - 1) / cchunks;
+    const int k = 256 / cpb;
+    constexpr int SW1 = 4, SW2 = 2;
+    const int strips = stride == 1 ? (Wo + SW1 - 1) / SW1 : (Wo + SW2 - 1) / SW2;
+    const long long items = (long long)IMGS * Ho * strips;
+    long long gx = (items + k - 1) / k;
+    const long long cap = 148LL * 4 / cchunks > 0 ? 148LL * 4 / cchunks : 1;
+    if (gx > cap) gx = cap;
+    dim3 grid((unsigned)gx, cchunks);
+    if (stride == 1)
+      dw_wgrad_vec_kernel<T, 1, SW1><<<grid, cpb * k, 0, stream>>>((const T*)x, (const T*)dy, dw, IMGS, H, W, C, Ho, Wo,
+                                                                   strips, cpb, k);
+    else
+      dw_wgrad_vec_kernel<T, 2, SW2><<<grid, cpb * k, 0, stream>>>((const T*)x, (const T*)dy, dw, IMGS, H, W, C, Ho, Wo,
+                                                                   strips, cpb, k);
+  });
+  return adamml_check_launch("dwconv_wgrad");
+}
+
+}  // extern "C"

@@ -135,6 +135,209 @@ __global__ void tpool_bwd_kernel(const T* __restrict__ x, const T* __restrict__ 
   }
 }
 
+// ---- 16-byte vectorised versions (C % VEC == 0): thread = (pixel, channel vector) ----------------------
+// 3x3/s2/p1 max-pool; optionally records the window position (r*3+s, first maximum in scan order) of
+// every output element so that the backward pass is a pure gather that never re-reads x.
+template <typename T>
+__global__ void __launch_bounds__(256)
+maxpool_fwd_vec_kernel(const T* __restrict__ x, T* __restrict__ y, unsigned char* __restrict__ pos, int IMGS, int H,
+                       int W, int C, int Ho, int Wo) {
+  constexpr int V = VecIO<T>::N;
+  const int cvecs = C / V;
+  const long long total = (long long)IMGS * Ho * Wo * cvecs;
+  const long long iv = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (iv >= total) return;
+  const int cv = (int)(iv % cvecs);
+  const long long pix = iv / cvecs;
+  const int wo = (int)(pix % Wo);
+  const int ho = (int)((pix / Wo) % Ho);
+  const long long img = pix / ((long long)Wo * Ho);
+  typename VecIO<T>::raw q[9];
+  bool ok[9];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const int hi = ho * 2 + r - 1;
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      const int wi = wo * 2 + s - 1;
+      ok[r * 3 + s] = hi >= 0 && hi < H && wi >= 0 && wi < W;
+      if (ok[r * 3 + s]) q[r * 3 + s] = VecIO<T>::load_raw(x + ((img * H + hi) * W + wi) * C + cv * V);
+    }
+  }
+  float best[V];
+  int bp[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) { best[i] = -INFINITY; bp[i] = 0; }
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    if (ok[t]) {
+      float v[V];
+      VecIO<T>::unpack(q[t], v);
+#pragma unroll
+      for (int i = 0; i < V; ++i)
+        if (v[i] > best[i] || v[i] != v[i]) { best[i] = v[i]; bp[i] = t; }
+    }
+  }
+  VecIO<T>::store(y + pix * C + cv * V, best);
+  if (pos) {
+    unsigned char* pp = pos + pix * C + cv * V;
+    if (V == 8) {
+      uint2 pk;
+      pk.x = (unsigned)bp[0] | ((unsigned)bp[1] << 8) | ((unsigned)bp[2] << 16) | ((unsigned)bp[3] << 24);
+      pk.y = (unsigned)bp[4 % V] | ((unsigned)bp[5 % V] << 8) | ((unsigned)bp[6 % V] << 16) | ((unsigned)bp[7 % V] << 24);
+      *reinterpret_cast<uint2*>(pp) = pk;
+    } else {
+      unsigned pk = (unsigned)bp[0] | ((unsigned)bp[1] << 8) | ((unsigned)bp[2] << 16) | ((unsigned)bp[3] << 24);
+      *reinterpret_cast<unsigned*>(pp) = pk;
+    }
+  }
+}
+
+// gather backward from recorded positions: input pixel (hi, wi) sits at row r = hi + 1 - 2*ho of window ho.
+template <typename T>
+__global__ void __launch_bounds__(256)
+maxpool_bwd_pos_kernel(const unsigned char* __restrict__ pos, const T* __restrict__ dy, T* __restrict__ dx, int IMGS,
+                       int H, int W, int C, int Ho, int Wo) {
+  constexpr int V = VecIO<T>::N;
+  const int cvecs = C / V;
+  const long long total = (long long)IMGS * H * W * cvecs;
+  const long long iv = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (iv >= total) return;
+  const int cv = (int)(iv % cvecs);
+  const long long pix = iv / cvecs;
+  const int wi = (int)(pix % W);
+  const int hi = (int)((pix / W) % H);
+  const long long img = pix / ((long long)W * H);
+  float acc[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) acc[i] = 0.f;
+  const int ho_lo = hi / 2, ho_hi = (hi + 1) / 2;  // windows containing row hi
+  const int wo_lo = wi / 2, wo_hi = (wi + 1) / 2;
+  for (int ho = ho_lo; ho <= ho_hi; ++ho) {
+    if (ho >= Ho) continue;
+    for (int wo = wo_lo; wo <= wo_hi; ++wo) {
+      if (wo >= Wo) continue;
+      const int code = (hi + 1 - 2 * ho) * 3 + (wi + 1 - 2 * wo);
+      const long long o = ((img * Ho + ho) * Wo + wo) * C + cv * V;
+      float g[V];
+      VecIO<T>::load(dy + o, g);
+      unsigned char pc[8];
+      if (V == 8) *reinterpret_cast<uint2*>(pc) = *reinterpret_cast<const uint2*>(pos + o);
+      else *reinterpret_cast<unsigned*>(pc) = *reinterpret_cast<const unsigned*>(pos + o);
+#pragma unroll
+      for (int i = 0; i < V; ++i)
+        if (pc[i] == code) acc[i] += g[i];
+    }
+  }
+  VecIO<T>::store(dx + pix * C + cv * V, acc);
+}
+
+// temporal pool k3 s2 p1, one thread per (video, element vector): all TN frames of that position in registers
+template <typename T, int TN>
+__global__ void __launch_bounds__(256)
+tpool_fwd_vec_kernel(const T* __restrict__ x, T* __restrict__ y, long long V_, long long E, int mode_avg) {
+  constexpr int V = VecIO<T>::N;
+  constexpr int TO = (TN + 2 - 3) / 2 + 1;
+  const long long evecs = E / V;
+  const long long iv = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (iv >= V_ * evecs) return;
+  const long long v = iv / evecs, e = (iv % evecs) * V;
+  typename VecIO<T>::raw q[TN];
+#pragma unroll
+  for (int t = 0; t < TN; ++t) q[t] = VecIO<T>::load_raw(x + (v * TN + t) * E + e);
+  float f[TN][V];
+#pragma unroll
+  for (int t = 0; t < TN; ++t) VecIO<T>::unpack(q[t], f[t]);
+#pragma unroll
+  for (int to = 0; to < TO; ++to) {
+    float best[V], sum[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) { best[i] = -INFINITY; sum[i] = 0.f; }
+#pragma unroll
+    for (int kk = 0; kk < 3; ++kk) {
+      const int t = to * 2 + kk - 1;
+      if (t < 0 || t >= TN) continue;
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        sum[i] += f[t][i];
+        if (f[t][i] > best[i] || f[t][i] != f[t][i]) best[i] = f[t][i];
+      }
+    }
+    if (mode_avg) {
+#pragma unroll
+      for (int i = 0; i < V; ++i) best[i] = sum[i] / 3.f;
+    }
+    VecIO<T>::store(y + (v * TO + to) * E + e, best);
+  }
+}
+
+template <typename T, int TN>
+__global__ void __launch_bounds__(256)
+tpool_bwd_vec_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx, long long V_, long long E,
+                     int mode_avg) {
+  constexpr int V = VecIO<T>::N;
+  constexpr int TO = (TN + 2 - 3) / 2 + 1;
+  const long long evecs = E / V;
+  const long long iv = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (iv >= V_ * evecs) return;
+  const long long v = iv / evecs, e = (iv % evecs) * V;
+  typename VecIO<T>::raw q[TN], qg[TO];
+#pragma unroll
+  for (int t = 0; t < TN; ++t) q[t] = VecIO<T>::load_raw(x + (v * TN + t) * E + e);
+#pragma unroll
+  for (int to = 0; to < TO; ++to) qg[to] = VecIO<T>::load_raw(dy + (v * TO + to) * E + e);
+  float f[TN][V], d[TN][V];
+#pragma unroll
+  for (int t = 0; t < TN; ++t) {
+    VecIO<T>::unpack(q[t], f[t]);
+#pragma unroll
+    for (int i = 0; i < V; ++i) d[t][i] = 0.f;
+  }
+#pragma unroll
+  for (int to = 0; to < TO; ++to) {
+    float g[V];
+    VecIO<T>::unpack(qg[to], g);
+    if (mode_avg) {
+#pragma unroll
+      for (int kk = 0; kk < 3; ++kk) {
+        const int t = to * 2 + kk - 1;
+        if (t < 0 || t >= TN) continue;
+#pragma unroll
+        for (int i = 0; i < V; ++i) d[t][i] += g[i] / 3.f;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        float best = -INFINITY;
+        int bt = -1;
+#pragma unroll
+        for (int kk = 0; kk < 3; ++kk) {
+          const int t = to * 2 + kk - 1;
+          if (t < 0 || t >= TN) continue;
+          if (f[t][i] > best || f[t][i] != f[t][i]) { best = f[t][i]; bt = t; }
+        }
+#pragma unroll
+        for (int kk = 0; kk < 3; ++kk) {
+          const int t = to * 2 + kk - 1;
+          if (t < 0 || t >= TN) continue;
+          if (bt == t) d[t][i] += g[i];
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < TN; ++t) VecIO<T>::store(dx + (v * TN + t) * E + e, d[t]);
+}
+
+template <typename T>
+inline bool pool_vec_ok(long long C, const void* a, const void* b = nullptr, const void* c = nullptr) {
+  if (C % VecIO<T>::N) return false;
+  const void* ps[3] = {a, b, c};
+  for (int i = 0; i < 3; ++i)
+    if (ps[i] && ((uintptr_t)ps[i] % 16)) return false;
+  return true;
+}
+
 // y[img][c] = mean over HW. block (32 channels, 8 pixel lanes) per (img, channel tile)
 template <typename T>
 __global__ void avgpool_fwd_kernel(const T* __restrict__ x, float* __restrict__ y, int HW, int C, long long y_ld) {
@@ -168,20 +371,38 @@ __global__ void avgpool_bwd_kernel(const float* __restrict__ dy, T* __restrict__
 
 extern "C" {
 
-int adamml_maxpool3x3s2_fwd(const void* x, void* y, int IMGS, int H, int W, int C, int Ho, int Wo, int dtype,
-                            cudaStream_t stream) {
+int adamml_maxpool3x3s2_fwd(const void* x, void* y, unsigned char* pos, int IMGS, int H, int W, int C, int Ho, int Wo,
+                            int dtype, cudaStream_t stream) {
   ADAMML_REQUIRE(Ho == (H + 2 - 3) / 2 + 1 && Wo == (W + 2 - 3) / 2 + 1, "maxpool: bad Ho/Wo");
   long long total = (long long)IMGS * Ho * Wo * C;
-  ADAMML_DISPATCH_DTYPE(dtype, T,
-    maxpool_fwd_kernel<T><<<ew_blocks(total), 256, 0, stream>>>((const T*)x, (T*)y, IMGS, H, W, C, Ho, Wo));
+  ADAMML_DISPATCH_DTYPE(dtype, T, {
+    if (pool_vec_ok<T>(C, x, y) && ((uintptr_t)pos % 8) == 0) {
+      long long tv = total / VecIO<T>::N;
+      maxpool_fwd_vec_kernel<T><<<(unsigned)((tv + 255) / 256), 256, 0, stream>>>((const T*)x, (T*)y, pos, IMGS, H, W,
+                                                                                   C, Ho, Wo);
+    } else {
+      ADAMML_REQUIRE(pos == nullptr, "maxpool: position output needs C %% 8 == 0 (bf16) / C %% 4 == 0 (fp32)");
+      maxpool_fwd_kernel<T><<<ew_blocks(total), 256, 0, stream>>>((const T*)x, (T*)y, IMGS, H, W, C, Ho, Wo);
+    }
+  });
   return adamml_check_launch("maxpool_fwd");
 }
 
-int adamml_maxpool3x3s2_bwd(const void* x, const void* dy, void* dx, int IMGS, int H, int W, int C, int Ho, int Wo,
-                            int dtype, cudaStream_t stream) {
+int adamml_maxpool3x3s2_bwd(const void* x, const unsigned char* pos, const void* dy, void* dx, int IMGS, int H, int W,
+                            int C, int Ho, int Wo, int dtype, cudaStream_t stream) {
+  ADAMML_REQUIRE(x || pos, "maxpool_bwd: needs either the forward input or the recorded positions");
   long long total = (long long)IMGS * H * W * C;
-  ADAMML_DISPATCH_DTYPE(dtype, T,
-    maxpool_bwd_kernel<T><<<ew_blocks(total), 256, 0, stream>>>((const T*)x, (const T*)dy, (T*)dx, IMGS, H, W, C, Ho, Wo));
+  ADAMML_DISPATCH_DTYPE(dtype, T, {
+    if (pos) {
+      ADAMML_REQUIRE(pool_vec_ok<T>(C, dy, dx) && ((uintptr_t)pos % 8) == 0, "maxpool_bwd: unaligned / ragged C");
+      long long tv = total / VecIO<T>::N;
+      maxpool_bwd_pos_kernel<T><<<(unsigned)((tv + 255) / 256), 256, 0, stream>>>(pos, (const T*)dy, (T*)dx, IMGS, H,
+                                                                                   W, C, Ho, Wo);
+    } else {
+      maxpool_bwd_kernel<T><<<ew_blocks(total), 256, 0, stream>>>((const T*)x, (const T*)dy, (T*)dx, IMGS, H, W, C, Ho,
+                                                                 Wo);
+    }
+  });
   return adamml_check_launch("maxpool_bwd");
 }
 
@@ -191,8 +412,15 @@ int adamml_tpool_fwd(const void* x, void* y, long long V, int Tn, long long E, i
   ADAMML_REQUIRE(V > 0 && Tn > 0 && E > 0, "tpool: empty dims");
   int To = (Tn + 2 - 3) / 2 + 1;
   long long total = V * To * E;
-  ADAMML_DISPATCH_DTYPE(dtype, T,
-    tpool_fwd_kernel<T><<<ew_blocks(total), 256, 0, stream>>>((const T*)x, (T*)y, V, Tn, To, E, mode_avg));
+  ADAMML_DISPATCH_DTYPE(dtype, T, {
+    const bool vec = pool_vec_ok<T>(E, x, y) && (Tn == 2 || Tn == 4 || Tn == 8);
+    const long long tv = V * (E / VecIO<T>::N);
+    const unsigned vb = (unsigned)((tv + 255) / 256);
+    if (vec && Tn == 8) tpool_fwd_vec_kernel<T, 8><<<vb, 256, 0, stream>>>((const T*)x, (T*)y, V, E, mode_avg);
+    else if (vec && Tn == 4) tpool_fwd_vec_kernel<T, 4><<<vb, 256, 0, stream>>>((const T*)x, (T*)y, V, E, mode_avg);
+    else if (vec && Tn == 2) tpool_fwd_vec_kernel<T, 2><<<vb, 256, 0, stream>>>((const T*)x, (T*)y, V, E, mode_avg);
+    else tpool_fwd_kernel<T><<<ew_blocks(total), 256, 0, stream>>>((const T*)x, (T*)y, V, Tn, To, E, mode_avg);
+  });
   return adamml_check_launch("tpool_fwd");
 }
 
@@ -201,8 +429,20 @@ int adamml_tpool_bwd(const void* x, const void* dy, void* dx, long long V, int T
   ADAMML_REQUIRE(V > 0 && Tn > 0 && E > 0, "tpool: empty dims");
   int To = (Tn + 2 - 3) / 2 + 1;
   long long total = V * Tn * E;
-  ADAMML_DISPATCH_DTYPE(dtype, T,
-    tpool_bwd_kernel<T><<<ew_blocks(total), 256, 0, stream>>>((const T*)x, (const T*)dy, (T*)dx, V, Tn, To, E, mode_avg));
+  ADAMML_DISPATCH_DTYPE(dtype, T, {
+    const bool vec = pool_vec_ok<T>(E, x, dy, dx) && (Tn == 2 || Tn == 4 || Tn == 8);
+    const long long tv = V * (E / VecIO<T>::N);
+    const unsigned vb = (unsigned)((tv + 255) / 256);
+    if (vec && Tn == 8)
+      tpool_bwd_vec_kernel<T, 8><<<vb, 256, 0, stream>>>((const T*)x, (const T*)dy, (T*)dx, V, E, mode_avg);
+    else if (vec && Tn == 4)
+      tpool_bwd_vec_kernel<T, 4><<<vb, 256, 0, stream>>>((const T*)x, (const T*)dy, (T*)dx, V, E, mode_avg);
+    else if (vec && Tn == 2)
+      tpool_bwd_vec_kernel<T, 2><<<vb, 256, 0, stream>>>((const T*)x, (const T*)dy, (T*)dx, V, E, mode_avg);
+    else
+      tpool_bwd_kernel<T><<<ew_blocks(total), 256, 0, stream>>>((const T*)x, (const T*)dy, (T*)dx, V, Tn, To, E,
+                                                               mode_avg);
+  });
   return adamml_check_launch("tpool_bwd");
 }
 

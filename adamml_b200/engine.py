@@ -207,14 +207,15 @@ class Exec:
 
     # ------------------------------------------------------------------ pools
     def maxpool(self, x):
-        y = ops.maxpool_fwd(x)
-        if self.save:
-            self.tape.append(dict(x=x))
+        if not self.save:
+            return ops.maxpool_fwd(x)
+        y, pos = ops.maxpool_fwd(x, want_pos=True)
+        self.tape.append(dict(x=x if pos is None else None, pos=pos, shape=tuple(x.shape)))
         return y
 
     def maxpool_bwd(self, dy):
         rec = self.tape.pop()
-        return ops.maxpool_bwd(rec["x"], dy)
+        return ops.maxpool_bwd(rec["x"], dy, pos=rec["pos"], x_shape=rec["shape"])
 
     def tpool(self, x, frames, mode_avg=False):
         y = ops.tpool_fwd(x, frames, mode_avg)

@@ -270,18 +270,24 @@ def bn_param_grad(sums, C, G):
 
 
 # ---------------------------------------------------------------- pools
-def maxpool_fwd(x):
+def maxpool_fwd(x, want_pos=False):
+    """-> y, or (y, pos) with pos = uint8 window position of every maximum (for the gather backward)."""
     IMGS, H, W, C = x.shape
     Ho, Wo = conv_out_hw(H, W, 3, 3, 2, 1)
     y = torch.empty((IMGS, Ho, Wo, C), device=x.device, dtype=x.dtype)
-    call("maxpool3x3s2_fwd", x, y, IMGS, H, W, C, Ho, Wo, dtype_code(x.dtype))
-    return y
+    pos = None
+    if want_pos and C % (8 if x.dtype == torch.bfloat16 else 4) == 0:
+        pos = torch.empty((IMGS, Ho, Wo, C), device=x.device, dtype=torch.uint8)
+    call("maxpool3x3s2_fwd", x, y, pos, IMGS, H, W, C, Ho, Wo, dtype_code(x.dtype))
+    return (y, pos) if want_pos else y
 
 
-def maxpool_bwd(x, dy):
-    IMGS, H, W, C = x.shape
-    dx = torch.empty_like(x)
-    call("maxpool3x3s2_bwd", x, dy, dx, IMGS, H, W, C, dy.shape[1], dy.shape[2], dtype_code(x.dtype))
+def maxpool_bwd(x, dy, pos=None, x_shape=None):
+    """dx from either the forward input x or the recorded positions (then x may be None, pass x_shape)."""
+    IMGS, H, W, C = x_shape if x is None else x.shape
+    dx = torch.empty((IMGS, H, W, C), device=dy.device, dtype=dy.dtype)
+    call("maxpool3x3s2_bwd", x if pos is None else None, pos, dy, dx, IMGS, H, W, C, dy.shape[1], dy.shape[2],
+         dtype_code(dy.dtype))
     return dx
 
 

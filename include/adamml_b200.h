@@ -133,11 +133,12 @@ int adamml_bn_param_grad(const double* sums, float* dgamma, float* dbeta, int C,
                          cudaStream_t stream);
 
 /* ---- pooling ---- */
-/* nn.MaxPool2d(3,2,1): resnet.py:141,202 */
-int adamml_maxpool3x3s2_fwd(const void* x, void* y, int IMGS, int H, int W, int C, int Ho, int Wo, int dtype,
-                            cudaStream_t stream);
-int adamml_maxpool3x3s2_bwd(const void* x, const void* dy, void* dx, int IMGS, int H, int W, int C, int Ho, int Wo,
+/* nn.MaxPool2d(3,2,1): resnet.py:141,202.  `pos` (optional, uint8 [IMGS,Ho,Wo,C]) records the window
+ * position r*3+s of the first maximum; the backward pass then is a gather over (pos, dy) and x may be NULL. */
+int adamml_maxpool3x3s2_fwd(const void* x, void* y, unsigned char* pos, int IMGS, int H, int W, int C, int Ho, int Wo,
                             int dtype, cudaStream_t stream);
+int adamml_maxpool3x3s2_bwd(const void* x, const unsigned char* pos, const void* dy, void* dx, int IMGS, int H, int W,
+                            int C, int Ho, int Wo, int dtype, cudaStream_t stream);
 /* TemporalPooling k3 s2 p1 over frames: common.py:4-33 ; x [V videos][Tn frames][E = H*W*C] */
 int adamml_tpool_fwd(const void* x, void* y, long long V, int Tn, long long E, int mode_avg, int dtype,
                      cudaStream_t stream);

@@ -260,6 +260,11 @@ def test_pools(cuda, dtype):
     # ties at zero may pick a different element than cuDNN; compare where x > 0
     m = (x.detach() > 0)
     assert relerr(nchw(dx).float() * m, x.grad * m) < (1e-6 if dtype == torch.float32 else 1e-2)
+    # recorded-position variant: forward stores the argmax code, backward is a gather that never reads x
+    y_p, pos = ops.maxpool_fwd(xn, want_pos=True)
+    assert pos is not None and torch.equal(y_p, y)
+    dx_p = ops.maxpool_bwd(None, nhwc(dy).to(dtype), pos=pos, x_shape=tuple(xn.shape))
+    assert torch.equal(dx_p, dx)
 
     for T in (8, 4, 2, 3):
         for mode in ("max", "avg"):
