@@ -239,6 +239,42 @@ int launch_wgrad(const WgMaps& maps, const WgGeom& geo, float* dW, cudaStream_t 
   return adamml_check_launch("tc_wgrad");
 }
 
+
+// fills the tiling / split-K fields of geo for ntaps x cin rows, cout columns and an [IMGS, Ho, Wo] pixel axis
+int wg_tiling(WgGeom& geo, int ntaps, int cin, int cout, int Wo, int Ho, int IMGS) {
+  geo.ntaps = ntaps;
+  geo.cin = cin;
+  geo.cout = cout;
+  geo.chunks_per_tap = (cin + 63) / 64;
+  geo.m_blocks = geo.ntaps * geo.chunks_per_tap;
+  geo.m_tiles = (geo.m_blocks + 1) / 2;
+  const int block_n = cout <= 64 ? 64 : (cout <= 128 ? 128 : 256);
+  geo.n_tiles = (cout + block_n - 1) / block_n;
+  pick_box(Wo, Ho, IMGS, PIX_BLOCK, &geo.BW, &geo.BH, &geo.BI);
+  geo.tiles_w = (Wo + geo.BW - 1) / geo.BW;
+  geo.tiles_h = (Ho + geo.BH - 1) / geo.BH;
+  geo.tiles_i = (IMGS + geo.BI - 1) / geo.BI;
+  const int pix_tiles = geo.tiles_w * geo.tiles_h * geo.tiles_i;
+  // enough splits for ~3 items per SM, at least 8 pixel tiles per item
+  long long base = (long long)geo.m_tiles * geo.n_tiles;
+  long long want = (3LL * num_sms() + base - 1) / base;
+  long long cap = (pix_tiles + 7) / 8;
+  long long ks = want < cap ? want : cap;
+  if (ks < 1) ks = 1;
+  // avoid empty trailing splits
+  int per = (int)((pix_tiles + ks - 1) / ks);
+  ks = (pix_tiles + per - 1) / per;
+  geo.ksplit = (int)ks;
+  return block_n;
+}
+
+int wg_launch(int block_n, const WgMaps& maps, const WgGeom& geo, float* dw, cudaStream_t stream) {
+  cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)geo.cout * geo.ntaps * geo.cin, stream);
+  if (block_n == 64) return launch_wgrad<64>(maps, geo, dw, stream);
+  if (block_n == 128) return launch_wgrad<128>(maps, geo, dw, stream);
+  return launch_wgrad<256>(maps, geo, dw, stream);
+}
+
 }  // namespace
 
 extern "C" {
@@ -263,29 +299,7 @@ int adamml_tc_wgrad_bf16(const void* x, const void* dy, float* dw, int IMGS, int
   ADAMML_REQUIRE(((uintptr_t)x % 16) == 0 && ((uintptr_t)dy % 16) == 0, "tc_wgrad: operands must be 16-byte aligned");
   WgGeom geo;
   memset(&geo, 0, sizeof(geo));
-  geo.ntaps = R * S;
-  geo.cin = Cin;
-  geo.cout = Cout;
-  geo.chunks_per_tap = (Cin + 63) / 64;
-  geo.m_blocks = geo.ntaps * geo.chunks_per_tap;
-  geo.m_tiles = (geo.m_blocks + 1) / 2;
-  const int block_n = Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 256);
-  geo.n_tiles = (Cout + block_n - 1) / block_n;
-  pick_box(Wo, Ho, IMGS, PIX_BLOCK, &geo.BW, &geo.BH, &geo.BI);
-  geo.tiles_w = (Wo + geo.BW - 1) / geo.BW;
-  geo.tiles_h = (Ho + geo.BH - 1) / geo.BH;
-  geo.tiles_i = (IMGS + geo.BI - 1) / geo.BI;
-  const int pix_tiles = geo.tiles_w * geo.tiles_h * geo.tiles_i;
-  // enough splits for ~3 items per SM, at least 8 pixel tiles per item
-  long long base = (long long)geo.m_tiles * geo.n_tiles;
-  long long want = (3LL * num_sms() + base - 1) / base;
-  long long cap = (pix_tiles + 7) / 8;
-  long long ks = want < cap ? want : cap;
-  if (ks < 1) ks = 1;
-  // avoid empty trailing splits
-  int per = (int)((pix_tiles + ks - 1) / ks);
-  ks = (pix_tiles + per - 1) / per;
-  geo.ksplit = (int)ks;
+  const int block_n = wg_tiling(geo, R * S, Cin, Cout, Wo, Ho, IMGS);
 
   bool used[4] = {false, false, false, false};
   for (int r = 0; r < R; ++r)
@@ -317,10 +331,37 @@ int adamml_tc_wgrad_bf16(const void* x, const void* dy, float* dw, int IMGS, int
   int rc = make_map_4d(&maps.dy, dy, Cout, Wo, Ho, IMGS, Cout, (long long)Wo * Cout, (long long)Ho * Wo * Cout, geo.BW,
                        geo.BH, geo.BI);
   if (rc) return rc;
-  cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Cout * R * S * Cin, stream);
-  if (block_n == 64) return launch_wgrad<64>(maps, geo, dw, stream);
-  if (block_n == 128) return launch_wgrad<128>(maps, geo, dw, stream);
-  return launch_wgrad<256>(maps, geo, dw, stream);
+  return wg_launch(block_n, maps, geo, dw, stream);
+}
+
+/* Weight gradient of the 7x7/s2 stem on the space-to-depth input (see adamml_tc_stem_conv_bf16):
+ * dw fp32 [Cout][4][4*Cs] (overwritten), unpacked to OIHW by adamml_unpack_wgrad_stem. */
+int adamml_tc_stem_wgrad_bf16(const void* xs, const void* dy, float* dw, int IMGS, int Hs, int Wp, int Cs, int Cout,
+                              int Ho, int Wo, cudaStream_t stream) {
+  if (Cs % 16 || Cout % 8 || Cs > 64) {
+    adamml_set_error("tc_stem_wgrad: Cs=%d Cout=%d outside the tcgen05 envelope", Cs, Cout);
+    return ADAMML_ERR_UNSUPPORTED;
+  }
+  ADAMML_REQUIRE(Ho == Hs && Wo + 4 <= Wp + 1, "tc_stem_wgrad: geometry (Ho == Hs, Wp >= Wo + 3)");
+  ADAMML_REQUIRE(((uintptr_t)xs % 16) == 0 && ((uintptr_t)dy % 16) == 0, "tc_stem_wgrad: operands must be 16-byte aligned");
+  const int VC = 4 * Cs;
+  WgGeom geo;
+  memset(&geo, 0, sizeof(geo));
+  const int block_n = wg_tiling(geo, 4, VC, Cout, Wo, Ho, IMGS);
+  for (int t = 0; t < 4; ++t) {
+    geo.tap_map[t] = 0;
+    geo.tap_dh[t] = (signed char)(t - 2);
+    geo.tap_dw[t] = 0;
+  }
+  WgMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  int rc = make_map_4d(&maps.x[0], xs, VC, Wp - 3, Hs, IMGS, Cs, (long long)Wp * Cs, (long long)Hs * Wp * Cs, geo.BW,
+                       geo.BH, geo.BI);
+  if (rc) return rc;
+  rc = make_map_4d(&maps.dy, dy, Cout, Wo, Ho, IMGS, Cout, (long long)Wo * Cout, (long long)Ho * Wo * Cout, geo.BW,
+                   geo.BH, geo.BI);
+  if (rc) return rc;
+  return wg_launch(block_n, maps, geo, dw, stream);
 }
 
 }  // extern "C"

@@ -120,6 +120,77 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ src, float* __rest
   }
 }
 
+
+// Space-to-depth input of the ResNet stem (see conv_tc.cu adamml_tc_stem_conv_bf16):
+// x NCHW fp32 [N, S*F*C, H, W] -> out bf16 [(s*N+n)*F+f, H/2, W/2+4, Cs], stored column ip holds s2d column
+// ip-2 (two zero columns left and right), channel (ph*2+pw)*C + c = x[.., c, 2j+ph, 2i+pw], rest zero.
+__global__ void pack_frames_s2d_kernel(const float* __restrict__ x, bf16* __restrict__ out, int N, int S, int F,
+                                       int C, int H, int W, int Cs) {
+  const int Hs = H / 2, Ws = W / 2, Wp = Ws + 4;
+  const long long total = (long long)S * N * F * Hs * Wp;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int ip = (int)(idx % Wp);
+    const int j = (int)((idx / Wp) % Hs);
+    const long long img = idx / ((long long)Wp * Hs);
+    const int f = (int)(img % F);
+    const int n = (int)((img / F) % N);
+    const int s = (int)(img / ((long long)F * N));
+    bf16* dst = out + idx * Cs;
+    const int i = ip - 2;
+    if (i < 0 || i >= Ws) {
+      for (int c = 0; c < Cs; c += 8) *reinterpret_cast<uint4*>(dst + c) = make_uint4(0, 0, 0, 0);
+      continue;
+    }
+    const float* src = x + (((long long)n * S * F * C + ((long long)s * F + f) * C) * H + 2 * j) * W + 2 * i;
+    for (int ph = 0; ph < 2; ++ph)
+      for (int c = 0; c < C; ++c) {
+        const float2 v = *reinterpret_cast<const float2*>(src + ((long long)c * H + ph) * W);
+        dst[(ph * 2 + 0) * C + c] = __float2bfloat16_rn(v.x);
+        dst[(ph * 2 + 1) * C + c] = __float2bfloat16_rn(v.y);
+      }
+    for (int c = 4 * C; c < Cs; ++c) dst[c] = __float2bfloat16_rn(0.f);
+  }
+}
+
+// stem weight OIHW fp32 [Cout][C][7][7] -> bf16 [Cout][4 (dh+2)][4 (dw+2)][Cs]:
+// tap (r, s) = (2*dh+ph+3, 2*dw+pw+3), channel (ph*2+pw)*C + c; everything else zero.
+__global__ void pack_weight_stem_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int Cout, int C,
+                                        int Cs) {
+  const long long total = (long long)Cout * 16 * Cs;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(idx % Cs);
+    const int dwi = (int)((idx / Cs) % 4);
+    const int dhi = (int)((idx / (Cs * 4)) % 4);
+    const int co = (int)(idx / (Cs * 16));
+    float v = 0.f;
+    if (q < 4 * C) {
+      const int c = q % C, pp = q / C, ph = pp >> 1, pw = pp & 1;
+      const int r = 2 * (dhi - 2) + ph + 3, s_ = 2 * (dwi - 2) + pw + 3;
+      if (r >= 0 && r < 7 && s_ >= 0 && s_ < 7) v = src[(((long long)co * C + c) * 7 + r) * 7 + s_];
+    }
+    dst[idx] = __float2bfloat16_rn(v);
+  }
+}
+
+// inverse of pack_weight_stem for the fp32 gradient: [Cout][4][4][Cs] -> OIHW [Cout][C][7][7]
+__global__ void unpack_wgrad_stem_kernel(const float* __restrict__ src, float* __restrict__ dst, int Cout, int C,
+                                         int Cs) {
+  const long long total = (long long)Cout * C * 49;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int s_ = (int)(idx % 7);
+    const int r = (int)((idx / 7) % 7);
+    const int c = (int)((idx / 49) % C);
+    const int co = (int)(idx / (49LL * C));
+    const int t = r - 3, u = s_ - 3;
+    const int dh = (t >= 0 ? t : t - 1) / 2, dw = (u >= 0 ? u : u - 1) / 2;  // floor division
+    const int ph = t - 2 * dh, pw = u - 2 * dw;
+    dst[idx] = src[(((long long)co * 4 + dh + 2) * 4 + dw + 2) * Cs + (ph * 2 + pw) * C + c];
+  }
+}
+
 template <typename TI, typename TO>
 __global__ void cast_kernel(const TI* __restrict__ src, TO* __restrict__ dst, long long total) {
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -175,6 +246,29 @@ int adamml_unpack_wgrad(const float* dw_ohwi, float* dw_oihw, int Cout, int Cin,
   long long total = (long long)Cout * Cin * R * S;
   unpack_wgrad_kernel<<<ew_blocks(total), 256, 0, stream>>>(dw_ohwi, dw_oihw, Cout, Cin, R, S, CinPad, accumulate);
   return adamml_check_launch("unpack_wgrad");
+}
+
+int adamml_pack_frames_s2d(const float* x, void* out, int N, int S, int F, int C, int H, int W, int Cs,
+                           cudaStream_t stream) {
+  ADAMML_REQUIRE(N > 0 && S > 0 && F > 0 && C > 0 && H > 0 && W > 0, "pack_frames_s2d: bad dims");
+  ADAMML_REQUIRE(H % 2 == 0 && W % 2 == 0 && Cs % 8 == 0 && Cs >= 4 * C, "pack_frames_s2d: needs even H, W and Cs >= 4C");
+  ADAMML_REQUIRE(((uintptr_t)x % 8) == 0 && ((uintptr_t)out % 16) == 0, "pack_frames_s2d: unaligned buffers");
+  long long total = (long long)S * N * F * (H / 2) * (W / 2 + 4);
+  pack_frames_s2d_kernel<<<ew_blocks(total), 256, 0, stream>>>(x, (bf16*)out, N, S, F, C, H, W, Cs);
+  return adamml_check_launch("pack_frames_s2d");
+}
+
+int adamml_pack_weight_stem(const float* w_oihw, void* w_packed, int Cout, int C, int Cs, cudaStream_t stream) {
+  ADAMML_REQUIRE(Cout > 0 && C > 0 && Cs >= 4 * C, "pack_weight_stem: bad dims");
+  pack_weight_stem_kernel<<<ew_blocks((long long)Cout * 16 * Cs), 256, 0, stream>>>(w_oihw, (bf16*)w_packed, Cout, C,
+                                                                                     Cs);
+  return adamml_check_launch("pack_weight_stem");
+}
+
+int adamml_unpack_wgrad_stem(const float* dw_packed, float* dw_oihw, int Cout, int C, int Cs, cudaStream_t stream) {
+  ADAMML_REQUIRE(Cout > 0 && C > 0 && Cs >= 4 * C, "unpack_wgrad_stem: bad dims");
+  unpack_wgrad_stem_kernel<<<ew_blocks((long long)Cout * C * 49), 256, 0, stream>>>(dw_packed, dw_oihw, Cout, C, Cs);
+  return adamml_check_launch("unpack_wgrad_stem");
 }
 
 // dtype codes for src/dst

@@ -69,7 +69,14 @@ class Exec:
         depthwise = conv.groups > 1
         sums = None
         fused = False
-        if depthwise:
+        stem = isinstance(x, ops.S2D)
+        if stem:
+            wp = None
+            if self.training:
+                sums = torch.empty((G, Cout, 2), device=x.device, dtype=torch.float64)
+            z = ops.stem_conv_fwd(x, w.detach(), stats=sums, imgs_per_group=x.shape[0] // G)
+            fused = sums is not None
+        elif depthwise:
             assert conv.groups == conv.in_channels == Cout and R == 3 and pad == 1
             wp = w.detach()
             z = ops.dwconv_fwd(x, wp, stride)
@@ -97,15 +104,17 @@ class Exec:
         else:
             mi, ss = ops.bn_finalize(None, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, 1,
                                      0.1, bn.eps, C, G, False, False)
-        return dict(x=x, z=z, mi=mi, ss=ss, w=wp, conv=conv, bn=bn, count=count, pg=pg, depthwise=depthwise)
+        return dict(x=x, z=z, mi=mi, ss=ss, w=wp, conv=conv, bn=bn, count=count, pg=pg, depthwise=depthwise, stem=stem)
 
-    def cba_bwd(self, dout, need_dx=True, addend=None):
+    def cba_bwd(self, dout, need_dx=True, addend=None, addend_sub=1):
         """Pops one cba record.  Returns (dx or None, dres or None)."""
         rec = self.tape.pop()
-        return self._bn_conv_bwd(rec, dout, rec["out"], rec["act"], need_dx, addend,
-                                 want_dres=rec["has_res"] and rec["act"] != ACT_NONE)
+        dx, dres, _ = self._bn_conv_bwd(rec, dout, rec["out"], rec["act"], need_dx, addend,
+                                        want_dres=rec["has_res"] and rec["act"] != ACT_NONE, addend_sub=addend_sub)
+        return dx, dres
 
-    def _bn_conv_bwd(self, rec, dout, out, act, need_dx, addend, want_dres):
+    def _bn_conv_bwd(self, rec, dout, out, act, need_dx, addend, want_dres, addend_sub=1, compact_ok=False):
+        """-> (dx, dres, dx_is_compact)"""
         G = self.G
         conv, bn, z, mi = rec["conv"], rec["bn"], rec["z"], rec["mi"]
         C = z.shape[-1]
@@ -122,7 +131,11 @@ class Exec:
         dx = None
         x = rec["x"]
         stride, pad = conv.stride[0], conv.padding[0]
-        if rec["depthwise"]:
+        if rec["stem"]:
+            assert not need_dx, "the s2d stem has no data gradient (its input is data)"
+            if need_w:
+                self._acc(conv.weight, ops.stem_wgrad(x, dz, conv.out_channels))
+        elif rec["depthwise"]:
             if need_w:
                 self._acc(conv.weight, ops.dwconv_wgrad(x, dz, stride))
             if need_dx:
@@ -134,11 +147,16 @@ class Exec:
                 self._acc(conv.weight, ops.unpack_wgrad(dw, conv.weight.shape[1]))
             if need_dx:
                 w_rot = None
-                if (self.dtype == torch.bfloat16 and stride == 1 and ops.TC_MODE == "auto"
-                        and w.shape[0] % 8 == 0 and w.shape[3] % 8 == 0 and w.shape[0] >= 32):
+                R, S = w.shape[1], w.shape[2]
+                if ops.tc_dgrad_ok(self.dtype, w.shape[0], w.shape[3], R, S, stride):
                     w_rot = ops.pack_weight_dgrad(conv.weight.detach(), self.dtype)
-                dx = ops.conv_dgrad(dz, w, tuple(x.shape), stride, pad, addend=addend, w_rot=w_rot)
-        return dx, dres
+                if w_rot is not None and stride == 2 and R == 1 and S == 1 and addend is None and compact_ok:
+                    # stride-2 1x1 (Bottleneck downsample): only the even pixels receive gradient -> compact GEMM,
+                    # scattered by the consumer's epilogue (conv_dgrad addend_sub=2)
+                    return ops.conv_dgrad_compact(dz, w_rot), dres, True
+                dx = ops.conv_dgrad(dz, w, tuple(x.shape), stride, pad, addend=addend, w_rot=w_rot,
+                                    addend_sub=addend_sub)
+        return dx, dres, False
 
     # ------------------------------------------------------------------ ResNet blocks
     def bottleneck(self, x, blk):
@@ -155,13 +173,19 @@ class Exec:
         ds = rec3["res_rec"]
         d_id = None
         dx_ds = None
+        compact = False
         if ds is not None:
-            # downsample branch shares (dout, out, act mask) with bn3
-            dx_ds, _ = self._bn_conv_bwd(ds, dout, rec3["out"], rec3["act"], need_dx, None, want_dres=False)
+            # downsample branch shares (dout, out, act mask) with bn3; conv1 of the block is a stride-1 1x1 whose
+            # tcgen05 dgrad epilogue can scatter a compact stride-2 downsample gradient
+            c1 = self.tape[-3]["conv"]
+            ok = ops.tc_dgrad_ok(self.dtype, c1.out_channels, c1.in_channels, 1, 1, 1) and c1.kernel_size == (1, 1)
+            dx_ds, _, compact = self._bn_conv_bwd(ds, dout, rec3["out"], rec3["act"], need_dx, None, want_dres=False,
+                                                  compact_ok=ok)
         da, d_id = self.cba_bwd(dout)          # conv3/bn3 (+identity grad)
         da, _ = self.cba_bwd(da)               # conv2/bn2
         addend = dx_ds if ds is not None else d_id
-        dx, _ = self.cba_bwd(da, need_dx=need_dx, addend=addend if need_dx else None)  # conv1/bn1
+        dx, _ = self.cba_bwd(da, need_dx=need_dx, addend=addend if need_dx else None,
+                             addend_sub=2 if compact else 1)  # conv1/bn1
         return dx
 
     def basicblock(self, x, blk):
@@ -177,7 +201,7 @@ class Exec:
         ds = rec2["res_rec"]
         dx_ds = None
         if ds is not None:
-            dx_ds, _ = self._bn_conv_bwd(ds, dout, rec2["out"], rec2["act"], need_dx, None, want_dres=False)
+            dx_ds, _, _ = self._bn_conv_bwd(ds, dout, rec2["out"], rec2["act"], need_dx, None, want_dres=False)
         da, d_id = self.cba_bwd(dout)
         addend = dx_ds if ds is not None else d_id
         dx, _ = self.cba_bwd(da, need_dx=need_dx, addend=addend if need_dx else None)

@@ -55,7 +55,8 @@ class AdaMML(nn.Module):
             if idx in self.p_data_idx:
                 p_x.append(ops.resize_frames(x_, S, F, c, p_rgb_size[0], p_rgb_size[1], 2, dt))
             if idx in self.m_data_idx:
-                m_x.append(ops.pack_frames(x_, S, F, c, dt))
+                net = self.main_net.nets[self.m_data_idx.index(idx)]
+                m_x.append(net.pack_input(x_, S) if hasattr(net, "pack_input") else ops.pack_frames(x_, S, F, c, dt))
         return p_x, m_x, S
 
     def forward(self, x, num_segments=None, noise=None):

@@ -119,6 +119,15 @@ class ResNet(nn.Module):
         d = ex.maxpool_bwd(d)
         ex.cba_bwd(d, need_dx=False)
 
+    def pack_input(self, x, S):
+        """NCHW fp32 [N, S*F*C, H, W] -> the stem operand of the engine: space-to-depth bf16 for the tensor-core
+        stem, plain NHWC otherwise (adamml.py:53,65 / resnet.py:197)."""
+        f = self.orig_num_frames
+        c = x.shape[1] // (S * f)
+        if ops.stem_s2d_ok(self.conv1, c, x.shape[2], x.shape[3], self.compute_dtype):
+            return ops.pack_frames_s2d(x, S, f, c)
+        return ops.pack_frames(x, S, f, c, self.compute_dtype)
+
     # ------------------------------------------------------------------ unimodal API (resnet.py:195)
     def draw_drop_mask(self, rows, device):
         if not self.training or self.dropout_p <= 0:
@@ -130,8 +139,7 @@ class ResNet(nn.Module):
         n, ct, h, w = x.shape
         if ct == 1:
             raise ValueError("single-channel (audio) input is served by sound_mobilenet_v2, not ResNet")
-        f = self.orig_num_frames
-        xn = ops.pack_frames(x.contiguous().float(), 1, f, ct // f, self.compute_dtype)
+        xn = self.pack_input(x.contiguous().float(), 1)
         if drop_mask is None:
             drop_mask = self.draw_drop_mask(n * self.out_frames, x.device)
         return run_backbone(self, xn, 1, dict(drop_mask=drop_mask))

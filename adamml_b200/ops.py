@@ -48,6 +48,65 @@ def resize_frames(x, S, F, C, OH, OW, fstep, dtype, cpad=None):
     return out
 
 
+class S2D:
+    """Space-to-depth operand of the tensor-core ResNet stem: `t` is bf16 [IMGS, H/2, W/2+4, Cs]
+    (csrc/data_layer.cu pack_frames_s2d); shape reports the logical NHWC input."""
+
+    def __init__(self, t, C, H, W):
+        self.t, self.C, self.H, self.W = t, C, H, W
+        self.Cs = t.shape[-1]
+
+    @property
+    def shape(self):
+        return (self.t.shape[0], self.H, self.W, self.C)
+
+    @property
+    def device(self):
+        return self.t.device
+
+    @property
+    def dtype(self):
+        return self.t.dtype
+
+
+def stem_s2d_ok(conv, C, H, W, dtype):
+    """7x7 / stride 2 / pad 3 stem on even-sized frames in bf16 mode -> tensor-core s2d path."""
+    return (TC_MODE == "auto" and dtype == torch.bfloat16 and conv.kernel_size == (7, 7) and conv.stride == (2, 2)
+            and conv.padding == (3, 3) and H % 2 == 0 and W % 2 == 0 and 4 * C <= 64 and conv.out_channels % 8 == 0)
+
+
+def pack_frames_s2d(x, S, F, C):
+    _chk(x, torch.float32)
+    N, SFC, H, W = x.shape
+    assert SFC == S * F * C, (x.shape, S, F, C)
+    Cs = ((4 * C + 15) // 16) * 16
+    out = torch.empty((S * N * F, H // 2, W // 2 + 4, Cs), device=x.device, dtype=torch.bfloat16)
+    call("pack_frames_s2d", x, out, N, S, F, C, H, W, Cs)
+    return S2D(out, C, H, W)
+
+
+def stem_conv_fwd(xs, w_oihw, stats=None, imgs_per_group=0):
+    """xs: S2D, w_oihw: fp32 [Cout, C, 7, 7] parameter -> z bf16 [IMGS, H/2, W/2, Cout] (+ fused BN statistics)."""
+    Cout = w_oihw.shape[0]
+    wp = torch.empty((Cout, 4, 4, xs.Cs), device=xs.device, dtype=torch.bfloat16)
+    call("pack_weight_stem", w_oihw, wp, Cout, xs.C, xs.Cs)
+    IMGS, Hs, Wp, Cs = xs.t.shape
+    Ho, Wo = xs.H // 2, xs.W // 2
+    z = torch.empty((IMGS, Ho, Wo, Cout), device=xs.device, dtype=torch.bfloat16)
+    call("tc_stem_conv_bf16", xs.t, wp, z, IMGS, Hs, Wp, Cs, Cout, Ho, Wo, stats, imgs_per_group)
+    return z
+
+
+def stem_wgrad(xs, dy, Cout):
+    """-> fp32 OIHW gradient [Cout, C, 7, 7] of the stem weight."""
+    IMGS, Hs, Wp, Cs = xs.t.shape
+    dwp = torch.empty((Cout, 4, 4, Cs), device=xs.device, dtype=torch.float32)
+    call("tc_stem_wgrad_bf16", xs.t, dy, dwp, IMGS, Hs, Wp, Cs, Cout, dy.shape[1], dy.shape[2])
+    dw = torch.empty((Cout, xs.C, 7, 7), device=xs.device, dtype=torch.float32)
+    call("unpack_wgrad_stem", dwp, dw, Cout, xs.C, Cs)
+    return dw
+
+
 def pack_weight(w, dtype, cin_pad=None):
     """OIHW fp32 parameter -> OHWI operand [Cout, R, S, cin_pad] in `dtype`."""
     _chk(w, torch.float32)
@@ -118,15 +177,33 @@ def conv_fwd(x, w, stride, pad, out=None, stats=None, rows_per_group=0):
         return out, stats is not None
     if _tc_conv_ok(x, Cin, Cout, R, S, stride):
         ipg = rows_per_group // (Ho * Wo) if stats is not None else 0
-        call("tc_conv_bf16", x, w, out, None, IMGS, H, W, Cin, Cout, R, S, stride, pad, Ho, Wo, stats, ipg)
+        call("tc_conv_bf16", x, w, out, None, IMGS, H, W, Cin, Cout, R, S, stride, pad, Ho, Wo, stats, ipg, 0)
         return out, stats is not None
     call("simt_conv_fwd", x, w, out, IMGS, H, W, Cin, Cout, R, S, stride, pad, Ho, Wo, 0, 0, 0, dtype_code(x.dtype))
     return out, False
 
 
-def conv_dgrad(dy, w, x_shape, stride, pad, addend=None, w_rot=None):
+def tc_dgrad_ok(dtype, Cout, Cin, R, S, stride):
+    """data gradients that run on the tcgen05 engine (bf16): stride 1, stride-2 RxS (parity classes),
+    stride-2 1x1 (compact GEMM, see conv_dgrad_compact)."""
+    return (TC_MODE == "auto" and dtype == torch.bfloat16 and Cout % 8 == 0 and Cin % 8 == 0 and Cout >= 32
+            and R * S <= 49 and stride in (1, 2))
+
+
+def conv_dgrad_compact(dy, w_rot):
+    """Stride-2 1x1 conv: the non-zero part of dx, [IMGS, Ho, Wo, Cin] = dy . w (one plain GEMM).  The caller
+    scatters it onto the even pixels of the input grid (conv_dgrad(..., addend_sub=2))."""
+    IMGS, Ho, Wo, Cout = dy.shape
+    Cin = w_rot.shape[0]
+    dxc = torch.empty((IMGS, Ho, Wo, Cin), device=dy.device, dtype=dy.dtype)
+    call("tc_gemm_bf16", dy, w_rot, dxc, IMGS * Ho * Wo, Cin, Cout, 0, 0, 0, _lib.BF16, None, 0)
+    return dxc
+
+
+def conv_dgrad(dy, w, x_shape, stride, pad, addend=None, w_rot=None, addend_sub=1):
     """dx = conv_transpose(dy, w) (+ addend).  w_rot: optional rotated operand [Cin, R, S, Cout] from
-    pack_weight_dgrad (bf16): stride-1 layers then run as a forward conv of dy on the tcgen05 engine."""
+    pack_weight_dgrad (bf16): the layer then runs as forward conv(s) of dy on the tcgen05 engine.
+    addend_sub=2: addend is a compact stride-2 gradient (conv_dgrad_compact) added at even pixels."""
     _chk(dy); _chk(w, dy.dtype)
     IMGS, H, W, Cin = x_shape
     Cout, R, S, _ = w.shape
@@ -136,7 +213,12 @@ def conv_dgrad(dy, w, x_shape, stride, pad, addend=None, w_rot=None):
         if addend is None and R == 1 and S == 1:
             call("tc_gemm_bf16", dy, w_rot, dx, IMGS * H * W, Cin, Cout, 0, 0, 0, _lib.BF16, None, 0)
         else:
-            call("tc_conv_bf16", dy, w_rot, dx, addend, IMGS, Ho, Wo, Cout, Cin, R, S, 1, R - 1 - pad, H, W, None, 0)
+            call("tc_conv_bf16", dy, w_rot, dx, addend, IMGS, Ho, Wo, Cout, Cin, R, S, 1, R - 1 - pad, H, W, None, 0,
+                 addend_sub if addend is not None else 0)
+        return dx
+    assert addend_sub == 1 or addend is None, "compact addends need the tcgen05 stride-1 path"
+    if w_rot is not None and stride == 2 and R >= 2 and S >= 2 and addend is None:
+        call("tc_dgrad_s2_bf16", dy, w_rot, dx, IMGS, H, W, Cin, Cout, R, S, pad, Ho, Wo)
         return dx
     call("simt_conv_dgrad", dy, w, dx, addend, IMGS, H, W, Cin, Cout, R, S, stride, pad, Ho, Wo, 0, 0, 0,
          dtype_code(dy.dtype))

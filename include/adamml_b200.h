@@ -55,6 +55,13 @@ int adamml_pack_weight_dgrad(const float* w_oihw, void* w_ihwo, int Cout, int Ci
 /* OHWI fp32 weight gradient -> OIHW fp32 .grad layout */
 int adamml_unpack_wgrad(const float* dw_ohwi, float* dw_oihw, int Cout, int Cin, int R, int S, int CinPad,
                         int accumulate, cudaStream_t stream);
+/* Space-to-depth operands of the tensor-core ResNet stem (7x7/s2/p3 conv1, resnet.py:138,199):
+ * frames  -> bf16 [(s*N+n)*F+f, H/2, W/2+4, Cs]  (two zero columns on either side, channel (ph*2+pw)*C+c)
+ * weights -> bf16 [Cout][4][4][Cs]; the fp32 gradient of that operand -> OIHW .grad layout */
+int adamml_pack_frames_s2d(const float* x, void* out, int N, int S, int F, int C, int H, int W, int Cs,
+                           cudaStream_t stream);
+int adamml_pack_weight_stem(const float* w_oihw, void* w_packed, int Cout, int C, int Cs, cudaStream_t stream);
+int adamml_unpack_wgrad_stem(const float* dw_packed, float* dw_oihw, int Cout, int C, int Cs, cudaStream_t stream);
 int adamml_cast(const void* src, void* dst, long long total, int src_dtype, int dst_dtype, cudaStream_t stream);
 
 /* ---- dense convolution / linear, exact fp32-math engine (CUDA cores) ----
@@ -92,10 +99,22 @@ int adamml_tc_supported(long long M, int Ncols, int K, long long lda, long long 
  * with adamml_pack_weight_dgrad weights and `addend` = the residual-branch gradient.
  * x [IMGS,H,W,Cin] bf16, w [Cout][R][S][Cin] bf16, y/addend [IMGS,Ho,Wo,Cout] bf16, stats double
  * [G][Cout][2] (optional fused BN statistics, G = IMGS / imgs_per_group). */
+/* addend_sub = 2: `addend` is the compact [IMGS, ceil(Ho/2), ceil(Wo/2), Cout] gradient of a stride-2 1x1 branch
+ * (the Bottleneck downsample, resnet.py:164-167) and is added at even (oh, ow) only; otherwise 0/1 = dense. */
 int adamml_tc_conv_bf16(const void* x, const void* w, void* y, const void* addend, int IMGS, int H, int W, int Cin,
                         int Cout, int R, int S, int stride, int pad, int Ho, int Wo, double* stats,
-                        int imgs_per_group, cudaStream_t stream);
+                        int imgs_per_group, int addend_sub, cudaStream_t stream);
 int adamml_tc_conv_supported(int Cin, int Cout, int R, int S, int stride);
+/* Data gradient of a stride-2 RxS convolution (R,S >= 2) as four stride-1 implicit GEMMs over the parity classes
+ * of the input grid; w_rot from adamml_pack_weight_dgrad; dx [IMGS,H,W,Cin] is fully overwritten. */
+int adamml_tc_dgrad_s2_bf16(const void* dy, const void* w_rot, void* dx, int IMGS, int H, int W, int Cin, int Cout,
+                            int R, int S, int pad, int Ho, int Wo, cudaStream_t stream);
+/* ResNet stem on the space-to-depth operands: y [IMGS,Ho,Wo,Cout] bf16 (+ fused BN statistics), and its weight
+ * gradient dw fp32 [Cout][4][4*Cs] (unpack with adamml_unpack_wgrad_stem). */
+int adamml_tc_stem_conv_bf16(const void* xs, const void* w, void* y, int IMGS, int Hs, int Wp, int Cs, int Cout,
+                             int Ho, int Wo, double* stats, int imgs_per_group, cudaStream_t stream);
+int adamml_tc_stem_wgrad_bf16(const void* xs, const void* dy, float* dw, int IMGS, int Hs, int Wp, int Cs, int Cout,
+                              int Ho, int Wo, cudaStream_t stream);
 /* Weight gradient on tcgen05: implicit GEMM whose reduction axis is the pixel axis, both operands MN-major
  * (64-channel x 64-pixel 4D TMA boxes of x and dy), split-K over pixel ranges with fp32 atomics.
  * dw fp32 [Cout][R][S][Cin] is overwritten.  Same call sites as adamml_simt_conv_wgrad. */

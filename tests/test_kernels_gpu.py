@@ -385,19 +385,40 @@ def test_tc_conv_fwd_stats_dgrad(cuda, case):
     G = 1 if IMGS % 2 else 2
     y = torch.full((IMGS, Ho, Wo, Cout), float("nan"), device=cuda, dtype=torch.bfloat16)
     stats = torch.full((G, Cout, 2), float("nan"), device=cuda, dtype=torch.float64)
-    _lib.call("tc_conv_bf16", xn, wp, y, None, IMGS, H, W, Cin, Cout, R, R, stride, pad, Ho, Wo, stats, IMGS // G)
+    _lib.call("tc_conv_bf16", xn, wp, y, None, IMGS, H, W, Cin, Cout, R, R, stride, pad, Ho, Wo, stats, IMGS // G, 0)
     torch.cuda.synchronize()
     assert torch.isfinite(y.float()).all()
     assert relerr(nchw(y), y_ref) < 1e-2
     yd = y.double().view(G, -1, Cout)
     ref_stats = torch.stack([yd.sum(1), (yd * yd).sum(1)], -1)
     assert relerr(stats, ref_stats) < 1e-5
-    if stride != 1:
-        return
     dy = torch.randn(y_ref.shape, generator=g).to(cuda).bfloat16().float()
     y_ref.backward(dy)
-    add = torch.randn(xn.shape, generator=g).to(cuda).bfloat16()
     w_rot = ops.pack_weight_dgrad(w.contiguous(), torch.bfloat16)
+    if stride == 2 and R >= 2:
+        # stride-2 data gradient = four parity-class stride-1 implicit GEMMs writing a strided output lattice
+        dx = torch.full(xn.shape, float("nan"), device=cuda, dtype=torch.bfloat16)
+        _lib.call("tc_dgrad_s2_bf16", nhwc(dy).bfloat16(), w_rot, dx, IMGS, H, W, Cin, Cout, R, R, pad, Ho, Wo)
+        assert torch.isfinite(dx.float()).all()
+        assert relerr(nchw(dx), x.grad) < 1e-2
+        dx_b = ops.conv_dgrad(nhwc(dy).bfloat16(), wp, tuple(xn.shape), 2, pad, w_rot=w_rot)
+        assert torch.equal(dx_b, dx)
+        return
+    if stride == 2:
+        # stride-2 1x1: compact GEMM, scattered onto the even pixels by the epilogue of a stride-1 1x1 dgrad
+        dxc = ops.conv_dgrad_compact(nhwc(dy).bfloat16(), w_rot)
+        full = torch.zeros(IMGS, Cin, H, W, device=cuda)
+        full[:, :, ::2, ::2] = nchw(dxc).float()
+        assert relerr(full, x.grad) < 1e-2
+        C1 = 64
+        w1 = (torch.randn(C1, Cin, 1, 1, generator=g) / Cin ** 0.5).to(cuda).bfloat16().float()
+        dy1 = torch.randn(IMGS, C1, H, W, generator=g).to(cuda).bfloat16().float()
+        ref = F.conv_transpose2d(dy1, w1) + full
+        dx1 = ops.conv_dgrad(nhwc(dy1).bfloat16(), ops.pack_weight(w1.contiguous(), torch.bfloat16), tuple(xn.shape), 1, 0,
+                             addend=dxc, w_rot=ops.pack_weight_dgrad(w1.contiguous(), torch.bfloat16), addend_sub=2)
+        assert relerr(nchw(dx1), ref) < 1e-2
+        return
+    add = torch.randn(xn.shape, generator=g).to(cuda).bfloat16()
     dx = ops.conv_dgrad(nhwc(dy).bfloat16(), wp, tuple(xn.shape), 1, pad, addend=None, w_rot=w_rot)
     assert relerr(nchw(dx), x.grad) < 1e-2
     dx2 = ops.conv_dgrad(nhwc(dy).bfloat16(), wp, tuple(xn.shape), 1, pad, addend=add, w_rot=w_rot)
@@ -431,3 +452,32 @@ def test_tc_wgrad(cuda, case):
     torch.cuda.synchronize()
     assert torch.isfinite(dw).all()
     assert relerr(ops.unpack_wgrad(dw, Cin), w.grad) < 1e-3
+
+
+@pytest.mark.parametrize("case", [(6, 3, 64, 64, 64, 3), (4, 10, 32, 48, 64, 2), (2, 3, 224, 224, 64, 1),
+                                  (3, 3, 20, 36, 64, 3)])
+def test_tc_stem_s2d(cuda, case):
+    """7x7/s2/p3 stem on the space-to-depth operand (overlapping-stride TMA view): fwd + BN stats + wgrad."""
+    from adamml_b200 import ops
+    IMGS, C, H, W, Cout, G = case
+    g = torch.Generator(device="cpu").manual_seed(13)
+    x = torch.randn(IMGS, C, H, W, generator=g).to(cuda).bfloat16().float()
+    w = (torch.randn(Cout, C, 7, 7, generator=g) / (C * 49) ** 0.5).to(cuda).bfloat16().float().requires_grad_(True)
+    y_ref = F.conv2d(x, w, None, 2, 3)
+    conv = torch.nn.Conv2d(C, Cout, 7, 2, 3, bias=False)
+    assert ops.stem_s2d_ok(conv, C, H, W, torch.bfloat16)
+    xs = ops.pack_frames_s2d(x.view(IMGS, 1 * 1 * C, H, W).contiguous(), 1, 1, C)   # N=IMGS, S=F=1
+    # the s2d operand holds exactly the input pixels
+    t = xs.t[:, :, 2:2 + W // 2, :4 * C].float().view(IMGS, H // 2, W // 2, 2, 2, C)
+    assert torch.equal(t.permute(0, 5, 1, 3, 2, 4).reshape(IMGS, C, H, W), x)
+    assert xs.t[:, :, :2].abs().max() == 0 and xs.t[:, :, 2 + W // 2:].abs().max() == 0
+    stats = torch.full((G, Cout, 2), float("nan"), device=cuda, dtype=torch.float64)
+    z = ops.stem_conv_fwd(xs, w.detach().contiguous(), stats=stats, imgs_per_group=IMGS // G)
+    torch.cuda.synchronize()
+    assert relerr(nchw(z), y_ref) < 1e-2
+    zd = z.double().view(G, -1, Cout)
+    assert relerr(stats, torch.stack([zd.sum(1), (zd * zd).sum(1)], -1)) < 1e-5
+    dy = torch.randn(y_ref.shape, generator=g).to(cuda).bfloat16().float()
+    y_ref.backward(dy)
+    dw = ops.stem_wgrad(xs, nhwc(dy).bfloat16(), Cout)
+    assert relerr(dw, w.grad) < 1e-3

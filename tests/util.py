@@ -101,7 +101,8 @@ def grad_errors(named, truth, floor_frac=0.02):
     return sum(errs.values()) / len(errs), errs[worst], worst
 
 
-def assert_grads_as_good_as_reference(prod, ref32, truth64, mean_factor=2.0, max_factor=4.0):
+def assert_grads_as_good_as_reference(prod, ref32, truth64, mean_factor=2.0, max_factor=4.0, mean_floor=1e-4,
+                                      max_floor=1e-3):
     """Training gradients of tiny-batch BatchNorm nets are ill-conditioned: the reference's own fp32
     gradients differ from the float64 truth by percents (scripts/diag_grad_sensitivity.py: CPU fp32 mean
     2.5 % / worst 11 %, torch-CUDA fp32 3.5 % / 25 % on resnet50_rgb_b2).  The bar is therefore: the
@@ -110,8 +111,8 @@ def assert_grads_as_good_as_reference(prod, ref32, truth64, mean_factor=2.0, max
     rm, rx, rk = grad_errors(ref32, truth64)
     print(f"grad error vs float64 truth: product mean {pm:.3e} max {px:.3e} ({pk}); "
           f"reference-fp32 mean {rm:.3e} max {rx:.3e} ({rk})")
-    assert pm <= mean_factor * rm + 1e-4, (pm, rm)
-    assert px <= max_factor * rx + 1e-3, (px, rx, pk)
+    assert pm <= mean_factor * rm + mean_floor, (pm, rm)
+    assert px <= max_factor * rx + max_floor, (px, rx, pk)
 
 
 def oracle_run(case, seed, dtype, sd0):
