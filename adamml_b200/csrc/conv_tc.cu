@@ -49,21 +49,51 @@ struct TcCfg {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8);
+  static constexpr int STAGES = (BLOCK_N == 256) ? 3 : (BLOCK_N == 128 ? 5 : 8);
+  static constexpr int SUBTILES = BLOCK_N / 64;              // 64-column (128-byte) output sub-tiles
+  static constexpr int OUT_BYTES = SUBTILES * BLOCK_M * 128;  // bf16 staging tile for the TMA store
   static constexpr int TMEM_COLS = 2 * BLOCK_N;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + OUT_BYTES + 1024 /*align slack*/ + 1024 /*barriers, row groups*/;
 };
 
-template <int BLOCK_N, bool D_F32, bool CONV>
+constexpr int EPI_THREADS = 128;
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
+
+// per-thread running BatchNorm statistics of one (4-column group, row slice): flushed with fp64 atomics when
+// the BN group / column block changes or the CTA retires
+struct StatAcc {
+  double S[4], Q[4];
+  long long g;
+  int col;
+  __device__ __forceinline__ void reset() {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { S[i] = 0.0; Q[i] = 0.0; }
+  }
+  __device__ __forceinline__ void flush(double* __restrict__ stats, int Ncols) {
+    if (g >= 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (col + i < Ncols) {
+          double* p = stats + (g * Ncols + col + i) * 2;
+          atomicAdd(p + 0, S[i]);
+          atomicAdd(p + 1, Q[i]);
+        }
+    }
+    reset();
+  }
+};
+
+template <int BLOCK_N, bool CONV>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ ConvMaps cmaps, const __grid_constant__ ConvGeom geo,
-               void* __restrict__ Dptr, const bf16* __restrict__ addend, long long M, int Ncols, int K, long long ldd,
-               double* __restrict__ stats, long long rows_per_group) {
+               const __grid_constant__ CUtensorMap tmD, const __grid_constant__ ConvMaps cmaps,
+               const __grid_constant__ ConvGeom geo, const bf16* __restrict__ addend, long long M, int Ncols, int K,
+               long long ldd, double* __restrict__ stats, long long rows_per_group) {
   using Cfg = TcCfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint8_t* stage_out = smem + Cfg::STAGES * Cfg::STAGE_BYTES;  // 1024-aligned (all sizes are multiples of 1024)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage_out + Cfg::OUT_BYTES);
   uint64_t* empty_bar = full_bar + Cfg::STAGES;
   uint64_t* tmem_full = empty_bar + Cfg::STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -163,49 +193,56 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..5, 128 threads) =====================
+    // TMEM -> registers (thread = accumulator row) -> (+ addend) -> bf16 -> 128B-swizzled smem staging tile ->
+    // one elected thread issues the TMA store(s) (fully coalesced, edge-clipped by the tensor map);
+    // train-mode BatchNorm statistics are column sums over the staged (bf16-rounded) tile, kept in registers
+    // across the tiles of this persistent CTA.
     const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int et = q * 32 + lane;  // == accumulator row inside the tile
+    const bool issuer = (warp == 2 && lane == 0);
+    constexpr int QUADS = BLOCK_N / 4;          // 4-column (8-byte) groups per tile
+    constexpr int RSPLIT = EPI_THREADS / QUADS; // row slices per column group (2, 4 or 8)
+    // statistics role of this thread: threads are numbered by `st` so that consecutive threads take
+    // consecutive column groups (conflict-free 8-byte smem reads); thread (squad, srs) sums rows srs, srs+RSPLIT, ...
+    const int st = (warp - 2) * 32 + lane;
+    const int squad = st % QUADS, srs = st / QUADS;
+    StatAcc sa_;
+    sa_.reset();
+    sa_.g = -1;
+    sa_.col = 0;
+    int last_n_blk = -1;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int n_blk = (int)(tile % num_n_blks);
       const int m_blk = (int)(tile / num_n_blks);
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
-      long long row, arow = 0;
+      long long arow = 0;
       bool row_ok, add_ok = addend != nullptr;
-      long long g_lo = 0, g_hi = 0, my_g = 0;
+      int w0 = 0, h0 = 0, i0 = 0;
       if (CONV) {
-        const int ml = q * 32 + lane;
-        const int ow = (m_blk % geo.tiles_w) * geo.BW + ml % geo.BW;
-        const int oh = ((m_blk / geo.tiles_w) % geo.tiles_h) * geo.BH + (ml / geo.BW) % geo.BH;
-        const int img = (m_blk / (geo.tiles_w * geo.tiles_h)) * geo.BI + ml / (geo.BW * geo.BH);
+        w0 = (m_blk % geo.tiles_w) * geo.BW;
+        h0 = ((m_blk / geo.tiles_w) % geo.tiles_h) * geo.BH;
+        i0 = (m_blk / (geo.tiles_w * geo.tiles_h)) * geo.BI;
+        const int ow = w0 + et % geo.BW;
+        const int oh = h0 + (et / geo.BW) % geo.BH;
+        const int img = i0 + et / (geo.BW * geo.BH);
         row_ok = ow < geo.Wo && oh < geo.Ho && img < geo.IMGS;
-        row = ((long long)img * geo.out_H + oh * geo.out_s + geo.out_ph) * geo.out_W + ow * geo.out_s + geo.out_pw;
-        arow = row;
+        arow = ((long long)img * geo.out_H + oh * geo.out_s + geo.out_ph) * geo.out_W + ow * geo.out_s + geo.out_pw;
         if (geo.addend_sub == 2) {
           add_ok = add_ok && !((oh | ow) & 1);
           arow = ((long long)img * geo.add_H + (oh >> 1)) * geo.add_W + (ow >> 1);
         }
-        if (stats) {
-          const int gi = row_ok ? img / geo.imgs_per_group : -1;
-          my_g = gi;
-          g_hi = __reduce_max_sync(0xffffffffu, gi);
-          g_lo = __reduce_min_sync(0xffffffffu, row_ok ? gi : 0x7fffffff);
-        }
       } else {
-        row = (long long)m_blk * BLOCK_M + q * 32 + lane;
+        const long long row = (long long)m_blk * BLOCK_M + et;
         arow = row;
         row_ok = row < M;
-        // BN groups touched by this warp's 32 rows
-        if (stats) {
-          long long r0 = (long long)m_blk * BLOCK_M + q * 32;
-          long long r1 = r0 + 31 < M - 1 ? r0 + 31 : M - 1;
-          g_lo = r0 / rows_per_group;
-          g_hi = r1 / rows_per_group;
-          my_g = row_ok ? row / rows_per_group : -1;
-        }
       }
+      // the staging tile (and row_group) of the previous tile must have been consumed
+      if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      epi_bar_sync();
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
 #pragma unroll 1
       for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
         const int col0 = n_blk * BLOCK_N + chunk * 32;
@@ -214,7 +251,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + chunk * 32), r);
         float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        for (int j = 0; j < 32; ++j) v[j] = row_ok ? __uint_as_float(r[j]) : 0.f;
         if (add_ok && row_ok) {
           const bf16* ap = addend + arow * ldd + col0;
 #pragma unroll
@@ -231,72 +268,97 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
         }
-        if (!D_F32) {
+        // staging address: sub-tile (chunk / 2), row et, logical 16-byte chunk c -> physical c ^ (et & 7)
+        uint8_t* srow = stage_out + (chunk >> 1) * (BLOCK_M * 128) + et * 128;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
-        }
-        if (row_ok) {
-          if (D_F32) {
-            float* dst = reinterpret_cast<float*>(Dptr) + row * ldd + col0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              if (col0 + j < Ncols)
-                *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          } else {
-            bf16* dst = reinterpret_cast<bf16*>(Dptr) + row * ldd + col0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              if (col0 + j < Ncols) {
-                __nv_bfloat162 p0 = __floats2bfloat162_rn(v[j], v[j + 1]);
-                __nv_bfloat162 p1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-                __nv_bfloat162 p2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
-                __nv_bfloat162 p3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-                uint4 pk;
-                pk.x = *reinterpret_cast<uint32_t*>(&p0);
-                pk.y = *reinterpret_cast<uint32_t*>(&p1);
-                pk.z = *reinterpret_cast<uint32_t*>(&p2);
-                pk.w = *reinterpret_cast<uint32_t*>(&p3);
-                *reinterpret_cast<uint4*>(dst + j) = pk;
-              }
-            }
-          }
-        }
-        if (stats) {
-          for (long long g = g_lo; g <= g_hi; ++g) {
-            // column sums over this warp's rows that belong to group g: recursive-halving
-            // transpose-reduce, 31 shuffles per quantity; lane j ends with column j.
-            float s[32], qq[32];
-            const bool mine = (my_g == g);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) { s[j] = mine ? v[j] : 0.f; qq[j] = s[j] * s[j]; }
-#pragma unroll
-            for (int half = 16; half >= 1; half >>= 1) {
-              const bool upper = (lane & half) != 0;
-#pragma unroll
-              for (int j = 0; j < half; ++j) {
-                // keep the half of the columns selected by this lane bit, send the other half
-                float keep_s = upper ? s[j + half] : s[j];
-                float send_s = upper ? s[j] : s[j + half];
-                float keep_q = upper ? qq[j + half] : qq[j];
-                float send_q = upper ? qq[j] : qq[j + half];
-                s[j] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, half);
-                qq[j] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, half);
-              }
-            }
-            // after the loop lane L holds column index L (bits assembled MSB-first)
-            const int col = col0 + lane;
-            if (col < Ncols) {
-              atomicAdd(&stats[(g * Ncols + col) * 2 + 0], (double)s[0]);
-              atomicAdd(&stats[(g * Ncols + col) * 2 + 1], (double)qq[0]);
-            }
-          }
+        for (int j = 0; j < 32; j += 8) {
+          __nv_bfloat162 p0 = __floats2bfloat162_rn(v[j], v[j + 1]);
+          __nv_bfloat162 p1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+          __nv_bfloat162 p2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
+          __nv_bfloat162 p3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+          uint4 pk;
+          pk.x = *reinterpret_cast<uint32_t*>(&p0);
+          pk.y = *reinterpret_cast<uint32_t*>(&p1);
+          pk.z = *reinterpret_cast<uint32_t*>(&p2);
+          pk.w = *reinterpret_cast<uint32_t*>(&p3);
+          const int c = (chunk & 1) * 4 + (j >> 3);
+          *reinterpret_cast<uint4*>(srow + ((c ^ (et & 7)) << 4)) = pk;
         }
       }
+      // accumulator drained: hand the TMEM stage back to the MMA warp
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      // publish the staged tile to the async proxy and store it
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      epi_bar_sync();
+      if (issuer) {
+#pragma unroll
+        for (int sub = 0; sub < Cfg::SUBTILES; ++sub) {
+          const int col = n_blk * BLOCK_N + sub * 64;
+          if (col < Ncols) {
+            if (CONV) tma_store_4d(&tmD, stage_out + sub * (BLOCK_M * 128), col, w0, h0, i0);
+            else tma_store_2d(&tmD, stage_out + sub * (BLOCK_M * 128), col, m_blk * BLOCK_M);
+          }
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      if (stats) {
+        if (n_blk != last_n_blk) {
+          sa_.flush(stats, Ncols);
+          last_n_blk = n_blk;
+          sa_.col = n_blk * BLOCK_N + squad * 4;
+        }
+        if (sa_.col < Ncols) {
+          // rows of a tile are ordered by BN group, so the tile is a few row segments of constant group;
+          // invalid rows were staged as zeros and may be summed into any group
+          const uint8_t* sbase = stage_out + (squad >> 4) * (BLOCK_M * 128) + ((squad & 1) << 3);
+          const int c = (squad & 15) >> 1;
+          int r0 = 0;
+          while (r0 < BLOCK_M) {
+            long long g;
+            int r1;
+            if (CONV) {
+              const int pb = geo.BW * geo.BH;
+              const int img = i0 + r0 / pb;
+              if (img >= geo.IMGS) break;
+              g = img / geo.imgs_per_group;
+              const long long e = ((g + 1) * geo.imgs_per_group - i0) * pb;
+              r1 = e < BLOCK_M ? (int)e : BLOCK_M;
+            } else {
+              const long long row0 = (long long)m_blk * BLOCK_M;
+              if (row0 + r0 >= M) break;
+              g = (row0 + r0) / rows_per_group;
+              const long long e = (g + 1) * rows_per_group - row0;
+              r1 = e < BLOCK_M ? (int)e : BLOCK_M;
+            }
+            if (g != sa_.g) {
+              sa_.flush(stats, Ncols);
+              sa_.g = g;
+            }
+            float s[4] = {0.f, 0.f, 0.f, 0.f}, qq[4] = {0.f, 0.f, 0.f, 0.f};
+            // first row of this thread's slice inside [r0, r1)
+            int rw = r0 + ((srs - r0) % RSPLIT + RSPLIT) % RSPLIT;
+#pragma unroll 8
+            for (; rw < r1; rw += RSPLIT) {
+              const uint2 pk = *reinterpret_cast<const uint2*>(sbase + rw * 128 + ((c ^ (rw & 7)) << 4));
+              const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk.x));
+              const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk.y));
+              s[0] += f0.x; qq[0] = fmaf(f0.x, f0.x, qq[0]);
+              s[1] += f0.y; qq[1] = fmaf(f0.y, f0.y, qq[1]);
+              s[2] += f1.x; qq[2] = fmaf(f1.x, f1.x, qq[2]);
+              s[3] += f1.y; qq[3] = fmaf(f1.y, f1.y, qq[3]);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { sa_.S[i] += (double)s[i]; sa_.Q[i] += (double)qq[i]; }
+            r0 = r1;
+          }
+        }
+      }
     }
+    if (stats) sa_.flush(stats, Ncols);
+    if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   tc_fence_before();
@@ -328,13 +390,13 @@ int make_map_2d(CUtensorMap* map, const void* ptr, long long rows, long long col
   return ADAMML_OK;
 }
 
-template <int BLOCK_N, bool D_F32, bool CONV>
-int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvMaps& cm, const ConvGeom& geo, void* D,
-              const void* addend, long long M, int Ncols, int K, long long ldd, double* stats, long long rpg,
-              cudaStream_t stream) {
+template <int BLOCK_N, bool CONV>
+int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, const ConvMaps& cm,
+              const ConvGeom& geo, const void* addend, long long M, int Ncols, int K, long long ldd, double* stats,
+              long long rpg, cudaStream_t stream) {
   using Cfg = TcCfg<BLOCK_N>;
   static bool configured = false;
-  auto kern = tc_gemm_kernel<BLOCK_N, D_F32, CONV>;
+  auto kern = tc_gemm_kernel<BLOCK_N, CONV>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) {
@@ -347,19 +409,17 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvMaps& cm
   long long tiles = m_blks * ((Ncols + BLOCK_N - 1) / BLOCK_N);
   const int sms = num_sms();
   int grid = (int)(tiles < sms ? tiles : sms);
-  kern<<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, cm, geo, D, (const bf16*)addend, M, Ncols, K, ldd,
+  kern<<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmD, cm, geo, (const bf16*)addend, M, Ncols, K, ldd,
                                                         stats, rpg);
   return adamml_check_launch(CONV ? "tc_conv" : "tc_gemm");
 }
 
 template <bool CONV>
-int dispatch_tc(int block_n, bool f32, const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvMaps& cm,
-                const ConvGeom& geo, void* D, const void* addend, long long M, int Ncols, int K, long long ldd,
-                double* stats, long long rpg, cudaStream_t stream) {
-#define ADAMML_TC_CASE(BN)                                                                                      \
-  if (block_n == BN)                                                                                            \
-    return f32 ? launch_tc<BN, true, CONV>(tmA, tmB, cm, geo, D, addend, M, Ncols, K, ldd, stats, rpg, stream)  \
-               : launch_tc<BN, false, CONV>(tmA, tmB, cm, geo, D, addend, M, Ncols, K, ldd, stats, rpg, stream);
+int dispatch_tc(int block_n, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, const ConvMaps& cm,
+                const ConvGeom& geo, const void* addend, long long M, int Ncols, int K, long long ldd, double* stats,
+                long long rpg, cudaStream_t stream) {
+#define ADAMML_TC_CASE(BN) \
+  if (block_n == BN) return launch_tc<BN, CONV>(tmA, tmB, tmD, cm, geo, addend, M, Ncols, K, ldd, stats, rpg, stream);
   ADAMML_TC_CASE(64)
   ADAMML_TC_CASE(128)
   ADAMML_TC_CASE(256)
@@ -384,11 +444,17 @@ int run_conv(const ConvGeom& geo, const ConvMaps& cm, const void* w, long long w
   CUtensorMap tmB;
   int rc = make_map_2d(&tmB, w, Cout, w_ld, w_ld, block_n);
   if (rc) return rc;
+  // output view: the (possibly strided) pixel lattice this launch writes, same {64 ch, BW, BH, BI} boxes as the input
+  CUtensorMap tmD;
+  rc = make_map_4d(&tmD, (const bf16*)y + ((long long)geo.out_ph * geo.out_W + geo.out_pw) * Cout, Cout, geo.Wo, geo.Ho,
+                   geo.IMGS, (long long)geo.out_s * Cout, (long long)geo.out_s * geo.out_W * Cout,
+                   (long long)geo.out_H * geo.out_W * Cout, geo.BW, geo.BH, geo.BI);
+  if (rc) return rc;
   if (stats) {
     int G = (geo.IMGS + geo.imgs_per_group - 1) / geo.imgs_per_group;
     cudaMemsetAsync(stats, 0, sizeof(double) * (size_t)G * Cout * 2, stream);
   }
-  return dispatch_tc<true>(block_n, false, tmB, tmB, cm, geo, y, addend, (long long)geo.IMGS * geo.Ho * geo.Wo, Cout,
+  return dispatch_tc<true>(block_n, tmB, tmB, tmD, cm, geo, addend, (long long)geo.IMGS * geo.Ho * geo.Wo, Cout,
                            geo.ntaps * geo.kb_per_tap * BLOCK_K, Cout, stats, 0, stream);
 }
 
@@ -420,7 +486,10 @@ int adamml_tc_gemm_bf16(const void* A, const void* B, void* D, long long M, int 
   }
   ADAMML_REQUIRE(((uintptr_t)A % 16) == 0 && ((uintptr_t)B % 16) == 0 && ((uintptr_t)D % 16) == 0,
                  "tc_gemm: operands must be 16-byte aligned");
-  ADAMML_REQUIRE(d_dtype == ADAMML_F32 || d_dtype == ADAMML_BF16, "tc_gemm: bad output dtype");
+  if (d_dtype != ADAMML_BF16) {
+    adamml_set_error("tc_gemm: only bf16 output (the epilogue stages bf16 tiles for the TMA store)");
+    return ADAMML_ERR_UNSUPPORTED;
+  }
   ADAMML_REQUIRE(!stats || rows_per_group > 0, "tc_gemm: stats need rows_per_group");
   const int block_n = Ncols <= 64 ? 64 : (Ncols <= 128 ? 128 : 256);
   CUtensorMap tmA, tmB;
@@ -432,13 +501,14 @@ int adamml_tc_gemm_bf16(const void* A, const void* B, void* D, long long M, int 
     long long G = (M + rows_per_group - 1) / rows_per_group;
     cudaMemsetAsync(stats, 0, sizeof(double) * (size_t)G * Ncols * 2, stream);
   }
-  const bool f32 = d_dtype == ADAMML_F32;
+  CUtensorMap tmD;
+  rc = make_map_2d(&tmD, D, M, Ncols, ldd, BLOCK_M);
+  if (rc) return rc;
   ConvMaps cm;
   ConvGeom geo;
   memset(&cm, 0, sizeof(cm));
   memset(&geo, 0, sizeof(geo));
-  return dispatch_tc<false>(block_n, f32, tmA, tmB, cm, geo, D, nullptr, M, Ncols, K, ldd, stats, rows_per_group,
-                            stream);
+  return dispatch_tc<false>(block_n, tmA, tmB, tmD, cm, geo, nullptr, M, Ncols, K, ldd, stats, rows_per_group, stream);
 }
 
 int adamml_tc_conv_supported(int Cin, int Cout, int R, int S, int stride) {
