@@ -108,7 +108,7 @@ def call(name, *args, allow_unsupported=False):
         e0.record()
         rc = fn(*[_conv(a) for a in args], stream)
         e1.record()
-        PROFILE.append((name, e0, e1, tuple(None if isinstance(a, torch.Tensor) else a for a in args)))
+        PROFILE.append((name, e0, e1, tuple("T" if isinstance(a, torch.Tensor) else a for a in args)))
     else:
         rc = fn(*[_conv(a) for a in args], stream)
     if rc != 0:

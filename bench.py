@@ -167,18 +167,58 @@ def run_reference_arm(a):
 
 
 # ------------------------------------------------------------------------------------------- GPU arm
-def kernel_flops(name, args):
-    """Algorithmic FLOPs of one C-ABI call from its scalar arguments (dense GEMM-shaped ops only)."""
+def kernel_work(name, a):
+    """(algorithmic FLOPs, algorithmic HBM bytes) of one C-ABI call from its arguments: tensors read + written once
+    (DESIGN.md §3); `a` holds "T" for tensor arguments, None for absent ones, scalars otherwise."""
+    T = lambda i: a[i] == "T"
     if name == "tc_gemm_bf16":
-        M, N, K = args[3], args[4], args[5]
-        return 2.0 * M * N * K
+        M, N, K = a[3], a[4], a[5]
+        return 2.0 * M * N * K, 2.0 * M * (N + K)
+    if name == "tc_conv_bf16":
+        I, H, W, Ci, Co, R, S, st, pad, Ho, Wo = a[4:15]
+        return 2.0 * I * Ho * Wo * Co * R * S * Ci, 2.0 * (I * H * W * Ci + I * Ho * Wo * Co * (2 if T(3) else 1))
+    if name == "tc_dgrad_s2_bf16":
+        I, H, W, Ci, Co, R, S, pad, Ho, Wo = a[3:13]
+        return 2.0 * I * Ho * Wo * Co * R * S * Ci, 2.0 * (I * H * W * Ci + I * Ho * Wo * Co)
+    if name == "tc_wgrad_bf16":
+        I, H, W, Ci, Co, R, S, st, pad, Ho, Wo = a[3:14]
+        return 2.0 * I * Ho * Wo * Co * R * S * Ci, 2.0 * (I * H * W * Ci + I * Ho * Wo * Co)
+    if name in ("tc_stem_conv_bf16", "tc_stem_wgrad_bf16"):
+        I, Hs, Wp, Cs, Co, Ho, Wo = a[3:10]
+        return 2.0 * I * Ho * Wo * Co * 16 * Cs, 2.0 * (I * Hs * Wp * Cs + I * Ho * Wo * Co)
     if name in ("simt_conv_fwd", "simt_conv_wgrad"):
-        IMGS, H, W, Cin, Cout, R, S, st, pad, Ho, Wo = args[3:14]
-        return 2.0 * IMGS * Ho * Wo * Cout * R * S * Cin
+        I, H, W, Ci, Co, R, S, st, pad, Ho, Wo = a[3:14]
+        esz = 2 if a[17] == 1 else 4
+        return 2.0 * I * Ho * Wo * Co * R * S * Ci, float(esz) * (I * H * W * Ci + I * Ho * Wo * Co)
     if name == "simt_conv_dgrad":
-        IMGS, H, W, Cin, Cout, R, S, st, pad, Ho, Wo = args[4:15]
-        return 2.0 * IMGS * Ho * Wo * Cout * R * S * Cin
-    return 0.0
+        I, H, W, Ci, Co, R, S, st, pad, Ho, Wo = a[4:15]
+        esz = 2 if a[18] == 1 else 4
+        return 2.0 * I * Ho * Wo * Co * R * S * Ci, float(esz) * (I * H * W * Ci + I * Ho * Wo * Co)
+    if name == "bn_apply":
+        n = a[6] * a[7] * a[8]
+        return 0.0, (2 if a[10] == 1 else 4) * n * (2.0 + (1 if T(2) or T(3) else 0))
+    if name == "bn_stats":
+        return 0.0, (2 if a[5] == 1 else 4) * float(a[2] * a[3] * a[4])
+    if name == "bn_bwd_reduce":
+        n = a[5] * a[6] * a[7]
+        return 0.0, (2 if a[9] == 1 else 4) * n * (2.0 + (1 if a[8] else 0))
+    if name == "bn_bwd_apply":
+        n = a[8] * a[9] * a[10]
+        return 0.0, (2 if a[14] == 1 else 4) * n * (1.0 + (1 if a[12] else 0) + (2 if T(6) else 0) + (1 if T(7) else 0))
+    if name in ("dwconv_fwd", "dwconv_dgrad"):
+        o = 0 if name == "dwconv_fwd" else 1
+        I, H, W, C, st, Ho, Wo, dt = a[3 + o:11 + o]
+        return 2.0 * 9 * I * Ho * Wo * C, (2 if dt == 1 else 4) * float(I * H * W * C + I * Ho * Wo * C)
+    if name == "dwconv_wgrad":
+        I, H, W, C, st, Ho, Wo, dt = a[3:11]
+        return 2.0 * 9 * I * Ho * Wo * C, (2 if dt == 1 else 4) * float(I * H * W * C + I * Ho * Wo * C)
+    if name == "maxpool3x3s2_fwd":
+        I, H, W, C, Ho, Wo, dt = a[3:10]
+        return 0.0, (2 if dt == 1 else 4) * float(I * H * W * C + I * Ho * Wo * C) + I * Ho * Wo * C
+    if name == "maxpool3x3s2_bwd":
+        I, H, W, C, Ho, Wo, dt = a[4:11]
+        return 0.0, (2 if dt == 1 else 4) * float(I * H * W * C + I * Ho * Wo * C) + I * Ho * Wo * C
+    return 0.0, 0.0
 
 
 def run_gpu_arm(a):
@@ -271,15 +311,17 @@ def run_gpu_arm(a):
         torch.cuda.synchronize()
         agg = {}
         for name, e0, e1, args in _lib.PROFILE:
-            d = agg.setdefault(name, [0.0, 0, 0.0])
+            d = agg.setdefault(name, [0.0, 0, 0.0, 0.0])
+            fl, by = kernel_work(name, args)
             d[0] += e0.elapsed_time(e1)
             d[1] += 1
-            d[2] += kernel_flops(name, args)
+            d[2] += fl
+            d[3] += by
         if a.dump_calls:
             with open(a.dump_calls, "w") as f:
                 for name, e0, e1, args in _lib.PROFILE:
                     f.write(json.dumps({"op": name, "ms": round(e0.elapsed_time(e1), 4),
-                                        "args": [x for x in args if x is not None]}) + "\n")
+                                        "args": [x for x in args if x is not None and x != "T"]}) + "\n")
         _lib.PROFILE = None
         prof = sorted(agg.items(), key=lambda kv: -kv[1][0])
 
@@ -305,13 +347,27 @@ def run_gpu_arm(a):
         "step_tflops": FLOP_PER_CLIP * N / (ms / a.steps / 1e3) / 1e12 if modality == ["rgb", "sound"] else None,
     }
     if prof:
+        # dominant kernel family = largest share of the step's device time (CUDA events around every launch on the
+        # launching stream); its roofline is HBM unless its arithmetic intensity exceeds the ridge
         total = sum(v[0] for _, v in prof)
-        name, (t_ms, cnt, fl) = next(((n, v) for n, v in prof if v[2] > 0), prof[0])
-        ach = fl / (t_ms / 1e3) / 1e12 if t_ms > 0 else 0.0
-        out["roofline"] = {"bound": "tensor", "kernel": name, "achieved": ach, "peak": pk["tf_sus"], "unit": "TFLOP/s",
-                           "frac": ach / pk["tf_sus"], "traffic": None, "peak_source": pk["src"] + " (sustained)",
-                           "launches_per_step": cnt, "share_of_step": t_ms / total}
-        out["kernel_breakdown_ms"] = {n: round(v[0], 2) for n, v in prof[:12]}
+        name, (t_ms, cnt, fl, by) = prof[0]
+        ridge = pk["tf_sus"] * 1e12 / (pk["hbm"] * 1e9)
+        if by > 0 and fl / by < ridge:
+            ach = by / (t_ms / 1e3) / 1e9
+            out["roofline"] = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
+                               "frac": ach / pk["hbm"], "traffic": None, "peak_source": pk["src"],
+                               "algorithmic_bytes_per_launch": by / cnt, "launches_per_step": cnt,
+                               "avg_launch_ms": t_ms / cnt, "share_of_step": t_ms / total}
+        else:
+            ach = fl / (t_ms / 1e3) / 1e12 if t_ms > 0 else 0.0
+            out["roofline"] = {"bound": "tensor", "kernel": name, "achieved": ach, "peak": pk["tf_sus"],
+                               "unit": "TFLOP/s", "frac": ach / pk["tf_sus"], "traffic": None,
+                               "peak_source": pk["src"] + " (sustained)", "launches_per_step": cnt,
+                               "avg_launch_ms": t_ms / cnt, "share_of_step": t_ms / total}
+        if out.get("step_tflops"):
+            out["step_tensor_frac"] = out["step_tflops"] / pk["tf_sus"]
+        out["kernel_breakdown_ms"] = {n: round(v[0], 2) for n, v in prof[:14]}
+        out["kernel_gbs"] = {n: round(v[3] / (v[0] / 1e3) / 1e9) for n, v in prof[:14] if v[3] > 0 and v[0] > 0}
     if world == 1 and not a.no_cpu_baseline:
         n_clips = 2
         t = cpu_step_time(modality, S, n_clips, 2, 1)
