@@ -298,13 +298,16 @@ bn_apply_rows_kernel(const T* __restrict__ z, const float* __restrict__ ss, cons
 // Persistent over row chunks: block b of a group handles chunks b, b+bpg, ...; per-thread partial sums
 // in fp32 over <= 16 rows are flushed into wide accumulators, one smem reduction + 2 atomics per
 // (block, channel) at the end.
-template <typename T, int MODE>
-__global__ void __launch_bounds__(EW_THREADS)
+template <typename T, int MODE, bool MASKZ>
+__global__ void __launch_bounds__(EW_THREADS, 2)
 bn_reduce_rows_kernel(const T* __restrict__ a /*z | dout*/, const T* __restrict__ out, const T* __restrict__ z,
-                      const float* __restrict__ mean_invstd, double* __restrict__ sums, long long rows_per_group,
-                      int C, int cpb, int k, int blocks_per_group, int act) {
+                      const float* __restrict__ mean_invstd, const float* __restrict__ mss,
+                      double* __restrict__ sums, long long rows_per_group, int C, int cpb, int k,
+                      int blocks_per_group, int act) {
   constexpr int V = VecIO<T>::N;
-  constexpr int CH = 4;  // row iterations per flush (x EW_UNROLL rows)
+  // bf16 backward mode streams three tensors: unroll 2 keeps the kernel at <= 128 registers (2 CTAs / SM)
+  constexpr int UN = (MODE == 1 && sizeof(T) == 2) ? 2 : EW_UNROLL;
+  constexpr int CH = 16 / UN;  // row iterations per flush
   extern __shared__ double shd[];
   const int cl = threadIdx.x % cpb, rl = threadIdx.x / cpb;
   const int c0 = (blockIdx.y * cpb + cl) * V;
@@ -319,43 +322,60 @@ bn_reduce_rows_kernel(const T* __restrict__ a /*z | dout*/, const T* __restrict_
     float mean[V], invstd[V];
 #pragma unroll
     for (int i = 0; i < V; ++i) { mean[i] = 0.f; invstd[i] = 1.f; }
+    float msc[V], msh[V];  // forward scale/shift: the activation mask is recomputed from z instead of reading `out`
+#pragma unroll
+    for (int i = 0; i < V; ++i) { msc[i] = 0.f; msh[i] = 0.f; }
     if (MODE == 1) {
 #pragma unroll
       for (int i = 0; i < V; ++i) {
         const float2 p = *reinterpret_cast<const float2*>(mean_invstd + ((long long)g * C + c0 + i) * 2);
         mean[i] = p.x; invstd[i] = p.y;
       }
+      if (MASKZ) {
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          const float2 p = *reinterpret_cast<const float2*>(mss + ((long long)g * C + c0 + i) * 2);
+          msc[i] = p.x; msh[i] = p.y;
+        }
+      }
     }
     const long long base = (long long)g * rows_per_group * C + c0;
-    const long long chunk_rows = (long long)k * EW_UNROLL * CH;
+    const long long chunk_rows = (long long)k * UN * CH;
     for (long long rc = (long long)bg * chunk_rows; rc < rows_per_group; rc += (long long)blocks_per_group * chunk_rows) {
       long long r1 = rc + chunk_rows;
       if (r1 > rows_per_group) r1 = rows_per_group;
       acc_t s[V], q[V];
 #pragma unroll
       for (int i = 0; i < V; ++i) { s[i] = 0; q[i] = 0; }
-      for (long long r = rc + rl; r < r1; r += (long long)k * EW_UNROLL) {
-        typename VecIO<T>::raw qa[EW_UNROLL], qz[EW_UNROLL], qo[EW_UNROLL];
+      for (long long r = rc + rl; r < r1; r += (long long)k * UN) {
+        typename VecIO<T>::raw qa[UN], qz[UN], qo[UN];
 #pragma unroll
-        for (int u = 0; u < EW_UNROLL; ++u) {
+        for (int u = 0; u < UN; ++u) {
           const long long rr = r + (long long)u * k;
           if (rr < r1) {
             qa[u] = VecIO<T>::load_raw(a + base + rr * C);
             if (MODE == 1) {
               qz[u] = VecIO<T>::load_raw(z + base + rr * C);
-              if (act != ADAMML_ACT_NONE) qo[u] = VecIO<T>::load_raw(out + base + rr * C);
+              if (act != ADAMML_ACT_NONE && !MASKZ) qo[u] = VecIO<T>::load_raw(out + base + rr * C);
             }
           }
         }
 #pragma unroll
-        for (int u = 0; u < EW_UNROLL; ++u) {
+        for (int u = 0; u < UN; ++u) {
           const long long rr = r + (long long)u * k;
           if (rr < r1) {
             float va[V], vz[V], vo[V];
             VecIO<T>::unpack(qa[u], va);
             if (MODE == 1) {
               VecIO<T>::unpack(qz[u], vz);
-              if (act != ADAMML_ACT_NONE) VecIO<T>::unpack(qo[u], vo);
+              if (act != ADAMML_ACT_NONE) {
+                if (MASKZ) {
+#pragma unroll
+                  for (int i = 0; i < V; ++i) vo[i] = fmaf(vz[i], msc[i], msh[i]);
+                } else {
+                  VecIO<T>::unpack(qo[u], vo);
+                }
+              }
             }
 #pragma unroll
             for (int i = 0; i < V; ++i) {
@@ -397,13 +417,13 @@ bn_reduce_rows_kernel(const T* __restrict__ a /*z | dout*/, const T* __restrict_
 }
 
 // training: dz = gamma*invstd*(gm - sum_g/cnt - xhat*sum_gx/cnt);  eval: dz = gamma*invstd*gm ; dres = gm
-template <typename T>
-__global__ void __launch_bounds__(EW_THREADS)
+template <typename T, bool MASKZ>
+__global__ void __launch_bounds__(EW_THREADS, 2)
 bn_bwd_apply_rows_kernel(const T* __restrict__ dout, const T* __restrict__ out, const T* __restrict__ z,
                          const float* __restrict__ mean_invstd, const float* __restrict__ gamma,
-                         const double* __restrict__ sums, T* __restrict__ dz, T* __restrict__ dres,
-                         long long rows_per_group, int C, int cpb, int k, int rows_per_block, int blocks_per_group,
-                         double count, int act, int training) {
+                         const float* __restrict__ mss, const double* __restrict__ sums, T* __restrict__ dz,
+                         T* __restrict__ dres, long long rows_per_group, int C, int cpb, int k, int rows_per_block,
+                         int blocks_per_group, double count, int act, int training) {
   constexpr int V = VecIO<T>::N;
   const int cl = threadIdx.x % cpb, rl = threadIdx.x / cpb;
   const int c0 = (blockIdx.y * cpb + cl) * V;
@@ -427,8 +447,18 @@ bn_bwd_apply_rows_kernel(const T* __restrict__ dout, const T* __restrict__ out, 
       m2[i] = (float)sums[gc * 2 + 1] * inv_count;
     }
   }
+  float msc[V], msh[V];  // forward scale/shift (MASKZ): mask = act'(z*scale+shift)
+#pragma unroll
+  for (int i = 0; i < V; ++i) { msc[i] = 0.f; msh[i] = 0.f; }
+  if (MASKZ) {
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float2 p = *reinterpret_cast<const float2*>(mss + ((long long)g * C + c0 + i) * 2);
+      msc[i] = p.x; msh[i] = p.y;
+    }
+  }
   const long long base = (long long)g * rows_per_group * C + c0;
-  const bool need_z = training && dz;
+  const bool need_z = (training && dz) || (MASKZ && act != ADAMML_ACT_NONE);
   for (long long r = r0 + rl; r < r1; r += (long long)k * EW_UNROLL) {
     typename VecIO<T>::raw qg[EW_UNROLL], qz[EW_UNROLL], qo[EW_UNROLL];
 #pragma unroll
@@ -436,7 +466,7 @@ bn_bwd_apply_rows_kernel(const T* __restrict__ dout, const T* __restrict__ out, 
       const long long rr = r + (long long)u * k;
       if (rr < r1) {
         qg[u] = VecIO<T>::load_raw(dout + base + rr * C);
-        if (act != ADAMML_ACT_NONE) qo[u] = VecIO<T>::load_raw(out + base + rr * C);
+        if (act != ADAMML_ACT_NONE && !MASKZ) qo[u] = VecIO<T>::load_raw(out + base + rr * C);
         if (need_z) qz[u] = VecIO<T>::load_raw(z + base + rr * C);
       }
     }
@@ -448,7 +478,12 @@ bn_bwd_apply_rows_kernel(const T* __restrict__ dout, const T* __restrict__ out, 
         VecIO<T>::unpack(qg[u], gm);
         if (need_z) VecIO<T>::unpack(qz[u], vz);
         if (act != ADAMML_ACT_NONE) {
-          VecIO<T>::unpack(qo[u], vo);
+          if (MASKZ) {
+#pragma unroll
+            for (int i = 0; i < V; ++i) vo[i] = fmaf(vz[i], msc[i], msh[i]);
+          } else {
+            VecIO<T>::unpack(qo[u], vo);
+          }
 #pragma unroll
           for (int i = 0; i < V; ++i) if (!act_pass(vo[i], act)) gm[i] = 0.f;
         }
@@ -518,7 +553,7 @@ int adamml_bn_stats(const void* z, double* sums, long long rows_per_group, int C
       const int bpg = reduce_bpg(rg, rows_per_group, G);
       const size_t sm = sizeof(double) * rg.threads * 2 * VecIO<T>::N;
       dim3 vg((unsigned)(bpg * (long long)G), rg.cchunks);
-      bn_reduce_rows_kernel<T, 0><<<vg, rg.threads, sm, stream>>>((const T*)z, nullptr, nullptr, nullptr, sums,
+      bn_reduce_rows_kernel<T, 0, false><<<vg, rg.threads, sm, stream>>>((const T*)z, nullptr, nullptr, nullptr, nullptr, sums,
                                                                   rows_per_group, C, rg.cpb, rg.k, bpg, 0);
     } else {
       int bpg = ceil_div(rows_per_group, ROWS_PER_BLOCK);
@@ -567,10 +602,12 @@ int adamml_bn_apply(const void* z, const float* scale_shift, const void* res, co
   return adamml_check_launch("bn_apply");
 }
 
-int adamml_bn_bwd_reduce(const void* dout, const void* out, const void* z, const float* mean_invstd, double* sums,
-                         long long rows_per_group, int C, int G, int act, int dtype, cudaStream_t stream) {
+int adamml_bn_bwd_reduce(const void* dout, const void* out, const void* z, const float* mean_invstd,
+                         const float* mask_scale_shift, double* sums, long long rows_per_group, int C, int G, int act,
+                         int dtype, cudaStream_t stream) {
   ADAMML_REQUIRE(rows_per_group > 0 && C > 0 && G > 0, "bn_bwd_reduce: empty dims");
-  ADAMML_REQUIRE(act == ADAMML_ACT_NONE || out, "bn_bwd_reduce: activation mask needs the saved output");
+  ADAMML_REQUIRE(act == ADAMML_ACT_NONE || out || mask_scale_shift,
+                 "bn_bwd_reduce: activation mask needs the saved output or the forward scale/shift");
   cudaMemsetAsync(sums, 0, sizeof(double) * (size_t)G * C * 2, stream);
   ADAMML_DISPATCH_DTYPE(dtype, T, {
     if (vec_ok<T>(C, dout, out, z)) {
@@ -578,10 +615,16 @@ int adamml_bn_bwd_reduce(const void* dout, const void* out, const void* z, const
       const int bpg = reduce_bpg(rg, rows_per_group, G);
       const size_t sm = sizeof(double) * rg.threads * 2 * VecIO<T>::N;
       dim3 vg((unsigned)(bpg * (long long)G), rg.cchunks);
-      bn_reduce_rows_kernel<T, 1><<<vg, rg.threads, sm, stream>>>((const T*)dout, (const T*)out, (const T*)z,
-                                                                  mean_invstd, sums, rows_per_group, C, rg.cpb, rg.k,
-                                                                  bpg, act);
+      if (mask_scale_shift && act != ADAMML_ACT_NONE)
+        bn_reduce_rows_kernel<T, 1, true><<<vg, rg.threads, sm, stream>>>((const T*)dout, nullptr, (const T*)z,
+                                                                          mean_invstd, mask_scale_shift, sums,
+                                                                          rows_per_group, C, rg.cpb, rg.k, bpg, act);
+      else
+        bn_reduce_rows_kernel<T, 1, false><<<vg, rg.threads, sm, stream>>>((const T*)dout, (const T*)out, (const T*)z,
+                                                                           mean_invstd, nullptr, sums, rows_per_group,
+                                                                           C, rg.cpb, rg.k, bpg, act);
     } else {
+      ADAMML_REQUIRE(act == ADAMML_ACT_NONE || out, "bn_bwd_reduce: ragged channel count needs the saved output");
       int bpg = ceil_div(rows_per_group, ROWS_PER_BLOCK);
       dim3 grid((unsigned)(bpg * (long long)G), ceil_div(C, 32));
       dim3 block(32, 8);
@@ -593,8 +636,11 @@ int adamml_bn_bwd_reduce(const void* dout, const void* out, const void* z, const
 }
 
 int adamml_bn_bwd_apply(const void* dout, const void* out, const void* z, const float* mean_invstd,
-                        const float* gamma, const double* sums, void* dz, void* dres, long long rows_per_group, int C,
-                        int G, double count, int act, int training, int dtype, cudaStream_t stream) {
+                        const float* gamma, const float* mask_scale_shift, const double* sums, void* dz, void* dres,
+                        long long rows_per_group, int C, int G, double count, int act, int training, int dtype,
+                        cudaStream_t stream) {
+  ADAMML_REQUIRE(act == ADAMML_ACT_NONE || out || mask_scale_shift,
+                 "bn_bwd_apply: activation mask needs the saved output or the forward scale/shift");
   ADAMML_REQUIRE(rows_per_group > 0 && C > 0 && G > 0, "bn_bwd_apply: empty dims");
   ADAMML_REQUIRE(dz || dres, "bn_bwd_apply: nothing to write");
   long long epg = rows_per_group * C;
@@ -605,11 +651,16 @@ int adamml_bn_bwd_apply(const void* dout, const void* out, const void* z, const 
       int rpb, bpg;
       stream_geom(rg, rows_per_group, &rpb, &bpg);
       dim3 vg((unsigned)(bpg * (long long)G), rg.cchunks);
-      bn_bwd_apply_rows_kernel<T><<<vg, rg.threads, 0, stream>>>((const T*)dout, (const T*)out, (const T*)z,
-                                                                 mean_invstd, gamma, sums, (T*)dz, (T*)dres,
-                                                                 rows_per_group, C, rg.cpb, rg.k, rpb, bpg, count, act,
-                                                                 training);
+      if (mask_scale_shift && act != ADAMML_ACT_NONE)
+        bn_bwd_apply_rows_kernel<T, true><<<vg, rg.threads, 0, stream>>>(
+            (const T*)dout, nullptr, (const T*)z, mean_invstd, gamma, mask_scale_shift, sums, (T*)dz, (T*)dres,
+            rows_per_group, C, rg.cpb, rg.k, rpb, bpg, count, act, training);
+      else
+        bn_bwd_apply_rows_kernel<T, false><<<vg, rg.threads, 0, stream>>>(
+            (const T*)dout, (const T*)out, (const T*)z, mean_invstd, gamma, nullptr, sums, (T*)dz, (T*)dres,
+            rows_per_group, C, rg.cpb, rg.k, rpb, bpg, count, act, training);
     } else {
+      ADAMML_REQUIRE(act == ADAMML_ACT_NONE || out, "bn_bwd_apply: ragged channel count needs the saved output");
       bn_bwd_apply_kernel<T><<<ew_blocks(total), 256, 0, stream>>>((const T*)dout, (const T*)out, (const T*)z,
                                                                   mean_invstd, gamma, sums, (T*)dz, (T*)dres, total,
                                                                   epg, C, count, act, training);

@@ -86,9 +86,10 @@ struct StatAcc {
 template <int BLOCK_N, bool CONV>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmD, const __grid_constant__ ConvMaps cmaps,
-               const __grid_constant__ ConvGeom geo, const bf16* __restrict__ addend, long long M, int Ncols, int K,
-               long long ldd, double* __restrict__ stats, long long rows_per_group) {
+               const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmAdd,
+               const __grid_constant__ ConvMaps cmaps, const __grid_constant__ ConvGeom geo,
+               const bf16* __restrict__ addend, long long M, int Ncols, int K, long long ldd,
+               double* __restrict__ stats, long long rows_per_group) {
   using Cfg = TcCfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -97,7 +98,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* empty_bar = full_bar + Cfg::STAGES;
   uint64_t* tmem_full = empty_bar + Cfg::STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* add_bar = tmem_empty + 2;  // dense addend tile landed in the staging buffer (TMA)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(add_bar + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -110,6 +112,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (threadIdx.x == 0) {
     for (int i = 0; i < Cfg::STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+    mbar_init(add_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -122,6 +125,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // dense residual-gradient addend (same pixel lattice as the output): fetched by TMA into the staging tile
+  const bool add_tma = CONV && addend != nullptr && geo.addend_sub != 2;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -213,12 +218,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     sa_.col = 0;
     int last_n_blk = -1;
     int acc = 0;
-    uint32_t acc_phase = 0;
+    uint32_t acc_phase = 0, add_phase = 0;
     for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int n_blk = (int)(tile % num_n_blks);
       const int m_blk = (int)(tile / num_n_blks);
       long long arow = 0;
-      bool row_ok, add_ok = addend != nullptr;
+      bool row_ok, add_ok = addend != nullptr && !add_tma;
       int w0 = 0, h0 = 0, i0 = 0;
       if (CONV) {
         w0 = (m_blk % geo.tiles_w) * geo.BW;
@@ -241,8 +246,25 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // the staging tile (and row_group) of the previous tile must have been consumed
       if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       epi_bar_sync();
+      if (add_tma) {
+        if (issuer) {
+          int nsub = 0;
+#pragma unroll
+          for (int sub = 0; sub < Cfg::SUBTILES; ++sub) nsub += (n_blk * BLOCK_N + sub * 64 < Ncols) ? 1 : 0;
+          mbar_expect_tx(add_bar, (uint32_t)nsub * (BLOCK_M * 128));
+#pragma unroll
+          for (int sub = 0; sub < Cfg::SUBTILES; ++sub) {
+            const int col = n_blk * BLOCK_N + sub * 64;
+            if (col < Ncols) tma_load_4d(stage_out + sub * (BLOCK_M * 128), &tmAdd, add_bar, col, w0, h0, i0);
+          }
+        }
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
+      if (add_tma) {
+        mbar_wait(add_bar, add_phase);
+        add_phase ^= 1;
+      }
 #pragma unroll 1
       for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
         const int col0 = n_blk * BLOCK_N + chunk * 32;
@@ -270,6 +292,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         // staging address: sub-tile (chunk / 2), row et, logical 16-byte chunk c -> physical c ^ (et & 7)
         uint8_t* srow = stage_out + (chunk >> 1) * (BLOCK_M * 128) + et * 128;
+        if (add_tma && row_ok) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            const int c = (chunk & 1) * 4 + (j >> 3);
+            const uint4 pk = *reinterpret_cast<const uint4*>(srow + ((c ^ (et & 7)) << 4));
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&pk);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              float2 f = __bfloat1622float2(h2[t]);
+              v[j + 2 * t] += f.x;
+              v[j + 2 * t + 1] += f.y;
+            }
+          }
+        }
 #pragma unroll
         for (int j = 0; j < 32; j += 8) {
           __nv_bfloat162 p0 = __floats2bfloat162_rn(v[j], v[j + 1]);
@@ -391,8 +427,8 @@ int make_map_2d(CUtensorMap* map, const void* ptr, long long rows, long long col
 }
 
 template <int BLOCK_N, bool CONV>
-int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, const ConvMaps& cm,
-              const ConvGeom& geo, const void* addend, long long M, int Ncols, int K, long long ldd, double* stats,
+int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, const CUtensorMap& tmAdd,
+              const ConvMaps& cm, const ConvGeom& geo, const void* addend, long long M, int Ncols, int K, long long ldd, double* stats,
               long long rpg, cudaStream_t stream) {
   using Cfg = TcCfg<BLOCK_N>;
   static bool configured = false;
@@ -409,17 +445,18 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap&
   long long tiles = m_blks * ((Ncols + BLOCK_N - 1) / BLOCK_N);
   const int sms = num_sms();
   int grid = (int)(tiles < sms ? tiles : sms);
-  kern<<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmD, cm, geo, (const bf16*)addend, M, Ncols, K, ldd,
-                                                        stats, rpg);
+  kern<<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmD, tmAdd, cm, geo, (const bf16*)addend, M, Ncols,
+                                                        K, ldd, stats, rpg);
   return adamml_check_launch(CONV ? "tc_conv" : "tc_gemm");
 }
 
 template <bool CONV>
-int dispatch_tc(int block_n, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, const ConvMaps& cm,
-                const ConvGeom& geo, const void* addend, long long M, int Ncols, int K, long long ldd, double* stats,
+int dispatch_tc(int block_n, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD,
+                const CUtensorMap& tmAdd, const ConvMaps& cm, const ConvGeom& geo, const void* addend, long long M, int Ncols, int K, long long ldd, double* stats,
                 long long rpg, cudaStream_t stream) {
 #define ADAMML_TC_CASE(BN) \
-  if (block_n == BN) return launch_tc<BN, CONV>(tmA, tmB, tmD, cm, geo, addend, M, Ncols, K, ldd, stats, rpg, stream);
+  if (block_n == BN)       \
+    return launch_tc<BN, CONV>(tmA, tmB, tmD, tmAdd, cm, geo, addend, M, Ncols, K, ldd, stats, rpg, stream);
   ADAMML_TC_CASE(64)
   ADAMML_TC_CASE(128)
   ADAMML_TC_CASE(256)
@@ -454,7 +491,14 @@ int run_conv(const ConvGeom& geo, const ConvMaps& cm, const void* w, long long w
     int G = (geo.IMGS + geo.imgs_per_group - 1) / geo.imgs_per_group;
     cudaMemsetAsync(stats, 0, sizeof(double) * (size_t)G * Cout * 2, stream);
   }
-  return dispatch_tc<true>(block_n, tmB, tmB, tmD, cm, geo, addend, (long long)geo.IMGS * geo.Ho * geo.Wo, Cout,
+  CUtensorMap tmAdd = tmD;
+  if (addend && geo.addend_sub != 2) {
+    rc = make_map_4d(&tmAdd, (const bf16*)addend + ((long long)geo.out_ph * geo.out_W + geo.out_pw) * Cout, Cout, geo.Wo,
+                     geo.Ho, geo.IMGS, (long long)geo.out_s * Cout, (long long)geo.out_s * geo.out_W * Cout,
+                     (long long)geo.out_H * geo.out_W * Cout, geo.BW, geo.BH, geo.BI);
+    if (rc) return rc;
+  }
+  return dispatch_tc<true>(block_n, tmB, tmB, tmD, tmAdd, cm, geo, addend, (long long)geo.IMGS * geo.Ho * geo.Wo, Cout,
                            geo.ntaps * geo.kb_per_tap * BLOCK_K, Cout, stats, 0, stream);
 }
 
@@ -508,7 +552,8 @@ int adamml_tc_gemm_bf16(const void* A, const void* B, void* D, long long M, int 
   ConvGeom geo;
   memset(&cm, 0, sizeof(cm));
   memset(&geo, 0, sizeof(geo));
-  return dispatch_tc<false>(block_n, tmA, tmB, tmD, cm, geo, nullptr, M, Ncols, K, ldd, stats, rows_per_group, stream);
+  return dispatch_tc<false>(block_n, tmA, tmB, tmD, tmD, cm, geo, nullptr, M, Ncols, K, ldd, stats, rows_per_group,
+                            stream);
 }
 
 int adamml_tc_conv_supported(int Cin, int Cout, int R, int S, int stride) {

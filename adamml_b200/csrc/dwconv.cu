@@ -223,7 +223,7 @@ dw_s2_dgrad_kernel(const T* __restrict__ dy, const float* __restrict__ w, T* __r
 // round-robin over a persistent grid; 9 x V fp32 accumulators per thread, block reduction through smem,
 // one atomic per (block, channel, tap).
 template <typename T, int STRIDE, int SW>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 dw_wgrad_vec_kernel(const T* __restrict__ x, const T* __restrict__ dy, float* __restrict__ dw, int IMGS, int H, int W,
                     int C, int Ho, int Wo, int strips, int cpb, int k) {
   constexpr int V = VecIO<T>::N;
@@ -374,11 +374,11 @@ int adamml_dwconv_wgrad(const void* x, const void* dy, float* dw, int IMGS, int 
     const int cchunks = (cvecs + 255) / 256;
     const int cpb = (cvecs + cchunks - 1) / cchunks;
     const int k = 256 / cpb;
-    constexpr int SW1 = 4, SW2 = 2;
+    constexpr int SW1 = 2, SW2 = 2;
     const int strips = stride == 1 ? (Wo + SW1 - 1) / SW1 : (Wo + SW2 - 1) / SW2;
     const long long items = (long long)IMGS * Ho * strips;
     long long gx = (items + k - 1) / k;
-    const long long cap = 148LL * 4 / cchunks > 0 ? 148LL * 4 / cchunks : 1;
+    const long long cap = 148LL * 8 / cchunks > 0 ? 148LL * 8 / cchunks : 1;
     if (gx > cap) gx = cap;
     dim3 grid((unsigned)gx, cchunks);
     if (stride == 1)

@@ -52,7 +52,10 @@ class Exec:
         rec = self.conv_bn_stats(x, conv, bn)
         out = ops.bn_apply(rec["z"], rec["ss"], self.G, act, res=res,
                            res_z=res_rec["z"] if res_rec else None, res_ss=res_rec["ss"] if res_rec else None)
-        rec["ss"] = None
+        # the forward scale/shift of a layer without residual input is kept (tiny): backward recomputes the
+        # ReLU/ReLU6 mask from z with it instead of streaming `out` again
+        if res is not None or res_rec is not None or act == ACT_NONE:
+            rec["ss"] = None
         if res_rec:
             res_rec["ss"] = None
         if self.save:
@@ -118,7 +121,8 @@ class Exec:
         G = self.G
         conv, bn, z, mi = rec["conv"], rec["bn"], rec["z"], rec["mi"]
         C = z.shape[-1]
-        sums = ops.bn_bwd_reduce(dout, out, z, mi, G, act)
+        mask_ss = rec.get("ss") if out is rec.get("out") else None
+        sums = ops.bn_bwd_reduce(dout, out, z, mi, G, act, mask_ss=mask_ss)
         if bn.weight.requires_grad or bn.bias.requires_grad:
             dgamma, dbeta = ops.bn_param_grad(sums, C, G)
             self._acc(bn.weight, dgamma)
@@ -127,7 +131,7 @@ class Exec:
             dist.all_reduce(sums, group=rec["pg"])
         need_w = conv.weight.requires_grad
         dz, dres = ops.bn_bwd_apply(dout, out, z, mi, bn.weight.detach(), sums, G, rec["count"], act, self.training,
-                                    want_dz=(need_w or need_dx), want_dres=want_dres)
+                                    want_dz=(need_w or need_dx), want_dres=want_dres, mask_ss=mask_ss)
         dx = None
         x = rec["x"]
         stride, pad = conv.stride[0], conv.padding[0]

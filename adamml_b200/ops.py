@@ -155,7 +155,7 @@ def _tc_ok(x, Cin, Cout, R, S, stride, pad):
 def _tc_conv_ok(x, Cin, Cout, R, S, stride):
     """tcgen05 implicit GEMM (4D TMA taps): any RxS <= 49 taps, stride 1|2.  Cin >= 32 keeps the 64-wide K
     block at least half full (the 3-channel stem stays on the exact engine)."""
-    return (TC_MODE == "auto" and x.dtype == torch.bfloat16 and Cin % 8 == 0 and Cout % 8 == 0 and Cin >= 32
+    return (TC_MODE == "auto" and x.dtype == torch.bfloat16 and Cin % 8 == 0 and Cout % 8 == 0 and Cin >= 16
             and R * S <= 49 and stride in (1, 2))
 
 
@@ -186,7 +186,7 @@ def conv_fwd(x, w, stride, pad, out=None, stats=None, rows_per_group=0):
 def tc_dgrad_ok(dtype, Cout, Cin, R, S, stride):
     """data gradients that run on the tcgen05 engine (bf16): stride 1, stride-2 RxS (parity classes),
     stride-2 1x1 (compact GEMM, see conv_dgrad_compact)."""
-    return (TC_MODE == "auto" and dtype == torch.bfloat16 and Cout % 8 == 0 and Cin % 8 == 0 and Cout >= 32
+    return (TC_MODE == "auto" and dtype == torch.bfloat16 and Cout % 8 == 0 and Cin % 8 == 0 and Cout >= 16
             and R * S <= 49 and stride in (1, 2))
 
 
@@ -326,21 +326,32 @@ def bn_apply(z, scale_shift, G, act, res=None, res_z=None, res_ss=None, out=None
     return out
 
 
-def bn_bwd_reduce(dout, out, z, mean_invstd, G, act):
+def _mask_ss(z, mask_ss):
+    """the z-recomputed activation mask needs the vectorised kernels (C % 16 bytes == 0)"""
+    if mask_ss is None or z.shape[-1] % (8 if z.dtype == torch.bfloat16 else 4):
+        return None
+    return mask_ss
+
+
+def bn_bwd_reduce(dout, out, z, mean_invstd, G, act, mask_ss=None):
+    """mask_ss: forward scale/shift [G,C,2] of a layer without residual input -> the ReLU/ReLU6 mask is recomputed
+    from z and `out` is not read."""
     C = z.shape[-1]
     rows = z.numel() // C
     sums = torch.empty((G, C, 2), device=z.device, dtype=torch.float64)
-    call("bn_bwd_reduce", dout, out, z, mean_invstd, sums, rows // G, C, G, act, dtype_code(z.dtype))
+    call("bn_bwd_reduce", dout, out, z, mean_invstd, _mask_ss(z, mask_ss), sums, rows // G, C, G, act,
+         dtype_code(z.dtype))
     return sums
 
 
-def bn_bwd_apply(dout, out, z, mean_invstd, gamma, sums, G, count, act, training, want_dz=True, want_dres=False):
+def bn_bwd_apply(dout, out, z, mean_invstd, gamma, sums, G, count, act, training, want_dz=True, want_dres=False,
+                 mask_ss=None):
     C = dout.shape[-1]
     rows = dout.numel() // C
     dz = torch.empty_like(dout) if want_dz else None
     dres = torch.empty_like(dout) if want_dres else None
-    call("bn_bwd_apply", dout, out, z, mean_invstd, gamma, sums, dz, dres, rows // G, C, G, float(count), act,
-         int(training), dtype_code(dout.dtype))
+    call("bn_bwd_apply", dout, out, z, mean_invstd, gamma, _mask_ss(z, mask_ss), sums, dz, dres, rows // G, C, G,
+         float(count), act, int(training), dtype_code(dout.dtype))
     return dz, dres
 
 

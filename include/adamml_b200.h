@@ -143,11 +143,16 @@ int adamml_bn_finalize(const double* sums, const float* gamma, const float* beta
 int adamml_bn_apply(const void* z, const float* scale_shift, const void* res, const void* res_z,
                     const float* res_scale_shift, void* out, long long rows_per_group, int C, int G, int act,
                     int dtype, cudaStream_t stream);
-int adamml_bn_bwd_reduce(const void* dout, const void* out, const void* z, const float* mean_invstd, double* sums,
-                         long long rows_per_group, int C, int G, int act, int dtype, cudaStream_t stream);
+/* mask_scale_shift (optional, float [G][C][2] = the forward scale/shift of a layer WITHOUT residual input): the
+ * ReLU/ReLU6 mask is recomputed as act'(z*scale+shift) and `out` is not read (may be NULL when C is a multiple of
+ * the 16-byte vector). */
+int adamml_bn_bwd_reduce(const void* dout, const void* out, const void* z, const float* mean_invstd,
+                         const float* mask_scale_shift, double* sums, long long rows_per_group, int C, int G, int act,
+                         int dtype, cudaStream_t stream);
 int adamml_bn_bwd_apply(const void* dout, const void* out, const void* z, const float* mean_invstd,
-                        const float* gamma, const double* sums, void* dz, void* dres, long long rows_per_group, int C,
-                        int G, double count, int act, int training, int dtype, cudaStream_t stream);
+                        const float* gamma, const float* mask_scale_shift, const double* sums, void* dz, void* dres,
+                        long long rows_per_group, int C, int G, double count, int act, int training, int dtype,
+                        cudaStream_t stream);
 int adamml_bn_param_grad(const double* sums, float* dgamma, float* dbeta, int C, int G, int accumulate,
                          cudaStream_t stream);
 

@@ -1,0 +1,114 @@
+#!/usr/bin/env python
+"""Micro-benchmark of single C-ABI ops at the shapes of the N=72 RGB+Audio step (CUDA events, L2 flushed by
+rotating over several operand sets larger than L2).  Usage: python scripts/bench_ops.py [filter]"""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from adamml_b200 import _lib, ops  # noqa: E402
+
+dev = torch.device("cuda:0")
+BF = torch.bfloat16
+HBM = 6463.0
+
+
+def timeit(fn, reps=8, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def report(name, ms, by, fl=0.0):
+    print(f"{name:58s} {ms:8.3f} ms {by / ms / 1e6:8.0f} GB/s ({by / ms / 1e6 / HBM * 100:5.1f}% hbm) {fl / ms / 1e9:8.1f} TF/s",
+          flush=True)
+
+
+def rnd(*shape, dtype=BF):
+    return torch.randn(*shape, device=dev, dtype=torch.float32).to(dtype)
+
+
+def gemm(M, N, K, stats, G=5):
+    A, B, D = rnd(M, K), rnd(N, K), torch.empty(M, N, device=dev, dtype=BF)
+    st = torch.empty(G, N, 2, device=dev, dtype=torch.float64) if stats else None
+    ms = timeit(lambda: _lib.call("tc_gemm_bf16", A, B, D, M, N, K, 0, 0, 0, _lib.BF16, st, M // G if stats else 0))
+    report(f"tc_gemm M={M} N={N} K={K} stats={int(stats)}", ms, 2.0 * M * (N + K), 2.0 * M * N * K)
+
+
+def conv(I, H, W, Ci, Co, R, stride, pad, stats, addend=False, G=5):
+    x, w = rnd(I, H, W, Ci), rnd(Co, R, R, Ci)
+    Ho, Wo = ops.conv_out_hw(H, W, R, R, stride, pad)
+    y = torch.empty(I, Ho, Wo, Co, device=dev, dtype=BF)
+    ad = rnd(I, Ho, Wo, Co) if addend else None
+    st = torch.empty(G, Co, 2, device=dev, dtype=torch.float64) if stats else None
+    ms = timeit(lambda: _lib.call("tc_conv_bf16", x, w, y, ad, I, H, W, Ci, Co, R, R, stride, pad, Ho, Wo, st,
+                                  I // G if stats else 0, 1 if addend else 0))
+    report(f"tc_conv I={I} {H}x{W} {Ci}->{Co} {R}x{R} s{stride} stats={int(stats)} add={int(addend)}", ms,
+           2.0 * (I * H * W * Ci + I * Ho * Wo * Co * (2 if addend else 1)), 2.0 * I * Ho * Wo * Co * R * R * Ci)
+
+
+def wgrad(I, H, W, Ci, Co, R, stride, pad):
+    Ho, Wo = ops.conv_out_hw(H, W, R, R, stride, pad)
+    x, dy = rnd(I, H, W, Ci), rnd(I, Ho, Wo, Co)
+    dw = torch.empty(Co, R, R, Ci, device=dev, dtype=torch.float32)
+    ms = timeit(lambda: _lib.call("tc_wgrad_bf16", x, dy, dw, I, H, W, Ci, Co, R, R, stride, pad, Ho, Wo))
+    report(f"tc_wgrad I={I} {H}x{W} {Ci}->{Co} {R}x{R} s{stride}", ms, 2.0 * (I * H * W * Ci + I * Ho * Wo * Co),
+           2.0 * I * Ho * Wo * Co * R * R * Ci)
+
+
+def bn(rows, C, G=5):
+    z, dout, out = rnd(rows * G, C), rnd(rows * G, C), rnd(rows * G, C)
+    mi = torch.rand(G, C, 2, device=dev) + 0.5
+    gamma = torch.rand(C, device=dev) + 0.5
+    ms = timeit(lambda: ops.bn_bwd_reduce(dout, out, z, mi, G, 1))
+    report(f"bn_bwd_reduce rows={rows}x{G} C={C}", ms, 3.0 * 2 * rows * G * C)
+    sums = ops.bn_bwd_reduce(dout, out, z, mi, G, 1)
+    ms = timeit(lambda: ops.bn_bwd_apply(dout, out, z, mi, gamma, sums, G, rows, 1, True))
+    report(f"bn_bwd_apply rows={rows}x{G} C={C}", ms, 4.0 * 2 * rows * G * C)
+    ss = torch.rand(G, C, 2, device=dev)
+    ms = timeit(lambda: ops.bn_apply(z, ss, G, 1))
+    report(f"bn_apply rows={rows}x{G} C={C}", ms, 2.0 * 2 * rows * G * C)
+
+
+def dw(I, H, C, stride):
+    x = rnd(I, H, H, C)
+    w = torch.randn(C, 1, 3, 3, device=dev)
+    y = ops.dwconv_fwd(x, w, stride)
+    dy = torch.randn_like(y)
+    by = 2.0 * (x.numel() + y.numel())
+    report(f"dwconv_fwd I={I} {H}x{H} C={C} s{stride}", timeit(lambda: ops.dwconv_fwd(x, w, stride)), by, 18.0 * y.numel())
+    report(f"dwconv_dgrad I={I} {H}x{H} C={C} s{stride}", timeit(lambda: ops.dwconv_dgrad(dy, w, tuple(x.shape), stride)), by)
+    report(f"dwconv_wgrad I={I} {H}x{H} C={C} s{stride}", timeit(lambda: ops.dwconv_wgrad(x, dy, stride)), by)
+
+
+CASES = {
+    "gemm": lambda: [gemm(9031680, 256, 64, True), gemm(9031680, 256, 64, False), gemm(9031680, 64, 256, True),
+                     gemm(9031680, 64, 64, True), gemm(4515840, 128, 256, True), gemm(1128960, 512, 128, True),
+                     gemm(9216000, 96, 16, True), gemm(2304000, 24, 144, True), gemm(282240, 1024, 256, True),
+                     gemm(282240, 256, 1024, True)],
+    "conv": lambda: [conv(2880, 56, 56, 64, 64, 3, 1, 1, True), conv(2880, 56, 56, 64, 64, 3, 1, 1, False),
+                     conv(2880, 56, 56, 64, 256, 1, 1, 0, False, addend=True),
+                     conv(1440, 28, 28, 128, 128, 3, 1, 1, True), conv(720, 14, 14, 256, 256, 3, 1, 1, True),
+                     conv(1440, 56, 56, 128, 128, 3, 2, 1, True)],
+    "wgrad": lambda: [wgrad(2880, 56, 56, 64, 64, 3, 1, 1), wgrad(2880, 56, 56, 256, 64, 1, 1, 0),
+                      wgrad(2880, 56, 56, 64, 256, 1, 1, 0), wgrad(1440, 28, 28, 128, 128, 3, 1, 1),
+                      wgrad(720, 14, 14, 256, 256, 3, 1, 1), wgrad(360, 7, 7, 512, 2048, 1, 1, 0)],
+    "bn": lambda: [bn(1806336, 256), bn(1806336, 64), bn(225792, 512), bn(1843200, 96)],
+    "dw": lambda: [dw(1440, 40, 144, 1), dw(360, 128, 96, 2), dw(1440, 80, 32, 1)],
+}
+
+if __name__ == "__main__":
+    flt = sys.argv[1] if len(sys.argv) > 1 else ""
+    for k, f in CASES.items():
+        if flt in k:
+            f()
+            torch.cuda.empty_cache()

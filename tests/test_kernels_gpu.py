@@ -221,6 +221,13 @@ def test_bn_train_fwd_bwd(cuda, act, residual, dtype):
     assert relerr(dgamma, bn.weight.grad) < 1e-4 and relerr(dbeta, bn.bias.grad) < 1e-4
     if residual == "plain":
         assert relerr(nchw(dres), res.grad) < 1e-5
+    if residual == "none" and act != 0:
+        # mask recomputed from z with the forward scale/shift: `out` is never read (None)
+        bs_z = ops.bn_bwd_reduce(doutn, None, zn, mi, G, act, mask_ss=ss)
+        assert relerr(bs_z, bs) < 1e-12
+        dz_z, _ = ops.bn_bwd_apply(doutn, None, zn, mi, bn.weight.detach(), bs_z, G, count, act, True, True, False,
+                                   mask_ss=ss)
+        assert torch.equal(dz_z, dz)
     if residual == "bn":
         bs2 = ops.bn_bwd_reduce(doutn, out, z2n, mi2, G, act)
         dz2, _ = ops.bn_bwd_apply(doutn, out, z2n, mi2, bn2.weight.detach(), bs2, G, count, act, True, True, False)
@@ -368,6 +375,8 @@ TC_CONV_CASES = [
     (3, 13, 17, 40, 72, 3, 1, 1),
     (2, 30, 30, 32, 64, 5, 2, 2),
     (2, 24, 24, 64, 64, 7, 2, 3),
+    (3, 20, 20, 144, 24, 1, 1, 0),   # MobileNetV2 project layer: its dgrad reduces over K = Cout = 24 (ragged K block)
+    (3, 20, 20, 32, 16, 1, 1, 0),
 ]
 
 
