@@ -71,6 +71,7 @@ template <typename T> struct VecIO;
 template <> struct VecIO<float> {
   static constexpr int N = 4;
   typedef float4 raw;
+  __device__ __forceinline__ static raw zero_raw() { return make_float4(0.f, 0.f, 0.f, 0.f); }
   __device__ __forceinline__ static raw load_raw(const float* p) { return *reinterpret_cast<const float4*>(p); }
   __device__ __forceinline__ static void unpack(const raw& t, float (&v)[4]) {
     v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
@@ -86,6 +87,7 @@ template <> struct VecIO<float> {
 template <> struct VecIO<bf16> {
   static constexpr int N = 8;
   typedef uint4 raw;
+  __device__ __forceinline__ static raw zero_raw() { return make_uint4(0u, 0u, 0u, 0u); }
   __device__ __forceinline__ static raw load_raw(const bf16* p) { return *reinterpret_cast<const uint4*>(p); }
   __device__ __forceinline__ static void unpack(const raw& t, float (&v)[8]) {
     const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);

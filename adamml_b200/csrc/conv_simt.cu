@@ -215,7 +215,7 @@ igemm_kernel(const T* __restrict__ Aptr, const T* __restrict__ Bptr, void* __res
   }
 }
 
-// ---- depthwise 3x3 (pad 1, stride 1|2), weights fp32 [C][3][3] ---------------------
+// ---- depthwise 3x3 (pad 1, stride 1|2), weights fp32 tap-major [9][C] (scalar fallbacks) ------
 template <typename T>
 __global__ void dw_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w, T* __restrict__ y,
                               int IMGS, int H, int W, int C, int stride, int Ho, int Wo) {
@@ -236,7 +236,7 @@ __global__ void dw_fwd_kernel(const T* __restrict__ x, const float* __restrict__
       for (int s = 0; s < 3; ++s) {
         int wi = wo * stride + s - 1;
         if (wi < 0 || wi >= W) continue;
-        acc = fmaf(to_f32(x[(((long long)img * H + hi) * W + wi) * C + c]), w[c * 9 + r * 3 + s], acc);
+        acc = fmaf(to_f32(x[(((long long)img * H + hi) * W + wi) * C + c]), w[(r * 3 + s) * C + c], acc);
       }
     }
     y[idx] = from_f32<T>(acc);
@@ -268,7 +268,7 @@ __global__ void dw_dgrad_kernel(const T* __restrict__ dy, const float* __restric
         if (wn < 0 || (wn % stride) != 0) continue;
         int wo = wn / stride;
         if (wo >= Wo) continue;
-        acc = fmaf(to_f32(dy[(((long long)img * Ho + ho) * Wo + wo) * C + c]), w[c * 9 + r * 3 + s], acc);
+        acc = fmaf(to_f32(dy[(((long long)img * Ho + ho) * Wo + wo) * C + c]), w[(r * 3 + s) * C + c], acc);
       }
     }
     if (addend) acc += to_f32(addend[idx]);
@@ -308,7 +308,7 @@ __global__ void dw_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ d
     }
   }
 #pragma unroll
-  for (int i = 0; i < 9; ++i) atomicAdd(&dw[c * 9 + i], acc[i]);
+  for (int i = 0; i < 9; ++i) atomicAdd(&dw[i * C + c], acc[i]);
 }
 
 int check_conv(const ConvP& p) {

@@ -50,14 +50,30 @@ struct TcCfg {
   static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BLOCK_N == 256) ? 3 : (BLOCK_N == 128 ? 5 : 8);
+  static constexpr int CTAS_PER_SM = 1;
+  // Epilogue warps: wide tiles (256 columns, issue bound) get TWO warps per TMEM lane quarter that split the
+  // accumulator columns; narrow tiles are latency bound and run best with one warp per quarter (measured).
+  static constexpr int EPI_WARPS = (BLOCK_N == 256) ? 8 : 4;
+  static constexpr int EPI_THREADS = EPI_WARPS * 32;
+  static constexpr int THREADS = 64 + EPI_THREADS;
+  static constexpr bool BACKOFF = (BLOCK_N == 256);  // control warps share SM sub-partitions with epilogue warps
   static constexpr int SUBTILES = BLOCK_N / 64;              // 64-column (128-byte) output sub-tiles
-  static constexpr int OUT_BYTES = SUBTILES * BLOCK_M * 128;  // bf16 staging tile for the TMA store
+  // the bf16 staging tile of the TMA store is double buffered when it fits (BLOCK_N <= 128): the store of tile i
+  // drains while tile i+1 is staged
+  static constexpr int OUT_BUFS = 1;
+  static constexpr int OUT_TILE_BYTES = SUBTILES * BLOCK_M * 128;
+  static constexpr int OUT_BYTES = OUT_BUFS * OUT_TILE_BYTES;
   static constexpr int TMEM_COLS = 2 * BLOCK_N;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + OUT_BYTES + 1024 /*align slack*/ + 1024 /*barriers, row groups*/;
 };
 
-constexpr int EPI_THREADS = 128;
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
+template <int THREADS>
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory"); }
+template <bool BACKOFF>
+__device__ __forceinline__ void ctl_wait(uint64_t* bar, uint32_t parity) {
+  if (BACKOFF) mbar_wait_backoff(bar, parity);
+  else mbar_wait(bar, parity);
+}
 
 // per-thread running BatchNorm statistics of one (4-column group, row slice): flushed with fp64 atomics when
 // the BN group / column block changes or the CTA retires
@@ -84,7 +100,7 @@ struct StatAcc {
 };
 
 template <int BLOCK_N, bool CONV>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(TcCfg<BLOCK_N>::THREADS, TcCfg<BLOCK_N>::CTAS_PER_SM)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmAdd,
                const __grid_constant__ ConvMaps cmaps, const __grid_constant__ ConvGeom geo,
@@ -92,9 +108,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                double* __restrict__ stats, long long rows_per_group) {
   using Cfg = TcCfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* stage_out = smem + Cfg::STAGES * Cfg::STAGE_BYTES;  // 1024-aligned (all sizes are multiples of 1024)
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage_out + Cfg::OUT_BYTES);
+  // 1024-byte alignment by pointer arithmetic (keeps the shared address space visible to the compiler: LDS/STS
+  // instead of generic LD/ST in the epilogue)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* stage_base = smem + Cfg::STAGES * Cfg::STAGE_BYTES;  // 1024-aligned (all sizes are multiples of 1024)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage_base + Cfg::OUT_BYTES);
   uint64_t* empty_bar = full_bar + Cfg::STAGES;
   uint64_t* tmem_full = empty_bar + Cfg::STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -111,7 +129,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < Cfg::STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], Cfg::EPI_WARPS); }
     mbar_init(add_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -145,7 +163,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           i0 = (m_blk / (geo.tiles_w * geo.tiles_h)) * geo.BI;
         }
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+          ctl_wait<Cfg::BACKOFF>(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
           mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
@@ -173,11 +191,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int acc = 0;
     uint32_t acc_phase = 0;
     for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      ctl_wait<Cfg::BACKOFF>(&tmem_empty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
       for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+        ctl_wait<Cfg::BACKOFF>(&full_bar[stage], phase);
         tc_fence_after();
         if (lane == 0) {
           const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
@@ -198,16 +216,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
-    // ===================== epilogue (warps 2..5, 128 threads) =====================
+    // ===================== epilogue (warps 2..9, 256 threads) =====================
     // TMEM -> registers (thread = accumulator row) -> (+ addend) -> bf16 -> 128B-swizzled smem staging tile ->
     // one elected thread issues the TMA store(s) (fully coalesced, edge-clipped by the tensor map);
     // train-mode BatchNorm statistics are column sums over the staged (bf16-rounded) tile, kept in registers
     // across the tiles of this persistent CTA.
     const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int chalf = (warp - 2) >> 2;  // which share of the 32-column chunks this warp drains (0 when 4 warps)
     const int et = q * 32 + lane;  // == accumulator row inside the tile
     const bool issuer = (warp == 2 && lane == 0);
     constexpr int QUADS = BLOCK_N / 4;          // 4-column (8-byte) groups per tile
-    constexpr int RSPLIT = EPI_THREADS / QUADS; // row slices per column group (2, 4 or 8)
+    constexpr int RSPLIT = Cfg::EPI_THREADS / QUADS; // row slices per column group
     // statistics role of this thread: threads are numbered by `st` so that consecutive threads take
     // consecutive column groups (conflict-free 8-byte smem reads); thread (squad, srs) sums rows srs, srs+RSPLIT, ...
     const int st = (warp - 2) * 32 + lane;
@@ -217,11 +236,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     sa_.g = -1;
     sa_.col = 0;
     int last_n_blk = -1;
-    int acc = 0;
+    int acc = 0, obuf = 0;
     uint32_t acc_phase = 0, add_phase = 0;
     for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int n_blk = (int)(tile % num_n_blks);
       const int m_blk = (int)(tile / num_n_blks);
+      uint8_t* stage_out = stage_base + obuf * Cfg::OUT_TILE_BYTES;
+      if (Cfg::OUT_BUFS == 2) obuf ^= 1;
       long long arow = 0;
       bool row_ok, add_ok = addend != nullptr && !add_tma;
       int w0 = 0, h0 = 0, i0 = 0;
@@ -244,8 +265,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         row_ok = row < M;
       }
       // the staging tile (and row_group) of the previous tile must have been consumed
-      if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      epi_bar_sync();
+      if (issuer) {
+        if (Cfg::OUT_BUFS == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      }
+      epi_bar_sync<Cfg::EPI_THREADS>();
       if (add_tma) {
         if (issuer) {
           int nsub = 0;
@@ -265,15 +289,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(add_bar, add_phase);
         add_phase ^= 1;
       }
+      constexpr int CHUNKS_PER_WARP = (BLOCK_N / 32) / (Cfg::EPI_WARPS / 4);
 #pragma unroll 1
-      for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
+      for (int chunk = chalf * CHUNKS_PER_WARP; chunk < (chalf + 1) * CHUNKS_PER_WARP; ++chunk) {
         const int col0 = n_blk * BLOCK_N + chunk * 32;
         if (col0 >= Ncols) break;  // warp-uniform
         uint32_t r[32];
         tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + chunk * 32), r);
         float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = row_ok ? __uint_as_float(r[j]) : 0.f;
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (!row_ok) {  // edge tiles only: rows outside the tensor are staged as zeros (statistics sum them)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        }
         if (add_ok && row_ok) {
           const bf16* ap = addend + arow * ldd + col0;
 #pragma unroll
@@ -328,7 +357,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       // publish the staged tile to the async proxy and store it
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      epi_bar_sync();
+      epi_bar_sync<Cfg::EPI_THREADS>();
       if (issuer) {
 #pragma unroll
         for (int sub = 0; sub < Cfg::SUBTILES; ++sub) {
@@ -443,9 +472,9 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap&
   }
   long long m_blks = CONV ? (long long)geo.tiles_w * geo.tiles_h * geo.tiles_i : (M + BLOCK_M - 1) / BLOCK_M;
   long long tiles = m_blks * ((Ncols + BLOCK_N - 1) / BLOCK_N);
-  const int sms = num_sms();
+  const int sms = num_sms() * Cfg::CTAS_PER_SM;
   int grid = (int)(tiles < sms ? tiles : sms);
-  kern<<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmD, tmAdd, cm, geo, (const bf16*)addend, M, Ncols,
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmD, tmAdd, cm, geo, (const bf16*)addend, M, Ncols,
                                                         K, ldd, stats, rpg);
   return adamml_check_launch(CONV ? "tc_conv" : "tc_gemm");
 }

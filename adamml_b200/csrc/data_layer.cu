@@ -191,6 +191,15 @@ __global__ void unpack_wgrad_stem_kernel(const float* __restrict__ src, float* _
   }
 }
 
+// depthwise weight [C][3][3] (torch [C,1,3,3]) <-> tap-major [9][C]
+__global__ void transpose_dw_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int to_tap_major) {
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < C * 9; idx += gridDim.x * blockDim.x) {
+    const int c = idx / 9, t = idx % 9;
+    if (to_tap_major) dst[t * C + c] = src[idx];
+    else dst[idx] = src[t * C + c];
+  }
+}
+
 template <typename TI, typename TO>
 __global__ void cast_kernel(const TI* __restrict__ src, TO* __restrict__ dst, long long total) {
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -269,6 +278,18 @@ int adamml_unpack_wgrad_stem(const float* dw_packed, float* dw_oihw, int Cout, i
   ADAMML_REQUIRE(Cout > 0 && C > 0 && Cs >= 4 * C, "unpack_wgrad_stem: bad dims");
   unpack_wgrad_stem_kernel<<<ew_blocks((long long)Cout * C * 49), 256, 0, stream>>>(dw_packed, dw_oihw, Cout, C, Cs);
   return adamml_check_launch("unpack_wgrad_stem");
+}
+
+int adamml_pack_weight_dw(const float* w_c33, float* w_9c, int C, cudaStream_t stream) {
+  ADAMML_REQUIRE(C > 0, "pack_weight_dw: bad dims");
+  transpose_dw_kernel<<<ceil_div(C * 9, 256), 256, 0, stream>>>(w_c33, w_9c, C, 1);
+  return adamml_check_launch("pack_weight_dw");
+}
+
+int adamml_unpack_wgrad_dw(const float* dw_9c, float* dw_c33, int C, cudaStream_t stream) {
+  ADAMML_REQUIRE(C > 0, "unpack_wgrad_dw: bad dims");
+  transpose_dw_kernel<<<ceil_div(C * 9, 256), 256, 0, stream>>>(dw_9c, dw_c33, C, 0);
+  return adamml_check_launch("unpack_wgrad_dw");
 }
 
 // dtype codes for src/dst

@@ -13,13 +13,17 @@ namespace {
 
 constexpr int DW_THREADS = 128;
 
-template <typename T>
-__device__ __forceinline__ void load_w9(const float* __restrict__ w, int c0, float (&wr)[9][VecIO<T>::N]) {
-  constexpr int V = VecIO<T>::N;
+// weights are TAP-MAJOR fp32 [9][C] (adamml_pack_weight_dw): a thread's V channels of one tap are one or two
+// 16-byte loads, coalesced across the warp
+template <int V>
+__device__ __forceinline__ void load_w9(const float* __restrict__ w, int C, int c0, float (&wr)[9][V]) {
 #pragma unroll
-  for (int i = 0; i < V; ++i)
+  for (int t = 0; t < 9; ++t)
 #pragma unroll
-    for (int t = 0; t < 9; ++t) wr[t][i] = w[(c0 + i) * 9 + t];
+    for (int i = 0; i < V; i += 4) {
+      const float4 f = *reinterpret_cast<const float4*>(w + (long long)t * C + c0 + i);
+      wr[t][i] = f.x; wr[t][i + 1] = f.y; wr[t][i + 2] = f.z; wr[t][i + 3] = f.w;
+    }
 }
 
 // Stride-1 stencil shared by forward (FLIP = false) and data gradient (FLIP = true: 180-degree rotated
@@ -41,7 +45,7 @@ dw_s1_kernel(const T* __restrict__ x, const float* __restrict__ w, T* __restrict
   const long long img = rest / H;
   const int c0 = cv * V;
   float wr[9][V];
-  load_w9<T>(w, c0, wr);
+  load_w9<V>(w, C, c0, wr);
   float acc[SW][V];
 #pragma unroll
   for (int j = 0; j < SW; ++j)
@@ -89,6 +93,117 @@ dw_s1_kernel(const T* __restrict__ x, const float* __restrict__ w, T* __restrict
   }
 }
 
+// Vector policy of the band kernel: 4 channels per thread (8-byte bf16 / 16-byte fp32 accesses) keep the 3x3 fp32
+// weights (36 registers) + the rolling window + accumulators under ~100 registers, i.e. >= 4 CTAs per SM.
+template <typename T> struct DwVec;
+template <> struct DwVec<float> : VecIO<float> {};
+template <> struct DwVec<bf16> {
+  static constexpr int N = 4;
+  typedef uint2 raw;
+  __device__ __forceinline__ static raw zero_raw() { return make_uint2(0u, 0u); }
+  __device__ __forceinline__ static raw load_raw(const bf16* p) { return *reinterpret_cast<const uint2*>(p); }
+  __device__ __forceinline__ static void unpack(const raw& t, float (&v)[4]) {
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.x));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.y));
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+  }
+  __device__ __forceinline__ static void load(const bf16* p, float (&v)[4]) { unpack(load_raw(p), v); }
+  __device__ __forceinline__ static void store(bf16* p, const float (&v)[4]) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+    uint2 t;
+    t.x = *reinterpret_cast<uint32_t*>(&a);
+    t.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = t;
+  }
+};
+
+// Stride-1 stencil over a BAND of RH output rows with a rolling 3-row register window: every input vector is
+// loaded once per band (+ 2 halo rows), the 3x3 weights once per thread.  Forward (FLIP = false) and data
+// gradient (FLIP = true, + optional addend).
+template <typename T, bool FLIP, int SW, int RH>
+__global__ void __launch_bounds__(DW_THREADS, 4)
+dw_s1_band_kernel(const T* __restrict__ x, const float* __restrict__ w, T* __restrict__ y,
+                  const T* __restrict__ addend, int IMGS, int H, int W, int C, int strips, int bands) {
+  typedef DwVec<T> VIO;
+  constexpr int V = VIO::N;
+  constexpr int NC = SW + 2;
+  typedef typename VIO::raw raw_t;
+  const int cvecs = C / V;
+  const long long total = (long long)IMGS * bands * strips * cvecs;
+  const long long iv = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (iv >= total) return;
+  const int cv = (int)(iv % cvecs);
+  long long rest = iv / cvecs;
+  const int w0 = (int)(rest % strips) * SW;
+  rest /= strips;
+  const int h0 = (int)(rest % bands) * RH;
+  const long long img = rest / bands;
+  const int c0 = cv * V;
+  const int h1 = h0 + RH < H ? h0 + RH : H;
+  float wr[9][V];
+  load_w9<V>(w, C, c0, wr);
+  const T* xb = x + (img * H * W) * C + c0;
+  auto load_row = [&](int hi, raw_t (&dst)[NC]) {
+    const bool rok = hi >= 0 && hi < H;
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+      const int wi = w0 + j - 1;
+      dst[j] = (rok && wi >= 0 && wi < W) ? VIO::load_raw(xb + ((long long)hi * W + wi) * C) : VIO::zero_raw();
+    }
+  };
+  auto emit = [&](int ho, const raw_t (&ra)[NC], const raw_t (&rb)[NC], const raw_t (&rc)[NC]) {
+    float acc[SW][V];
+#pragma unroll
+    for (int j = 0; j < SW; ++j)
+#pragma unroll
+      for (int i = 0; i < V; ++i) acc[j][i] = 0.f;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+      for (int j = 0; j < NC; ++j) {
+        float v[V];
+        VIO::unpack(r == 0 ? ra[j] : (r == 1 ? rb[j] : rc[j]), v);
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+          const int o = j - s;
+          if (o < 0 || o >= SW) continue;
+          const int t = FLIP ? (2 - r) * 3 + (2 - s) : r * 3 + s;
+#pragma unroll
+          for (int i = 0; i < V; ++i) acc[o][i] = fmaf(v[i], wr[t][i], acc[o][i]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < SW; ++j) {
+      const int wo = w0 + j;
+      if (wo >= W) continue;
+      const long long o = ((img * H + ho) * W + wo) * C + c0;
+      if (addend) {
+        float a[V];
+        VIO::load(addend + o, a);
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc[j][i] += a[i];
+      }
+      VIO::store(y + o, acc[j]);
+    }
+  };
+  raw_t r0[NC], r1[NC], r2[NC];
+  load_row(h0 - 1, r0);
+  load_row(h0, r1);
+  for (int ho = h0; ho < h1; ho += 3) {
+    load_row(ho + 1, r2);
+    emit(ho, r0, r1, r2);
+    if (ho + 1 < h1) {
+      load_row(ho + 2, r0);
+      emit(ho + 1, r1, r2, r0);
+    }
+    if (ho + 2 < h1) {
+      load_row(ho + 3, r1);
+      emit(ho + 2, r2, r0, r1);
+    }
+  }
+}
+
 // Stride-2 forward: strip of SW outputs needs 2*SW+1 input columns per row.
 template <typename T, int SW>
 __global__ void __launch_bounds__(DW_THREADS)
@@ -107,7 +222,7 @@ dw_s2_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w, T* __rest
   const long long img = rest / Ho;
   const int c0 = cv * V;
   float wr[9][V];
-  load_w9<T>(w, c0, wr);
+  load_w9<V>(w, C, c0, wr);
   float acc[SW][V];
 #pragma unroll
   for (int j = 0; j < SW; ++j)
@@ -168,7 +283,7 @@ dw_s2_dgrad_kernel(const T* __restrict__ dy, const float* __restrict__ w, T* __r
   const long long img = rest / QH;
   const int c0 = cv * V;
   float wr[9][V];
-  load_w9<T>(w, c0, wr);
+  load_w9<V>(w, C, c0, wr);
   float g[2][2][V];
 #pragma unroll
   for (int a = 0; a < 2; ++a)
@@ -292,7 +407,7 @@ dw_wgrad_vec_kernel(const T* __restrict__ x, const T* __restrict__ dy, float* __
       for (int i = 0; i < V; ++i) {
         float s = 0.f;
         for (int y = 0; y < k; ++y) s += sh[y * cpb + cl][i];
-        atomicAdd(&dw[(c0 + i) * 9 + t], s);
+        atomicAdd(&dw[(long long)t * C + c0 + i], s);
       }
     }
     __syncthreads();
@@ -323,11 +438,11 @@ int adamml_dwconv_fwd(const void* x, const float* w, void* y, int IMGS, int H, i
       return adamml_dwconv_fwd_scalar(x, w, y, IMGS, H, W, C, stride, Ho, Wo, dtype, stream);
     const int cvecs = C / VecIO<T>::N;
     if (stride == 1) {
-      constexpr int SW = 4;
-      const int strips = (W + SW - 1) / SW;
-      const long long total = (long long)IMGS * H * strips * cvecs;
-      dw_s1_kernel<T, false, SW><<<blocks_for(total, DW_THREADS), DW_THREADS, 0, stream>>>(
-          (const T*)x, w, (T*)y, nullptr, IMGS, H, W, C, strips);
+      constexpr int SW = 2, RH = 16;
+      const int strips = (W + SW - 1) / SW, bands = (H + RH - 1) / RH;
+      const long long total = (long long)IMGS * bands * strips * (C / DwVec<T>::N);
+      dw_s1_band_kernel<T, false, SW, RH><<<blocks_for(total, DW_THREADS), DW_THREADS, 0, stream>>>(
+          (const T*)x, w, (T*)y, nullptr, IMGS, H, W, C, strips, bands);
     } else {
       constexpr int SW = 2;
       const int strips = (Wo + SW - 1) / SW;
@@ -348,11 +463,11 @@ int adamml_dwconv_dgrad(const void* dy, const float* w, void* dx, const void* ad
       return adamml_dwconv_dgrad_scalar(dy, w, dx, addend, IMGS, H, W, C, stride, Ho, Wo, dtype, stream);
     const int cvecs = C / VecIO<T>::N;
     if (stride == 1) {
-      constexpr int SW = 4;
-      const int strips = (W + SW - 1) / SW;
-      const long long total = (long long)IMGS * H * strips * cvecs;
-      dw_s1_kernel<T, true, SW><<<blocks_for(total, DW_THREADS), DW_THREADS, 0, stream>>>(
-          (const T*)dy, w, (T*)dx, (const T*)addend, IMGS, H, W, C, strips);
+      constexpr int SW = 2, RH = 16;
+      const int strips = (W + SW - 1) / SW, bands = (H + RH - 1) / RH;
+      const long long total = (long long)IMGS * bands * strips * (C / DwVec<T>::N);
+      dw_s1_band_kernel<T, true, SW, RH><<<blocks_for(total, DW_THREADS), DW_THREADS, 0, stream>>>(
+          (const T*)dy, w, (T*)dx, (const T*)addend, IMGS, H, W, C, strips, bands);
     } else {
       const long long total = (long long)IMGS * ((H + 1) / 2) * ((W + 1) / 2) * cvecs;
       dw_s2_dgrad_kernel<T><<<blocks_for(total, DW_THREADS), DW_THREADS, 0, stream>>>(

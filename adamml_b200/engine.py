@@ -8,9 +8,9 @@ backward pops them; both only call the C-ABI (adamml_b200.ops).  torch is used f
 streams, autograd plumbing and (sync-BN) torch.distributed collectives.
 """
 import torch
-import torch.distributed as dist
 
 from . import ops
+from .dist_utils import allreduce_stats, sync_bn_group
 from .ops import ACT_NONE, ACT_RELU, ACT_RELU6
 
 
@@ -37,11 +37,7 @@ class Exec:
 
     @staticmethod
     def _sync_group(bn):
-        if isinstance(bn, torch.nn.SyncBatchNorm) and dist.is_available() and dist.is_initialized():
-            pg = bn.process_group if bn.process_group is not None else dist.group.WORLD
-            if dist.get_world_size(pg) > 1:
-                return pg
-        return None
+        return sync_bn_group(bn)
 
     # ------------------------------------------------------------------ conv + BN + act (+ residual)
     def cba(self, x, conv, bn, act, res=None, res_rec=None):
@@ -81,7 +77,7 @@ class Exec:
             fused = sums is not None
         elif depthwise:
             assert conv.groups == conv.in_channels == Cout and R == 3 and pad == 1
-            wp = w.detach()
+            wp = ops.pack_weight_dw(w.detach())
             z = ops.dwconv_fwd(x, wp, stride)
         else:
             wp = ops.pack_weight(w.detach(), self.dtype)
@@ -97,8 +93,7 @@ class Exec:
                 sums = ops.bn_stats(z, G)
             pg = self._sync_group(bn)
             if pg is not None:
-                dist.all_reduce(sums, group=pg)
-                count = count * dist.get_world_size(pg)
+                count = allreduce_stats(sums, count, pg)
             mi, ss = ops.bn_finalize(sums, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var,
                                      count, bn.momentum if bn.momentum is not None else 0.1, bn.eps, C, G, True,
                                      bn.track_running_stats)
@@ -128,7 +123,7 @@ class Exec:
             self._acc(bn.weight, dgamma)
             self._acc(bn.bias, dbeta)
         if rec["pg"] is not None:
-            dist.all_reduce(sums, group=rec["pg"])
+            allreduce_stats(sums, 0, rec["pg"])
         need_w = conv.weight.requires_grad
         dz, dres = ops.bn_bwd_apply(dout, out, z, mi, bn.weight.detach(), sums, G, rec["count"], act, self.training,
                                     want_dz=(need_w or need_dx), want_dres=want_dres, mask_ss=mask_ss)

@@ -276,8 +276,19 @@ def linear_wgrad(x, dy, K=None, x_ld=0, y_ld=0):
 
 
 # ---------------------------------------------------------------- depthwise
+def pack_weight_dw(w):
+    """nn.Conv2d(groups=C).weight [C,1,3,3] fp32 -> tap-major operand [9, C] fp32."""
+    _chk(w, torch.float32)
+    C = w.shape[0]
+    out = torch.empty((9, C), device=w.device, dtype=torch.float32)
+    call("pack_weight_dw", w, out, C)
+    return out
+
+
 def dwconv_fwd(x, w, stride):
+    """w: tap-major [9, C] (pack_weight_dw)."""
     _chk(x); _chk(w, torch.float32)
+    assert w.shape == (9, x.shape[-1]), "depthwise weights must be tap-major [9, C] (ops.pack_weight_dw)"
     IMGS, H, W, C = x.shape
     Ho, Wo = conv_out_hw(H, W, 3, 3, stride, 1)
     y = torch.empty((IMGS, Ho, Wo, C), device=x.device, dtype=x.dtype)
@@ -293,9 +304,12 @@ def dwconv_dgrad(dy, w, x_shape, stride, addend=None):
 
 
 def dwconv_wgrad(x, dy, stride):
+    """-> fp32 gradient in torch's [C,1,3,3] layout."""
     IMGS, H, W, C = x.shape
+    dwt = torch.empty((9, C), device=x.device, dtype=torch.float32)
+    call("dwconv_wgrad", x, dy, dwt, IMGS, H, W, C, stride, dy.shape[1], dy.shape[2], dtype_code(x.dtype))
     dw = torch.empty((C, 1, 3, 3), device=x.device, dtype=torch.float32)
-    call("dwconv_wgrad", x, dy, dw, IMGS, H, W, C, stride, dy.shape[1], dy.shape[2], dtype_code(x.dtype))
+    call("unpack_wgrad_dw", dwt, dw, C)
     return dw
 
 

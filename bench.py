@@ -236,7 +236,9 @@ def run_gpu_arm(a):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        # a rank that falls out of step must fail fast, not hold the box for the default 10 minutes
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     modality = a.modality.split(",")
     S, N = a.segments, a.batch
     torch.manual_seed(0)
@@ -294,6 +296,13 @@ def run_gpu_arm(a):
     ms = timed(lambda: step(dx, dy), a.steps)
     launches = (_lib.launch_count() - n0) // a.steps
     clocks = sampler.stop() if rank == 0 else None
+    # host time to ENQUEUE one step (python + ctypes + torch dispatch), GPU idle at the start: if it approaches
+    # ms_per_step the step is launch-bound and needs CUDA-graph capture
+    barrier()
+    t0 = time.perf_counter()
+    step(dx, dy)
+    host_issue_ms = (time.perf_counter() - t0) * 1e3
+    barrier()
     peak_mem = torch.cuda.max_memory_allocated() / 2 ** 30
 
     # ---- end-to-end: host (pinned) inputs -> H2D -> step -> D2H of the loss, every step ----
@@ -306,11 +315,13 @@ def run_gpu_arm(a):
     ms_e2e = timed(e2e_step, a.steps)
 
     # ---- per-kernel device time of one extra step (CUDA events around every C-ABI call) ----
+    # (every rank runs the step — it contains collectives — but only rank 0 records the events)
     prof = None
     if rank == 0:
         _lib.PROFILE = []
-        step(dx, dy)
-        torch.cuda.synchronize()
+    step(dx, dy)
+    torch.cuda.synchronize()
+    if rank == 0:
         agg = {}
         for name, e0, e1, args in _lib.PROFILE:
             d = agg.setdefault(name, [0.0, 0, 0.0, 0.0])
@@ -345,6 +356,7 @@ def run_gpu_arm(a):
                    "peak_mem_gib": round(peak_mem, 1)},
         "e2e": {"value": clips / (ms_e2e / 1e3), "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches),
+        "host_issue_ms_per_step": round(host_issue_ms, 1),
         "clocks": clocks,
         "step_tflops": FLOP_PER_CLIP * N / (ms / a.steps / 1e3) / 1e12 if modality == ["rgb", "sound"] else None,
     }

@@ -122,8 +122,12 @@ int adamml_tc_wgrad_bf16(const void* x, const void* dy, float* dw, int IMGS, int
                          int S, int stride, int pad, int Ho, int Wo, cudaStream_t stream);
 int adamml_tc_wgrad_supported(int Cin, int Cout, int R, int S, int stride);
 
-/* ---- depthwise 3x3 conv, pad 1, stride 1|2; weights fp32 [C][3][3] (= torch [C,1,3,3]) ----
- * sound_mobilenet_v2.py:58 ; policy_net.py:66,80 */
+/* ---- depthwise 3x3 conv, pad 1, stride 1|2 ----
+ * sound_mobilenet_v2.py:58 ; policy_net.py:66,80.  Weights and weight gradients are fp32 TAP-MAJOR [9][C]
+ * (coalesced per-thread loads); adamml_pack_weight_dw / adamml_unpack_wgrad_dw convert from / to torch's
+ * [C,1,3,3]. */
+int adamml_pack_weight_dw(const float* w_c33, float* w_9c, int C, cudaStream_t stream);
+int adamml_unpack_wgrad_dw(const float* dw_9c, float* dw_c33, int C, cudaStream_t stream);
 int adamml_dwconv_fwd(const void* x, const float* w, void* y, int IMGS, int H, int W, int C, int stride, int Ho,
                       int Wo, int dtype, cudaStream_t stream);
 int adamml_dwconv_dgrad(const void* dy, const float* w, void* dx, const void* addend, int IMGS, int H, int W, int C,

@@ -81,7 +81,7 @@ def bn(rows, C, G=5):
 
 def dw(I, H, C, stride):
     x = rnd(I, H, H, C)
-    w = torch.randn(C, 1, 3, 3, device=dev)
+    w = ops.pack_weight_dw(torch.randn(C, 1, 3, 3, device=dev))
     y = ops.dwconv_fwd(x, w, stride)
     dy = torch.randn_like(y)
     by = 2.0 * (x.numel() + y.numel())

@@ -141,7 +141,8 @@ def test_dwconv(cuda, case, dtype):
         dy = dy.bfloat16().float()
     y_ref.backward(dy)
     xn = nhwc(x.detach()).to(dtype)
-    wd = w.detach().contiguous()
+    wd = ops.pack_weight_dw(w.detach().contiguous())   # tap-major [9, C]
+    assert torch.equal(wd, w.detach().view(C, 9).t().contiguous())
     y = ops.dwconv_fwd(xn, wd, stride)
     assert relerr(nchw(y), y_ref) < TOL[dtype]
     dyn = nhwc(dy).to(dtype)
