@@ -39,3 +39,22 @@ def max_over_ranks(ms, device=None):
 def shard_batch(global_batch, world_size):
     """per-rank batch as train_adamml.py:122 (`-b` is the global batch)."""
     return int(global_batch / world_size)
+
+
+def allreduce_grads(params, group=None):
+    """Gradient averaging of DistributedDataParallel (train_adamml.py:129) as ONE flat all-reduce: used when the
+    step is captured in a CUDA graph (DDP's reducer hooks are host-driven).  Parameters without a gradient are
+    skipped, exactly like unused parameters under find_unused_parameters=True."""
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return
+    world = dist.get_world_size(group)
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, group=group)
+    flat.div_(world)
+    views, off = [], 0
+    for g in grads:
+        n = g.numel()
+        views.append(flat[off:off + n].view_as(g))
+        off += n
+    torch._foreach_copy_(grads, views)

@@ -246,13 +246,17 @@ def run_gpu_arm(a):
     model = model.to(dev).train()
     net = model
     sync_bn = world > 1 and not a.no_sync_bn
+    use_graph = not a.no_graph
     if world > 1:
         if sync_bn:  # train_adamml.py:125-127
             model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)
-        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=True)
-    p_opt = torch.optim.Adam(model.policy_net.parameters(), 0.01, weight_decay=1e-4)
+        net = model
+        if not use_graph:  # eager mode: the reference's DDP wrap (train_adamml.py:129)
+            net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=True)
+    p_opt = torch.optim.Adam(model.policy_net.parameters(), 0.01, weight_decay=1e-4, capturable=use_graph)
     opt = torch.optim.SGD(model.main_net.parameters(), 0.01, momentum=0.9, weight_decay=1e-4)
     cost_weights = [1.0] * model.num_modality
+    params = list(model.parameters())
 
     hx, hy = synth_inputs(modality, N, S, 123 + rank, dev, pin=True)
     dx = [t.to(dev) for t in hx]
@@ -260,13 +264,17 @@ def run_gpu_arm(a):
     h2d = sum(t.numel() * t.element_size() for t in hx) + hy.numel() * hy.element_size()
 
     def step(xs, y):
+        """one training iteration of train_adamml() (utils/utils.py:349-400) on device-resident inputs"""
+        p_opt.zero_grad(set_to_none=True)
+        opt.zero_grad(set_to_none=True)
         out, sel = net(xs)
         loss = F.cross_entropy(out, y) + policy_loss(sel, cost_weights, 10.0, out, y)
         loss.backward()
+        if world > 1 and use_graph:  # DDP's gradient averaging as one flat NCCL all-reduce inside the graph
+            from adamml_b200.dist_utils import allreduce_grads
+            allreduce_grads(params)
         p_opt.step()
         opt.step()
-        p_opt.zero_grad(set_to_none=True)
-        opt.zero_grad(set_to_none=True)
         return loss
 
     def barrier():
@@ -287,39 +295,24 @@ def run_gpu_arm(a):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
 
+    # ---- eager warm-up (also initialises optimizer state / function attributes before any capture) ----
     for _ in range(a.warmup):
         step(dx, dy)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    n0 = _lib.launch_count()
-    ms = timed(lambda: step(dx, dy), a.steps)
-    launches = (_lib.launch_count() - n0) // a.steps
-    clocks = sampler.stop() if rank == 0 else None
-    # host time to ENQUEUE one step (python + ctypes + torch dispatch), GPU idle at the start: if it approaches
-    # ms_per_step the step is launch-bound and needs CUDA-graph capture
+    # host time to ENQUEUE one eager step (python + ctypes + torch dispatch)
     barrier()
     t0 = time.perf_counter()
     step(dx, dy)
     host_issue_ms = (time.perf_counter() - t0) * 1e3
     barrier()
-    peak_mem = torch.cuda.max_memory_allocated() / 2 ** 30
 
-    # ---- end-to-end: host (pinned) inputs -> H2D -> step -> D2H of the loss, every step ----
-    def e2e_step():
-        xs = [t.to(dev, non_blocking=True) for t in hx]
-        y = hy.to(dev, non_blocking=True)
-        return step(xs, y).item()
-
-    e2e_step()
-    ms_e2e = timed(e2e_step, a.steps)
-
-    # ---- per-kernel device time of one extra step (CUDA events around every C-ABI call) ----
+    # ---- per-kernel device time of one eager step (CUDA events around every C-ABI call on the launching stream) ----
     # (every rank runs the step — it contains collectives — but only rank 0 records the events)
     prof = None
     if rank == 0:
         _lib.PROFILE = []
+    n0 = _lib.launch_count()
     step(dx, dy)
+    launches = _lib.launch_count() - n0
     torch.cuda.synchronize()
     if rank == 0:
         agg = {}
@@ -338,6 +331,38 @@ def run_gpu_arm(a):
         _lib.PROFILE = None
         prof = sorted(agg.items(), key=lambda kv: -kv[1][0])
 
+    run_step = lambda: step(dx, dy)  # noqa: E731
+    if use_graph:
+        from adamml_b200.graph import GraphedTrainStep
+        p_opt.zero_grad(set_to_none=True)
+        opt.zero_grad(set_to_none=True)
+        graphed = GraphedTrainStep(lambda: step(dx, dy)).capture()
+        launches = graphed.launches
+        run_step = graphed
+        for _ in range(2):
+            run_step()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms = timed(run_step, a.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    peak_mem = torch.cuda.max_memory_allocated() / 2 ** 30
+
+    # ---- end-to-end: host (pinned) inputs -> H2D -> step -> D2H of the loss, every step ----
+    def e2e_step():
+        if use_graph:  # refresh the graph's static input tensors in place
+            for d_, h_ in zip(dx, hx):
+                d_.copy_(h_, non_blocking=True)
+            dy.copy_(hy, non_blocking=True)
+            return run_step().item()
+        xs = [t.to(dev, non_blocking=True) for t in hx]
+        y = hy.to(dev, non_blocking=True)
+        return step(xs, y).item()
+
+    e2e_step()
+    ms_e2e = timed(e2e_step, a.steps)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -351,12 +376,12 @@ def run_gpu_arm(a):
         "dtype": a.precision, "data": "synthetic",
         "config": {"workload": f"AdaMML {'+'.join(modality)} S={S} F=8 224^2, batch {N}/GPU, "
                                f"fwd+loss+bwd+Adam(policy)+SGD(main)", "batch_per_gpu": N, "segments": S,
-                   "sync_bn": sync_bn, "parallelism": f"dp{world}",
+                   "sync_bn": sync_bn, "parallelism": f"dp{world}", "cuda_graph": use_graph,
                    "l2": "inputs (1.8 GB/step) and activations exceed the 126 MB L2; no explicit flush",
                    "peak_mem_gib": round(peak_mem, 1)},
         "e2e": {"value": clips / (ms_e2e / 1e3), "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches),
-        "host_issue_ms_per_step": round(host_issue_ms, 1),
+        "host_issue_ms_per_step_eager": round(host_issue_ms, 1),
         "clocks": clocks,
         "step_tflops": FLOP_PER_CLIP * N / (ms / a.steps / 1e3) / 1e12 if modality == ["rgb", "sound"] else None,
     }
@@ -404,6 +429,8 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-sync-bn", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches (+ DDP wrapper for N>1) instead of one "
+                                                            "captured CUDA graph per step")
     ap.add_argument("--dump-calls", default=None, help="write one JSON line per C-ABI call of one step (op, ms, args)")
     a = ap.parse_args()
     if a.warmup < 3 and a.impl == "ours":

@@ -14,7 +14,7 @@ def _worker(rank, world, port, q):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from adamml_b200.dist_utils import allreduce_stats, max_over_ranks, shard_batch, sync_bn_group
+    from adamml_b200.dist_utils import allreduce_grads, allreduce_stats, max_over_ranks, shard_batch, sync_bn_group
     try:
         G, C, per_rank = 3, 5, 7
         g = torch.Generator().manual_seed(0)
@@ -36,6 +36,14 @@ def _worker(rank, world, port, q):
         assert torch.allclose(mean, allz.mean(1)) and torch.allclose(var, allz.var(1, unbiased=False))
         assert max_over_ranks(10.0 + rank) == 10.0 + world - 1
         assert shard_batch(72, world) == 72 // world
+        # flat gradient averaging == DDP semantics (mean over ranks; parameters without grad are skipped)
+        ps = [torch.nn.Parameter(torch.zeros(3, 2)), torch.nn.Parameter(torch.zeros(5)), torch.nn.Parameter(torch.zeros(1))]
+        ps[0].grad = torch.full((3, 2), float(rank + 1))
+        ps[1].grad = torch.arange(5.0) * (rank + 1)
+        allreduce_grads(ps)
+        mean = sum(range(1, world + 1)) / world
+        assert torch.allclose(ps[0].grad, torch.full((3, 2), mean)) and torch.allclose(ps[1].grad, torch.arange(5.0) * mean)
+        assert ps[2].grad is None
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         q.put((rank, repr(e)))
