@@ -305,8 +305,10 @@ bn_reduce_rows_kernel(const T* __restrict__ a /*z | dout*/, const T* __restrict_
                       double* __restrict__ sums, long long rows_per_group, int C, int cpb, int k,
                       int blocks_per_group, int act) {
   constexpr int V = VecIO<T>::N;
-  // bf16 backward mode streams three tensors: unroll 2 keeps the kernel at <= 128 registers (2 CTAs / SM)
-  constexpr int UN = (MODE == 1 && sizeof(T) == 2) ? 2 : EW_UNROLL;
+  // the wide (fp64) accumulators live in the thread's shared-memory slot, not in registers: that leaves room for
+  // 4 independent 16-byte loads per tensor in flight at <= 128 registers (2 CTAs / SM) — the kernel is
+  // memory-level-parallelism bound
+  constexpr int UN = EW_UNROLL;
   constexpr int CH = 16 / UN;  // row iterations per flush
   extern __shared__ double shd[];
   const int cl = threadIdx.x % cpb, rl = threadIdx.x / cpb;
@@ -315,22 +317,14 @@ bn_reduce_rows_kernel(const T* __restrict__ a /*z | dout*/, const T* __restrict_
   const int g = blockIdx.x / blocks_per_group;
   const int bg = blockIdx.x % blocks_per_group;
   typedef typename AccT<T>::type acc_t;
-  double S[V], Q[V];
+  double* sh = shd + (size_t)threadIdx.x * (2 * V);
 #pragma unroll
-  for (int i = 0; i < V; ++i) { S[i] = 0.0; Q[i] = 0.0; }
+  for (int i = 0; i < 2 * V; ++i) sh[i] = 0.0;
   if (ok) {
-    float mean[V], invstd[V];
-#pragma unroll
-    for (int i = 0; i < V; ++i) { mean[i] = 0.f; invstd[i] = 1.f; }
     float msc[V], msh[V];  // forward scale/shift: the activation mask is recomputed from z instead of reading `out`
 #pragma unroll
     for (int i = 0; i < V; ++i) { msc[i] = 0.f; msh[i] = 0.f; }
     if (MODE == 1) {
-#pragma unroll
-      for (int i = 0; i < V; ++i) {
-        const float2 p = *reinterpret_cast<const float2*>(mean_invstd + ((long long)g * C + c0 + i) * 2);
-        mean[i] = p.x; invstd[i] = p.y;
-      }
       if (MASKZ) {
 #pragma unroll
         for (int i = 0; i < V; ++i) {
@@ -386,20 +380,17 @@ bn_reduce_rows_kernel(const T* __restrict__ a /*z | dout*/, const T* __restrict_
                 float gm = va[i];
                 if (act != ADAMML_ACT_NONE && !act_pass(vo[i], act)) gm = 0.f;
                 s[i] += (acc_t)gm;
-                q[i] += (acc_t)gm * (acc_t)((vz[i] - mean[i]) * invstd[i]);
+                q[i] += (acc_t)gm * (acc_t)vz[i];  // sum gm*z; turned into sum gm*xhat at the end (fp64)
               }
             }
           }
         }
       }
 #pragma unroll
-      for (int i = 0; i < V; ++i) { S[i] += (double)s[i]; Q[i] += (double)q[i]; }
+      for (int i = 0; i < V; ++i) { sh[i] += (double)s[i]; sh[V + i] += (double)q[i]; }
     }
   }
   // block reduce over the k row lanes
-  double* sh = shd + (size_t)threadIdx.x * (2 * V);
-#pragma unroll
-  for (int i = 0; i < V; ++i) { sh[i] = S[i]; sh[V + i] = Q[i]; }
   __syncthreads();
   if (rl == 0 && ok) {
 #pragma unroll
@@ -409,6 +400,10 @@ bn_reduce_rows_kernel(const T* __restrict__ a /*z | dout*/, const T* __restrict_
         const double* o = shd + ((size_t)y * cpb + cl) * (2 * V);
         ds += o[i];
         dq += o[V + i];
+      }
+      if (MODE == 1) {  // sum gm*xhat = invstd * (sum gm*z - mean * sum gm)
+        const float2 p = *reinterpret_cast<const float2*>(mean_invstd + ((long long)g * C + c0 + i) * 2);
+        dq = (double)p.y * (dq - (double)p.x * ds);
       }
       atomicAdd(&sums[((long long)g * C + c0 + i) * 2 + 0], ds);
       atomicAdd(&sums[((long long)g * C + c0 + i) * 2 + 1], dq);

@@ -414,6 +414,108 @@ dw_wgrad_vec_kernel(const T* __restrict__ x, const T* __restrict__ dy, float* __
   }
 }
 
+// Stride-1 weight gradient with the same rolling-window scheme: a thread owns 4 channels (36 fp32 accumulators),
+// walks (image, row band, column strip) items of a persistent grid, and per step streams two new x rows and two
+// dy rows (12 independent loads in flight).
+template <typename T, int SW, int RH>
+__global__ void __launch_bounds__(256, 2)
+dw_wgrad_band_kernel(const T* __restrict__ x, const T* __restrict__ dy, float* __restrict__ dw, int IMGS, int H, int W,
+                     int C, int strips, int bands, int cpb, int k) {
+  typedef DwVec<T> VIO;
+  constexpr int V = VIO::N;
+  constexpr int NC = SW + 2;
+  typedef typename VIO::raw raw_t;
+  __shared__ float sh[256][V + 1];
+  const int cl = threadIdx.x % cpb, rl = threadIdx.x / cpb;
+  const int c0 = (blockIdx.y * cpb + cl) * V;
+  const bool ok = c0 < C;
+  float acc[9][V];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc[t][i] = 0.f;
+  const long long items = (long long)IMGS * bands * strips;
+  if (ok) {
+    for (long long it = (long long)blockIdx.x * k + rl; it < items; it += (long long)gridDim.x * k) {
+      const int w0 = (int)(it % strips) * SW;
+      const long long rest = it / strips;
+      const int h0 = (int)(rest % bands) * RH;
+      const long long img = rest / bands;
+      const int h1 = h0 + RH < H ? h0 + RH : H;
+      const T* xb = x + (img * H * W) * C + c0;
+      const T* gb = dy + (img * H * W) * C + c0;
+      auto load_x = [&](int hi, raw_t (&dst)[NC]) {
+        const bool rok = hi >= 0 && hi < H;
+#pragma unroll
+        for (int j = 0; j < NC; ++j) {
+          const int wi = w0 + j - 1;
+          dst[j] = (rok && wi >= 0 && wi < W) ? VIO::load_raw(xb + ((long long)hi * W + wi) * C) : VIO::zero_raw();
+        }
+      };
+      auto load_g = [&](int ho, raw_t (&dst)[SW]) {
+        const bool rok = ho < h1;
+#pragma unroll
+        for (int j = 0; j < SW; ++j)
+          dst[j] = (rok && w0 + j < W) ? VIO::load_raw(gb + ((long long)ho * W + w0 + j) * C) : VIO::zero_raw();
+      };
+      auto emit = [&](const raw_t (&g)[SW], const raw_t (&ra)[NC], const raw_t (&rb)[NC], const raw_t (&rc)[NC]) {
+        float gv[SW][V];
+#pragma unroll
+        for (int j = 0; j < SW; ++j) VIO::unpack(g[j], gv[j]);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+#pragma unroll
+          for (int j = 0; j < NC; ++j) {
+            float v[V];
+            VIO::unpack(r == 0 ? ra[j] : (r == 1 ? rb[j] : rc[j]), v);
+#pragma unroll
+            for (int s_ = 0; s_ < 3; ++s_) {
+              const int o = j - s_;
+              if (o < 0 || o >= SW) continue;
+#pragma unroll
+              for (int i = 0; i < V; ++i) acc[r * 3 + s_][i] = fmaf(gv[o][i], v[i], acc[r * 3 + s_][i]);
+            }
+          }
+        }
+      };
+      raw_t r0[NC], r1[NC], r2[NC], r3[NC], g0[SW], g1[SW];
+      load_x(h0 - 1, r0);
+      load_x(h0, r1);
+      for (int ho = h0; ho < h1; ho += 4) {
+        load_x(ho + 1, r2);
+        load_x(ho + 2, r3);
+        load_g(ho, g0);
+        load_g(ho + 1, g1);
+        emit(g0, r0, r1, r2);
+        emit(g1, r1, r2, r3);  // rows past the band contribute zeros (g1 = 0)
+        if (ho + 2 < h1) {
+          load_x(ho + 3, r0);
+          load_x(ho + 4, r1);
+          load_g(ho + 2, g0);
+          load_g(ho + 3, g1);
+          emit(g0, r2, r3, r0);
+          emit(g1, r3, r0, r1);
+        }
+      }
+    }
+  }
+#pragma unroll 1
+  for (int t = 0; t < 9; ++t) {
+#pragma unroll
+    for (int i = 0; i < V; ++i) sh[threadIdx.x][i] = acc[t][i];
+    __syncthreads();
+    if (rl == 0 && ok) {
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        float s_ = 0.f;
+        for (int y = 0; y < k; ++y) s_ += sh[y * cpb + cl][i];
+        atomicAdd(&dw[(long long)t * C + c0 + i], s_);
+      }
+    }
+    __syncthreads();
+  }
+}
+
 template <typename T>
 inline bool dw_vec_ok(int C, const void* a, const void* b, const void* c = nullptr, const void* d = nullptr) {
   if (C % VecIO<T>::N) return false;
@@ -485,6 +587,22 @@ int adamml_dwconv_wgrad(const void* x, const void* dy, float* dw, int IMGS, int 
     if (!dw_vec_ok<T>(C, x, dy))
       return adamml_dwconv_wgrad_scalar(x, dy, dw, IMGS, H, W, C, stride, Ho, Wo, dtype, stream);
     cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)C * 9, stream);
+    if (stride == 1) {
+      constexpr int SW = 2, RH = 16;
+      const int cv4 = C / DwVec<T>::N;
+      const int cch = (cv4 + 255) / 256;
+      const int cpb4 = (cv4 + cch - 1) / cch;
+      const int k4 = 256 / cpb4;
+      const int strips = (W + SW - 1) / SW, bands = (H + RH - 1) / RH;
+      const long long items = (long long)IMGS * bands * strips;
+      long long gx = (items + k4 - 1) / k4;
+      const long long cap = 148LL * 2 * 4 / cch > 0 ? 148LL * 2 * 4 / cch : 1;
+      if (gx > cap) gx = cap;
+      dim3 grid((unsigned)gx, cch);
+      dw_wgrad_band_kernel<T, SW, RH><<<grid, cpb4 * k4, 0, stream>>>((const T*)x, (const T*)dy, dw, IMGS, H, W, C,
+                                                                       strips, bands, cpb4, k4);
+      return adamml_check_launch("dwconv_wgrad");
+    }
     const int cvecs = C / VecIO<T>::N;
     const int cchunks = (cvecs + 255) / 256;
     const int cpb = (cvecs + cchunks - 1) / cchunks;
