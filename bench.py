@@ -382,9 +382,17 @@ def run_gpu_arm(a):
     e2e_step()
     ms_e2e = timed(e2e_step, a.steps)
 
-    if rank != 0:
+    def finish():
+        """NCCL communicators referenced by a captured CUDA graph do not always tear down cleanly: after a last
+        barrier every rank leaves through os._exit so the launcher never waits on a hung destructor."""
+        sys.stdout.flush()
+        sys.stderr.flush()
         if world > 1:
-            dist.destroy_process_group()
+            barrier()
+            os._exit(0)
+
+    if rank != 0:
+        finish()
         return
     pk = peaks()
     clips = N * world * a.steps
@@ -432,8 +440,7 @@ def run_gpu_arm(a):
         out["cpu_baseline"] = {"value": n_clips / t, "unit": "clips/s", "cores": torch.get_num_threads(), "kind": "port",
                                "sample": f"{n_clips} clips per step (of the {N}-clip batch), 1 warm-up + 2 timed steps"}
     print(json.dumps(out), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    finish()
 
 
 def main():
