@@ -300,9 +300,9 @@ bn_apply_rows_kernel(const T* __restrict__ z, const float* __restrict__ ss, cons
 // (block, channel) at the end.
 template <typename T, int MODE, bool MASKZ>
 __global__ void __launch_bounds__(EW_THREADS, 2)
-bn_reduce_rows_kernel(const T* __restrict__ a /*z | dout*/, const T* __restrict__ out, const T* __restrict__ z,
+bn_reduce_rows_kernel(const T* a /*z | dout (may alias gm_out)*/, const T* __restrict__ out, const T* __restrict__ z,
                       const float* __restrict__ mean_invstd, const float* __restrict__ mss,
-                      double* __restrict__ sums, long long rows_per_group, int C, int cpb, int k,
+                      double* __restrict__ sums, T* gm_out, long long rows_per_group, int C, int cpb, int k,
                       int blocks_per_group, int act) {
   constexpr int V = VecIO<T>::N;
   // the wide (fp64) accumulators live in the thread's shared-memory slot, not in registers: that leaves room for
@@ -379,10 +379,12 @@ bn_reduce_rows_kernel(const T* __restrict__ a /*z | dout*/, const T* __restrict_
               } else {
                 float gm = va[i];
                 if (act != ADAMML_ACT_NONE && !act_pass(vo[i], act)) gm = 0.f;
+                va[i] = gm;
                 s[i] += (acc_t)gm;
                 q[i] += (acc_t)gm * (acc_t)vz[i];  // sum gm*z; turned into sum gm*xhat at the end (fp64)
               }
             }
+            if (MODE == 1 && gm_out) VecIO<T>::store(gm_out + base + rr * C, va);
           }
         }
       }
@@ -549,7 +551,7 @@ int adamml_bn_stats(const void* z, double* sums, long long rows_per_group, int C
       const size_t sm = sizeof(double) * rg.threads * 2 * VecIO<T>::N;
       dim3 vg((unsigned)(bpg * (long long)G), rg.cchunks);
       bn_reduce_rows_kernel<T, 0, false><<<vg, rg.threads, sm, stream>>>((const T*)z, nullptr, nullptr, nullptr, nullptr, sums,
-                                                                  rows_per_group, C, rg.cpb, rg.k, bpg, 0);
+                                                                  nullptr, rows_per_group, C, rg.cpb, rg.k, bpg, 0);
     } else {
       int bpg = ceil_div(rows_per_group, ROWS_PER_BLOCK);
       dim3 grid((unsigned)(bpg * (long long)G), ceil_div(C, 32));
@@ -598,8 +600,8 @@ int adamml_bn_apply(const void* z, const float* scale_shift, const void* res, co
 }
 
 int adamml_bn_bwd_reduce(const void* dout, const void* out, const void* z, const float* mean_invstd,
-                         const float* mask_scale_shift, double* sums, long long rows_per_group, int C, int G, int act,
-                         int dtype, cudaStream_t stream) {
+                         const float* mask_scale_shift, double* sums, void* gm_out, long long rows_per_group, int C,
+                         int G, int act, int dtype, cudaStream_t stream) {
   ADAMML_REQUIRE(rows_per_group > 0 && C > 0 && G > 0, "bn_bwd_reduce: empty dims");
   ADAMML_REQUIRE(act == ADAMML_ACT_NONE || out || mask_scale_shift,
                  "bn_bwd_reduce: activation mask needs the saved output or the forward scale/shift");
@@ -613,13 +615,15 @@ int adamml_bn_bwd_reduce(const void* dout, const void* out, const void* z, const
       if (mask_scale_shift && act != ADAMML_ACT_NONE)
         bn_reduce_rows_kernel<T, 1, true><<<vg, rg.threads, sm, stream>>>((const T*)dout, nullptr, (const T*)z,
                                                                           mean_invstd, mask_scale_shift, sums,
-                                                                          rows_per_group, C, rg.cpb, rg.k, bpg, act);
+                                                                          (T*)gm_out, rows_per_group, C, rg.cpb, rg.k,
+                                                                          bpg, act);
       else
         bn_reduce_rows_kernel<T, 1, false><<<vg, rg.threads, sm, stream>>>((const T*)dout, (const T*)out, (const T*)z,
-                                                                           mean_invstd, nullptr, sums, rows_per_group,
-                                                                           C, rg.cpb, rg.k, bpg, act);
+                                                                           mean_invstd, nullptr, sums, (T*)gm_out,
+                                                                           rows_per_group, C, rg.cpb, rg.k, bpg, act);
     } else {
       ADAMML_REQUIRE(act == ADAMML_ACT_NONE || out, "bn_bwd_reduce: ragged channel count needs the saved output");
+      ADAMML_REQUIRE(!gm_out, "bn_bwd_reduce: gm_out needs a vectorisable channel count");
       int bpg = ceil_div(rows_per_group, ROWS_PER_BLOCK);
       dim3 grid((unsigned)(bpg * (long long)G), ceil_div(C, 32));
       dim3 block(32, 8);

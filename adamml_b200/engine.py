@@ -107,17 +107,27 @@ class Exec:
     def cba_bwd(self, dout, need_dx=True, addend=None, addend_sub=1):
         """Pops one cba record.  Returns (dx or None, dres or None)."""
         rec = self.tape.pop()
+        shared = (rec["has_res"] or rec["res_rec"] is not None) and rec["act"] != ACT_NONE
         dx, dres, _ = self._bn_conv_bwd(rec, dout, rec["out"], rec["act"], need_dx, addend,
-                                        want_dres=rec["has_res"] and rec["act"] != ACT_NONE, addend_sub=addend_sub)
+                                        want_dres=rec["has_res"] and rec["act"] != ACT_NONE, addend_sub=addend_sub,
+                                        mask_inplace=shared)
         return dx, dres
 
-    def _bn_conv_bwd(self, rec, dout, out, act, need_dx, addend, want_dres, addend_sub=1, compact_ok=False):
+    def _bn_conv_bwd(self, rec, dout, out, act, need_dx, addend, want_dres, addend_sub=1, compact_ok=False,
+                     mask_inplace=False):
         """-> (dx, dres, dx_is_compact)"""
         G = self.G
         conv, bn, z, mi = rec["conv"], rec["bn"], rec["z"], rec["mi"]
         C = z.shape[-1]
         mask_ss = rec.get("ss") if out is rec.get("out") else None
-        sums = ops.bn_bwd_reduce(dout, out, z, mi, G, act, mask_ss=mask_ss)
+        # residual layers: the reduce pass masks dout IN PLACE (gm = dout * relu'(out)); gm is the gradient of the
+        # residual input and lets the apply pass (and a downsample branch sharing dout) skip `out` entirely
+        inplace = mask_inplace and act != ACT_NONE and ops.vec_channels(z)
+        had_dres = want_dres
+        sums = ops.bn_bwd_reduce(dout, out, z, mi, G, act, mask_ss=mask_ss, gm_inplace=inplace)
+        if inplace:
+            rec["dout_masked"] = True
+            out, act, want_dres = None, ACT_NONE, False
         if bn.weight.requires_grad or bn.bias.requires_grad:
             dgamma, dbeta = ops.bn_param_grad(sums, C, G)
             self._acc(bn.weight, dgamma)
@@ -127,6 +137,8 @@ class Exec:
         need_w = conv.weight.requires_grad
         dz, dres = ops.bn_bwd_apply(dout, out, z, mi, bn.weight.detach(), sums, G, rec["count"], act, self.training,
                                     want_dz=(need_w or need_dx), want_dres=want_dres, mask_ss=mask_ss)
+        if inplace and had_dres:
+            dres = dout
         dx = None
         x = rec["x"]
         stride, pad = conv.stride[0], conv.padding[0]
@@ -173,14 +185,17 @@ class Exec:
         d_id = None
         dx_ds = None
         compact = False
+        c1 = self.tape[-3]["conv"]
+        out3, act3 = rec3["out"], rec3["act"]
+        da, d_id = self.cba_bwd(dout)          # conv3/bn3 (+identity grad); may mask dout in place
         if ds is not None:
             # downsample branch shares (dout, out, act mask) with bn3; conv1 of the block is a stride-1 1x1 whose
             # tcgen05 dgrad epilogue can scatter a compact stride-2 downsample gradient
-            c1 = self.tape[-3]["conv"]
             ok = ops.tc_dgrad_ok(self.dtype, c1.out_channels, c1.in_channels, 1, 1, 1) and c1.kernel_size == (1, 1)
-            dx_ds, _, compact = self._bn_conv_bwd(ds, dout, rec3["out"], rec3["act"], need_dx, None, want_dres=False,
+            if rec3.get("dout_masked"):
+                out3, act3 = None, ACT_NONE
+            dx_ds, _, compact = self._bn_conv_bwd(ds, dout, out3, act3, need_dx, None, want_dres=False,
                                                   compact_ok=ok)
-        da, d_id = self.cba_bwd(dout)          # conv3/bn3 (+identity grad)
         da, _ = self.cba_bwd(da)               # conv2/bn2
         addend = dx_ds if ds is not None else d_id
         dx, _ = self.cba_bwd(da, need_dx=need_dx, addend=addend if need_dx else None,
@@ -199,9 +214,12 @@ class Exec:
         rec2 = self.tape[-1]
         ds = rec2["res_rec"]
         dx_ds = None
+        out2, act2 = rec2["out"], rec2["act"]
+        da, d_id = self.cba_bwd(dout)          # may mask dout in place
         if ds is not None:
-            dx_ds, _, _ = self._bn_conv_bwd(ds, dout, rec2["out"], rec2["act"], need_dx, None, want_dres=False)
-        da, d_id = self.cba_bwd(dout)
+            if rec2.get("dout_masked"):
+                out2, act2 = None, ACT_NONE
+            dx_ds, _, _ = self._bn_conv_bwd(ds, dout, out2, act2, need_dx, None, want_dres=False)
         addend = dx_ds if ds is not None else d_id
         dx, _ = self.cba_bwd(da, need_dx=need_dx, addend=addend if need_dx else None)
         return dx

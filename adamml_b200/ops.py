@@ -347,14 +347,20 @@ def _mask_ss(z, mask_ss):
     return mask_ss
 
 
-def bn_bwd_reduce(dout, out, z, mean_invstd, G, act, mask_ss=None):
+def vec_channels(t):
+    """True when the row-streaming (16-byte vector) kernels take this tensor."""
+    return t.shape[-1] % (8 if t.dtype == torch.bfloat16 else 4) == 0
+
+
+def bn_bwd_reduce(dout, out, z, mean_invstd, G, act, mask_ss=None, gm_inplace=False):
     """mask_ss: forward scale/shift [G,C,2] of a layer without residual input -> the ReLU/ReLU6 mask is recomputed
-    from z and `out` is not read."""
+    from z and `out` is not read.  gm_inplace: dout is overwritten with the masked gradient dout * act'(out), which
+    is also the gradient of a residual input; the following bn_bwd_apply then runs with act = NONE."""
     C = z.shape[-1]
     rows = z.numel() // C
     sums = torch.empty((G, C, 2), device=z.device, dtype=torch.float64)
-    call("bn_bwd_reduce", dout, out, z, mean_invstd, _mask_ss(z, mask_ss), sums, rows // G, C, G, act,
-         dtype_code(z.dtype))
+    call("bn_bwd_reduce", dout, out, z, mean_invstd, _mask_ss(z, mask_ss), sums, dout if gm_inplace else None,
+         rows // G, C, G, act, dtype_code(z.dtype))
     return sums
 
 

@@ -199,13 +199,14 @@ def kernel_work(name, a):
         return 0.0, (2 if a[10] == 1 else 4) * n * (2.0 + (1 if T(2) or T(3) else 0))
     if name == "bn_stats":
         return 0.0, (2 if a[5] == 1 else 4) * float(a[2] * a[3] * a[4])
-    if name == "bn_bwd_reduce":   # (dout, out, z, mi, mask_ss, sums, rpg, C, G, act, dtype)
-        n = a[6] * a[7] * a[8]
-        return 0.0, (2 if a[10] == 1 else 4) * n * (2.0 + (1 if (a[9] and not T(4)) else 0))
+    if name == "bn_bwd_reduce":   # (dout, out, z, mi, mask_ss, sums, gm_out, rpg, C, G, act, dtype)
+        n = a[7] * a[8] * a[9]
+        return 0.0, (2 if a[11] == 1 else 4) * n * (2.0 + (1 if (a[10] and T(1) and not T(4)) else 0)
+                                                    + (1 if T(6) else 0))
     if name == "bn_bwd_apply":    # (dout, out, z, mi, gamma, mask_ss, sums, dz, dres, rpg, C, G, count, act, training, dtype)
         n = a[9] * a[10] * a[11]
         need_z = T(7) or (T(5) and a[13])
-        return 0.0, (2 if a[15] == 1 else 4) * n * (1.0 + (1 if (a[13] and not T(5)) else 0) + (1 if need_z else 0)
+        return 0.0, (2 if a[15] == 1 else 4) * n * (1.0 + (1 if (a[13] and T(1) and not T(5)) else 0) + (1 if need_z else 0)
                                                     + (1 if T(7) else 0) + (1 if T(8) else 0))
     if name in ("dwconv_fwd", "dwconv_dgrad"):
         o = 0 if name == "dwconv_fwd" else 1
@@ -318,7 +319,10 @@ def run_gpu_arm(a):
         agg = {}
         for name, e0, e1, args in _lib.PROFILE:
             d = agg.setdefault(name, [0.0, 0, 0.0, 0.0])
-            fl, by = kernel_work(name, args)
+            try:
+                fl, by = kernel_work(name, args)
+            except Exception:  # an ABI change must never take the benchmark down
+                fl, by = 0.0, 0.0
             d[0] += e0.elapsed_time(e1)
             d[1] += 1
             d[2] += fl

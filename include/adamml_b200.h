@@ -150,9 +150,11 @@ int adamml_bn_apply(const void* z, const float* scale_shift, const void* res, co
 /* mask_scale_shift (optional, float [G][C][2] = the forward scale/shift of a layer WITHOUT residual input): the
  * ReLU/ReLU6 mask is recomputed as act'(z*scale+shift) and `out` is not read (may be NULL when C is a multiple of
  * the 16-byte vector). */
+/* gm_out (optional, may alias dout): the masked gradient gm = dout * act'(out) is written back, so that the following
+ * bn_bwd_apply (and the residual branch, whose gradient IS gm) run with act = NONE and never read `out`. */
 int adamml_bn_bwd_reduce(const void* dout, const void* out, const void* z, const float* mean_invstd,
-                         const float* mask_scale_shift, double* sums, long long rows_per_group, int C, int G, int act,
-                         int dtype, cudaStream_t stream);
+                         const float* mask_scale_shift, double* sums, void* gm_out, long long rows_per_group, int C,
+                         int G, int act, int dtype, cudaStream_t stream);
 int adamml_bn_bwd_apply(const void* dout, const void* out, const void* z, const float* mean_invstd,
                         const float* gamma, const float* mask_scale_shift, const double* sums, void* dz, void* dres,
                         long long rows_per_group, int C, int G, double count, int act, int training, int dtype,

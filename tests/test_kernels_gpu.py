@@ -222,6 +222,13 @@ def test_bn_train_fwd_bwd(cuda, act, residual, dtype):
     assert relerr(dgamma, bn.weight.grad) < 1e-4 and relerr(dbeta, bn.bias.grad) < 1e-4
     if residual == "plain":
         assert relerr(nchw(dres), res.grad) < 1e-5
+    if residual != "none" and act != 0:
+        # in-place masking: the reduce pass turns dout into gm = dout * act'(out); apply then needs no mask / out
+        gm = doutn.clone()
+        bs_i = ops.bn_bwd_reduce(gm, out, zn, mi, G, act, gm_inplace=True)
+        assert relerr(bs_i, bs) < 1e-12 and torch.equal(gm, dres)
+        dz_i, _ = ops.bn_bwd_apply(gm, None, zn, mi, bn.weight.detach(), bs_i, G, count, 0, True, True, False)
+        assert torch.equal(dz_i, dz)
     if residual == "none" and act != 0:
         # mask recomputed from z with the forward scale/shift: `out` is never read (None)
         bs_z = ops.bn_bwd_reduce(doutn, None, zn, mi, G, act, mask_ss=ss)
