@@ -167,6 +167,13 @@ def run_reference_arm(a):
 
 
 # ------------------------------------------------------------------------------------------- GPU arm
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (ncu --set full, profiles/r1_ncu_ops_N72.txt) divided by
+# the algorithmic bytes of that launch: measured traffic == algorithmic traffic to within 1-2 % for the streaming
+# kernels, 1.2x for the weight-gradient kernel (dy is re-read per 128-row M tile).
+NCU_TRAFFIC_RATIO = {"bn_bwd_reduce": 14.014 / 13.873, "bn_bwd_apply": 18.479 / 18.498, "bn_apply": 9.205 / 9.249,
+                     "tc_gemm_bf16": 5.722 / 5.780, "tc_wgrad_bf16": 6.941 / 5.780}
+
+
 def kernel_work(name, a):
     """(algorithmic FLOPs, algorithmic HBM bytes) of one C-ABI call from its arguments: tensors read + written once
     (DESIGN.md §3); `a` holds "T" for tensor arguments, None for absent ones, scalars otherwise."""
@@ -424,8 +431,13 @@ def run_gpu_arm(a):
         ridge = pk["tf_sus"] * 1e12 / (pk["hbm"] * 1e9)
         if by > 0 and fl / by < ridge:
             ach = by / (t_ms / 1e3) / 1e9
+            ratio = NCU_TRAFFIC_RATIO.get(name)
             out["roofline"] = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
-                               "frac": ach / pk["hbm"], "traffic": None, "peak_source": pk["src"],
+                               "frac": ach / pk["hbm"], "traffic": (by / cnt) * ratio if ratio else None,
+                               "traffic_source": "ncu --set full capture profiles/r1_ncu_ops_N72.txt (measured / "
+                                                 "algorithmic DRAM bytes of the largest launch), applied to the mean "
+                                                 "launch" if ratio else None,
+                               "peak_source": pk["src"],
                                "algorithmic_bytes_per_launch": by / cnt, "launches_per_step": cnt,
                                "avg_launch_ms": t_ms / cnt, "share_of_step": t_ms / total}
         else:
