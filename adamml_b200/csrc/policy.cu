@@ -328,6 +328,35 @@ inline int ew_blocks(long long total) {
   return (int)(b < cap ? (b > 0 ? b : 1) : cap);
 }
 
+
+// Stand-alone hard Gumbel-softmax over [R, 2] logits (causality_modeling=None branch, policy_net.py:330-339):
+// g = -log(Exp(1)); y = softmax((l+g)/tau); dec = (onehot(argmax) - y + y)[:, 1]
+__global__ void gumbel_hard_fwd_kernel(const float* __restrict__ logits, const float* __restrict__ expo, float tau,
+                                       float* __restrict__ ysoft, float* __restrict__ dec, long long R) {
+  long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  const float l0 = logits[2 * r], l1 = logits[2 * r + 1];
+  const float g0 = -logf(expo[2 * r]), g1 = -logf(expo[2 * r + 1]);
+  const float v0 = (l0 + g0) / tau, v1 = (l1 + g1) / tau;
+  const float mx = fmaxf(v0, v1);
+  const float e0 = expf(v0 - mx), e1 = expf(v1 - mx);
+  const float ssum = e0 + e1;
+  const float y0 = e0 / ssum, y1 = e1 / ssum;
+  ysoft[2 * r] = y0;
+  ysoft[2 * r + 1] = y1;
+  const float hard1 = (y1 > y0) ? 1.f : 0.f;  // torch.max keeps the first index on ties
+  dec[r] = (hard1 - y1) + y1;
+}
+// straight-through gradient: d dec / d l1 = y0*y1/tau, d dec / d l0 = -y0*y1/tau
+__global__ void gumbel_hard_bwd_kernel(const float* __restrict__ d_dec, const float* __restrict__ ysoft, float tau,
+                                       float* __restrict__ dlogits, long long R) {
+  long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  const float t = d_dec[r] * ysoft[2 * r] * ysoft[2 * r + 1] / tau;
+  dlogits[2 * r] = -t;
+  dlogits[2 * r + 1] = t;
+}
+
 }  // namespace
 
 extern "C" {
@@ -422,6 +451,21 @@ int adamml_frame_mean_bwd(const float* dy, float* dx, long long V, int Tn, int C
   if (dy_ld <= 0) dy_ld = C;
   frame_mean_bwd_kernel<<<ew_blocks(V * Tn * C), 256, 0, stream>>>(dy, dx, V, Tn, C, dy_ld);
   return adamml_check_launch("frame_mean_bwd");
+}
+
+
+int adamml_gumbel_hard_fwd(const float* logits, const float* expo, float tau, float* ysoft, float* dec, long long R,
+                           cudaStream_t stream) {
+  ADAMML_REQUIRE(R > 0 && tau > 0.f, "gumbel_hard_fwd: bad arguments");
+  gumbel_hard_fwd_kernel<<<(unsigned)((R + 255) / 256), 256, 0, stream>>>(logits, expo, tau, ysoft, dec, R);
+  return adamml_check_launch("gumbel_hard_fwd");
+}
+
+int adamml_gumbel_hard_bwd(const float* d_dec, const float* ysoft, float tau, float* dlogits, long long R,
+                           cudaStream_t stream) {
+  ADAMML_REQUIRE(R > 0 && tau > 0.f, "gumbel_hard_bwd: bad arguments");
+  gumbel_hard_bwd_kernel<<<(unsigned)((R + 255) / 256), 256, 0, stream>>>(d_dec, ysoft, tau, dlogits, R);
+  return adamml_check_launch("gumbel_hard_bwd");
 }
 
 }  // extern "C"

@@ -16,6 +16,8 @@ class _GateFuse(torch.autograd.Function):
     @staticmethod
     def forward(ctx, logits, dec, lf):
         M, S, N, C = logits.shape
+        logits = logits.contiguous()
+        dec = dec.contiguous() if dec is not None else None  # the kernel indexes [S][M][N] densely
         out = torch.empty((N, C), device=logits.device, dtype=torch.float32)
         call("fuse_fwd", logits, dec, lf, out, M, S, N, C)
         ctx.save_for_backward(logits, dec, lf)

@@ -230,6 +230,79 @@ class _PolicyHead(torch.autograd.Function):
         return (None, None, None, None, None) + tuple(dfeats) + tuple(grads)
 
 
+class _PolicyHeadNoCausal(torch.autograd.Function):
+    """causality_modeling=None (policy_net.py:330-339): joint MLP -> per-modality Linear(2048, 2) on every
+    (segment, video) feature -> ONE hard Gumbel-softmax over all (modality, segment, video) rows."""
+
+    @staticmethod
+    def forward(ctx, expo, tau, save, nfeat, S, *args):
+        feats, params = args[:nfeat], args[nfeat:]
+        j0w, j0b, j2w, j2b = params[:4]
+        fcp = params[4:]
+        M = len(fcp) // 2
+        SN = feats[0].shape[0]
+        dev = feats[0].device
+        f = torch.cat(feats, 1) if nfeat > 1 else feats[0]
+        h1 = ops.linear_fwd(f, j0w)
+        ops.bias_act_(h1, j0b, ACT_RELU)
+        o = ops.linear_fwd(h1, j2w)
+        ops.bias_act_(o, j2b, ACT_RELU)
+        logits = torch.empty((M, SN, 2), device=dev)
+        for m in range(M):
+            ops.linear_fwd(o, fcp[2 * m], out=logits[m])
+            ops.bias_act_(logits[m], fcp[2 * m + 1], ACT_NONE)
+        ysoft = torch.empty_like(logits)
+        dec = torch.empty((M, SN), device=dev)
+        call("gumbel_hard_fwd", logits, expo, float(tau), ysoft, dec, M * SN)
+        ctx.saved = (f, h1, o, ysoft, params) if save else None
+        ctx.dims = (M, SN, nfeat, float(tau))
+        N = SN // S
+        ctx.mark_non_differentiable(logits)
+        # (MSN) -> [M,S,N] -> [S,M,N]   /   logits [M,S,N,2] -> [S,M,N,2]
+        return dec.view(M, S, N).transpose(0, 1).contiguous(), logits.view(M, S, N, 2).transpose(0, 1).contiguous()
+
+    @staticmethod
+    def backward(ctx, d_dec, _d_logits):
+        n_in = 5
+        if ctx.saved is None:
+            raise RuntimeError("policy head was run without a tape (no_grad)")
+        f, h1, o, ysoft, params = ctx.saved
+        M, SN, nfeat, tau = ctx.dims
+        j0w, j0b, j2w, j2b = params[:4]
+        fcp = params[4:]
+        dd = d_dec.transpose(0, 1).contiguous().view(M, SN)
+        dl = torch.empty((M, SN, 2), device=f.device)
+        call("gumbel_hard_bwd", dd, ysoft, tau, dl, M * SN)
+        need = ctx.needs_input_grad[n_in + nfeat:]
+        grads = [None] * len(params)
+        d_o = None
+        for m in range(M):
+            if need[4 + 2 * m]:
+                grads[4 + 2 * m] = ops.linear_wgrad(o, dl[m])
+            if need[5 + 2 * m]:
+                grads[5 + 2 * m] = ops.colsum(dl[m])
+            dm = ops.linear_dgrad(dl[m], fcp[2 * m])
+            d_o = dm if d_o is None else d_o + dm
+        dz2 = ops.act_bwd(d_o, o, ACT_RELU)
+        if need[2]:
+            grads[2] = ops.linear_wgrad(h1, dz2)
+        if need[3]:
+            grads[3] = ops.colsum(dz2)
+        dh1 = ops.linear_dgrad(dz2, j2w)
+        dz1 = ops.act_bwd(dh1, h1, ACT_RELU)
+        if need[0]:
+            grads[0] = ops.linear_wgrad(f, dz1)
+        if need[1]:
+            grads[1] = ops.colsum(dz1)
+        dfeats = [None] * nfeat
+        if any(ctx.needs_input_grad[n_in:n_in + nfeat]):
+            df = ops.linear_dgrad(dz1, j0w)
+            w = df.shape[1] // nfeat
+            dfeats = [df[:, i * w:(i + 1) * w].contiguous() for i in range(nfeat)]
+        ctx.saved = None
+        return (None,) * n_in + tuple(dfeats) + tuple(grads)
+
+
 class PolicyNet(nn.Module):
     def __init__(self, joint_net, modality, causality_modeling="lstm"):
         super().__init__()
@@ -242,9 +315,8 @@ class PolicyNet(nn.Module):
         if causality_modeling == "lstm":
             self.lstm = nn.LSTMCell(feature_dim + 2 * self.num_modality, 256)
             self.fcs = nn.ModuleList([nn.Linear(256, 2) for _ in range(self.num_modality)])
-        elif causality_modeling is None:
-            raise NotImplementedError("causality_modeling=None (per-segment FC policy, policy_net.py:330-339) is "
-                                      "outside the accelerated path (SURVEY.md §8f rank 4)")
+        elif causality_modeling is None:  # policy_net.py:281
+            self.fcs = nn.ModuleList([nn.Linear(feature_dim, 2) for _ in range(self.num_modality)])
         else:
             raise ValueError("unknown mode")
 
@@ -261,7 +333,10 @@ class PolicyNet(nn.Module):
         return "j_mobilenet_v2{}".format("-" + self.causality_modeling if self.causality_modeling else "")
 
     def draw_gumbel_noise(self, S, N, device):
-        """Exp(1) samples, one [M*N, 2] draw per segment like F.gumbel_softmax (policy_net.py:288)."""
+        """Exp(1) samples in the reference's draw order (F.gumbel_softmax, policy_net.py:288): one [M*N, 2] draw per
+        segment for the LSTM policy, a single [M*S*N, 2] draw for causality_modeling=None."""
+        if self.causality_modeling is None:
+            return torch.empty((1, self.num_modality * S * N, 2), device=device).exponential_()
         return torch.stack([torch.empty((self.num_modality * N, 2), device=device).exponential_() for _ in range(S)])
 
     def forward(self, p_x, S, N, expo=None):
@@ -275,8 +350,15 @@ class PolicyNet(nn.Module):
             feats.append(f)
         if expo is None:
             expo = self.draw_gumbel_noise(S, N, feats[0].device)
-        expo = expo.reshape(S, self.num_modality * N, 2).contiguous().float()
         j = self.joint_net.joint
+        if self.causality_modeling is None:
+            expo = expo.reshape(self.num_modality * S * N, 2).contiguous().float()
+            params = [j[0].weight, j[0].bias, j[2].weight, j[2].bias]
+            for fc in self.fcs:
+                params += [fc.weight, fc.bias]
+            return _PolicyHeadNoCausal.apply(expo, self.temperature, torch.is_grad_enabled(), len(feats), S, *feats,
+                                             *params)
+        expo = expo.reshape(S, self.num_modality * N, 2).contiguous().float()
         params = [j[0].weight, j[0].bias, j[2].weight, j[2].bias, self.lstm.weight_ih, self.lstm.weight_hh,
                   self.lstm.bias_ih, self.lstm.bias_hh]
         for fc in self.fcs:

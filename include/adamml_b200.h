@@ -209,6 +209,13 @@ int adamml_policy_step_bwd(const float* d_dec, const float* d_logits_fb, const f
                            float tau, float* dl_out, long long dl_ms, float* dgates_out, float* dh_prev,
                            float* dc_prev, float* d_prev_logits, int N, int M, int Hd, cudaStream_t stream);
 
+/* Stand-alone hard Gumbel-softmax over [R,2] logits: the causality_modeling=None policy (policy_net.py:330-339)
+ * calls F.gumbel_softmax once on all (modality, segment, video) rows.  dec = straight-through column 1. */
+int adamml_gumbel_hard_fwd(const float* logits, const float* expo, float tau, float* ysoft, float* dec, long long R,
+                           cudaStream_t stream);
+int adamml_gumbel_hard_bwd(const float* d_dec, const float* ysoft, float tau, float* dlogits, long long R,
+                           cudaStream_t stream);
+
 /* ---- gate x logits, late-fusion weights, sum over modalities, mean over segments ----
  * joint_resnet_mobilenetv2.py:92-97,112-127 ; adamml.py:88.
  * logits [M][S][N][C]; dec [S][M][N] (NULL = ungated); lf [M-1] (NULL = plain mean); out [N][C] */

@@ -81,7 +81,10 @@ def draw_noise(seed, cfg, N, S, training, generator=None):
         g = torch.Generator()
         g.manual_seed(seed)
     M = len(cfg["p_modality"])
-    expo = [torch.empty(M * N, 2).exponential_(generator=g) for _ in range(S)]
+    if cfg["causality_modeling"] is None:  # one F.gumbel_softmax call over all (modality, segment, video) rows
+        expo = [torch.empty(M * S * N, 2).exponential_(generator=g)]
+    else:
+        expo = [torch.empty(M * N, 2).exponential_(generator=g) for _ in range(S)]
     drop = []
     if training and cfg["dropout"] > 0:
         p = cfg["dropout"]

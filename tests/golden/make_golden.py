@@ -29,6 +29,9 @@ CASES = {
     "adamml_rgb_flow_train": dict(kind="adamml", modality=["rgb", "flow", "rgbdiff"], N=1, S=2, hw=96, training=True),
     "adamml_rgb_sound_flow_train": dict(kind="adamml", modality=["rgb", "sound", "flow", "rgbdiff"], N=2, S=2, hw=64,
                                         training=True),
+    # causality_modeling=None: per-segment FC policy, one Gumbel draw over all rows (policy_net.py:330-339)
+    "adamml_rgb_sound_nocausal_train": dict(kind="adamml", modality=["rgb", "sound"], N=2, S=2, hw=64, training=True,
+                                            causality=None),
 }
 
 
@@ -45,7 +48,7 @@ def build_reference(models, case):
     mod = case["modality"]
     ns = dict(groups=8, frames_per_group=4, num_segments=case["S"], depth=50, num_classes=31, dropout=0.5,
               pooling_method="max", without_t_stride=False, fusion_point="logits", learnable_lf_weights=True,
-              causality_modeling="lstm", rng_policy=False, rng_threshold=0.5, unimodality_pretrained=[],
+              causality_modeling=case.get("causality", "lstm"), rng_policy=False, rng_threshold=0.5, unimodality_pretrained=[],
               imagenet_pretrained=False, dataset="kinetics-sounds", dense_sampling=False, lr_scheduler="cosine",
               sync_bn=False, batch_size=72, prefix="", epochs=1)
     if case["kind"] == "resnet":
@@ -66,7 +69,7 @@ def fingerprint(t):
 def run_case(name, case, models):
     torch.set_num_threads(os.cpu_count())
     seed = 1
-    cfg = O.make_cfg(case["modality"], num_segments=case["S"])
+    cfg = O.make_cfg(case["modality"], num_segments=case["S"], causality_modeling=case.get("causality", "lstm"))
     model, arch = build_reference(models, case)
     ref_sd = model.state_dict()
     sd = O.fill_state_dict({k: v.shape for k, v in ref_sd.items()}, seed=0)

@@ -6,14 +6,14 @@ import torch
 from util import O, fingerprint, load_golden, rel
 
 CASES = ["resnet50_rgb_b2", "adamml_rgb_sound_eval", "adamml_rgb_flow_train", "adamml_rgb_sound_flow_train",
-         "adamml_rgb_sound_train"]
+         "adamml_rgb_sound_train", "adamml_rgb_sound_nocausal_train"]
 
 
 @pytest.mark.parametrize("name", CASES)
 def test_oracle_matches_reference_golden(name):
     g = load_golden(name)
     case = g["case"]
-    cfg = O.make_cfg(case["modality"], num_segments=case["S"])
+    cfg = O.make_cfg(case["modality"], num_segments=case["S"], causality_modeling=case.get("causality", "lstm"))
     shapes = None
     # parameter shapes come from the oracle-independent key list + a shape probe of the product model
     from adamml_b200.models import build_model

@@ -15,7 +15,7 @@ from util import (O, assert_grads_as_good_as_reference, compare_grads, fingerpri
 pytestmark = pytest.mark.gpu
 
 CASES = ["resnet50_rgb_b2", "adamml_rgb_sound_eval", "adamml_rgb_flow_train", "adamml_rgb_sound_flow_train",
-         "adamml_rgb_sound_train"]
+         "adamml_rgb_sound_train", "adamml_rgb_sound_nocausal_train"]
 LOGIT_TOL = 1e-3
 
 
@@ -28,7 +28,7 @@ def build(case, dtype, cuda):
 
 
 def run_product(model, case, g_seed, cuda):
-    cfg = O.make_cfg(case["modality"], num_segments=case["S"])
+    cfg = O.make_cfg(case["modality"], num_segments=case["S"], causality_modeling=case.get("causality", "lstm"))
     N, S_run, training = case["N"], case.get("S_run", case["S"]), case["training"]
     xs, y = O.make_inputs(cfg, N, S_run, hw=case["hw"])
     xs = [x.to(cuda) for x in xs]

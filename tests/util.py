@@ -18,7 +18,7 @@ def namespace(case, **over):
     mod = case["modality"]
     ns = dict(groups=8, frames_per_group=4, num_segments=case["S"], depth=50, num_classes=31, dropout=0.5,
               pooling_method="max", without_t_stride=False, fusion_point="logits", learnable_lf_weights=True,
-              causality_modeling="lstm", rng_policy=False, rng_threshold=0.5, unimodality_pretrained=[],
+              causality_modeling=case.get("causality", "lstm"), rng_policy=False, rng_threshold=0.5, unimodality_pretrained=[],
               imagenet_pretrained=False, dataset="kinetics-sounds", dense_sampling=False, lr_scheduler="cosine",
               sync_bn=False, batch_size=72, prefix="", epochs=1)
     if case["kind"] == "resnet":
@@ -118,7 +118,7 @@ def assert_grads_as_good_as_reference(prod, ref32, truth64, mean_factor=2.0, max
 def oracle_run(case, seed, dtype, sd0):
     """Runs the oracle (fp32 = bit-identical to the reference, or float64 = truth) -> logits, dec, grads, sd."""
     import torch.nn.functional as F
-    cfg = O.make_cfg(case["modality"], num_segments=case["S"])
+    cfg = O.make_cfg(case["modality"], num_segments=case["S"], causality_modeling=case.get("causality", "lstm"))
     N, S_run, training = case["N"], case.get("S_run", case["S"]), case["training"]
     xs, y = O.make_inputs(cfg, N, S_run, hw=case["hw"])
     sd = {}
