@@ -83,6 +83,69 @@ def test_resnet_block(cuda, cfg):
         assert relerr(ex.grads[p], want[k]) < 1e-3, k
 
 
+@pytest.mark.parametrize("cfg", [(256, 128, 2, True), (512, 128, 1, False), (64, 64, 1, True)])
+def test_resnet_bottleneck_bf16_engine(cuda, cfg):
+    """bf16 engine path of ONE Bottleneck (tcgen05 GEMM / implicit-GEMM conv with fused BN statistics, parity-class
+    stride-2 dgrad, compact stride-2 downsample gradient scattered by conv1's dgrad epilogue, TMA-fetched addend,
+    in-place masked gradient) against torch fp32 with bf16 rounding at the engine's storage points.  Three layers
+    deep, so bf16 noise stays at the percent level and a wrong kernel would stand out."""
+    from adamml_b200.engine import Exec
+    import copy
+    import importlib
+    _Block = importlib.import_module("adamml_b200.models.resnet")._Block
+    inpl, planes, stride, ds = cfg
+    g = torch.Generator().manual_seed(0)
+    blk = _Block(inpl, planes, stride, True, ds)
+    randomize(blk, g)
+    blk = blk.to(cuda).train()
+    G, ipg, H = 2, 6, 28
+    q = lambda t: t.bfloat16().float()  # noqa: E731
+
+    class Q(torch.autograd.Function):  # bf16 storage in both directions
+        @staticmethod
+        def forward(ctx, t):
+            return q(t)
+
+        @staticmethod
+        def backward(ctx, gr):
+            return q(gr)
+
+    x = q(torch.randn(G * ipg, inpl, H, H, generator=g).to(cuda)).requires_grad_(True)
+    ref_blk = copy.deepcopy(blk)
+    # bf16 weight operand, straight-through gradient to the fp32 parameter
+    conv = lambda m, a: Q.apply(F.conv2d(a, q(m.weight).detach() + (m.weight - m.weight.detach()), None, m.stride,  # noqa: E731
+                                         m.padding))
+    outs = []
+    for xs in x.chunk(G):
+        o = Q.apply(F.relu(ref_blk.bn1(conv(ref_blk.conv1, xs))))
+        o = Q.apply(F.relu(ref_blk.bn2(conv(ref_blk.conv2, o))))
+        o = ref_blk.bn3(conv(ref_blk.conv3, o))
+        idn = ref_blk.downsample[1](conv(ref_blk.downsample[0], xs)) if ds else xs
+        outs.append(Q.apply(F.relu(o + idn)))
+    ref = torch.cat(outs)
+    dy = q(torch.randn(ref.shape, generator=g).to(cuda))
+    ref.backward(dy)
+    def rms(a, b):
+        a, b = a.float(), b.float()
+        return ((a - b).pow(2).mean().sqrt() / b.pow(2).mean().sqrt()).item()
+
+    ex = Exec(torch.bfloat16, True, G, save=True)
+    out = ex.bottleneck(nhwc(x.detach()).bfloat16(), blk)
+    assert relerr(nchw(out), ref) < 2e-2
+    dx = ex.bottleneck_bwd(nhwc(dy).bfloat16())
+    assert not ex.tape
+    # gradients are judged in rms: ReLU masks are discontinuous, so a 1-ulp difference in a pre-activation that sits
+    # at zero flips a whole gradient element (max-norm is meaningless), while the rms stays at bf16 noise level.
+    # Against PURE fp32 the same quantities are off by 6e-2 rms (scripts/diag_block_bwd.py): masks flip wherever the
+    # rounding noise of the previous layers exceeds |pre-activation|.
+    e_dx = rms(nchw(dx), x.grad)
+    want = dict(ref_blk.named_parameters())
+    e_p = {k: rms(ex.grads[p], want[k].grad) for k, p in blk.named_parameters()}
+    print(f"bf16 block {cfg}: dx rms {e_dx:.3e}; param grads rms max {max(e_p.values()):.3e} ({max(e_p, key=e_p.get)})")
+    assert e_dx < 2e-2, e_dx
+    assert max(e_p.values()) < 3e-2, e_p
+
+
 @pytest.mark.parametrize("variant", ["sound", "policy"])
 @pytest.mark.parametrize("cfg", [(16, 16, 1, 6), (16, 24, 2, 6), (32, 16, 1, 1), (24, 24, 1, 6)])
 def test_inverted_residual(cuda, variant, cfg):

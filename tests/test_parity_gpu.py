@@ -176,6 +176,123 @@ def test_bf16_mode_close_to_oracle(cuda):
         assert p.grad is not None and torch.isfinite(p.grad).all(), k
 
 
+def test_bf16_mode_vs_fp32_mode_same_decisions(cuda):
+    """bf16 speed mode against the (oracle-verified) fp32 parity mode on a batch large enough for stable BatchNorm
+    statistics (16 clips x 2 segments, 112^2).  rng_policy=True draws the gating decisions from torch's RNG instead
+    of the policy net (adamml.py:76-78), so both precisions gate identically and the comparison isolates the
+    numerical error of the main path (ResNet-50 + sound MobileNetV2 + fusion): train-mode logits and the
+    classifier gradients must agree to bf16 noise."""
+    from adamml_b200.models import build_model
+    case = dict(kind="adamml", modality=["rgb", "sound"], N=16, S=2, hw=112, training=True)
+    cfg = O.make_cfg(case["modality"], num_segments=2)
+    gen = torch.Generator(device=cuda).manual_seed(7)
+    rgb = torch.randn(16, 2 * 8 * 3, 112, 112, device=cuda, generator=gen)
+    snd = torch.randn(16, 2, 256, 256, device=cuda, generator=gen) * 3 - 5
+    y = torch.randint(0, 31, (16,), device=cuda, generator=gen)
+    res = {}
+    sd0 = None
+    for tag, dt in (("fp32", torch.float32), ("bf16", torch.bfloat16)):
+        model, _ = build_model(namespace(case, compute_dtype=dt, rng_policy=True, rng_threshold=0.5))
+        if sd0 is None:
+            sd0 = O.fill_state_dict({k: v.shape for k, v in model.state_dict().items()}, seed=0)
+        model.load_state_dict(sd0)
+        model = model.to(cuda).train()
+        torch.manual_seed(11)  # same decisions and dropout masks for both precisions
+        logits, dec = model([rgb, snd])
+        F.cross_entropy(logits, y).backward()
+        torch.cuda.synchronize()
+        res[tag] = (logits.detach(), dec.detach(), model.main_net.nets[0].fc.weight.grad.clone(),
+                    model.main_net.nets[1].classifier[1].weight.grad.clone())
+    assert torch.equal(res["fp32"][1], res["bf16"][1])
+    e_logits = rel(res["bf16"][0], res["fp32"][0])
+    e_g0, e_g1 = rel(res["bf16"][2], res["fp32"][2]), rel(res["bf16"][3], res["fp32"][3])
+    print(f"bf16 vs fp32 mode (N=16): logits rel {e_logits:.3e}, fc grad rel {e_g0:.3e} / {e_g1:.3e}")
+    # measured 0.12 / ... on randomly initialised weights: this is the price of bf16 STORAGE through 53 stacked
+    # conv+BN layers, not of the kernels — test_bf16_resnet_matches_bf16_storage_emulation pins the kernels
+    assert e_logits < 0.3 and e_g0 < 0.3 and e_g1 < 0.3
+
+
+def test_bf16_resnet_tracks_bf16_storage_emulation(cuda):
+    """The bf16 engine (s2d tcgen05 stem, tcgen05 GEMM/conv with fused BN statistics, row-streaming BN) against a
+    torch fp32 computation that rounds to bf16 exactly where the engine stores bf16 (conv operands, conv outputs z,
+    block outputs), stage by stage through ResNet-50 (8 clips x 8 frames, 112^2, train-mode BN).
+
+    On randomly initialised weights the network amplifies any perturbation by ~1.25x per block (the emulation itself
+    drifts to ~50 % rms from pure fp32 at layer4 — scripts/diag_bf16_drift.py), so end-to-end closeness proves
+    nothing.  What pins the kernels: (1) the first stages agree to far better than one bf16 ulp of noise
+    (stem 3e-5, layer1.0 7e-4 rms measured), (2) at EVERY stage the engine is closer to the emulation than the
+    emulation is to fp32, i.e. it never adds error beyond bf16 storage noise, and the growth has no jump."""
+    from adamml_b200.engine import Exec
+    from adamml_b200.models.resnet import ResNet
+    from adamml_b200.ops import ACT_RELU
+    torch.manual_seed(3)
+    net = ResNet(50, 8, num_classes=31, dropout=0.5, input_channels=3, compute_dtype=torch.bfloat16)
+    g = torch.Generator().manual_seed(3)
+    with torch.no_grad():
+        for m in net.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.weight.copy_(torch.rand(m.weight.shape, generator=g) * 0.5 + 0.75)
+                m.bias.copy_(torch.randn(m.bias.shape, generator=g) * 0.1)
+    net = net.to(cuda).train()
+    N = 8
+    x = torch.randn(N, 24, 112, 112, generator=g).to(cuda)
+
+    def rms(a, b):
+        return ((a.float() - b.float()).pow(2).mean().sqrt() / b.float().pow(2).mean().sqrt()).item()
+
+    def run_torch(rounding):
+        q = (lambda t: t.bfloat16().float()) if rounding else (lambda t: t)
+        conv = lambda m, a: q(F.conv2d(a, q(m.weight), None, m.stride, m.padding))  # noqa: E731
+        bn = lambda m, z: F.batch_norm(z, None, None, m.weight, m.bias, True, 0.1, m.eps)  # noqa: E731
+        outs = []
+        with torch.no_grad():
+            a = q(F.relu(bn(net.bn1, conv(net.conv1, q(x.view(N * 8, 3, 112, 112))))))
+            outs.append(a)
+            a = F.max_pool2d(a, 3, 2, 1)
+            frames = 8
+            for li in range(4):
+                for blk in getattr(net, f"layer{li + 1}"):
+                    idn = a
+                    o = q(F.relu(bn(blk.bn1, conv(blk.conv1, a))))
+                    o = q(F.relu(bn(blk.bn2, conv(blk.conv2, o))))
+                    o = bn(blk.bn3, conv(blk.conv3, o))
+                    if blk.downsample is not None:
+                        idn = bn(blk.downsample[1], conv(blk.downsample[0], a))
+                    a = q(F.relu(o + idn))
+                    outs.append(a)
+                if li < 3:
+                    nt, c, h, w = a.shape
+                    v = a.view(-1, frames, c, h, w).transpose(1, 2)
+                    a = F.max_pool3d(v, (3, 1, 1), (2, 1, 1), (1, 0, 0)).transpose(1, 2).contiguous().view(-1, c, h, w)
+                    frames //= 2
+        return outs
+
+    eng = []
+    with torch.no_grad():
+        ex = Exec(torch.bfloat16, True, 1, save=False)
+        a = ex.cba(net.pack_input(x, 1), net.conv1, net.bn1, ACT_RELU)
+        eng.append(a.permute(0, 3, 1, 2).float())
+        a = ex.maxpool(a)
+        frames = 8
+        for li in range(4):
+            for blk in getattr(net, f"layer{li + 1}"):
+                a = ex.bottleneck(a, blk)
+                eng.append(a.permute(0, 3, 1, 2).float())
+            if li < 3:
+                a = ex.tpool(a, frames, False)
+                frames //= 2
+    t16, t32 = run_torch(True), run_torch(False)
+    d_eng = [rms(a, b) for a, b in zip(eng, t16)]
+    d_sto = [rms(b, c) for b, c in zip(t16, t32)]
+    print("engine~emulation rms:", " ".join(f"{v:.1e}" for v in d_eng))
+    print("emulation~fp32  rms:", " ".join(f"{v:.1e}" for v in d_sto))
+    assert d_eng[0] < 1e-3 and d_eng[1] < 5e-3, d_eng[:2]
+    for i, (de, ds) in enumerate(zip(d_eng, d_sto)):
+        assert de <= ds, (i, de, ds)                      # never worse than bf16 storage noise itself
+        if i:
+            assert de < 3.0 * max(d_eng[i - 1], 1e-3), (i, de, d_eng[i - 1])  # smooth growth, no jump at a block
+
+
 def test_unimodal_sound_mobilenet_matches_oracle(cuda):
     from adamml_b200.models import build_model
     ns = namespace(dict(kind="resnet", modality=["sound"], S=1), backbone_net="sound_mobilenet_v2", modality="sound",
