@@ -697,7 +697,9 @@ int adamml_tc_dgrad_s2_bf16(const void* dy, const void* w_rot, void* dx, int IMG
   return ADAMML_OK;
 }
 
-/* 7x7 / stride 2 / pad 3 ResNet stem (resnet.py:138,199) on the space-to-depth input written by
+/* Stride-2 first convolutions on a space-to-depth operand: the 7x7 / pad 3 ResNet stem (resnet.py:138,199; taps = 4)
+ * and the 3x3 / pad 1 first conv of the MobileNetV2s (sound_mobilenet_v2.py:120, policy_net.py:117; taps = 2).
+ * Described for the stem: 7x7 / stride 2 / pad 3 on the space-to-depth input written by
  * adamml_pack_frames_s2d: xs [IMGS, Hs, Wp, Cs] bf16 (Hs = H/2 rows, Wp = W/2 + 4 columns of which the first two
  * and the last two are zeros, Cs = 4*C padded to a multiple of 16).  In that layout the stem is a 4-tap
  * (dh = -2..1) stride-1 convolution whose "pixel" is the 4*Cs-wide window of four consecutive s2d columns:
@@ -705,25 +707,25 @@ int adamml_tc_dgrad_s2_bf16(const void* dy, const void* w_rot, void* dx, int IMG
  * smaller than its innermost extent (4*Cs elements) — an overlapping, im2col-free view.  K = 16*Cs.
  * w: adamml_pack_weight_stem operand [Cout][4][4*Cs] bf16. */
 int adamml_tc_stem_conv_bf16(const void* xs, const void* w, void* y, int IMGS, int Hs, int Wp, int Cs, int Cout,
-                             int Ho, int Wo, double* stats, int imgs_per_group, cudaStream_t stream) {
-  if (Cs % 16 || Cout % 8 || Cs > 64) {
-    adamml_set_error("tc_stem_conv: Cs=%d Cout=%d outside the tcgen05 envelope", Cs, Cout);
+                             int Ho, int Wo, int taps, double* stats, int imgs_per_group, cudaStream_t stream) {
+  if (Cs % 8 || Cout % 8 || (taps != 4 && taps != 2) || taps * Cs > 256) {
+    adamml_set_error("tc_stem_conv: Cs=%d Cout=%d taps=%d outside the tcgen05 envelope", Cs, Cout, taps);
     return ADAMML_ERR_UNSUPPORTED;
   }
-  ADAMML_REQUIRE(Ho == Hs && Wo + 4 <= Wp + 1, "tc_stem_conv: geometry (Ho == Hs, Wp >= Wo + 3)");
+  ADAMML_REQUIRE(Ho == Hs && Wo + taps - 1 <= Wp, "tc_stem_conv: geometry (Ho == Hs, Wp >= Wo + taps - 1)");
   ADAMML_REQUIRE(((uintptr_t)xs % 16) == 0 && ((uintptr_t)w % 16) == 0 && ((uintptr_t)y % 16) == 0,
                  "tc_stem_conv: operands must be 16-byte aligned");
   ADAMML_REQUIRE(!stats || imgs_per_group > 0, "tc_stem_conv: stats need imgs_per_group");
-  const int VC = 4 * Cs;  // virtual channels per position
+  const int VC = taps * Cs;  // virtual channels per position: `taps` consecutive s2d columns
   ConvGeom geo;
   memset(&geo, 0, sizeof(geo));
-  geo.ntaps = 4;
+  geo.ntaps = taps;
   geo.cin = VC;
   geo.kb_per_tap = (VC + BLOCK_K - 1) / BLOCK_K;
-  for (int t = 0; t < 4; ++t) {
+  for (int t = 0; t < taps; ++t) {
     geo.tap_koff[t] = t * VC;
     geo.tap_map[t] = 0;
-    geo.tap_dh[t] = (signed char)(t - 2);
+    geo.tap_dh[t] = (signed char)(t - taps / 2);
     geo.tap_dw[t] = 0;
   }
   set_tiles(geo, Wo, Ho, IMGS);
@@ -731,11 +733,11 @@ int adamml_tc_stem_conv_bf16(const void* xs, const void* w, void* y, int IMGS, i
   geo.imgs_per_group = imgs_per_group > 0 ? imgs_per_group : IMGS;
   ConvMaps cm;
   memset(&cm, 0, sizeof(cm));
-  // positions 0..Wp-4: position p covers stored columns p..p+3
-  int rc = make_map_4d(&cm.m[0], xs, VC, Wp - 3, Hs, IMGS, Cs, (long long)Wp * Cs, (long long)Hs * Wp * Cs, geo.BW,
-                       geo.BH, geo.BI);
+  // positions 0..Wp-taps: position p covers stored columns p..p+taps-1
+  int rc = make_map_4d(&cm.m[0], xs, VC, Wp - (taps - 1), Hs, IMGS, Cs, (long long)Wp * Cs, (long long)Hs * Wp * Cs,
+                       geo.BW, geo.BH, geo.BI);
   if (rc) return rc;
-  return run_conv(geo, cm, w, 4LL * VC, y, nullptr, Cout, stats, stream);
+  return run_conv(geo, cm, w, (long long)taps * VC, y, nullptr, Cout, stats, stream);
 }
 
 }  // extern "C"

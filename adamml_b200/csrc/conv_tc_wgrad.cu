@@ -337,26 +337,26 @@ int adamml_tc_wgrad_bf16(const void* x, const void* dy, float* dw, int IMGS, int
 /* Weight gradient of the 7x7/s2 stem on the space-to-depth input (see adamml_tc_stem_conv_bf16):
  * dw fp32 [Cout][4][4*Cs] (overwritten), unpacked to OIHW by adamml_unpack_wgrad_stem. */
 int adamml_tc_stem_wgrad_bf16(const void* xs, const void* dy, float* dw, int IMGS, int Hs, int Wp, int Cs, int Cout,
-                              int Ho, int Wo, cudaStream_t stream) {
-  if (Cs % 16 || Cout % 8 || Cs > 64) {
-    adamml_set_error("tc_stem_wgrad: Cs=%d Cout=%d outside the tcgen05 envelope", Cs, Cout);
+                              int Ho, int Wo, int taps, cudaStream_t stream) {
+  if (Cs % 8 || Cout % 8 || (taps != 4 && taps != 2) || taps * Cs > 256) {
+    adamml_set_error("tc_stem_wgrad: Cs=%d Cout=%d taps=%d outside the tcgen05 envelope", Cs, Cout, taps);
     return ADAMML_ERR_UNSUPPORTED;
   }
-  ADAMML_REQUIRE(Ho == Hs && Wo + 4 <= Wp + 1, "tc_stem_wgrad: geometry (Ho == Hs, Wp >= Wo + 3)");
+  ADAMML_REQUIRE(Ho == Hs && Wo + taps - 1 <= Wp, "tc_stem_wgrad: geometry (Ho == Hs, Wp >= Wo + taps - 1)");
   ADAMML_REQUIRE(((uintptr_t)xs % 16) == 0 && ((uintptr_t)dy % 16) == 0, "tc_stem_wgrad: operands must be 16-byte aligned");
-  const int VC = 4 * Cs;
+  const int VC = taps * Cs;
   WgGeom geo;
   memset(&geo, 0, sizeof(geo));
-  const int block_n = wg_tiling(geo, 4, VC, Cout, Wo, Ho, IMGS);
-  for (int t = 0; t < 4; ++t) {
+  const int block_n = wg_tiling(geo, taps, VC, Cout, Wo, Ho, IMGS);
+  for (int t = 0; t < taps; ++t) {
     geo.tap_map[t] = 0;
-    geo.tap_dh[t] = (signed char)(t - 2);
+    geo.tap_dh[t] = (signed char)(t - taps / 2);
     geo.tap_dw[t] = 0;
   }
   WgMaps maps;
   memset(&maps, 0, sizeof(maps));
-  int rc = make_map_4d(&maps.x[0], xs, VC, Wp - 3, Hs, IMGS, Cs, (long long)Wp * Cs, (long long)Hs * Wp * Cs, geo.BW,
-                       geo.BH, geo.BI);
+  int rc = make_map_4d(&maps.x[0], xs, VC, Wp - (taps - 1), Hs, IMGS, Cs, (long long)Wp * Cs, (long long)Hs * Wp * Cs,
+                       geo.BW, geo.BH, geo.BI);
   if (rc) return rc;
   rc = make_map_4d(&maps.dy, dy, Cout, Wo, Ho, IMGS, Cout, (long long)Wo * Cout, (long long)Ho * Wo * Cout, geo.BW,
                    geo.BH, geo.BI);

@@ -153,41 +153,70 @@ __global__ void pack_frames_s2d_kernel(const float* __restrict__ x, bf16* __rest
   }
 }
 
-// stem weight OIHW fp32 [Cout][C][7][7] -> bf16 [Cout][4 (dh+2)][4 (dw+2)][Cs]:
-// tap (r, s) = (2*dh+ph+3, 2*dw+pw+3), channel (ph*2+pw)*C + c; everything else zero.
+// NHWC bf16 [IMGS, H, W, C] -> space-to-depth bf16 [IMGS, H/2, W/2 + padl + padr, Cs] (zero pad columns, channel
+// (ph*2+pw)*C + c): operand of the stride-2 first convolutions of the MobileNetV2s on the tensor-core path.
+__global__ void nhwc_to_s2d_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, long long IMGS, int C, int H,
+                                   int W, int Cs, int padl, int padr) {
+  const int Hs = H / 2, Ws = W / 2, Wp = Ws + padl + padr;
+  const long long total = IMGS * Hs * Wp;
+  const bf16 zero = __float2bfloat16_rn(0.f);
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int ip = (int)(idx % Wp);
+    const int j = (int)((idx / Wp) % Hs);
+    const long long img = idx / ((long long)Wp * Hs);
+    bf16* dst = out + idx * Cs;
+    const int i = ip - padl;
+    if (i < 0 || i >= Ws) {
+      for (int c = 0; c < Cs; ++c) dst[c] = zero;
+      continue;
+    }
+    const bf16* src = x + ((img * H + 2 * j) * W + 2 * i) * C;
+    for (int ph = 0; ph < 2; ++ph)
+      for (int pw = 0; pw < 2; ++pw)
+        for (int c = 0; c < C; ++c) dst[(ph * 2 + pw) * C + c] = src[((long long)ph * W + pw) * C + c];
+    for (int c = 4 * C; c < Cs; ++c) dst[c] = zero;
+  }
+}
+
+// stride-2 first-conv weight OIHW fp32 [Cout][C][R][R] (R = 7, pad 3 -> T = 4 taps per axis; R = 3, pad 1 -> T = 2)
+// -> bf16 [Cout][T (dh + T/2)][T (dw + T/2)][Cs]: tap (r, s) = (2*dh+ph+pad, 2*dw+pw+pad), channel (ph*2+pw)*C + c;
+// everything else zero.
 __global__ void pack_weight_stem_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int Cout, int C,
-                                        int Cs) {
-  const long long total = (long long)Cout * 16 * Cs;
+                                        int Cs, int R, int T) {
+  const int pad = R / 2;
+  const long long total = (long long)Cout * T * T * Cs;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
     const int q = (int)(idx % Cs);
-    const int dwi = (int)((idx / Cs) % 4);
-    const int dhi = (int)((idx / (Cs * 4)) % 4);
-    const int co = (int)(idx / (Cs * 16));
+    const int dwi = (int)((idx / Cs) % T);
+    const int dhi = (int)((idx / (Cs * T)) % T);
+    const int co = (int)(idx / ((long long)Cs * T * T));
     float v = 0.f;
     if (q < 4 * C) {
       const int c = q % C, pp = q / C, ph = pp >> 1, pw = pp & 1;
-      const int r = 2 * (dhi - 2) + ph + 3, s_ = 2 * (dwi - 2) + pw + 3;
-      if (r >= 0 && r < 7 && s_ >= 0 && s_ < 7) v = src[(((long long)co * C + c) * 7 + r) * 7 + s_];
+      const int r = 2 * (dhi - T / 2) + ph + pad, s_ = 2 * (dwi - T / 2) + pw + pad;
+      if (r >= 0 && r < R && s_ >= 0 && s_ < R) v = src[(((long long)co * C + c) * R + r) * R + s_];
     }
     dst[idx] = __float2bfloat16_rn(v);
   }
 }
 
-// inverse of pack_weight_stem for the fp32 gradient: [Cout][4][4][Cs] -> OIHW [Cout][C][7][7]
+// inverse of pack_weight_stem for the fp32 gradient: [Cout][T][T][Cs] -> OIHW [Cout][C][R][R]
 __global__ void unpack_wgrad_stem_kernel(const float* __restrict__ src, float* __restrict__ dst, int Cout, int C,
-                                         int Cs) {
-  const long long total = (long long)Cout * C * 49;
+                                         int Cs, int R, int T) {
+  const int pad = R / 2;
+  const long long total = (long long)Cout * C * R * R;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
-    const int s_ = (int)(idx % 7);
-    const int r = (int)((idx / 7) % 7);
-    const int c = (int)((idx / 49) % C);
-    const int co = (int)(idx / (49LL * C));
-    const int t = r - 3, u = s_ - 3;
+    const int s_ = (int)(idx % R);
+    const int r = (int)((idx / R) % R);
+    const int c = (int)((idx / (R * R)) % C);
+    const int co = (int)(idx / ((long long)R * R * C));
+    const int t = r - pad, u = s_ - pad;
     const int dh = (t >= 0 ? t : t - 1) / 2, dw = (u >= 0 ? u : u - 1) / 2;  // floor division
     const int ph = t - 2 * dh, pw = u - 2 * dw;
-    dst[idx] = src[(((long long)co * 4 + dh + 2) * 4 + dw + 2) * Cs + (ph * 2 + pw) * C + c];
+    dst[idx] = src[(((long long)co * T + dh + T / 2) * T + dw + T / 2) * Cs + (ph * 2 + pw) * C + c];
   }
 }
 
@@ -267,16 +296,30 @@ int adamml_pack_frames_s2d(const float* x, void* out, int N, int S, int F, int C
   return adamml_check_launch("pack_frames_s2d");
 }
 
-int adamml_pack_weight_stem(const float* w_oihw, void* w_packed, int Cout, int C, int Cs, cudaStream_t stream) {
-  ADAMML_REQUIRE(Cout > 0 && C > 0 && Cs >= 4 * C, "pack_weight_stem: bad dims");
-  pack_weight_stem_kernel<<<ew_blocks((long long)Cout * 16 * Cs), 256, 0, stream>>>(w_oihw, (bf16*)w_packed, Cout, C,
-                                                                                     Cs);
+int adamml_nhwc_to_s2d(const void* x, void* out, long long IMGS, int C, int H, int W, int Cs, int padl, int padr,
+                       cudaStream_t stream) {
+  ADAMML_REQUIRE(IMGS > 0 && C > 0 && H > 0 && W > 0 && padl >= 0 && padr >= 0, "nhwc_to_s2d: bad dims");
+  ADAMML_REQUIRE(H % 2 == 0 && W % 2 == 0 && Cs >= 4 * C, "nhwc_to_s2d: needs even H, W and Cs >= 4C");
+  long long total = IMGS * (H / 2) * (W / 2 + padl + padr);
+  nhwc_to_s2d_kernel<<<ew_blocks(total), 256, 0, stream>>>((const bf16*)x, (bf16*)out, IMGS, C, H, W, Cs, padl, padr);
+  return adamml_check_launch("nhwc_to_s2d");
+}
+
+int adamml_pack_weight_stem(const float* w_oihw, void* w_packed, int Cout, int C, int Cs, int R,
+                            cudaStream_t stream) {
+  ADAMML_REQUIRE(Cout > 0 && C > 0 && Cs >= 4 * C && (R == 7 || R == 3), "pack_weight_stem: bad dims");
+  const int T = (R + 1) / 2;
+  pack_weight_stem_kernel<<<ew_blocks((long long)Cout * T * T * Cs), 256, 0, stream>>>(w_oihw, (bf16*)w_packed, Cout,
+                                                                                        C, Cs, R, T);
   return adamml_check_launch("pack_weight_stem");
 }
 
-int adamml_unpack_wgrad_stem(const float* dw_packed, float* dw_oihw, int Cout, int C, int Cs, cudaStream_t stream) {
-  ADAMML_REQUIRE(Cout > 0 && C > 0 && Cs >= 4 * C, "unpack_wgrad_stem: bad dims");
-  unpack_wgrad_stem_kernel<<<ew_blocks((long long)Cout * C * 49), 256, 0, stream>>>(dw_packed, dw_oihw, Cout, C, Cs);
+int adamml_unpack_wgrad_stem(const float* dw_packed, float* dw_oihw, int Cout, int C, int Cs, int R,
+                             cudaStream_t stream) {
+  ADAMML_REQUIRE(Cout > 0 && C > 0 && Cs >= 4 * C && (R == 7 || R == 3), "unpack_wgrad_stem: bad dims");
+  const int T = (R + 1) / 2;
+  unpack_wgrad_stem_kernel<<<ew_blocks((long long)Cout * C * R * R), 256, 0, stream>>>(dw_packed, dw_oihw, Cout, C, Cs,
+                                                                                        R, T);
   return adamml_check_launch("unpack_wgrad_stem");
 }
 

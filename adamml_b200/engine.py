@@ -68,6 +68,10 @@ class Exec:
         depthwise = conv.groups > 1
         sums = None
         fused = False
+        if (not isinstance(x, ops.S2D) and not depthwise and w.shape[1] < 16 and (R, S) == (3, 3)
+                and ops.first_conv_s2d_ok(conv, w.shape[1], x.shape[1], x.shape[2], x.dtype)):
+            # 1- / 3-channel stride-2 first conv of a MobileNetV2: tensor cores through the space-to-depth view
+            x = ops.nhwc_to_s2d(x, 3)
         stem = isinstance(x, ops.S2D)
         if stem:
             wp = None

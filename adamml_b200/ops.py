@@ -49,12 +49,14 @@ def resize_frames(x, S, F, C, OH, OW, fstep, dtype, cpad=None):
 
 
 class S2D:
-    """Space-to-depth operand of the tensor-core ResNet stem: `t` is bf16 [IMGS, H/2, W/2+4, Cs]
-    (csrc/data_layer.cu pack_frames_s2d); shape reports the logical NHWC input."""
+    """Space-to-depth operand of a stride-2 first convolution on the tensor-core path: `t` is bf16
+    [IMGS, H/2, W/2 + pads, Cs] (csrc/data_layer.cu); `R` = filter size (7: ResNet stem, 3: MobileNetV2 first conv),
+    `taps` = (R+1)/2 s2d taps per axis; shape reports the logical NHWC input."""
 
-    def __init__(self, t, C, H, W):
-        self.t, self.C, self.H, self.W = t, C, H, W
+    def __init__(self, t, C, H, W, R):
+        self.t, self.C, self.H, self.W, self.R = t, C, H, W, R
         self.Cs = t.shape[-1]
+        self.taps = (R + 1) // 2
 
     @property
     def shape(self):
@@ -69,41 +71,62 @@ class S2D:
         return self.t.dtype
 
 
-def stem_s2d_ok(conv, C, H, W, dtype):
-    """7x7 / stride 2 / pad 3 stem on even-sized frames in bf16 mode -> tensor-core s2d path."""
-    return (TC_MODE == "auto" and dtype == torch.bfloat16 and conv.kernel_size == (7, 7) and conv.stride == (2, 2)
-            and conv.padding == (3, 3) and H % 2 == 0 and W % 2 == 0 and 4 * C <= 64 and conv.out_channels % 8 == 0)
+def first_conv_s2d_ok(conv, C, H, W, dtype):
+    """stride-2 first convolutions that run on tcgen05 through the space-to-depth view: 7x7/p3 (ResNet stem) and
+    3x3/p1 (MobileNetV2 first conv), even-sized frames, bf16 mode."""
+    k = conv.kernel_size
+    ok_geom = (k == (7, 7) and conv.padding == (3, 3)) or (k == (3, 3) and conv.padding == (1, 1))
+    return (TC_MODE == "auto" and dtype == torch.bfloat16 and ok_geom and conv.stride == (2, 2) and conv.groups == 1
+            and H % 2 == 0 and W % 2 == 0 and 4 * C <= 64 and conv.out_channels % 8 == 0)
+
+
+stem_s2d_ok = first_conv_s2d_ok
 
 
 def pack_frames_s2d(x, S, F, C):
+    """NCHW fp32 clip -> S2D operand of the 7x7 ResNet stem (two zero columns on either side)."""
     _chk(x, torch.float32)
     N, SFC, H, W = x.shape
     assert SFC == S * F * C, (x.shape, S, F, C)
     Cs = ((4 * C + 15) // 16) * 16
     out = torch.empty((S * N * F, H // 2, W // 2 + 4, Cs), device=x.device, dtype=torch.bfloat16)
     call("pack_frames_s2d", x, out, N, S, F, C, H, W, Cs)
-    return S2D(out, C, H, W)
+    return S2D(out, C, H, W, 7)
+
+
+def nhwc_to_s2d(x, R):
+    """NHWC bf16 image batch -> S2D operand of an RxR stride-2 first conv (pad columns: T/2 left, T/2-1 right)."""
+    _chk(x, torch.bfloat16)
+    IMGS, H, W, C = x.shape
+    T = (R + 1) // 2
+    Cs = ((4 * C + 7) // 8) * 8
+    padl, padr = T // 2, T // 2 - 1
+    out = torch.empty((IMGS, H // 2, W // 2 + padl + padr, Cs), device=x.device, dtype=torch.bfloat16)
+    call("nhwc_to_s2d", x, out, IMGS, C, H, W, Cs, padl, padr)
+    return S2D(out, C, H, W, R)
 
 
 def stem_conv_fwd(xs, w_oihw, stats=None, imgs_per_group=0):
-    """xs: S2D, w_oihw: fp32 [Cout, C, 7, 7] parameter -> z bf16 [IMGS, H/2, W/2, Cout] (+ fused BN statistics)."""
+    """xs: S2D, w_oihw: fp32 [Cout, C, R, R] parameter -> z bf16 [IMGS, H/2, W/2, Cout] (+ fused BN statistics)."""
     Cout = w_oihw.shape[0]
-    wp = torch.empty((Cout, 4, 4, xs.Cs), device=xs.device, dtype=torch.bfloat16)
-    call("pack_weight_stem", w_oihw, wp, Cout, xs.C, xs.Cs)
+    T = xs.taps
+    wp = torch.empty((Cout, T, T, xs.Cs), device=xs.device, dtype=torch.bfloat16)
+    call("pack_weight_stem", w_oihw, wp, Cout, xs.C, xs.Cs, xs.R)
     IMGS, Hs, Wp, Cs = xs.t.shape
     Ho, Wo = xs.H // 2, xs.W // 2
     z = torch.empty((IMGS, Ho, Wo, Cout), device=xs.device, dtype=torch.bfloat16)
-    call("tc_stem_conv_bf16", xs.t, wp, z, IMGS, Hs, Wp, Cs, Cout, Ho, Wo, stats, imgs_per_group)
+    call("tc_stem_conv_bf16", xs.t, wp, z, IMGS, Hs, Wp, Cs, Cout, Ho, Wo, T, stats, imgs_per_group)
     return z
 
 
 def stem_wgrad(xs, dy, Cout):
-    """-> fp32 OIHW gradient [Cout, C, 7, 7] of the stem weight."""
+    """-> fp32 OIHW gradient [Cout, C, R, R] of the first-conv weight."""
     IMGS, Hs, Wp, Cs = xs.t.shape
-    dwp = torch.empty((Cout, 4, 4, Cs), device=xs.device, dtype=torch.float32)
-    call("tc_stem_wgrad_bf16", xs.t, dy, dwp, IMGS, Hs, Wp, Cs, Cout, dy.shape[1], dy.shape[2])
-    dw = torch.empty((Cout, xs.C, 7, 7), device=xs.device, dtype=torch.float32)
-    call("unpack_wgrad_stem", dwp, dw, Cout, xs.C, Cs)
+    T = xs.taps
+    dwp = torch.empty((Cout, T, T, Cs), device=xs.device, dtype=torch.float32)
+    call("tc_stem_wgrad_bf16", xs.t, dy, dwp, IMGS, Hs, Wp, Cs, Cout, dy.shape[1], dy.shape[2], T)
+    dw = torch.empty((Cout, xs.C, xs.R, xs.R), device=xs.device, dtype=torch.float32)
+    call("unpack_wgrad_stem", dwp, dw, Cout, xs.C, Cs, xs.R)
     return dw
 
 

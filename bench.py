@@ -156,8 +156,11 @@ def run_reference_arm(a):
         "impl": "reference", "metric": METRIC, "value": val, "unit": "clips/s", "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"AdaMML {'+'.join(modality)} S={a.segments} F=8 224^2, fwd+loss+bwd, CPU",
-                   "clips_per_step": n_clips},
+        "config": {"workload": f"AdaMML {'+'.join(modality)} S={a.segments} F=8 224^2, batch {a.batch}/GPU, "
+                               f"fwd+loss+bwd+Adam(policy)+SGD(main)", "batch_per_gpu": a.batch, "segments": a.segments,
+                   "sample_clips_per_step": n_clips,
+                   "note": "reference algorithm (oracle port) on the host cores; a bounded sample of the workload: "
+                           "fwd + CE/policy loss + bwd on 2 clips per step, optimizer excluded"},
         "cpu_baseline": {"value": val, "unit": "clips/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": f"{n_clips} clips per step (of the 72-clip batch), {a.steps} steps"},
         "e2e": {"value": val, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

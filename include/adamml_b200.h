@@ -57,11 +57,17 @@ int adamml_unpack_wgrad(const float* dw_ohwi, float* dw_oihw, int Cout, int Cin,
                         int accumulate, cudaStream_t stream);
 /* Space-to-depth operands of the tensor-core ResNet stem (7x7/s2/p3 conv1, resnet.py:138,199):
  * frames  -> bf16 [(s*N+n)*F+f, H/2, W/2+4, Cs]  (two zero columns on either side, channel (ph*2+pw)*C+c)
- * weights -> bf16 [Cout][4][4][Cs]; the fp32 gradient of that operand -> OIHW .grad layout */
+ * weights -> bf16 [Cout][T][T][Cs] (T = 4 for R = 7, T = 2 for R = 3); the fp32 gradient of that operand -> OIHW */
 int adamml_pack_frames_s2d(const float* x, void* out, int N, int S, int F, int C, int H, int W, int Cs,
                            cudaStream_t stream);
-int adamml_pack_weight_stem(const float* w_oihw, void* w_packed, int Cout, int C, int Cs, cudaStream_t stream);
-int adamml_unpack_wgrad_stem(const float* dw_packed, float* dw_oihw, int Cout, int C, int Cs, cudaStream_t stream);
+int adamml_pack_weight_stem(const float* w_oihw, void* w_packed, int Cout, int C, int Cs, int R,
+                            cudaStream_t stream);
+int adamml_unpack_wgrad_stem(const float* dw_packed, float* dw_oihw, int Cout, int C, int Cs, int R,
+                             cudaStream_t stream);
+/* NHWC bf16 -> space-to-depth bf16 [IMGS, H/2, W/2+padl+padr, Cs] (operand of the stride-2 3x3 first convolutions
+ * of the MobileNetV2s: sound_mobilenet_v2.py:120, policy_net.py:117; R = 3 -> T = 2 taps, padl = 1, padr = 0) */
+int adamml_nhwc_to_s2d(const void* x, void* out, long long IMGS, int C, int H, int W, int Cs, int padl, int padr,
+                       cudaStream_t stream);
 int adamml_cast(const void* src, void* dst, long long total, int src_dtype, int dst_dtype, cudaStream_t stream);
 
 /* ---- dense convolution / linear, exact fp32-math engine (CUDA cores) ----
@@ -112,9 +118,9 @@ int adamml_tc_dgrad_s2_bf16(const void* dy, const void* w_rot, void* dx, int IMG
 /* ResNet stem on the space-to-depth operands: y [IMGS,Ho,Wo,Cout] bf16 (+ fused BN statistics), and its weight
  * gradient dw fp32 [Cout][4][4*Cs] (unpack with adamml_unpack_wgrad_stem). */
 int adamml_tc_stem_conv_bf16(const void* xs, const void* w, void* y, int IMGS, int Hs, int Wp, int Cs, int Cout,
-                             int Ho, int Wo, double* stats, int imgs_per_group, cudaStream_t stream);
+                             int Ho, int Wo, int taps, double* stats, int imgs_per_group, cudaStream_t stream);
 int adamml_tc_stem_wgrad_bf16(const void* xs, const void* dy, float* dw, int IMGS, int Hs, int Wp, int Cs, int Cout,
-                              int Ho, int Wo, cudaStream_t stream);
+                              int Ho, int Wo, int taps, cudaStream_t stream);
 /* Weight gradient on tcgen05: implicit GEMM whose reduction axis is the pixel axis, both operands MN-major
  * (64-channel x 64-pixel 4D TMA boxes of x and dy), split-K over pixel ranges with fp32 atomics.
  * dw fp32 [Cout][R][S][Cin] is overwritten.  Same call sites as adamml_simt_conv_wgrad. */

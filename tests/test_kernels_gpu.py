@@ -473,23 +473,32 @@ def test_tc_wgrad(cuda, case):
     assert relerr(ops.unpack_wgrad(dw, Cin), w.grad) < 1e-3
 
 
-@pytest.mark.parametrize("case", [(6, 3, 64, 64, 64, 3), (4, 10, 32, 48, 64, 2), (2, 3, 224, 224, 64, 1),
-                                  (3, 3, 20, 36, 64, 3)])
+@pytest.mark.parametrize("case", [(6, 3, 64, 64, 64, 3, 7), (4, 10, 32, 48, 64, 2, 7), (2, 3, 224, 224, 64, 1, 7),
+                                  (3, 3, 20, 36, 64, 3, 7), (6, 3, 40, 40, 32, 3, 3), (4, 1, 64, 64, 32, 2, 3),
+                                  (2, 15, 32, 48, 32, 1, 3)])
 def test_tc_stem_s2d(cuda, case):
-    """7x7/s2/p3 stem on the space-to-depth operand (overlapping-stride TMA view): fwd + BN stats + wgrad."""
+    """Stride-2 first convs (7x7/p3 ResNet stem, 3x3/p1 MobileNetV2) on the space-to-depth operand (overlapping-stride
+    TMA view): fwd + BN stats + wgrad."""
     from adamml_b200 import ops
-    IMGS, C, H, W, Cout, G = case
+    IMGS, C, H, W, Cout, G, R = case
     g = torch.Generator(device="cpu").manual_seed(13)
     x = torch.randn(IMGS, C, H, W, generator=g).to(cuda).bfloat16().float()
-    w = (torch.randn(Cout, C, 7, 7, generator=g) / (C * 49) ** 0.5).to(cuda).bfloat16().float().requires_grad_(True)
-    y_ref = F.conv2d(x, w, None, 2, 3)
-    conv = torch.nn.Conv2d(C, Cout, 7, 2, 3, bias=False)
-    assert ops.stem_s2d_ok(conv, C, H, W, torch.bfloat16)
-    xs = ops.pack_frames_s2d(x.view(IMGS, 1 * 1 * C, H, W).contiguous(), 1, 1, C)   # N=IMGS, S=F=1
+    w = (torch.randn(Cout, C, R, R, generator=g) / (C * R * R) ** 0.5).to(cuda).bfloat16().float().requires_grad_(True)
+    y_ref = F.conv2d(x, w, None, 2, R // 2)
+    conv = torch.nn.Conv2d(C, Cout, R, 2, R // 2, bias=False)
+    assert ops.first_conv_s2d_ok(conv, C, H, W, torch.bfloat16)
+    if R == 7:
+        xs = ops.pack_frames_s2d(x.view(IMGS, 1 * 1 * C, H, W).contiguous(), 1, 1, C)   # N=IMGS, S=F=1
+        padl = 2
+    else:
+        xs = ops.nhwc_to_s2d(nhwc(x).bfloat16(), 3)
+        padl = 1
     # the s2d operand holds exactly the input pixels
-    t = xs.t[:, :, 2:2 + W // 2, :4 * C].float().view(IMGS, H // 2, W // 2, 2, 2, C)
+    t = xs.t[:, :, padl:padl + W // 2, :4 * C].float().view(IMGS, H // 2, W // 2, 2, 2, C)
     assert torch.equal(t.permute(0, 5, 1, 3, 2, 4).reshape(IMGS, C, H, W), x)
-    assert xs.t[:, :, :2].abs().max() == 0 and xs.t[:, :, 2 + W // 2:].abs().max() == 0
+    assert xs.t[:, :, :padl].abs().max() == 0
+    if xs.t.shape[2] > padl + W // 2:
+        assert xs.t[:, :, padl + W // 2:].abs().max() == 0
     stats = torch.full((G, Cout, 2), float("nan"), device=cuda, dtype=torch.float64)
     z = ops.stem_conv_fwd(xs, w.detach().contiguous(), stats=stats, imgs_per_group=IMGS // G)
     torch.cuda.synchronize()
