@@ -341,3 +341,42 @@ def run_backbone(net, x, groups, extra=None):
     # grad mode is invisible inside Function.forward, so capture it here
     extra["_save"] = torch.is_grad_enabled()
     return BackboneFunction.apply(net, x, groups, extra, *params)
+
+
+# ---------------------------------------------------------------------------------------------- multi-stream
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device, i):
+    key = (device.index, i)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[key]
+
+
+def run_backbones_parallel(jobs):
+    """jobs: list of (net, x, groups, extra).  The backbones of one AdaMML step (policy MobileNetV2s, main ResNets /
+    sound MobileNetV2) are independent until the policy head / late fusion, so each runs on its own CUDA stream:
+    inside the captured graph they become parallel branches and the latency-bound kernels of one net (narrow
+    MobileNetV2 GEMMs, late ResNet layers) fill the gaps of another.  autograd replays every backward on its
+    forward stream, so the backward passes overlap the same way."""
+    import os
+    if len(jobs) <= 1 or os.environ.get("ADAMML_B200_STREAMS", "1") == "0":
+        return [run_backbone(net, x, g, extra) for net, x, g, extra in jobs]
+    cur = torch.cuda.current_stream()
+    outs = []
+    for i, (net, x, g, extra) in enumerate(jobs):
+        s = _side_stream(cur.device, i)
+        s.wait_stream(cur)
+        with torch.cuda.stream(s):
+            xt = x.t if isinstance(x, ops.S2D) else x
+            xt.record_stream(s)          # allocated on the caller's stream, consumed (and kept on the tape) here
+            for v in (extra or {}).values():
+                if isinstance(v, torch.Tensor):
+                    v.record_stream(s)
+            y = run_backbone(net, x, g, extra)
+        outs.append((y, s))
+    for y, s in outs:
+        cur.wait_stream(s)
+        y.record_stream(cur)
+    return [y for y, _ in outs]

@@ -4,6 +4,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
+from ..engine import run_backbones_parallel
 from .joint_resnet_mobilenetv2 import joint_resnet_mobilenetv2
 from .policy_net import p_joint_mobilenet
 from .resnet import default_compute_dtype
@@ -68,15 +69,26 @@ class AdaMML(nn.Module):
         p_x, m_x, S = self.data_layer(x, S)
         dev = x[0].device
         expo = noise["expo"] if noise else None
+        drop_masks = noise.get("drop") if noise else None
+        # RNG draws in the reference's order (policy Gumbel noise | rng decisions first, then the dropout masks)
         if not self.rng_policy:
-            if expo is None:  # drawn first, like the reference (policy runs before the main nets)
+            if expo is None:
                 expo = self.policy_net.draw_gumbel_noise(S, N, dev)
-            decisions, _ = self.policy_net(p_x, S, N, expo=expo)
+            p_jobs = self.policy_net.backbone_jobs(p_x, S)
         else:  # adamml.py:76-78
             decisions = (torch.rand((S, self.num_modality, N), dtype=torch.float32, device=dev)
                          > self.rng_threshold).float()
-        del p_x
-        logits = self.main_net(m_x, decisions, S, N, drop_masks=noise.get("drop") if noise else None)
+            p_jobs = []
+        if drop_masks is None:
+            drop_masks = self.main_net.draw_drop_masks(S, N, dev)
+        m_jobs = self.main_net.backbone_jobs(m_x, S, drop_masks)
+        # every backbone of the step (policy + main) is independent until the policy head / late fusion
+        outs = run_backbones_parallel(p_jobs + m_jobs)
+        del p_x, m_x, p_jobs, m_jobs
+        if not self.rng_policy:
+            decisions, _ = self.policy_net(None, S, N, expo=expo, feats=outs[:len(self.policy_net.joint_net.nets)])
+            outs = outs[len(self.policy_net.joint_net.nets):]
+        logits = self.main_net(None, decisions, S, N, per_mod=outs)
         return logits, decisions.permute(2, 0, 1)
 
     def mean(self, modality="rgb"):

@@ -88,14 +88,18 @@ class JointResNetMobileNetV2(nn.Module):
             return None
         return [torch.cat([per_seg[s][m] for s in range(S)], 0) for m in range(len(self.nets))]
 
-    def forward(self, m_x, decisions, S, N, drop_masks=None):
-        """m_x: NHWC image batches (segment-major) per main modality; decisions [S, M, N] or None.
-        -> fused logits [N, classes]."""
-        if drop_masks is None:
-            drop_masks = self.draw_drop_masks(S, N, m_x[0].device)
-        per_mod = []
-        for i, (net, x) in enumerate(zip(self.nets, m_x)):
-            per_mod.append(run_backbone(net, x, S, dict(drop_mask=drop_masks[i] if drop_masks else None)))
+    def backbone_jobs(self, m_x, S, drop_masks):
+        """(net, x, groups, extra) per main modality, for engine.run_backbones_parallel"""
+        return [(net, x, S, dict(drop_mask=drop_masks[i] if drop_masks else None))
+                for i, (net, x) in enumerate(zip(self.nets, m_x))]
+
+    def forward(self, m_x, decisions, S, N, drop_masks=None, per_mod=None):
+        """m_x: NHWC image batches (segment-major) per main modality; decisions [S, M, N] or None; per_mod: per-modality
+        logits when the caller already ran the backbones.  -> fused logits [N, classes]."""
+        if per_mod is None:
+            if drop_masks is None:
+                drop_masks = self.draw_drop_masks(S, N, m_x[0].device)
+            per_mod = [run_backbone(*job) for job in self.backbone_jobs(m_x, S, drop_masks)]
         logits = torch.stack(per_mod, 0).view(len(per_mod), S, N, -1)
         return _GateFuse.apply(logits, decisions, self.lf_weights)
 

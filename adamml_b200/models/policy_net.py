@@ -339,15 +339,19 @@ class PolicyNet(nn.Module):
             return torch.empty((1, self.num_modality * S * N, 2), device=device).exponential_()
         return torch.stack([torch.empty((self.num_modality * N, 2), device=device).exponential_() for _ in range(S)])
 
-    def forward(self, p_x, S, N, expo=None):
-        """p_x: list over policy modalities of NHWC image batches (segment-major).
+    def backbone_jobs(self, p_x, S):
+        """(net, x, groups, extra) per policy modality, for engine.run_backbones_parallel"""
+        return [(net, x, S, None) for net, x in zip(self.joint_net.nets, p_x)]
+
+    def forward(self, p_x, S, N, expo=None, feats=None):
+        """p_x: list over policy modalities of NHWC image batches (segment-major); feats: backbone features when the
+        caller already ran them (AdaMML runs all backbones of the step on parallel streams).
         -> decisions [S, M, N] (float 0/1, straight-through grad), logits [S, M, N, 2]."""
-        feats = []
-        for net, x in zip(self.joint_net.nets, p_x):
-            f = run_backbone(net, x, S)
+        if feats is None:
+            feats = [run_backbone(net, x, S) for net, x in zip(self.joint_net.nets, p_x)]
+        for f in feats:
             if f.shape[0] != S * N:
                 raise ValueError("policy backbone must reduce every clip to one frame (groups in {2,4,8})")
-            feats.append(f)
         if expo is None:
             expo = self.draw_gumbel_noise(S, N, feats[0].device)
         j = self.joint_net.joint
