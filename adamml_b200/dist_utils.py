@@ -58,3 +58,74 @@ def allreduce_grads(params, group=None):
         views.append(flat[off:off + n].view_as(g))
         off += n
     torch._foreach_copy_(grads, views)
+
+
+class P2PStats:
+    """Symmetric-memory arena for the sync-BN statistic exchange over NVLink peer memory (csrc/p2p.cu).
+
+    Every BatchNorm layer owns one slot per pass (forward statistics / backward sums): the producing kernels write
+    this rank's partial sums straight into the slot, `allreduce` launches the one-shot peer-memory reduction.
+    Lanes = independent streams (backbones), each with its own flag row and epoch counter.  Requires
+    torch.distributed symmetric memory (CUDA P2P over NVLink); `get()` returns None when unavailable so that the
+    caller falls back to the NCCL all-reduce."""
+
+    _instances = {}
+    LANES = 16
+
+    def __init__(self, pg, device, arena_doubles=8 << 20):
+        import torch.distributed._symmetric_memory as symm
+        self.pg = pg
+        self.world = dist.get_world_size(pg)
+        self.rank = dist.get_rank(pg)
+        self.arena = symm.empty(arena_doubles, dtype=torch.float64, device=device)
+        self.flags = symm.empty(self.LANES * self.world, dtype=torch.int32, device=device)
+        self.arena.zero_()
+        self.flags.zero_()
+        self._h_arena = symm.rendezvous(self.arena, pg)
+        self._h_flags = symm.rendezvous(self.flags, pg)
+        self.peer_bufs = torch.tensor(list(self._h_arena.buffer_ptrs), dtype=torch.int64, device=device)
+        self.peer_flags = torch.tensor(list(self._h_flags.buffer_ptrs), dtype=torch.int64, device=device)
+        self.epoch = torch.zeros(self.LANES, dtype=torch.int32, device=device)
+        self.err = torch.zeros(1, dtype=torch.int32, device=device)
+        self.cursor = 0
+        self.slots = {}
+        torch.cuda.synchronize(device)
+        dist.barrier(pg)  # every rank's flags are zero before the first exchange
+
+    @classmethod
+    def get(cls, pg, device):
+        import os
+        if os.environ.get("ADAMML_B200_SYNCBN_P2P", "1") == "0":
+            return None
+        key = (id(pg), device.index)
+        if key not in cls._instances:
+            try:
+                cls._instances[key] = cls(pg, device)
+            except Exception as e:  # no symmetric memory (no P2P, old driver): NCCL path
+                print(f"[adamml_b200] sync-BN over peer memory unavailable ({type(e).__name__}: {e}); using NCCL",
+                      flush=True)
+                cls._instances[key] = None
+        return cls._instances[key]
+
+    def slot(self, key, n):
+        """-> (offset in doubles, float64 view [n]) of this layer's slot (allocated on first use, 256-byte aligned)"""
+        if key not in self.slots:
+            if self.cursor + n > self.arena.numel():
+                raise RuntimeError("P2PStats arena exhausted")
+            self.slots[key] = (self.cursor, n)
+            self.cursor += (n + 31) // 32 * 32
+        off, n0 = self.slots[key]
+        assert n0 == n, "a BatchNorm layer changed its statistic size"
+        return off, self.arena[off:off + n]
+
+    def allreduce(self, off, n, lane):
+        from ._lib import call
+        out = torch.empty(n, dtype=torch.float64, device=self.arena.device)
+        call("p2p_allreduce_f64", self.peer_bufs, self.peer_flags, off, out, n, self.world, self.rank,
+             lane % self.LANES, self.epoch, self.err)
+        return out
+
+    def check(self):
+        """host-side check (synchronises): raises if a peer never arrived at some exchange"""
+        if int(self.err.item()):
+            raise RuntimeError("sync-BN peer-memory exchange timed out (a rank fell out of step)")

@@ -10,14 +10,15 @@ streams, autograd plumbing and (sync-BN) torch.distributed collectives.
 import torch
 
 from . import ops
-from .dist_utils import allreduce_stats, sync_bn_group
+from .dist_utils import P2PStats, allreduce_stats, sync_bn_group
 from .ops import ACT_NONE, ACT_RELU, ACT_RELU6
 
 
 class Exec:
     """State of one backbone pass."""
 
-    def __init__(self, dtype, training, groups, save, param_needs_grad=True):
+    def __init__(self, dtype, training, groups, save, param_needs_grad=True, lane=0):
+        self.lane = lane  # stream / backbone index: the sync-BN peer-memory exchange keeps one flag row per lane
         self.dtype = dtype
         self.training = training
         self.G = groups
@@ -68,6 +69,12 @@ class Exec:
         depthwise = conv.groups > 1
         sums = None
         fused = False
+        pg = self._sync_group(bn) if self.training else None
+        p2p = P2PStats.get(pg, w.device) if pg is not None else None
+        slot_off = None
+        if p2p is not None:  # this rank's partial sums are produced straight into the layer's symmetric slot
+            slot_off, flat = p2p.slot((id(bn), "f"), G * Cout * 2)
+            p2p_sums = flat.view(G, Cout, 2)
         if (not isinstance(x, ops.S2D) and not depthwise and w.shape[1] < 16 and (R, S) == (3, 3)
                 and ops.first_conv_s2d_ok(conv, w.shape[1], x.shape[1], x.shape[2], x.dtype)):
             # 1- / 3-channel stride-2 first conv of a MobileNetV2: tensor cores through the space-to-depth view
@@ -76,7 +83,7 @@ class Exec:
         if stem:
             wp = None
             if self.training:
-                sums = torch.empty((G, Cout, 2), device=x.device, dtype=torch.float64)
+                sums = p2p_sums if p2p is not None else torch.empty((G, Cout, 2), device=x.device, dtype=torch.float64)
             z = ops.stem_conv_fwd(x, w.detach(), stats=sums, imgs_per_group=x.shape[0] // G)
             fused = sums is not None
         elif depthwise:
@@ -86,17 +93,18 @@ class Exec:
         else:
             wp = ops.pack_weight(w.detach(), self.dtype)
             if self.training:
-                sums = torch.empty((G, Cout, 2), device=x.device, dtype=torch.float64)
+                sums = p2p_sums if p2p is not None else torch.empty((G, Cout, 2), device=x.device, dtype=torch.float64)
             rows = x.shape[0] * ((x.shape[1] + 2 * pad - R) // stride + 1) * ((x.shape[2] + 2 * pad - S) // stride + 1)
             z, fused = ops.conv_fwd(x, wp, stride, pad, stats=sums, rows_per_group=rows // G)
         C = z.shape[-1]
         count = z.numel() // C // G
-        pg = None
         if self.training:
             if not fused:
-                sums = ops.bn_stats(z, G)
-            pg = self._sync_group(bn)
-            if pg is not None:
+                sums = ops.bn_stats(z, G, out=p2p_sums if p2p is not None else None)
+            if p2p is not None:
+                sums = p2p.allreduce(slot_off, G * C * 2, self.lane).view(G, C, 2)
+                count = count * p2p.world
+            elif pg is not None:
                 count = allreduce_stats(sums, count, pg)
             mi, ss = ops.bn_finalize(sums, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var,
                                      count, bn.momentum if bn.momentum is not None else 0.1, bn.eps, C, G, True,
@@ -128,7 +136,12 @@ class Exec:
         # residual input and lets the apply pass (and a downsample branch sharing dout) skip `out` entirely
         inplace = mask_inplace and act != ACT_NONE and ops.vec_channels(z)
         had_dres = want_dres
-        sums = ops.bn_bwd_reduce(dout, out, z, mi, G, act, mask_ss=mask_ss, gm_inplace=inplace)
+        p2p = P2PStats.get(rec["pg"], z.device) if rec["pg"] is not None else None
+        sums_out = slot_off = None
+        if p2p is not None:
+            slot_off, flat = p2p.slot((id(bn), "b"), G * C * 2)
+            sums_out = flat.view(G, C, 2)
+        sums = ops.bn_bwd_reduce(dout, out, z, mi, G, act, mask_ss=mask_ss, gm_inplace=inplace, sums_out=sums_out)
         if inplace:
             rec["dout_masked"] = True
             out, act, want_dres = None, ACT_NONE, False
@@ -136,7 +149,9 @@ class Exec:
             dgamma, dbeta = ops.bn_param_grad(sums, C, G)
             self._acc(bn.weight, dgamma)
             self._acc(bn.bias, dbeta)
-        if rec["pg"] is not None:
+        if p2p is not None:
+            sums = p2p.allreduce(slot_off, G * C * 2, self.lane).view(G, C, 2)
+        elif rec["pg"] is not None:
             allreduce_stats(sums, 0, rec["pg"])
         need_w = conv.weight.requires_grad
         dz, dres = ops.bn_bwd_apply(dout, out, z, mi, bn.weight.detach(), sums, G, rec["count"], act, self.training,
@@ -316,7 +331,7 @@ class BackboneFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, net, x, groups, extra, *params):
         need = bool(extra.get("_save")) and any(ctx.needs_input_grad[4:])
-        ex = Exec(net.compute_dtype, net.training, groups, save=need)
+        ex = Exec(net.compute_dtype, net.training, groups, save=need, lane=int(extra.get("_lane", 0)))
         y = net.run_forward(ex, x, extra)
         ctx.ex = ex if need else None
         ctx.net = net
@@ -374,7 +389,7 @@ def run_backbones_parallel(jobs):
             for v in (extra or {}).values():
                 if isinstance(v, torch.Tensor):
                     v.record_stream(s)
-            y = run_backbone(net, x, g, extra)
+            y = run_backbone(net, x, g, dict(extra or {}, _lane=i))
         outs.append((y, s))
     for y, s in outs:
         cur.wait_stream(s)

@@ -337,10 +337,10 @@ def dwconv_wgrad(x, dy, stride):
 
 
 # ---------------------------------------------------------------- batch norm
-def bn_stats(z, G):
+def bn_stats(z, G, out=None):
     C = z.shape[-1]
     rows = z.numel() // C
-    sums = torch.empty((G, C, 2), device=z.device, dtype=torch.float64)
+    sums = out if out is not None else torch.empty((G, C, 2), device=z.device, dtype=torch.float64)
     call("bn_stats", z, sums, rows // G, C, G, dtype_code(z.dtype))
     return sums
 
@@ -375,13 +375,13 @@ def vec_channels(t):
     return t.shape[-1] % (8 if t.dtype == torch.bfloat16 else 4) == 0
 
 
-def bn_bwd_reduce(dout, out, z, mean_invstd, G, act, mask_ss=None, gm_inplace=False):
+def bn_bwd_reduce(dout, out, z, mean_invstd, G, act, mask_ss=None, gm_inplace=False, sums_out=None):
     """mask_ss: forward scale/shift [G,C,2] of a layer without residual input -> the ReLU/ReLU6 mask is recomputed
     from z and `out` is not read.  gm_inplace: dout is overwritten with the masked gradient dout * act'(out), which
     is also the gradient of a residual input; the following bn_bwd_apply then runs with act = NONE."""
     C = z.shape[-1]
     rows = z.numel() // C
-    sums = torch.empty((G, C, 2), device=z.device, dtype=torch.float64)
+    sums = sums_out if sums_out is not None else torch.empty((G, C, 2), device=z.device, dtype=torch.float64)
     call("bn_bwd_reduce", dout, out, z, mean_invstd, _mask_ss(z, mask_ss), sums, dout if gm_inplace else None,
          rows // G, C, G, act, dtype_code(z.dtype))
     return sums

@@ -168,6 +168,15 @@ int adamml_bn_bwd_apply(const void* dout, const void* out, const void* z, const 
 int adamml_bn_param_grad(const double* sums, float* dgamma, float* dbeta, int C, int G, int accumulate,
                          cudaStream_t stream);
 
+/* ---- sync-BN statistic exchange over NVLink peer memory (train_adamml.py:125-127 SyncBatchNorm) ----
+ * One-shot all-reduce (sum in rank order) of n doubles: every rank's partial sums sit at `slot_off` doubles inside a
+ * symmetric buffer; peer_bufs / peer_flags are DEVICE arrays [world] holding the peers' mapped base addresses of the
+ * data buffer and of the 32-bit flag array [lanes][world]; epoch_ctr [lanes] and err_flag live in local device
+ * memory.  Asynchronous on `stream`, capturable in a CUDA graph; a peer that never arrives sets *err_flag. */
+int adamml_p2p_allreduce_f64(const unsigned long long* peer_bufs, const unsigned long long* peer_flags,
+                             long long slot_off, double* out, int n, int world, int rank, int lane,
+                             unsigned* epoch_ctr, unsigned* err_flag, cudaStream_t stream);
+
 /* ---- pooling ---- */
 /* nn.MaxPool2d(3,2,1): resnet.py:141,202.  `pos` (optional, uint8 [IMGS,Ho,Wo,C]) records the window
  * position r*3+s of the first maximum; the backward pass then is a gather over (pos, dy) and x may be NULL. */
