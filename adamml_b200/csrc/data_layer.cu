@@ -124,6 +124,8 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ src, float* __rest
 // Space-to-depth input of the ResNet stem (see conv_tc.cu adamml_tc_stem_conv_bf16):
 // x NCHW fp32 [N, S*F*C, H, W] -> out bf16 [(s*N+n)*F+f, H/2, W/2+4, Cs], stored column ip holds s2d column
 // ip-2 (two zero columns left and right), channel (ph*2+pw)*C + c = x[.., c, 2j+ph, 2i+pw], rest zero.
+// CT/CST > 0: compile-time channel counts, so the pixel is assembled in registers and stored as 16-byte vectors
+template <int CT, int CST>
 __global__ void pack_frames_s2d_kernel(const float* __restrict__ x, bf16* __restrict__ out, int N, int S, int F,
                                        int C, int H, int W, int Cs) {
   const int Hs = H / 2, Ws = W / 2, Wp = Ws + 4;
@@ -143,13 +145,30 @@ __global__ void pack_frames_s2d_kernel(const float* __restrict__ x, bf16* __rest
       continue;
     }
     const float* src = x + (((long long)n * S * F * C + ((long long)s * F + f) * C) * H + 2 * j) * W + 2 * i;
-    for (int ph = 0; ph < 2; ++ph)
-      for (int c = 0; c < C; ++c) {
-        const float2 v = *reinterpret_cast<const float2*>(src + ((long long)c * H + ph) * W);
-        dst[(ph * 2 + 0) * C + c] = __float2bfloat16_rn(v.x);
-        dst[(ph * 2 + 1) * C + c] = __float2bfloat16_rn(v.y);
-      }
-    for (int c = 4 * C; c < Cs; ++c) dst[c] = __float2bfloat16_rn(0.f);
+    if (CT > 0) {
+      constexpr int CSV = CST > 0 ? CST : 8;
+      __align__(16) bf16 v[CSV];
+#pragma unroll
+      for (int c = 0; c < CSV; ++c) v[c] = __float2bfloat16_rn(0.f);
+#pragma unroll
+      for (int ph = 0; ph < 2; ++ph)
+#pragma unroll
+        for (int c = 0; c < CT; ++c) {
+          const float2 t = *reinterpret_cast<const float2*>(src + ((long long)c * H + ph) * W);
+          v[(ph * 2 + 0) * CT + c] = __float2bfloat16_rn(t.x);
+          v[(ph * 2 + 1) * CT + c] = __float2bfloat16_rn(t.y);
+        }
+#pragma unroll
+      for (int c = 0; c < CSV; c += 8) *reinterpret_cast<uint4*>(dst + c) = *reinterpret_cast<const uint4*>(v + c);
+    } else {
+      for (int ph = 0; ph < 2; ++ph)
+        for (int c = 0; c < C; ++c) {
+          const float2 v = *reinterpret_cast<const float2*>(src + ((long long)c * H + ph) * W);
+          dst[(ph * 2 + 0) * C + c] = __float2bfloat16_rn(v.x);
+          dst[(ph * 2 + 1) * C + c] = __float2bfloat16_rn(v.y);
+        }
+      for (int c = 4 * C; c < Cs; ++c) dst[c] = __float2bfloat16_rn(0.f);
+    }
   }
 }
 
@@ -292,7 +311,12 @@ int adamml_pack_frames_s2d(const float* x, void* out, int N, int S, int F, int C
   ADAMML_REQUIRE(H % 2 == 0 && W % 2 == 0 && Cs % 8 == 0 && Cs >= 4 * C, "pack_frames_s2d: needs even H, W and Cs >= 4C");
   ADAMML_REQUIRE(((uintptr_t)x % 8) == 0 && ((uintptr_t)out % 16) == 0, "pack_frames_s2d: unaligned buffers");
   long long total = (long long)S * N * F * (H / 2) * (W / 2 + 4);
-  pack_frames_s2d_kernel<<<ew_blocks(total), 256, 0, stream>>>(x, (bf16*)out, N, S, F, C, H, W, Cs);
+  if (C == 3 && Cs == 16)
+    pack_frames_s2d_kernel<3, 16><<<ew_blocks(total), 256, 0, stream>>>(x, (bf16*)out, N, S, F, C, H, W, Cs);
+  else if (C == 1 && Cs == 8)
+    pack_frames_s2d_kernel<1, 8><<<ew_blocks(total), 256, 0, stream>>>(x, (bf16*)out, N, S, F, C, H, W, Cs);
+  else
+    pack_frames_s2d_kernel<0, 0><<<ew_blocks(total), 256, 0, stream>>>(x, (bf16*)out, N, S, F, C, H, W, Cs);
   return adamml_check_launch("pack_frames_s2d");
 }
 

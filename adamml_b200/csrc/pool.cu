@@ -193,43 +193,68 @@ maxpool_fwd_vec_kernel(const T* __restrict__ x, T* __restrict__ y, unsigned char
   }
 }
 
-// gather backward from recorded positions: input pixel (hi, wi) sits at row r = hi + 1 - 2*ho of window ho.
+// gather backward from recorded positions, one thread per 2x2 input quad (rows 2m, 2m+1; cols 2n, 2n+1) and channel
+// vector: the quad is covered by the windows (m..m+1) x (n..n+1) only, so 4 (position, dy) loads feed 4 outputs.
+// Input pixel (hi, wi) sits at row r = hi + 1 - 2*ho, column s = wi + 1 - 2*wo of window (ho, wo).
 template <typename T>
 __global__ void __launch_bounds__(256)
 maxpool_bwd_pos_kernel(const unsigned char* __restrict__ pos, const T* __restrict__ dy, T* __restrict__ dx, int IMGS,
                        int H, int W, int C, int Ho, int Wo) {
   constexpr int V = VecIO<T>::N;
   const int cvecs = C / V;
-  const long long total = (long long)IMGS * H * W * cvecs;
+  const int QH = (H + 1) / 2, QW = (W + 1) / 2;
+  const long long total = (long long)IMGS * QH * QW * cvecs;
   const long long iv = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (iv >= total) return;
   const int cv = (int)(iv % cvecs);
-  const long long pix = iv / cvecs;
-  const int wi = (int)(pix % W);
-  const int hi = (int)((pix / W) % H);
-  const long long img = pix / ((long long)W * H);
-  float acc[V];
+  long long rest = iv / cvecs;
+  const int n = (int)(rest % QW);
+  rest /= QW;
+  const int m = (int)(rest % QH);
+  const long long img = rest / QH;
+  float g[2][2][V];
+  unsigned char pc[2][2][8];
 #pragma unroll
-  for (int i = 0; i < V; ++i) acc[i] = 0.f;
-  const int ho_lo = hi / 2, ho_hi = (hi + 1) / 2;  // windows containing row hi
-  const int wo_lo = wi / 2, wo_hi = (wi + 1) / 2;
-  for (int ho = ho_lo; ho <= ho_hi; ++ho) {
-    if (ho >= Ho) continue;
-    for (int wo = wo_lo; wo <= wo_hi; ++wo) {
-      if (wo >= Wo) continue;
-      const int code = (hi + 1 - 2 * ho) * 3 + (wi + 1 - 2 * wo);
-      const long long o = ((img * Ho + ho) * Wo + wo) * C + cv * V;
-      float g[V];
-      VecIO<T>::load(dy + o, g);
-      unsigned char pc[8];
-      if (V == 8) *reinterpret_cast<uint2*>(pc) = *reinterpret_cast<const uint2*>(pos + o);
-      else *reinterpret_cast<unsigned*>(pc) = *reinterpret_cast<const unsigned*>(pos + o);
+  for (int a = 0; a < 2; ++a)
 #pragma unroll
-      for (int i = 0; i < V; ++i)
-        if (pc[i] == code) acc[i] += g[i];
+    for (int b = 0; b < 2; ++b) {
+      const bool ok = (m + a) < Ho && (n + b) < Wo;
+      const long long o = ((img * Ho + m + a) * Wo + n + b) * C + cv * V;
+      if (ok) {
+        VecIO<T>::load(dy + o, g[a][b]);
+        if (V == 8) *reinterpret_cast<uint2*>(pc[a][b]) = *reinterpret_cast<const uint2*>(pos + o);
+        else *reinterpret_cast<unsigned*>(pc[a][b]) = *reinterpret_cast<const unsigned*>(pos + o);
+      } else {
+#pragma unroll
+        for (int i = 0; i < V; ++i) { g[a][b][i] = 0.f; pc[a][b][i] = 255; }
+      }
+    }
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+    const int hi = 2 * m + p;
+    if (hi >= H) continue;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int wi = 2 * n + q;
+      if (wi >= W) continue;
+      float acc[V];
+#pragma unroll
+      for (int i = 0; i < V; ++i) acc[i] = 0.f;
+      // windows containing row hi: ho = m (r = p + 1) and, for odd rows, ho = m + 1 (r = 0)
+#pragma unroll
+      for (int a = 0; a <= p; ++a) {
+        const int r = hi + 1 - 2 * (m + a);
+#pragma unroll
+        for (int b = 0; b <= q; ++b) {
+          const int code = r * 3 + (wi + 1 - 2 * (n + b));
+#pragma unroll
+          for (int i = 0; i < V; ++i)
+            if (pc[a][b][i] == code) acc[i] += g[a][b][i];
+        }
+      }
+      VecIO<T>::store(dx + ((img * H + hi) * W + wi) * C + cv * V, acc);
     }
   }
-  VecIO<T>::store(dx + pix * C + cv * V, acc);
 }
 
 // temporal pool k3 s2 p1, one thread per (video, element vector): all TN frames of that position in registers
@@ -395,7 +420,7 @@ int adamml_maxpool3x3s2_bwd(const void* x, const unsigned char* pos, const void*
   ADAMML_DISPATCH_DTYPE(dtype, T, {
     if (pos) {
       ADAMML_REQUIRE(pool_vec_ok<T>(C, dy, dx) && ((uintptr_t)pos % 8) == 0, "maxpool_bwd: unaligned / ragged C");
-      long long tv = total / VecIO<T>::N;
+      long long tv = (long long)IMGS * ((H + 1) / 2) * ((W + 1) / 2) * (C / VecIO<T>::N);
       maxpool_bwd_pos_kernel<T><<<(unsigned)((tv + 255) / 256), 256, 0, stream>>>(pos, (const T*)dy, (T*)dx, IMGS, H,
                                                                                    W, C, Ho, Wo);
     } else {
