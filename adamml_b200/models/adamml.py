@@ -1,5 +1,7 @@
 """AdaMML wrapper (drop-in for reference models/adamml.py): data layer -> policy -> gated main
 nets -> late fusion, with the segment x modality loop packed into batched launches."""
+import os
+
 import torch
 import torch.nn as nn
 
@@ -29,6 +31,9 @@ class AdaMML(nn.Module):
         self.update_policy_net = True
         self.update_main_net = True
         self.compute_dtype = compute_dtype or default_compute_dtype()
+        # inference: run the main backbones only on the (segment, video) pairs the policy selected (see forward)
+        self.skip_unselected = os.environ.get("ADAMML_B200_EVAL_SKIP", "1") != "0"
+        self.last_selected_fraction = None
         if rng_policy:
             self.freeze_policy_net()
             del self.policy_net.fcs
@@ -79,6 +84,8 @@ class AdaMML(nn.Module):
             decisions = (torch.rand((S, self.num_modality, N), dtype=torch.float32, device=dev)
                          > self.rng_threshold).float()
             p_jobs = []
+        if self._can_skip():
+            return self._forward_selected(p_jobs, m_x, S, N, expo, None if not self.rng_policy else decisions)
         if drop_masks is None:
             drop_masks = self.main_net.draw_drop_masks(S, N, dev)
         m_jobs = self.main_net.backbone_jobs(m_x, S, drop_masks)
@@ -89,6 +96,50 @@ class AdaMML(nn.Module):
             decisions, _ = self.policy_net(None, S, N, expo=expo, feats=outs[:len(self.policy_net.joint_net.nets)])
             outs = outs[len(self.policy_net.joint_net.nets):]
         logits = self.main_net(None, decisions, S, N, per_mod=outs)
+        return logits, decisions.permute(2, 0, 1)
+
+    # ------------------------------------------------------------------ inference with decision-driven skipping
+    def _can_skip(self):
+        """The reference always runs every main backbone and multiplies its logits by the 0/1 decision
+        (adamml.py:81-86, joint_resnet_mobilenetv2.py:94).  Without a tape and with every main BN on running
+        statistics (utils/utils.py:427-507, validate_adamml) a (segment, video) pair is independent of the rest
+        of the batch, so an unselected pair contributes exactly 0 and its backbone pass can be dropped."""
+        return (self.skip_unselected and not torch.is_grad_enabled()
+                and not any(mod.training for mod in self.main_net.modules()))
+
+    def _forward_selected(self, p_jobs, m_x, S, N, expo, decisions):
+        if decisions is None:
+            feats = run_backbones_parallel(p_jobs)
+            decisions, _ = self.policy_net(None, S, N, expo=expo, feats=feats)
+            del feats
+        dev = decisions.device
+        dec_host = decisions.detach().to("cpu", torch.float32)            # [S, M, N]; the one D2H sync of the pass
+        SN = S * N
+        jobs, slots, per_mod = [], [], [None] * len(m_x)
+        chosen = 0
+        for m, (net, x) in enumerate(zip(self.main_net.nets, m_x)):
+            idx = torch.nonzero(dec_host[:, m, :].reshape(SN) > 0).squeeze(1)   # packed order is (segment, video)
+            K = idx.numel()
+            chosen += K
+            if K == 0:
+                per_mod[m] = torch.zeros((SN, self.main_net.num_classes), device=dev, dtype=torch.float32)
+                continue
+            if K < SN:
+                idx = idx.to(dev, non_blocking=True)
+                x = ops.select_clips(x, idx, SN)
+            else:
+                idx = None
+            jobs.append((net, x, 1, None))
+            slots.append((m, idx))
+        outs = run_backbones_parallel(jobs)
+        for (m, idx), y in zip(slots, outs):
+            if idx is None:
+                per_mod[m] = y
+            else:
+                full = torch.zeros((SN, y.shape[1]), device=dev, dtype=y.dtype)
+                per_mod[m] = full.index_copy_(0, idx, y)
+        self.last_selected_fraction = chosen / float(SN * len(m_x))
+        logits = self.main_net(None, decisions, S, N, per_mod=per_mod)
         return logits, decisions.permute(2, 0, 1)
 
     def mean(self, modality="rgb"):

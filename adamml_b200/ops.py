@@ -71,6 +71,17 @@ class S2D:
         return self.t.dtype
 
 
+def select_clips(x, idx, clips):
+    """x: NHWC image batch (or S2D operand) holding `clips` (segment, video) pairs of T consecutive frames each;
+    -> the same layout restricted to the pairs listed in idx (int64, ascending)."""
+    t = x.t if isinstance(x, S2D) else x
+    if t.shape[0] % clips:
+        raise ValueError("select_clips: %d images do not split into %d clips" % (t.shape[0], clips))
+    T = t.shape[0] // clips
+    sel = t.view(clips, -1).index_select(0, idx).view((idx.numel() * T,) + tuple(t.shape[1:]))
+    return S2D(sel, x.C, x.H, x.W, x.R) if isinstance(x, S2D) else sel
+
+
 def first_conv_s2d_ok(conv, C, H, W, dtype):
     """stride-2 first convolutions that run on tcgen05 through the space-to-depth view: 7x7/p3 (ResNet stem) and
     3x3/p1 (MobileNetV2 first conv), even-sized frames, bf16 mode."""
