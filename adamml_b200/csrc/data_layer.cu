@@ -11,10 +11,25 @@ inline int ew_blocks(long long total) {
   return (int)(b < cap ? (b > 0 ? b : 1) : cap);
 }
 
-// x: NCHW fp32 [N, S*F*C, H, W]  ->  out: NHWC [(s*N+n)*F+f, H, W, Cpad]   (adamml.py:53,65)
-template <typename T>
-__global__ void pack_frames_kernel(const float* __restrict__ x, T* __restrict__ out, int N, int S, int F, int C,
-                                   int H, int W, int Cpad) {
+// Input element of the data layer.  fp32 clips arrive normalised.  uint8 clips (decoded frames, the CHW byte
+// tensor ToTorchFormatTensor holds before .float()) are normalised here with the reference's own fp32 arithmetic:
+// x.float().div(255) (utils/video_transforms.py:343) then t.sub_(mean).div_(std) per channel plane (:81-82).
+struct InNorm {
+  const float* mean;  // [C] per-frame channel, device memory (uint8 input only)
+  const float* stdv;
+};
+__device__ __forceinline__ float in_val(float v, const InNorm&, int) { return v; }
+__device__ __forceinline__ float in_val(unsigned char v, const InNorm& nm, int c) {
+  return __fdiv_rn(__fsub_rn(__fdiv_rn((float)v, 255.f), nm.mean[c]), nm.stdv[c]);
+}
+template <typename TIn> struct Pair;
+template <> struct Pair<float> { using type = float2; };
+template <> struct Pair<unsigned char> { using type = uchar2; };
+
+// x: NCHW [N, S*F*C, H, W]  ->  out: NHWC [(s*N+n)*F+f, H, W, Cpad]   (adamml.py:53,65)
+template <typename TIn, typename T>
+__global__ void pack_frames_kernel(const TIn* __restrict__ x, InNorm nm, T* __restrict__ out, int N, int S, int F,
+                                   int C, int H, int W, int Cpad) {
   long long total = (long long)S * N * F * H * W;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -24,18 +39,18 @@ __global__ void pack_frames_kernel(const float* __restrict__ x, T* __restrict__ 
     int f = (int)(img % F);
     int n = (int)((img / F) % N);
     int s = (int)(img / ((long long)F * N));
-    const float* src = x + (((long long)n * S * F * C + ((long long)s * F + f) * C) * H + h) * W + w;
+    const TIn* src = x + (((long long)n * S * F * C + ((long long)s * F + f) * C) * H + h) * W + w;
     T* dst = out + idx * Cpad;
-    for (int c = 0; c < C; ++c) dst[c] = from_f32<T>(src[(long long)c * H * W]);
+    for (int c = 0; c < C; ++c) dst[c] = from_f32<T>(in_val(src[(long long)c * H * W], nm, c));
     for (int c = C; c < Cpad; ++c) dst[c] = from_f32<T>(0.f);
   }
 }
 
 // bilinear, align_corners=False, no antialias (F.interpolate at adamml.py:59), keeping
 // frames 0, fstep, 2*fstep, ... of each segment (adamml.py:60-62).
-template <typename T>
-__global__ void resize_frames_kernel(const float* __restrict__ x, T* __restrict__ out, int N, int S, int F, int C,
-                                     int H, int W, int OH, int OW, int fstep, int Fk, int Cpad) {
+template <typename TIn, typename T>
+__global__ void resize_frames_kernel(const TIn* __restrict__ x, InNorm nm, T* __restrict__ out, int N, int S, int F,
+                                     int C, int H, int W, int OH, int OW, int fstep, int Fk, int Cpad) {
   const float sh = (float)H / (float)OH;
   const float sw = (float)W / (float)OW;
   long long total = (long long)S * N * Fk * OH * OW;
@@ -58,14 +73,14 @@ __global__ void resize_frames_kernel(const float* __restrict__ x, T* __restrict_
     int wp = w0 < W - 1 ? 1 : 0;
     float lh1 = fminf(fmaxf(hr - (float)h0, 0.f), 1.f), lh0 = 1.f - lh1;
     float lw1 = fminf(fmaxf(wr - (float)w0, 0.f), 1.f), lw0 = 1.f - lw1;
-    const float* src = x + ((long long)n * S * F * C + ((long long)s * F + f) * C) * H * W;
+    const TIn* src = x + ((long long)n * S * F * C + ((long long)s * F + f) * C) * H * W;
     T* dst = out + idx * Cpad;
     for (int c = 0; c < C; ++c) {
-      const float* pl = src + (long long)c * H * W;
-      float p00 = pl[(long long)h0 * W + w0];
-      float p01 = pl[(long long)h0 * W + w0 + wp];
-      float p10 = pl[(long long)(h0 + hp) * W + w0];
-      float p11 = pl[(long long)(h0 + hp) * W + w0 + wp];
+      const TIn* pl = src + (long long)c * H * W;
+      float p00 = in_val(pl[(long long)h0 * W + w0], nm, c);
+      float p01 = in_val(pl[(long long)h0 * W + w0 + wp], nm, c);
+      float p10 = in_val(pl[(long long)(h0 + hp) * W + w0], nm, c);
+      float p11 = in_val(pl[(long long)(h0 + hp) * W + w0 + wp], nm, c);
       float v = lh0 * (lw0 * p00 + lw1 * p01) + lh1 * (lw0 * p10 + lw1 * p11);
       dst[c] = from_f32<T>(v);
     }
@@ -125,9 +140,10 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ src, float* __rest
 // x NCHW fp32 [N, S*F*C, H, W] -> out bf16 [(s*N+n)*F+f, H/2, W/2+4, Cs], stored column ip holds s2d column
 // ip-2 (two zero columns left and right), channel (ph*2+pw)*C + c = x[.., c, 2j+ph, 2i+pw], rest zero.
 // CT/CST > 0: compile-time channel counts, so the pixel is assembled in registers and stored as 16-byte vectors
-template <int CT, int CST>
-__global__ void pack_frames_s2d_kernel(const float* __restrict__ x, bf16* __restrict__ out, int N, int S, int F,
-                                       int C, int H, int W, int Cs) {
+template <typename TIn, int CT, int CST>
+__global__ void pack_frames_s2d_kernel(const TIn* __restrict__ x, InNorm nm, bf16* __restrict__ out, int N, int S,
+                                       int F, int C, int H, int W, int Cs) {
+  using P2 = typename Pair<TIn>::type;
   const int Hs = H / 2, Ws = W / 2, Wp = Ws + 4;
   const long long total = (long long)S * N * F * Hs * Wp;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -144,7 +160,7 @@ __global__ void pack_frames_s2d_kernel(const float* __restrict__ x, bf16* __rest
       for (int c = 0; c < Cs; c += 8) *reinterpret_cast<uint4*>(dst + c) = make_uint4(0, 0, 0, 0);
       continue;
     }
-    const float* src = x + (((long long)n * S * F * C + ((long long)s * F + f) * C) * H + 2 * j) * W + 2 * i;
+    const TIn* src = x + (((long long)n * S * F * C + ((long long)s * F + f) * C) * H + 2 * j) * W + 2 * i;
     if (CT > 0) {
       constexpr int CSV = CST > 0 ? CST : 8;
       __align__(16) bf16 v[CSV];
@@ -154,18 +170,18 @@ __global__ void pack_frames_s2d_kernel(const float* __restrict__ x, bf16* __rest
       for (int ph = 0; ph < 2; ++ph)
 #pragma unroll
         for (int c = 0; c < CT; ++c) {
-          const float2 t = *reinterpret_cast<const float2*>(src + ((long long)c * H + ph) * W);
-          v[(ph * 2 + 0) * CT + c] = __float2bfloat16_rn(t.x);
-          v[(ph * 2 + 1) * CT + c] = __float2bfloat16_rn(t.y);
+          const P2 t = *reinterpret_cast<const P2*>(src + ((long long)c * H + ph) * W);
+          v[(ph * 2 + 0) * CT + c] = __float2bfloat16_rn(in_val(t.x, nm, c));
+          v[(ph * 2 + 1) * CT + c] = __float2bfloat16_rn(in_val(t.y, nm, c));
         }
 #pragma unroll
       for (int c = 0; c < CSV; c += 8) *reinterpret_cast<uint4*>(dst + c) = *reinterpret_cast<const uint4*>(v + c);
     } else {
       for (int ph = 0; ph < 2; ++ph)
         for (int c = 0; c < C; ++c) {
-          const float2 v = *reinterpret_cast<const float2*>(src + ((long long)c * H + ph) * W);
-          dst[(ph * 2 + 0) * C + c] = __float2bfloat16_rn(v.x);
-          dst[(ph * 2 + 1) * C + c] = __float2bfloat16_rn(v.y);
+          const P2 v = *reinterpret_cast<const P2*>(src + ((long long)c * H + ph) * W);
+          dst[(ph * 2 + 0) * C + c] = __float2bfloat16_rn(in_val(v.x, nm, c));
+          dst[(ph * 2 + 1) * C + c] = __float2bfloat16_rn(in_val(v.y, nm, c));
         }
       for (int c = 4 * C; c < Cs; ++c) dst[c] = __float2bfloat16_rn(0.f);
     }
@@ -257,26 +273,70 @@ __global__ void cast_kernel(const TI* __restrict__ src, TO* __restrict__ dst, lo
 
 }  // namespace
 
-extern "C" {
-
-int adamml_pack_frames(const float* x, void* out, int N, int S, int F, int C, int H, int W, int Cpad, int dtype,
-                       cudaStream_t stream) {
+template <typename TIn>
+static int pack_frames_any(const TIn* x, InNorm nm, void* out, int N, int S, int F, int C, int H, int W, int Cpad,
+                           int dtype, cudaStream_t stream) {
   ADAMML_REQUIRE(N > 0 && S > 0 && F > 0 && C > 0 && H > 0 && W > 0 && Cpad >= C, "pack_frames: bad dims");
   long long total = (long long)S * N * F * H * W;
   ADAMML_DISPATCH_DTYPE(dtype, T,
-    pack_frames_kernel<T><<<ew_blocks(total), 256, 0, stream>>>(x, (T*)out, N, S, F, C, H, W, Cpad));
+    (pack_frames_kernel<TIn, T><<<ew_blocks(total), 256, 0, stream>>>(x, nm, (T*)out, N, S, F, C, H, W, Cpad)));
   return adamml_check_launch("pack_frames");
 }
 
-int adamml_resize_frames(const float* x, void* out, int N, int S, int F, int C, int H, int W, int OH, int OW,
-                         int fstep, int Cpad, int dtype, cudaStream_t stream) {
+template <typename TIn>
+static int resize_frames_any(const TIn* x, InNorm nm, void* out, int N, int S, int F, int C, int H, int W, int OH,
+                             int OW, int fstep, int Cpad, int dtype, cudaStream_t stream) {
   ADAMML_REQUIRE(N > 0 && S > 0 && F > 0 && C > 0 && H > 0 && W > 0 && OH > 0 && OW > 0 && fstep > 0 && Cpad >= C,
                  "resize_frames: bad dims");
   int Fk = (F + fstep - 1) / fstep;
   long long total = (long long)S * N * Fk * OH * OW;
   ADAMML_DISPATCH_DTYPE(dtype, T,
-    resize_frames_kernel<T><<<ew_blocks(total), 256, 0, stream>>>(x, (T*)out, N, S, F, C, H, W, OH, OW, fstep, Fk, Cpad));
+    (resize_frames_kernel<TIn, T><<<ew_blocks(total), 256, 0, stream>>>(x, nm, (T*)out, N, S, F, C, H, W, OH, OW,
+                                                                        fstep, Fk, Cpad)));
   return adamml_check_launch("resize_frames");
+}
+
+template <typename TIn>
+static int pack_frames_s2d_any(const TIn* x, InNorm nm, void* out, int N, int S, int F, int C, int H, int W, int Cs,
+                               cudaStream_t stream) {
+  ADAMML_REQUIRE(N > 0 && S > 0 && F > 0 && C > 0 && H > 0 && W > 0, "pack_frames_s2d: bad dims");
+  ADAMML_REQUIRE(H % 2 == 0 && W % 2 == 0 && Cs % 8 == 0 && Cs >= 4 * C, "pack_frames_s2d: needs even H, W and Cs >= 4C");
+  ADAMML_REQUIRE(((uintptr_t)x % (2 * sizeof(TIn))) == 0 && ((uintptr_t)out % 16) == 0,
+                 "pack_frames_s2d: unaligned buffers");
+  long long total = (long long)S * N * F * (H / 2) * (W / 2 + 4);
+  bf16* o = (bf16*)out;
+  if (C == 3 && Cs == 16)
+    pack_frames_s2d_kernel<TIn, 3, 16><<<ew_blocks(total), 256, 0, stream>>>(x, nm, o, N, S, F, C, H, W, Cs);
+  else
+    pack_frames_s2d_kernel<TIn, 0, 0><<<ew_blocks(total), 256, 0, stream>>>(x, nm, o, N, S, F, C, H, W, Cs);
+  return adamml_check_launch("pack_frames_s2d");
+}
+
+extern "C" {
+
+int adamml_pack_frames(const float* x, void* out, int N, int S, int F, int C, int H, int W, int Cpad, int dtype,
+                       cudaStream_t stream) {
+  return pack_frames_any<float>(x, InNorm{nullptr, nullptr}, out, N, S, F, C, H, W, Cpad, dtype, stream);
+}
+
+int adamml_pack_frames_u8(const unsigned char* x, const float* mean, const float* stdv, void* out, int N, int S, int F,
+                          int C, int H, int W, int Cpad, int dtype, cudaStream_t stream) {
+  ADAMML_REQUIRE(mean && stdv, "pack_frames_u8: needs the per-channel mean and std");
+  return pack_frames_any<unsigned char>(x, InNorm{mean, stdv}, out, N, S, F, C, H, W, Cpad, dtype, stream);
+}
+
+int adamml_resize_frames(const float* x, void* out, int N, int S, int F, int C, int H, int W, int OH, int OW,
+                         int fstep, int Cpad, int dtype, cudaStream_t stream) {
+  return resize_frames_any<float>(x, InNorm{nullptr, nullptr}, out, N, S, F, C, H, W, OH, OW, fstep, Cpad, dtype,
+                                  stream);
+}
+
+int adamml_resize_frames_u8(const unsigned char* x, const float* mean, const float* stdv, void* out, int N, int S,
+                            int F, int C, int H, int W, int OH, int OW, int fstep, int Cpad, int dtype,
+                            cudaStream_t stream) {
+  ADAMML_REQUIRE(mean && stdv, "resize_frames_u8: needs the per-channel mean and std");
+  return resize_frames_any<unsigned char>(x, InNorm{mean, stdv}, out, N, S, F, C, H, W, OH, OW, fstep, Cpad, dtype,
+                                          stream);
 }
 
 int adamml_pack_weight(const float* w_oihw, void* w_ohwi, int Cout, int Cin, int R, int S, int CinPad, int dtype,
@@ -307,17 +367,13 @@ int adamml_unpack_wgrad(const float* dw_ohwi, float* dw_oihw, int Cout, int Cin,
 
 int adamml_pack_frames_s2d(const float* x, void* out, int N, int S, int F, int C, int H, int W, int Cs,
                            cudaStream_t stream) {
-  ADAMML_REQUIRE(N > 0 && S > 0 && F > 0 && C > 0 && H > 0 && W > 0, "pack_frames_s2d: bad dims");
-  ADAMML_REQUIRE(H % 2 == 0 && W % 2 == 0 && Cs % 8 == 0 && Cs >= 4 * C, "pack_frames_s2d: needs even H, W and Cs >= 4C");
-  ADAMML_REQUIRE(((uintptr_t)x % 8) == 0 && ((uintptr_t)out % 16) == 0, "pack_frames_s2d: unaligned buffers");
-  long long total = (long long)S * N * F * (H / 2) * (W / 2 + 4);
-  if (C == 3 && Cs == 16)
-    pack_frames_s2d_kernel<3, 16><<<ew_blocks(total), 256, 0, stream>>>(x, (bf16*)out, N, S, F, C, H, W, Cs);
-  else if (C == 1 && Cs == 8)
-    pack_frames_s2d_kernel<1, 8><<<ew_blocks(total), 256, 0, stream>>>(x, (bf16*)out, N, S, F, C, H, W, Cs);
-  else
-    pack_frames_s2d_kernel<0, 0><<<ew_blocks(total), 256, 0, stream>>>(x, (bf16*)out, N, S, F, C, H, W, Cs);
-  return adamml_check_launch("pack_frames_s2d");
+  return pack_frames_s2d_any<float>(x, InNorm{nullptr, nullptr}, out, N, S, F, C, H, W, Cs, stream);
+}
+
+int adamml_pack_frames_s2d_u8(const unsigned char* x, const float* mean, const float* stdv, void* out, int N, int S,
+                              int F, int C, int H, int W, int Cs, cudaStream_t stream) {
+  ADAMML_REQUIRE(mean && stdv, "pack_frames_s2d_u8: needs the per-channel mean and std");
+  return pack_frames_s2d_any<unsigned char>(x, InNorm{mean, stdv}, out, N, S, F, C, H, W, Cs, stream);
 }
 
 int adamml_nhwc_to_s2d(const void* x, void* out, long long IMGS, int C, int H, int W, int Cs, int padl, int padr,

@@ -39,13 +39,33 @@ class AdaMML(nn.Module):
             del self.policy_net.fcs
 
     # ------------------------------------------------------------------ data layer (adamml.py:42-67)
+    def _input_norm(self, m, c, device):
+        """(mean, std) per frame channel for decoded uint8 frames of modality m, as GroupNormalize repeats them
+        (utils/video_transforms.py:77-78; values from mean()/std() below, adamml.py:93-109)."""
+        key = (m, c, device)
+        cache = self.__dict__.setdefault("_norm_cache", {})
+        if key not in cache:
+            mean, std = self.mean(m), self.std(m)
+            if c % len(mean):
+                raise ValueError("%d channels per frame cannot repeat a %d-entry mean" % (c, len(mean)))
+            cache[key] = (torch.tensor(mean * (c // len(mean)), dtype=torch.float32, device=device),
+                          torch.tensor(std * (c // len(std)), dtype=torch.float32, device=device))
+        return cache[key]
+
     def data_layer(self, x, num_segments, p_rgb_size=(160, 160)):
-        """-> (p_x, m_x): NHWC image batches ordered (segment, video, frame) in the compute dtype."""
+        """-> (p_x, m_x): NHWC image batches ordered (segment, video, frame) in the compute dtype.
+        A visual modality may arrive as decoded uint8 frames (same [N, S*F*C, H, W] shape): the scaling to [0,1] and
+        the mean/std normalisation of the loader (ToTorchFormatTensor + GroupNormalize) then run inside the
+        re-layout kernels, bit-identical to normalising on the host first."""
         p_x, m_x = [], []
         S, F = num_segments, self.num_frames_per_segment
         dt = self.compute_dtype
         for idx, (x_, m) in enumerate(zip(x, self.modality)):
-            x_ = x_.float()
+            norm = None
+            if x_.dtype == torch.uint8 and m != "sound":
+                norm = self._input_norm(m, x_.size(1) // (S * F), x_.device)
+            else:
+                x_ = x_.float()
             if m == "sound":
                 if x_.size(-1) != x_.size(-2):  # segments stacked along the last dim
                     x_ = torch.stack(x_.chunk(S, dim=-1), dim=1).reshape(x_.size(0), -1, x_.size(-2),
@@ -59,10 +79,11 @@ class AdaMML(nn.Module):
             x_ = x_.contiguous()
             c = x_.size(1) // (S * F)
             if idx in self.p_data_idx:
-                p_x.append(ops.resize_frames(x_, S, F, c, p_rgb_size[0], p_rgb_size[1], 2, dt))
+                p_x.append(ops.resize_frames(x_, S, F, c, p_rgb_size[0], p_rgb_size[1], 2, dt, norm=norm))
             if idx in self.m_data_idx:
                 net = self.main_net.nets[self.m_data_idx.index(idx)]
-                m_x.append(net.pack_input(x_, S) if hasattr(net, "pack_input") else ops.pack_frames(x_, S, F, c, dt))
+                m_x.append(net.pack_input(x_, S, norm=norm) if hasattr(net, "pack_input")
+                           else ops.pack_frames(x_, S, F, c, dt, norm=norm))
         return p_x, m_x, S
 
     def forward(self, x, num_segments=None, noise=None):

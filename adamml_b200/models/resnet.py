@@ -119,14 +119,14 @@ class ResNet(nn.Module):
         d = ex.maxpool_bwd(d)
         ex.cba_bwd(d, need_dx=False)
 
-    def pack_input(self, x, S):
-        """NCHW fp32 [N, S*F*C, H, W] -> the stem operand of the engine: space-to-depth bf16 for the tensor-core
-        stem, plain NHWC otherwise (adamml.py:53,65 / resnet.py:197)."""
+    def pack_input(self, x, S, norm=None):
+        """NCHW fp32 (or uint8 + norm) [N, S*F*C, H, W] -> the stem operand of the engine: space-to-depth bf16 for
+        the tensor-core stem, plain NHWC otherwise (adamml.py:53,65 / resnet.py:197)."""
         f = self.orig_num_frames
         c = x.shape[1] // (S * f)
         if ops.stem_s2d_ok(self.conv1, c, x.shape[2], x.shape[3], self.compute_dtype):
-            return ops.pack_frames_s2d(x, S, f, c)
-        return ops.pack_frames(x, S, f, c, self.compute_dtype)
+            return ops.pack_frames_s2d(x, S, f, c, norm=norm)
+        return ops.pack_frames(x, S, f, c, self.compute_dtype, norm=norm)
 
     # ------------------------------------------------------------------ unimodal API (resnet.py:195)
     def draw_drop_mask(self, rows, device):

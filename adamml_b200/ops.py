@@ -26,25 +26,47 @@ def conv_out_hw(H, W, R, S, stride, pad):
 
 
 # ---------------------------------------------------------------- data layer
-def pack_frames(x, S, F, C, dtype, cpad=None):
-    """x NCHW fp32 [N, S*F*C, H, W] -> NHWC [(s*N+n)*F+f, H, W, cpad]."""
-    _chk(x, torch.float32)
+def _u8_norm(x, C, norm):
+    """uint8 clips carry their normalisation onto the device: norm = (mean [C], std [C]) fp32 device tensors."""
+    if x.dtype != torch.uint8:
+        _chk(x, torch.float32)
+        return None
+    if norm is None:
+        raise ValueError("uint8 frames need norm=(mean, std) per channel")
+    mean, std = norm
+    _chk(x, torch.uint8)
+    _chk(mean, torch.float32)
+    _chk(std, torch.float32)
+    if mean.numel() != C or std.numel() != C:
+        raise ValueError("norm must hold one mean/std per frame channel (%d)" % C)
+    return mean, std
+
+
+def pack_frames(x, S, F, C, dtype, cpad=None, norm=None):
+    """x NCHW fp32 (or uint8 + norm) [N, S*F*C, H, W] -> NHWC [(s*N+n)*F+f, H, W, cpad]."""
+    nm = _u8_norm(x, C, norm)
     N, SFC, H, W = x.shape
     assert SFC == S * F * C, (x.shape, S, F, C)
     cpad = cpad or C
     out = torch.empty((S * N * F, H, W, cpad), device=x.device, dtype=dtype)
-    call("pack_frames", x, out, N, S, F, C, H, W, cpad, dtype_code(dtype))
+    if nm is None:
+        call("pack_frames", x, out, N, S, F, C, H, W, cpad, dtype_code(dtype))
+    else:
+        call("pack_frames_u8", x, nm[0], nm[1], out, N, S, F, C, H, W, cpad, dtype_code(dtype))
     return out
 
 
-def resize_frames(x, S, F, C, OH, OW, fstep, dtype, cpad=None):
-    _chk(x, torch.float32)
+def resize_frames(x, S, F, C, OH, OW, fstep, dtype, cpad=None, norm=None):
+    nm = _u8_norm(x, C, norm)
     N, SFC, H, W = x.shape
     assert SFC == S * F * C
     cpad = cpad or C
     Fk = (F + fstep - 1) // fstep
     out = torch.empty((S * N * Fk, OH, OW, cpad), device=x.device, dtype=dtype)
-    call("resize_frames", x, out, N, S, F, C, H, W, OH, OW, fstep, cpad, dtype_code(dtype))
+    if nm is None:
+        call("resize_frames", x, out, N, S, F, C, H, W, OH, OW, fstep, cpad, dtype_code(dtype))
+    else:
+        call("resize_frames_u8", x, nm[0], nm[1], out, N, S, F, C, H, W, OH, OW, fstep, cpad, dtype_code(dtype))
     return out
 
 
@@ -94,14 +116,17 @@ def first_conv_s2d_ok(conv, C, H, W, dtype):
 stem_s2d_ok = first_conv_s2d_ok
 
 
-def pack_frames_s2d(x, S, F, C):
-    """NCHW fp32 clip -> S2D operand of the 7x7 ResNet stem (two zero columns on either side)."""
-    _chk(x, torch.float32)
+def pack_frames_s2d(x, S, F, C, norm=None):
+    """NCHW fp32 (or uint8 + norm) clip -> S2D operand of the 7x7 ResNet stem (two zero columns on either side)."""
+    nm = _u8_norm(x, C, norm)
     N, SFC, H, W = x.shape
     assert SFC == S * F * C, (x.shape, S, F, C)
     Cs = ((4 * C + 15) // 16) * 16
     out = torch.empty((S * N * F, H // 2, W // 2 + 4, Cs), device=x.device, dtype=torch.bfloat16)
-    call("pack_frames_s2d", x, out, N, S, F, C, H, W, Cs)
+    if nm is None:
+        call("pack_frames_s2d", x, out, N, S, F, C, H, W, Cs)
+    else:
+        call("pack_frames_s2d_u8", x, nm[0], nm[1], out, N, S, F, C, H, W, Cs)
     return S2D(out, C, H, W, 7)
 
 

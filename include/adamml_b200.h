@@ -45,6 +45,17 @@ int adamml_pack_frames(const float* x, void* out, int N, int S, int F, int C, in
 /* F.interpolate(bilinear, align_corners=False) to OHxOW + keep frames 0,fstep,.. (adamml.py:59-62) */
 int adamml_resize_frames(const float* x, void* out, int N, int S, int F, int C, int H, int W, int OH, int OW,
                          int fstep, int Cpad, int dtype, cudaStream_t stream);
+/* The same two passes (and the stem operand below) on decoded uint8 frames: x is the CHW byte tensor
+ * ToTorchFormatTensor holds before .float() (utils/video_transforms.py:321-343); the kernels apply
+ * x.float().div(255) (:343) and GroupNormalize's t.sub_(mean).div_(std) per channel plane (:62-84) in the reference's
+ * fp32 arithmetic while re-laying out, so H2D traffic is 1 byte per sample.  mean/std: device fp32 [C]. */
+int adamml_pack_frames_u8(const unsigned char* x, const float* mean, const float* stdv, void* out, int N, int S, int F,
+                          int C, int H, int W, int Cpad, int dtype, cudaStream_t stream);
+int adamml_resize_frames_u8(const unsigned char* x, const float* mean, const float* stdv, void* out, int N, int S,
+                            int F, int C, int H, int W, int OH, int OW, int fstep, int Cpad, int dtype,
+                            cudaStream_t stream);
+int adamml_pack_frames_s2d_u8(const unsigned char* x, const float* mean, const float* stdv, void* out, int N, int S,
+                              int F, int C, int H, int W, int Cs, cudaStream_t stream);
 /* nn.Conv2d.weight OIHW fp32 -> OHWI operand (CinPad >= Cin, zero filled) */
 int adamml_pack_weight(const float* w_oihw, void* w_ohwi, int Cout, int Cin, int R, int S, int CinPad, int dtype,
                        cudaStream_t stream);
