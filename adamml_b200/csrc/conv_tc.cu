@@ -8,15 +8,16 @@
 // channels-last activations a 1x1 conv IS this GEMM with M = images*H*W pixels.  dgrad of the
 // same layers is the same GEMM with A = dy and B = w^T.
 //
-// Structure (one CTA per SM, 192 threads):
-//   warp 0      TMA producer   : cp.async.bulk.tensor 2D tiles (128B swizzle) -> smem ring
+// Structure (persistent, one CTA per SM, 64 + 128|256 threads):
+//   warp 0      TMA producer   : cp.async.bulk.tensor 2D tiles / shifted 4D boxes (128B swizzle) -> smem ring
 //   warp 1      MMA issuer     : one lane issues tcgen05.mma (M=128, N=BLOCK_N, K=16) x4 per stage,
 //                                tcgen05.commit releases smem stages / publishes the accumulator
-//   warps 2..5  epilogue       : tcgen05.ld TMEM -> registers -> (bf16|fp32) global stores, plus the
-//                                optional fused train-mode BatchNorm statistics (per-column sum and
-//                                sum of squares, reduced with warp shuffles, fp64 atomics)
+//   warps 2..   epilogue       : tcgen05.ld TMEM -> registers -> (+ addend tile fetched by TMA) -> bf16 tile staged in
+//                                128B-swizzled smem -> TMA store; optional fused train-mode BatchNorm statistics
+//                                (per-column sum / sum of squares of the staged, bf16-rounded tile, accumulated in
+//                                fp64 registers across the CTA's tiles, flushed with fp64 atomics per BN group)
 // Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
-// Ragged M / Ncols / K edges are handled by TMA out-of-bounds zero fill + masked stores.
+// Ragged M / Ncols / K edges are handled by TMA out-of-bounds zero fill on loads and clipping on stores.
 #include "tc_common.cuh"
 
 namespace {
@@ -58,8 +59,8 @@ struct TcCfg {
   static constexpr int THREADS = 64 + EPI_THREADS;
   static constexpr bool BACKOFF = (BLOCK_N == 256);  // control warps share SM sub-partitions with epilogue warps
   static constexpr int SUBTILES = BLOCK_N / 64;              // 64-column (128-byte) output sub-tiles
-  // the bf16 staging tile of the TMA store is double buffered when it fits (BLOCK_N <= 128): the store of tile i
-  // drains while tile i+1 is staged
+  // staging tiles of the TMA store: double buffering (store of tile i drains while tile i+1 is staged) measured
+  // no faster than a single buffer, which leaves the smem to the operand ring
   static constexpr int OUT_BUFS = 1;
   static constexpr int OUT_TILE_BYTES = SUBTILES * BLOCK_M * 128;
   static constexpr int OUT_BYTES = OUT_BUFS * OUT_TILE_BYTES;

@@ -95,6 +95,10 @@ CASES = {
                      gemm(9031680, 64, 64, True), gemm(4515840, 128, 256, True), gemm(1128960, 512, 128, True),
                      gemm(9216000, 96, 16, True), gemm(2304000, 24, 144, True), gemm(282240, 1024, 256, True),
                      gemm(282240, 256, 1024, True)],
+    "shallow": lambda: [gemm(9216000, 96, 16, True), gemm(5898240, 96, 16, True), gemm(2304000, 144, 24, True),
+                        gemm(1474560, 144, 24, True), gemm(368640, 192, 32, True), gemm(5898240, 16, 96, True),
+                        gemm(9216000, 16, 32, True), gemm(5898240, 32, 16, False), gemm(9031680, 64, 64, True),
+                        gemm(1474560, 24, 96, True), gemm(92160, 64, 64, True)],
     "conv": lambda: [conv(2880, 56, 56, 64, 64, 3, 1, 1, True), conv(2880, 56, 56, 64, 64, 3, 1, 1, False),
                      conv(2880, 56, 56, 64, 256, 1, 1, 0, False, addend=True),
                      conv(1440, 28, 28, 128, 128, 3, 1, 1, True), conv(720, 14, 14, 256, 256, 3, 1, 1, True),
