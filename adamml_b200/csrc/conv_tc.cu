@@ -45,13 +45,17 @@ struct ConvMaps {
   CUtensorMap m[4];
 };
 
-template <int BLOCK_N>
+// SHALLOW: reductions of one or two K blocks (the MobileNetV2 expand / project-gradient GEMMs, K = 16..96).  Their
+// tiles are all epilogue; two stages suffice, and two co-resident CTAs per SM overlap one tile's epilogue chain
+// (accumulator wait, tcgen05.ld, staging, store drain, statistics) with the other's.
+template <int BLOCK_N, bool SHALLOW = false>
 struct TcCfg {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BLOCK_N == 256) ? 3 : (BLOCK_N == 128 ? 5 : 8);
-  static constexpr int CTAS_PER_SM = 1;
+  static_assert(!SHALLOW || BLOCK_N <= 128, "two CTAs per SM need 2 x (2 x BLOCK_N) <= 512 TMEM columns");
+  static constexpr int STAGES = SHALLOW ? 3 : ((BLOCK_N == 256) ? 3 : (BLOCK_N == 128 ? 5 : 8));
+  static constexpr int CTAS_PER_SM = SHALLOW ? 2 : 1;
   // Epilogue warps: wide tiles (256 columns, issue bound) get TWO warps per TMEM lane quarter that split the
   // accumulator columns; narrow tiles are latency bound and run best with one warp per quarter (measured).
   static constexpr int EPI_WARPS = (BLOCK_N == 256) ? 8 : 4;
@@ -65,7 +69,8 @@ struct TcCfg {
   static constexpr int OUT_TILE_BYTES = SUBTILES * BLOCK_M * 128;
   static constexpr int OUT_BYTES = OUT_BUFS * OUT_TILE_BYTES;
   static constexpr int TMEM_COLS = 2 * BLOCK_N;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + OUT_BYTES + 1024 /*align slack*/ + 1024 /*barriers, row groups*/;
+  static constexpr int RED_BYTES = BLOCK_N * 2 * 8;  // per-CTA fp64 column sums, combined before the global atomics
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + OUT_BYTES + 1024 /*align slack*/ + 1024 /*barriers*/ + RED_BYTES;
 };
 
 template <int THREADS>
@@ -76,38 +81,51 @@ __device__ __forceinline__ void ctl_wait(uint64_t* bar, uint32_t parity) {
   else mbar_wait(bar, parity);
 }
 
-// per-thread running BatchNorm statistics of one (4-column group, row slice): flushed with fp64 atomics when
-// the BN group / column block changes or the CTA retires
+// per-thread running BatchNorm statistics of one (4-column group, row slice).  A flush (BN group or column block
+// changes, CTA retires) is a collective of the epilogue threads: the row slices are first combined per column in
+// shared memory, then ONE fp64 atomic per (column, sum|sum of squares) leaves the CTA -- narrow layers (16..96
+// columns) would otherwise serialise hundreds of thousands of same-address atomics in L2.
 struct StatAcc {
   double S[4], Q[4];
-  long long g;
+  long long g;   // uniform over the CTA
   int col;
   __device__ __forceinline__ void reset() {
 #pragma unroll
     for (int i = 0; i < 4; ++i) { S[i] = 0.0; Q[i] = 0.0; }
   }
-  __device__ __forceinline__ void flush(double* __restrict__ stats, int Ncols) {
+  template <int BLOCK_N, int EPI_THREADS>
+  __device__ __forceinline__ void flush(double* __restrict__ stats, int Ncols, double* red, int col_base, int st) {
     if (g >= 0) {
+      if (col < Ncols) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-        if (col + i < Ncols) {
-          double* p = stats + (g * Ncols + col + i) * 2;
-          atomicAdd(p + 0, S[i]);
-          atomicAdd(p + 1, Q[i]);
+        for (int i = 0; i < 4; ++i)
+          if (col + i < Ncols) {
+            atomicAdd(red + (col - col_base + i) * 2 + 0, S[i]);
+            atomicAdd(red + (col - col_base + i) * 2 + 1, Q[i]);
+          }
+      }
+      epi_bar_sync<EPI_THREADS>();
+      for (int j = st; j < BLOCK_N * 2; j += EPI_THREADS) {
+        const double v = red[j];
+        if (v != 0.0) {  // (col_base + j/2 < Ncols holds: columns beyond Ncols are never accumulated)
+          atomicAdd(stats + (g * Ncols + col_base + (j >> 1)) * 2 + (j & 1), v);
+          red[j] = 0.0;
         }
+      }
+      epi_bar_sync<EPI_THREADS>();
     }
     reset();
   }
 };
 
-template <int BLOCK_N, bool CONV>
-__global__ void __launch_bounds__(TcCfg<BLOCK_N>::THREADS, TcCfg<BLOCK_N>::CTAS_PER_SM)
+template <int BLOCK_N, bool CONV, bool SHALLOW = false>
+__global__ void __launch_bounds__(TcCfg<BLOCK_N, SHALLOW>::THREADS, TcCfg<BLOCK_N, SHALLOW>::CTAS_PER_SM)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmAdd,
                const __grid_constant__ ConvMaps cmaps, const __grid_constant__ ConvGeom geo,
                const bf16* __restrict__ addend, long long M, int Ncols, int K, long long ldd,
                double* __restrict__ stats, long long rows_per_group) {
-  using Cfg = TcCfg<BLOCK_N>;
+  using Cfg = TcCfg<BLOCK_N, SHALLOW>;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment by pointer arithmetic (keeps the shared address space visible to the compiler: LDS/STS
   // instead of generic LD/ST in the epilogue)
@@ -119,6 +137,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* add_bar = tmem_empty + 2;  // dense addend tile landed in the staging buffer (TMA)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(add_bar + 1);
+  double* red = reinterpret_cast<double*>(stage_base + Cfg::OUT_BYTES + 1024);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -237,6 +256,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     sa_.g = -1;
     sa_.col = 0;
     int last_n_blk = -1;
+    if (stats) {
+      for (int j = st; j < BLOCK_N * 2; j += Cfg::EPI_THREADS) red[j] = 0.0;
+      epi_bar_sync<Cfg::EPI_THREADS>();
+    }
     int acc = 0, obuf = 0;
     uint32_t acc_phase = 0, add_phase = 0;
     for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -372,11 +395,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       if (stats) {
         if (n_blk != last_n_blk) {
-          sa_.flush(stats, Ncols);
+          sa_.template flush<BLOCK_N, Cfg::EPI_THREADS>(stats, Ncols, red, last_n_blk * BLOCK_N, st);
           last_n_blk = n_blk;
           sa_.col = n_blk * BLOCK_N + squad * 4;
         }
-        if (sa_.col < Ncols) {
+        const bool col_ok = sa_.col < Ncols;
+        {  // every epilogue thread walks the row segments (the flushes inside are collectives)
           // rows of a tile are ordered by BN group, so the tile is a few row segments of constant group;
           // invalid rows were staged as zeros and may be summed into any group
           const uint8_t* sbase = stage_out + (squad >> 4) * (BLOCK_M * 128) + ((squad & 1) << 3);
@@ -400,12 +424,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               r1 = e < BLOCK_M ? (int)e : BLOCK_M;
             }
             if (g != sa_.g) {
-              sa_.flush(stats, Ncols);
+              sa_.template flush<BLOCK_N, Cfg::EPI_THREADS>(stats, Ncols, red, n_blk * BLOCK_N, st);
               sa_.g = g;
             }
             float s[4] = {0.f, 0.f, 0.f, 0.f}, qq[4] = {0.f, 0.f, 0.f, 0.f};
             // first row of this thread's slice inside [r0, r1)
             int rw = r0 + ((srs - r0) % RSPLIT + RSPLIT) % RSPLIT;
+            if (!col_ok) rw = r1;
 #pragma unroll 8
             for (; rw < r1; rw += RSPLIT) {
               const uint2 pk = *reinterpret_cast<const uint2*>(sbase + rw * 128 + ((c ^ (rw & 7)) << 4));
@@ -423,7 +448,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
-    if (stats) sa_.flush(stats, Ncols);
+    if (stats) sa_.template flush<BLOCK_N, Cfg::EPI_THREADS>(stats, Ncols, red, last_n_blk * BLOCK_N, st);
     if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
@@ -456,13 +481,13 @@ int make_map_2d(CUtensorMap* map, const void* ptr, long long rows, long long col
   return ADAMML_OK;
 }
 
-template <int BLOCK_N, bool CONV>
+template <int BLOCK_N, bool CONV, bool SHALLOW = false>
 int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, const CUtensorMap& tmAdd,
               const ConvMaps& cm, const ConvGeom& geo, const void* addend, long long M, int Ncols, int K, long long ldd, double* stats,
               long long rpg, cudaStream_t stream) {
-  using Cfg = TcCfg<BLOCK_N>;
+  using Cfg = TcCfg<BLOCK_N, SHALLOW>;
   static bool configured = false;
-  auto kern = tc_gemm_kernel<BLOCK_N, CONV>;
+  auto kern = tc_gemm_kernel<BLOCK_N, CONV, SHALLOW>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) {
@@ -565,6 +590,10 @@ int adamml_tc_gemm_bf16(const void* A, const void* B, void* D, long long M, int 
     return ADAMML_ERR_UNSUPPORTED;
   }
   ADAMML_REQUIRE(!stats || rows_per_group > 0, "tc_gemm: stats need rows_per_group");
+  // shallow reductions under narrow tiles: two co-resident CTAs per SM (measured: 64x64 layer1 conv1 0.64 -> 0.39 ms;
+  // wider outputs split into 128-column blocks lose against one 256-column CTA, so those keep the deep config)
+  static const bool shallow_on = []() { const char* e = getenv("ADAMML_B200_TC_SHALLOW"); return !(e && e[0] == '0'); }();
+  const bool shallow = shallow_on && K <= 2 * BLOCK_K && Ncols <= 128;
   const int block_n = Ncols <= 64 ? 64 : (Ncols <= 128 ? 128 : 256);
   CUtensorMap tmA, tmB;
   int rc = make_map_2d(&tmA, A, M, K, lda, BLOCK_M);
@@ -582,6 +611,13 @@ int adamml_tc_gemm_bf16(const void* A, const void* B, void* D, long long M, int 
   ConvGeom geo;
   memset(&cm, 0, sizeof(cm));
   memset(&geo, 0, sizeof(geo));
+  if (shallow) {
+    if (block_n == 64)
+      return launch_tc<64, false, true>(tmA, tmB, tmD, tmD, cm, geo, nullptr, M, Ncols, K, ldd, stats, rows_per_group,
+                                        stream);
+    return launch_tc<128, false, true>(tmA, tmB, tmD, tmD, cm, geo, nullptr, M, Ncols, K, ldd, stats, rows_per_group,
+                                       stream);
+  }
   return dispatch_tc<false>(block_n, tmA, tmB, tmD, tmD, cm, geo, nullptr, M, Ncols, K, ldd, stats, rows_per_group,
                             stream);
 }
