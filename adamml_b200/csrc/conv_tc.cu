@@ -54,7 +54,8 @@ struct TcCfg {
   static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static_assert(!SHALLOW || BLOCK_N <= 128, "two CTAs per SM need 2 x (2 x BLOCK_N) <= 512 TMEM columns");
-  static constexpr int STAGES = SHALLOW ? 3 : ((BLOCK_N == 256) ? 3 : (BLOCK_N == 128 ? 5 : 8));
+  // (stage counts that divide by the common K-block counts 1, 2, 4 keep the weight tile resident, see the producer)
+  static constexpr int STAGES = SHALLOW ? 2 : ((BLOCK_N == 256) ? 3 : (BLOCK_N == 128 ? 4 : 8));
   static constexpr int CTAS_PER_SM = SHALLOW ? 2 : 1;
   // Epilogue warps: wide tiles (256 columns, issue bound) get TWO warps per TMEM lane quarter that split the
   // accumulator columns; narrow tiles are latency bound and run best with one warp per quarter (measured).
@@ -65,7 +66,7 @@ struct TcCfg {
   static constexpr int SUBTILES = BLOCK_N / 64;              // 64-column (128-byte) output sub-tiles
   // staging tiles of the TMA store: double buffering (store of tile i drains while tile i+1 is staged) measured
   // no faster than a single buffer, which leaves the smem to the operand ring
-  static constexpr int OUT_BUFS = 1;
+  static constexpr int OUT_BUFS = (SHALLOW && BLOCK_N == 64) ? 2 : 1;
   static constexpr int OUT_TILE_BYTES = SUBTILES * BLOCK_M * 128;
   static constexpr int OUT_BYTES = OUT_BUFS * OUT_TILE_BYTES;
   static constexpr int TMEM_COLS = 2 * BLOCK_N;
@@ -124,7 +125,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmAdd,
                const __grid_constant__ ConvMaps cmaps, const __grid_constant__ ConvGeom geo,
                const bf16* __restrict__ addend, long long M, int Ncols, int K, long long ldd,
-               double* __restrict__ stats, long long rows_per_group) {
+               double* __restrict__ stats, long long rows_per_group, bf16* __restrict__ dlin) {
   using Cfg = TcCfg<BLOCK_N, SHALLOW>;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment by pointer arithmetic (keeps the shared address space visible to the compiler: LDS/STS
@@ -173,6 +174,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
       int stage = 0;
       uint32_t phase = 0;
+      // One column block and a K-block count that divides the ring: slot s always carries K block s % num_kb, and
+      // every tile multiplies by the SAME weight tiles, so each slot receives its weight tile once and later tiles
+      // load only their A rows.  (Re-fetching the few weight lines per tile from all 148 SMs hot-spots one L2
+      // slice: narrow MobileNetV2 layers ran up to 3x slower with the reload.)
+      const bool b_resident = num_n_blks == 1 && (Cfg::STAGES % num_kb) == 0;
+      int b_loaded = 0;
       for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int n_blk = (int)(tile % num_n_blks);
         const int m_blk = (int)(tile / num_n_blks);
@@ -186,16 +193,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           ctl_wait<Cfg::BACKOFF>(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
-          mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          const bool need_b = !b_resident || b_loaded < Cfg::STAGES;
+          if (b_resident && need_b) ++b_loaded;
+          mbar_expect_tx(&full_bar[stage], need_b ? Cfg::STAGE_BYTES : Cfg::A_BYTES);
           if (CONV) {
             const int tap = kb / geo.kb_per_tap;
             const int c0 = (kb - tap * geo.kb_per_tap) * BLOCK_K;
             tma_load_4d(sa, &cmaps.m[geo.tap_map[tap]], &full_bar[stage], c0, w0 + geo.tap_dw[tap],
                         h0 + geo.tap_dh[tap], i0);
-            tma_load_2d(sb, &tmB, &full_bar[stage], geo.tap_koff[tap] + c0, n_blk * BLOCK_N);
+            if (need_b) tma_load_2d(sb, &tmB, &full_bar[stage], geo.tap_koff[tap] + c0, n_blk * BLOCK_N);
           } else {
             tma_load_2d(sa, &tmA, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
-            tma_load_2d(sb, &tmB, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);
+            if (need_b) tma_load_2d(sb, &tmB, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);
           }
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
@@ -343,8 +352,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
         }
-        // staging address: sub-tile (chunk / 2), row et, logical 16-byte chunk c -> physical c ^ (et & 7)
+        // staging address: sub-tile (chunk / 2), row et, logical 16-byte chunk c -> physical c ^ (et & 7);
+        // linear mode (dlin): plain row-major rows of Ncols elements, the image of the contiguous output tile
         uint8_t* srow = stage_out + (chunk >> 1) * (BLOCK_M * 128) + et * 128;
+        uint8_t* lrow = stage_out + (size_t)et * (size_t)(Ncols * 2) + chunk * 64;
         if (add_tma && row_ok) {
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
@@ -371,7 +382,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           pk.z = *reinterpret_cast<uint32_t*>(&p2);
           pk.w = *reinterpret_cast<uint32_t*>(&p3);
           const int c = (chunk & 1) * 4 + (j >> 3);
-          *reinterpret_cast<uint4*>(srow + ((c ^ (et & 7)) << 4)) = pk;
+          if (!CONV && dlin) {
+            if (col0 + j < Ncols) *reinterpret_cast<uint4*>(lrow + (j << 1)) = pk;
+          } else {
+            *reinterpret_cast<uint4*>(srow + ((c ^ (et & 7)) << 4)) = pk;
+          }
         }
       }
       // accumulator drained: hand the TMEM stage back to the MMA warp
@@ -383,12 +398,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       epi_bar_sync<Cfg::EPI_THREADS>();
       if (issuer) {
+        if (!CONV && dlin) {
+          // the tile's rows are one contiguous chunk of the output: a single bulk copy of full 128-byte lines
+          // instead of 128 narrow row requests per 64-column sub-tile
+          const long long row0 = (long long)m_blk * BLOCK_M;
+          const long long rows = (M - row0) < BLOCK_M ? (M - row0) : BLOCK_M;
+          bulk_store_1d(dlin + row0 * Ncols, stage_out, (uint32_t)(rows * Ncols * 2));
+        } else {
 #pragma unroll
-        for (int sub = 0; sub < Cfg::SUBTILES; ++sub) {
-          const int col = n_blk * BLOCK_N + sub * 64;
-          if (col < Ncols) {
-            if (CONV) tma_store_4d(&tmD, stage_out + sub * (BLOCK_M * 128), col, w0, h0, i0);
-            else tma_store_2d(&tmD, stage_out + sub * (BLOCK_M * 128), col, m_blk * BLOCK_M);
+          for (int sub = 0; sub < Cfg::SUBTILES; ++sub) {
+            const int col = n_blk * BLOCK_N + sub * 64;
+            if (col < Ncols) {
+              if (CONV) tma_store_4d(&tmD, stage_out + sub * (BLOCK_M * 128), col, w0, h0, i0);
+              else tma_store_2d(&tmD, stage_out + sub * (BLOCK_M * 128), col, m_blk * BLOCK_M);
+            }
           }
         }
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -403,7 +426,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         {  // every epilogue thread walks the row segments (the flushes inside are collectives)
           // rows of a tile are ordered by BN group, so the tile is a few row segments of constant group;
           // invalid rows were staged as zeros and may be summed into any group
-          const uint8_t* sbase = stage_out + (squad >> 4) * (BLOCK_M * 128) + ((squad & 1) << 3);
+          const bool lin = !CONV && dlin != nullptr;
+          const uint8_t* sbase = lin ? stage_out + squad * 8
+                                     : stage_out + (squad >> 4) * (BLOCK_M * 128) + ((squad & 1) << 3);
+          const int pitch = lin ? Ncols * 2 : 128;
           const int c = (squad & 15) >> 1;
           int r0 = 0;
           while (r0 < BLOCK_M) {
@@ -433,7 +459,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (!col_ok) rw = r1;
 #pragma unroll 8
             for (; rw < r1; rw += RSPLIT) {
-              const uint2 pk = *reinterpret_cast<const uint2*>(sbase + rw * 128 + ((c ^ (rw & 7)) << 4));
+              const uint2 pk = *reinterpret_cast<const uint2*>(sbase + rw * pitch + (lin ? 0 : ((c ^ (rw & 7)) << 4)));
               const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk.x));
               const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk.y));
               s[0] += f0.x; qq[0] = fmaf(f0.x, f0.x, qq[0]);
@@ -484,7 +510,7 @@ int make_map_2d(CUtensorMap* map, const void* ptr, long long rows, long long col
 template <int BLOCK_N, bool CONV, bool SHALLOW = false>
 int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, const CUtensorMap& tmAdd,
               const ConvMaps& cm, const ConvGeom& geo, const void* addend, long long M, int Ncols, int K, long long ldd, double* stats,
-              long long rpg, cudaStream_t stream) {
+              long long rpg, cudaStream_t stream, void* dlin = nullptr) {
   using Cfg = TcCfg<BLOCK_N, SHALLOW>;
   static bool configured = false;
   auto kern = tc_gemm_kernel<BLOCK_N, CONV, SHALLOW>;
@@ -501,17 +527,17 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap&
   const int sms = num_sms() * Cfg::CTAS_PER_SM;
   int grid = (int)(tiles < sms ? tiles : sms);
   kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmD, tmAdd, cm, geo, (const bf16*)addend, M, Ncols,
-                                                        K, ldd, stats, rpg);
+                                                        K, ldd, stats, rpg, (bf16*)dlin);
   return adamml_check_launch(CONV ? "tc_conv" : "tc_gemm");
 }
 
 template <bool CONV>
 int dispatch_tc(int block_n, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD,
                 const CUtensorMap& tmAdd, const ConvMaps& cm, const ConvGeom& geo, const void* addend, long long M, int Ncols, int K, long long ldd, double* stats,
-                long long rpg, cudaStream_t stream) {
+                long long rpg, cudaStream_t stream, void* dlin = nullptr) {
 #define ADAMML_TC_CASE(BN) \
   if (block_n == BN)       \
-    return launch_tc<BN, CONV>(tmA, tmB, tmD, tmAdd, cm, geo, addend, M, Ncols, K, ldd, stats, rpg, stream);
+    return launch_tc<BN, CONV>(tmA, tmB, tmD, tmAdd, cm, geo, addend, M, Ncols, K, ldd, stats, rpg, stream, dlin);
   ADAMML_TC_CASE(64)
   ADAMML_TC_CASE(128)
   ADAMML_TC_CASE(256)
@@ -611,15 +637,19 @@ int adamml_tc_gemm_bf16(const void* A, const void* B, void* D, long long M, int 
   ConvGeom geo;
   memset(&cm, 0, sizeof(cm));
   memset(&geo, 0, sizeof(geo));
+  // contiguous output whose rows are not whole 128-byte lines (N = 16, 24, 32, 96, 144, ...): the TMA unit retires
+  // about one box row per 4 cycles whatever its width, so the tile is stored as ONE linear bulk copy instead
+  static const bool linear_on = []() { const char* e = getenv("ADAMML_B200_TC_LINEAR"); return !(e && e[0] == '0'); }();
+  void* dlin = (linear_on && ldd == Ncols && Ncols <= block_n && (Ncols % 64) != 0) ? D : nullptr;
   if (shallow) {
     if (block_n == 64)
       return launch_tc<64, false, true>(tmA, tmB, tmD, tmD, cm, geo, nullptr, M, Ncols, K, ldd, stats, rows_per_group,
-                                        stream);
+                                        stream, dlin);
     return launch_tc<128, false, true>(tmA, tmB, tmD, tmD, cm, geo, nullptr, M, Ncols, K, ldd, stats, rows_per_group,
-                                       stream);
+                                       stream, dlin);
   }
   return dispatch_tc<false>(block_n, tmA, tmB, tmD, tmD, cm, geo, nullptr, M, Ncols, K, ldd, stats, rows_per_group,
-                            stream);
+                            stream, dlin);
 }
 
 int adamml_tc_conv_supported(int Cin, int Cout, int R, int S, int stride) {

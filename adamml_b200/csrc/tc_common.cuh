@@ -80,6 +80,12 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void*
                "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
 }
+// contiguous shared -> global bulk copy (16-byte aligned addresses, size a multiple of 16), same bulk async-group
+__device__ __forceinline__ void bulk_store_1d(void* gptr, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gptr), "r"(smem_u32(src)),
+               "r"(bytes)
+               : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 

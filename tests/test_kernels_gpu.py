@@ -77,6 +77,12 @@ TC_CASES = [
     (1000, 256, 128),
     (3136 * 2, 64, 256),
     (777, 24, 144),
+    # narrow / shallow MobileNetV2 pointwise shapes: linear bulk-store epilogue, two-CTA shallow-K config
+    (1000, 16, 32),
+    (5000, 96, 16),
+    (300, 32, 16),
+    (777, 144, 24),
+    (129, 8, 8),
     (513, 1280, 320),
     (4096, 512, 1024),
     (130, 16, 32),
@@ -104,7 +110,8 @@ def test_tc_gemm(cuda, case):
 
 
 @pytest.mark.parametrize("case", [(3136 * 4, 64, 64, 3136 * 2), (1000, 256, 128, 250), (6 * 98, 512, 256, 98),
-                                  (777, 24, 144, 777)])
+                                  (777, 24, 144, 777), (1000, 16, 32, 250), (5000, 96, 16, 1000), (768, 144, 24, 256),
+                                  (6 * 640, 192, 32, 640)])
 def test_tc_gemm_bn_stats(cuda, case):
     from adamml_b200 import _lib
     M, N, K, rpg = case
