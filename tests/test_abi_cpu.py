@@ -85,3 +85,36 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dp, f)).read()
                 assert "oracle" not in src.replace("oracle/", "oracle/").lower() or f == "__none__", (dp, f)
+
+
+def test_every_call_site_matches_the_header_arity():
+    """Static ABI check without a GPU: every `call("op", ...)` in the package passes exactly the parameters the header
+    declares for `adamml_op` (minus the trailing stream, which `_lib.call` appends)."""
+    import ast
+    import glob
+    from adamml_b200 import _lib
+    protos = _lib.parse_header()
+    pkg = os.path.join(ROOT, "adamml_b200")
+    files = glob.glob(os.path.join(pkg, "**", "*.py"), recursive=True) + [os.path.join(ROOT, "bench.py")]
+    seen, bad = set(), []
+    for f in files:
+        tree = ast.parse(open(f).read(), f)
+        for node in ast.walk(tree):
+            if not isinstance(node, ast.Call) or not node.args:
+                continue
+            fn = node.func
+            name = fn.id if isinstance(fn, ast.Name) else (fn.attr if isinstance(fn, ast.Attribute) else None)
+            if name != "call" or not isinstance(node.args[0], ast.Constant) or not isinstance(node.args[0].value, str):
+                continue
+            if any(isinstance(a, ast.Starred) for a in node.args):
+                continue
+            op = "adamml_" + node.args[0].value
+            assert op in protos, f"{f}:{node.lineno}: {op} is not declared in include/adamml_b200.h"
+            params = protos[op][1]
+            want = len(params) - (1 if params and params[-1][0].startswith("cudaStream_t") else 0)
+            got = len(node.args) - 1
+            seen.add(op)
+            if got != want:
+                bad.append((os.path.relpath(f, ROOT), node.lineno, op, got, want))
+    assert not bad, bad
+    assert len(seen) > 40, len(seen)   # the walk really found the call sites
