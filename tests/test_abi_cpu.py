@@ -95,7 +95,8 @@ def test_every_call_site_matches_the_header_arity():
     from adamml_b200 import _lib
     protos = _lib.parse_header()
     pkg = os.path.join(ROOT, "adamml_b200")
-    files = glob.glob(os.path.join(pkg, "**", "*.py"), recursive=True) + [os.path.join(ROOT, "bench.py")]
+    files = (glob.glob(os.path.join(pkg, "**", "*.py"), recursive=True) + [os.path.join(ROOT, "bench.py")] +
+             glob.glob(os.path.join(ROOT, "scripts", "*.py")) + glob.glob(os.path.join(ROOT, "tests", "*.py")))
     seen, bad = set(), []
     for f in files:
         tree = ast.parse(open(f).read(), f)
