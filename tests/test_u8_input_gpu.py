@@ -14,8 +14,6 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from util import namespace  # noqa: E402
 
-pytestmark = pytest.mark.gpu
-
 MEAN = {"rgb": [0.485, 0.456, 0.406], "flow": [0.5]}
 STD = {"rgb": [0.229, 0.224, 0.225], "flow": [sum([0.229, 0.224, 0.225]) / 3]}
 
@@ -33,6 +31,34 @@ def loader_normalise(x_u8, mean, std):
     return torch.stack(out)
 
 
+@pytest.mark.parametrize("m", ["rgb", "flow"])
+def test_loader_restatement_matches_reference_transforms(m):
+    """not gpu: `loader_normalise` above is pinned, bit for bit, to the reference's own Stack -> ToTorchFormatTensor
+    -> GroupNormalize run (tests/golden/make_golden_u8.py -> u8_normalize.pt)."""
+    from util import load_golden
+    gold = load_golden("u8_normalize")[m]
+    assert gold["mean"] == MEAN[m] and gold["std"] == pytest.approx(STD[m], abs=0, rel=1e-15)
+    got = loader_normalise(gold["u8"][None], gold["mean"], gold["std"])[0]
+    assert torch.equal(got, gold["normalized"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("m,F", [("rgb", 4), ("flow", 1)])
+def test_u8_kernel_matches_reference_transform_golden(cuda, m, F):
+    """The device-side normalisation reproduces the reference loader's output on its own golden vector."""
+    from adamml_b200 import ops
+    from util import load_golden
+    gold = load_golden("u8_normalize")[m]
+    x8 = gold["u8"][None].to(cuda)                                  # [1, F*C, 6, 5]
+    C = x8.shape[1] // F
+    norm = (torch.tensor(gold["mean"] * (C // len(gold["mean"])), device=cuda),
+            torch.tensor(gold["std"] * (C // len(gold["std"])), dtype=torch.float32, device=cuda))
+    y = ops.pack_frames(x8, 1, F, C, torch.float32, norm=norm)      # NHWC [F, 6, 5, C]
+    ref = gold["normalized"].view(F, C, 6, 5).permute(0, 2, 3, 1).to(cuda)
+    assert torch.equal(y, ref)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("m,C", [("rgb", 3), ("flow", 10)])
 def test_u8_relayout_kernels_bit_identical(cuda, m, C):
     from adamml_b200 import ops
@@ -52,6 +78,7 @@ def test_u8_relayout_kernels_bit_identical(cuda, m, C):
         ops.pack_frames(x8, S, F, C, torch.bfloat16)          # uint8 without its normalisation
 
 
+@pytest.mark.gpu
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_model_accepts_u8_frames(cuda, dtype):
     from adamml_b200.models import build_model
