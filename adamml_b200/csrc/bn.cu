@@ -233,12 +233,11 @@ inline int num_sms_ew() {
 }
 
 // out = act( z*scale+shift  [+ res]  [+ res_z*res_scale+res_shift] )
-template <typename T>
-__global__ void __launch_bounds__(EW_THREADS)
-bn_apply_rows_kernel(const T* __restrict__ z, const float* __restrict__ ss, const T* __restrict__ res,
-                     const T* __restrict__ res_z, const float* __restrict__ res_ss, T* __restrict__ out,
-                     long long rows_per_group, int C, int cpb, int k, int rows_per_block, int blocks_per_group,
-                     int act) {
+template <typename T, typename CP, typename MP>
+__device__ __forceinline__ void
+bn_apply_rows_body(CP z, const float* __restrict__ ss, CP res, CP res_z, const float* __restrict__ res_ss, MP out,
+                   long long rows_per_group, int C, int cpb, int k, int rows_per_block, int blocks_per_group,
+                   int act) {
   constexpr int V = VecIO<T>::N;
   const int cl = threadIdx.x % cpb, rl = threadIdx.x / cpb;
   const int c0 = (blockIdx.y * cpb + cl) * V;
@@ -290,6 +289,88 @@ bn_apply_rows_kernel(const T* __restrict__ z, const float* __restrict__ ss, cons
         }
         VecIO<T>::store(out + base + rr * C, vo);
       }
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(EW_THREADS)
+bn_apply_rows_kernel(const T* __restrict__ z, const float* __restrict__ ss, const T* __restrict__ res,
+                     const T* __restrict__ res_z, const float* __restrict__ res_ss, T* __restrict__ out,
+                     long long rows_per_group, int C, int cpb, int k, int rows_per_block, int blocks_per_group,
+                     int act) {
+  bn_apply_rows_body<T, const T*, T*>(z, ss, res, res_z, res_ss, out, rows_per_group, C, cpb, k, rows_per_block,
+                                      blocks_per_group, act);
+}
+// x2 planes (forward pass of the default precision mode)
+__global__ void __launch_bounds__(EW_THREADS)
+bn_apply_rows_x2_kernel(X2CPtr z, const float* __restrict__ ss, X2CPtr res, X2CPtr res_z,
+                        const float* __restrict__ res_ss, X2Ptr out, long long rows_per_group, int C, int cpb, int k,
+                        int rows_per_block, int blocks_per_group, int act) {
+  bn_apply_rows_body<x2_t, X2CPtr, X2Ptr>(z, ss, res, res_z, res_ss, out, rows_per_group, C, cpb, k, rows_per_block,
+                                          blocks_per_group, act);
+}
+
+// sums[g][c][0] += sum z ; sums[g][c][1] += sum z^2 over x2 planes (depthwise-conv outputs: their BN statistics are
+// not produced by a GEMM epilogue).  Same persistent row-chunk scheme as bn_reduce_rows_kernel<MODE 0>.
+__global__ void __launch_bounds__(EW_THREADS, 2)
+bn_stats_rows_x2_kernel(X2CPtr a, double* __restrict__ sums, long long rows_per_group, int C, int cpb, int k,
+                        int blocks_per_group) {
+  constexpr int V = 8;
+  constexpr int UN = 2;
+  constexpr int CH = 8;
+  extern __shared__ double shd[];
+  const int cl = threadIdx.x % cpb, rl = threadIdx.x / cpb;
+  const int c0 = (blockIdx.y * cpb + cl) * V;
+  const bool ok = c0 < C;
+  const int g = blockIdx.x / blocks_per_group;
+  const int bg = blockIdx.x % blocks_per_group;
+  double* sh = shd + (size_t)threadIdx.x * (2 * V);
+#pragma unroll
+  for (int i = 0; i < 2 * V; ++i) sh[i] = 0.0;
+  if (ok) {
+    const long long base = (long long)g * rows_per_group * C + c0;
+    const long long chunk_rows = (long long)k * UN * CH;
+    for (long long rc = (long long)bg * chunk_rows; rc < rows_per_group; rc += (long long)blocks_per_group * chunk_rows) {
+      long long r1 = rc + chunk_rows;
+      if (r1 > rows_per_group) r1 = rows_per_group;
+      float s[V], q[V];
+#pragma unroll
+      for (int i = 0; i < V; ++i) { s[i] = 0.f; q[i] = 0.f; }
+      for (long long r = rc + rl; r < r1; r += (long long)k * UN) {
+        X2Raw qa[UN];
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+          const long long rr = r + (long long)u * k;
+          if (rr < r1) qa[u] = VecIO<x2_t>::load_raw(a + (base + rr * C));
+        }
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+          const long long rr = r + (long long)u * k;
+          if (rr < r1) {
+            float va[V];
+            VecIO<x2_t>::unpack(qa[u], va);
+#pragma unroll
+            for (int i = 0; i < V; ++i) { s[i] += va[i]; q[i] = fmaf(va[i], va[i], q[i]); }
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < V; ++i) { sh[i] += (double)s[i]; sh[V + i] += (double)q[i]; }
+    }
+  }
+  __syncthreads();
+  if (rl == 0 && ok) {
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      double ds = 0.0, dq = 0.0;
+      for (int y = 0; y < k; ++y) {
+        const double* o = shd + ((size_t)y * cpb + cl) * (2 * V);
+        ds += o[i];
+        dq += o[V + i];
+      }
+      atomicAdd(&sums[((long long)g * C + c0 + i) * 2 + 0], ds);
+      atomicAdd(&sums[((long long)g * C + c0 + i) * 2 + 1], dq);
     }
   }
 }
@@ -597,6 +678,40 @@ int adamml_bn_apply(const void* z, const float* scale_shift, const void* res, co
     }
   });
   return adamml_check_launch("bn_apply");
+}
+
+/* x2 planes: z/res/res_z/out are (hi, lo) plane pairs; C must be a multiple of 8 */
+int adamml_bn_apply_x2(const void* z_hi, const void* z_lo, const float* scale_shift, const void* res_hi,
+                       const void* res_lo, const void* resz_hi, const void* resz_lo, const float* res_scale_shift,
+                       void* out_hi, void* out_lo, long long rows_per_group, int C, int G, int act,
+                       cudaStream_t stream) {
+  ADAMML_REQUIRE(rows_per_group > 0 && C > 0 && G > 0, "bn_apply_x2: empty dims");
+  ADAMML_REQUIRE(!resz_hi || res_scale_shift, "bn_apply_x2: res_z needs res_scale_shift");
+  ADAMML_REQUIRE(z_hi && z_lo && out_hi && out_lo && (!res_hi == !res_lo) && (!resz_hi == !resz_lo),
+                 "bn_apply_x2: every tensor needs both planes");
+  ADAMML_REQUIRE(C % 8 == 0 && vec_ok<bf16>(C, z_hi, z_lo, res_hi, res_lo) && vec_ok<bf16>(C, resz_hi, resz_lo, out_hi, out_lo),
+                 "bn_apply_x2: needs C %% 8 == 0 and 16-byte aligned planes");
+  const RowGeom rg = row_geom<x2_t>(C);
+  int rpb, bpg;
+  stream_geom(rg, rows_per_group, &rpb, &bpg);
+  dim3 vg((unsigned)(bpg * (long long)G), rg.cchunks);
+  bn_apply_rows_x2_kernel<<<vg, rg.threads, 0, stream>>>(x2c(z_hi, z_lo), scale_shift, x2c(res_hi, res_lo),
+                                                        x2c(resz_hi, resz_lo), res_scale_shift, x2m(out_hi, out_lo),
+                                                        rows_per_group, C, rg.cpb, rg.k, rpb, bpg, act);
+  return adamml_check_launch("bn_apply_x2");
+}
+
+int adamml_bn_stats_x2(const void* z_hi, const void* z_lo, double* sums, long long rows_per_group, int C, int G,
+                       cudaStream_t stream) {
+  ADAMML_REQUIRE(rows_per_group > 0 && C > 0 && G > 0, "bn_stats_x2: empty dims");
+  ADAMML_REQUIRE(C % 8 == 0 && vec_ok<bf16>(C, z_hi, z_lo), "bn_stats_x2: needs C %% 8 == 0 and aligned planes");
+  cudaMemsetAsync(sums, 0, sizeof(double) * (size_t)G * C * 2, stream);
+  const RowGeom rg = row_geom<x2_t>(C);
+  const int bpg = reduce_bpg(rg, rows_per_group, G);
+  const size_t sm = sizeof(double) * rg.threads * 2 * 8;
+  dim3 vg((unsigned)(bpg * (long long)G), rg.cchunks);
+  bn_stats_rows_x2_kernel<<<vg, rg.threads, sm, stream>>>(x2c(z_hi, z_lo), sums, rows_per_group, C, rg.cpb, rg.k, bpg);
+  return adamml_check_launch("bn_stats_x2");
 }
 
 int adamml_bn_bwd_reduce(const void* dout, const void* out, const void* z, const float* mean_invstd,

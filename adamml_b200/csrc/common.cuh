@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -12,6 +13,10 @@
 
 #define ADAMML_F32 0
 #define ADAMML_BF16 1
+// "x2" activations: TWO planes per tensor, hi = bf16(v) and lo = fp16(v - hi)  (about 20 mantissa bits, bf16 range).
+// The forward pass of the default precision mode stores every activation this way and multiplies on the tensor
+// cores as hi*hi + hi*lo + lo*hi + lo*lo with fp32 accumulation; the backward pass reads the hi planes as bf16.
+#define ADAMML_X2 2
 
 #define ADAMML_ACT_NONE 0
 #define ADAMML_ACT_RELU 1
@@ -55,6 +60,37 @@ __device__ __forceinline__ bool act_pass(float out, int act) {
   if (act == ADAMML_ACT_RELU6) return out > 0.f && out < 6.f;
   return true;
 }
+
+// ---- x2 planes ---------------------------------------------------------------------------------
+struct x2_t {};  // tag type of the two-plane activation format
+__device__ __forceinline__ void x2_split(float v, bf16& hi, __half& lo) {
+  hi = __float2bfloat16_rn(v);
+  const float r = v - __bfloat162float(hi);
+  lo = __float2half_rn(r == r ? r : 0.f);  // inf - inf: keep the non-finite value in hi only
+}
+__device__ __forceinline__ float x2_join(bf16 hi, __half lo) { return __bfloat162float(hi) + __half2float(lo); }
+struct X2CPtr {
+  const bf16* hi;
+  const __half* lo;
+  __host__ __device__ __forceinline__ X2CPtr operator+(long long i) const { return X2CPtr{hi + i, lo + i}; }
+  __host__ __device__ __forceinline__ explicit operator bool() const { return hi != nullptr; }
+};
+struct X2Ptr {
+  bf16* hi;
+  __half* lo;
+  __host__ __device__ __forceinline__ X2Ptr operator+(long long i) const { return X2Ptr{hi + i, lo + i}; }
+  __host__ __device__ __forceinline__ explicit operator bool() const { return hi != nullptr; }
+  __host__ __device__ __forceinline__ operator X2CPtr() const { return X2CPtr{hi, lo}; }
+};
+static inline X2CPtr x2c(const void* hi, const void* lo) { return X2CPtr{(const bf16*)hi, (const __half*)lo}; }
+static inline X2Ptr x2m(void* hi, void* lo) { return X2Ptr{(bf16*)hi, (__half*)lo}; }
+// scalar element access through either a plain pointer or a plane pair
+__device__ __forceinline__ float ld_elem(const float* p, long long i) { return p[i]; }
+__device__ __forceinline__ float ld_elem(const bf16* p, long long i) { return __bfloat162float(p[i]); }
+__device__ __forceinline__ float ld_elem(const X2CPtr& p, long long i) { return x2_join(p.hi[i], p.lo[i]); }
+__device__ __forceinline__ void st_elem(float* p, long long i, float v) { p[i] = v; }
+__device__ __forceinline__ void st_elem(bf16* p, long long i, float v) { p[i] = __float2bfloat16_rn(v); }
+__device__ __forceinline__ void st_elem(const X2Ptr& p, long long i, float v) { x2_split(v, p.hi[i], p.lo[i]); }
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
@@ -114,3 +150,44 @@ template <> struct VecIO<bf16> {
     *reinterpret_cast<uint4*>(p) = t;
   }
 };
+
+// x2: 8 channels per thread = one 16-byte vector of each plane
+struct X2Raw { uint4 hi, lo; };
+template <> struct VecIO<x2_t> {
+  static constexpr int N = 8;
+  typedef X2Raw raw;
+  __device__ __forceinline__ static raw zero_raw() { return X2Raw{make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u)}; }
+  __device__ __forceinline__ static raw load_raw(const X2CPtr& p) {
+    return X2Raw{*reinterpret_cast<const uint4*>(p.hi), *reinterpret_cast<const uint4*>(p.lo)};
+  }
+  __device__ __forceinline__ static void unpack(const raw& t, float (&v)[8]) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t.hi);
+    const __half2* l = reinterpret_cast<const __half2*>(&t.lo);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __bfloat1622float2(h[i]);
+      const float2 g = __half22float2(l[i]);
+      v[2 * i] = f.x + g.x; v[2 * i + 1] = f.y + g.y;
+    }
+  }
+  __device__ __forceinline__ static void load(const X2CPtr& p, float (&v)[8]) { unpack(load_raw(p), v); }
+  __device__ __forceinline__ static void store(const X2Ptr& p, const float (&v)[8]) {
+    uint4 th, tl;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&th);
+    __half2* l = reinterpret_cast<__half2*>(&tl);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      bf16 h0, h1;
+      __half l0, l1;
+      x2_split(v[2 * i], h0, l0);
+      x2_split(v[2 * i + 1], h1, l1);
+      h[i] = __halves2bfloat162(h0, h1);
+      l[i] = __halves2half2(l0, l1);
+    }
+    *reinterpret_cast<uint4*>(p.hi) = th;
+    *reinterpret_cast<uint4*>(p.lo) = tl;
+  }
+};
+// pointer types of an activation tensor of element type T
+template <typename T> struct PtrOf { typedef const T* c; typedef T* m; };
+template <> struct PtrOf<x2_t> { typedef X2CPtr c; typedef X2Ptr m; };

@@ -44,18 +44,37 @@ struct ConvGeom {
 struct ConvMaps {
   CUtensorMap m[4];
 };
+// x2 mode (two-plane activations, see common.cuh): tensor maps of the lo (fp16 remainder) planes of A / D, the lo conv
+// tap maps, the lo plane of a linear-mode output, and the three further weight planes.  tcgen05.mma kind::f16 needs
+// both operands of one instruction in the SAME 16-bit format (a mixed bf16 x fp16 descriptor is an illegal
+// instruction), so the weight operand comes as FOUR planes (adamml_pack_weight_x2): the bf16 cascade b1 = bf16(w),
+// b2 = bf16(w - b1), b3 = bf16(w - b1 - b2) multiplies the bf16 hi plane of the activations (exact to 24 bits of w),
+// and f = fp16(w) multiplies their fp16 lo plane.  b[0..2] = {b2, b3, f}; b1 is the kernel's tmB.
+struct X2Maps {
+  CUtensorMap a, d;
+  CUtensorMap b[3];
+  ConvMaps c;
+  void* dlin_lo;
+};
 
 // SHALLOW: reductions of one or two K blocks (the MobileNetV2 expand / project-gradient GEMMs, K = 16..96).  Their
 // tiles are all epilogue; two stages suffice, and two co-resident CTAs per SM overlap one tile's epilogue chain
 // (accumulator wait, tcgen05.ld, staging, store drain, statistics) with the other's.
-template <int BLOCK_N, bool SHALLOW = false>
+// X2: the activations and the output are two-plane (hi bf16 + lo fp16) tensors, the weights four-plane (X2Maps); a
+// stage holds [A_hi][A_lo][B1][B2][B3][Bf] and every K step issues A_lo*Bf, A_hi*B3, A_hi*B2, A_hi*B1 into the same
+// fp32 accumulator.
+template <int BLOCK_N, bool SHALLOW = false, bool X2 = false>
 struct TcCfg {
-  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int PLANES = X2 ? 2 : 1;              // planes of A and of D
+  static constexpr int B_PLANES = X2 ? 4 : 1;
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;  // per plane
   static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int A_ALL = PLANES * A_BYTES;
+  static constexpr int STAGE_BYTES = A_ALL + B_PLANES * B_BYTES;
   static_assert(!SHALLOW || BLOCK_N <= 128, "two CTAs per SM need 2 x (2 x BLOCK_N) <= 512 TMEM columns");
+  static_assert(!X2 || (BLOCK_N == 64 && !SHALLOW), "x2: 64-column tiles (64 KB per stage), one CTA per SM");
   // (stage counts that divide by the common K-block counts 1, 2, 4 keep the weight tile resident, see the producer)
-  static constexpr int STAGES = SHALLOW ? 2 : ((BLOCK_N == 256) ? 3 : (BLOCK_N == 128 ? 4 : 8));
+  static constexpr int STAGES = X2 ? 2 : (SHALLOW ? 2 : ((BLOCK_N == 256) ? 3 : (BLOCK_N == 128 ? 4 : 8)));
   static constexpr int CTAS_PER_SM = SHALLOW ? 2 : 1;
   // Epilogue warps: wide tiles (256 columns, issue bound) get TWO warps per TMEM lane quarter that split the
   // accumulator columns; narrow tiles are latency bound and run best with one warp per quarter (measured).
@@ -67,7 +86,8 @@ struct TcCfg {
   // staging tiles of the TMA store: double buffering (store of tile i drains while tile i+1 is staged) measured
   // no faster than a single buffer, which leaves the smem to the operand ring
   static constexpr int OUT_BUFS = (SHALLOW && BLOCK_N == 64) ? 2 : 1;
-  static constexpr int OUT_TILE_BYTES = SUBTILES * BLOCK_M * 128;
+  static constexpr int OUT_PLANE_BYTES = SUBTILES * BLOCK_M * 128;
+  static constexpr int OUT_TILE_BYTES = PLANES * OUT_PLANE_BYTES;
   static constexpr int OUT_BYTES = OUT_BUFS * OUT_TILE_BYTES;
   static constexpr int TMEM_COLS = 2 * BLOCK_N;
   static constexpr int RED_BYTES = BLOCK_N * 2 * 8;  // per-CTA fp64 column sums, combined before the global atomics
@@ -119,14 +139,14 @@ struct StatAcc {
   }
 };
 
-template <int BLOCK_N, bool CONV, bool SHALLOW = false>
-__global__ void __launch_bounds__(TcCfg<BLOCK_N, SHALLOW>::THREADS, TcCfg<BLOCK_N, SHALLOW>::CTAS_PER_SM)
+template <int BLOCK_N, bool CONV, bool SHALLOW = false, bool X2 = false>
+__global__ void __launch_bounds__(TcCfg<BLOCK_N, SHALLOW, X2>::THREADS, TcCfg<BLOCK_N, SHALLOW, X2>::CTAS_PER_SM)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmAdd,
                const __grid_constant__ ConvMaps cmaps, const __grid_constant__ ConvGeom geo,
-               const bf16* __restrict__ addend, long long M, int Ncols, int K, long long ldd,
-               double* __restrict__ stats, long long rows_per_group, bf16* __restrict__ dlin) {
-  using Cfg = TcCfg<BLOCK_N, SHALLOW>;
+               const __grid_constant__ X2Maps x2, const bf16* __restrict__ addend, long long M, int Ncols, int K,
+               long long ldd, double* __restrict__ stats, long long rows_per_group, bf16* __restrict__ dlin) {
+  using Cfg = TcCfg<BLOCK_N, SHALLOW, X2>;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment by pointer arithmetic (keeps the shared address space visible to the compiler: LDS/STS
   // instead of generic LD/ST in the epilogue)
@@ -172,6 +192,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       if (!CONV) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+      if (X2) {
+        if (!CONV) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&x2.a)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&x2.b[0])) : "memory");
+      }
       int stage = 0;
       uint32_t phase = 0;
       // One column block and a K-block count that divides the ring: slot s always carries K block s % num_kb, and
@@ -192,19 +216,38 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = 0; kb < num_kb; ++kb) {
           ctl_wait<Cfg::BACKOFF>(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-          uint8_t* sb = sa + Cfg::A_BYTES;
+          uint8_t* sb = sa + Cfg::A_ALL;
           const bool need_b = !b_resident || b_loaded < Cfg::STAGES;
           if (b_resident && need_b) ++b_loaded;
-          mbar_expect_tx(&full_bar[stage], need_b ? Cfg::STAGE_BYTES : Cfg::A_BYTES);
+          mbar_expect_tx(&full_bar[stage], need_b ? Cfg::STAGE_BYTES : Cfg::A_ALL);
           if (CONV) {
             const int tap = kb / geo.kb_per_tap;
             const int c0 = (kb - tap * geo.kb_per_tap) * BLOCK_K;
             tma_load_4d(sa, &cmaps.m[geo.tap_map[tap]], &full_bar[stage], c0, w0 + geo.tap_dw[tap],
                         h0 + geo.tap_dh[tap], i0);
             if (need_b) tma_load_2d(sb, &tmB, &full_bar[stage], geo.tap_koff[tap] + c0, n_blk * BLOCK_N);
+            if (X2) {
+              tma_load_4d(sa + Cfg::A_BYTES, &x2.c.m[geo.tap_map[tap]], &full_bar[stage], c0, w0 + geo.tap_dw[tap],
+                          h0 + geo.tap_dh[tap], i0);
+              if (need_b) {
+#pragma unroll
+                for (int pl = 0; pl < 3; ++pl)
+                  tma_load_2d(sb + (pl + 1) * Cfg::B_BYTES, &x2.b[pl], &full_bar[stage], geo.tap_koff[tap] + c0,
+                              n_blk * BLOCK_N);
+              }
+            }
           } else {
             tma_load_2d(sa, &tmA, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
             if (need_b) tma_load_2d(sb, &tmB, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);
+            if (X2) {
+              tma_load_2d(sa + Cfg::A_BYTES, &x2.a, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
+              if (need_b) {
+#pragma unroll
+                for (int pl = 0; pl < 3; ++pl)
+                  tma_load_2d(sb + (pl + 1) * Cfg::B_BYTES, &x2.b[pl], &full_bar[stage], kb * BLOCK_K,
+                              n_blk * BLOCK_N);
+              }
+            }
           }
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
@@ -213,8 +256,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     // instruction descriptor: D=f32, A=B=bf16, K-major both, N=BLOCK_N, M=128
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) |
-                           ((uint32_t)(BLOCK_M >> 4) << 24);
+    // (a_format bits [7,10), b_format bits [10,13): 1 = bf16, 0 = fp16; both operands of one MMA share the format)
+    const uint32_t idesc_f16 = (1u << 4) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+    const uint32_t idesc = idesc_f16 | (1u << 7) | (1u << 10);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
@@ -228,13 +272,29 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_after();
         if (lane == 0) {
           const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-          const uint32_t sb = sa + Cfg::A_BYTES;
+          const uint32_t sb = sa + Cfg::A_ALL;
           const uint64_t da = make_smem_desc_sw128(sa);
           const uint64_t db = make_smem_desc_sw128(sb);
+          if (X2) {
+            const uint64_t da_lo = make_smem_desc_sw128(sa + Cfg::A_BYTES);
+            const uint64_t db2 = make_smem_desc_sw128(sb + Cfg::B_BYTES);
+            const uint64_t db3 = make_smem_desc_sw128(sb + 2 * Cfg::B_BYTES);
+            const uint64_t dbf = make_smem_desc_sw128(sb + 3 * Cfg::B_BYTES);
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            // advance 32 bytes (16 bf16) along K inside the swizzle row: +2 in 16-byte units
-            umma_bf16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              const uint64_t o = (uint64_t)(k * 2);
+              // small terms first: lo * fp16(w), hi * b3, hi * b2, hi * b1
+              umma_bf16(tmem_d, da_lo + o, dbf + o, idesc_f16, (kb > 0 || k > 0) ? 1u : 0u);
+              umma_bf16(tmem_d, da + o, db3 + o, idesc, 1u);
+              umma_bf16(tmem_d, da + o, db2 + o, idesc, 1u);
+              umma_bf16(tmem_d, da + o, db + o, idesc, 1u);
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              // advance 32 bytes (16 bf16) along K inside the swizzle row: +2 in 16-byte units
+              umma_bf16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            }
           }
           umma_commit(&empty_bar[stage]);
           if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);
@@ -387,6 +447,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           } else {
             *reinterpret_cast<uint4*>(srow + ((c ^ (et & 7)) << 4)) = pk;
           }
+          if (X2) {  // lo plane: fp16 of the remainder v - bf16(v)
+            const float2 h0 = __bfloat1622float2(p0), h1 = __bfloat1622float2(p1);
+            const float2 h2 = __bfloat1622float2(p2), h3 = __bfloat1622float2(p3);
+            __half2 l0 = __floats2half2_rn(v[j] - h0.x, v[j + 1] - h0.y);
+            __half2 l1 = __floats2half2_rn(v[j + 2] - h1.x, v[j + 3] - h1.y);
+            __half2 l2 = __floats2half2_rn(v[j + 4] - h2.x, v[j + 5] - h2.y);
+            __half2 l3 = __floats2half2_rn(v[j + 6] - h3.x, v[j + 7] - h3.y);
+            uint4 pl;
+            pl.x = *reinterpret_cast<uint32_t*>(&l0);
+            pl.y = *reinterpret_cast<uint32_t*>(&l1);
+            pl.z = *reinterpret_cast<uint32_t*>(&l2);
+            pl.w = *reinterpret_cast<uint32_t*>(&l3);
+            if (!CONV && dlin) {
+              if (col0 + j < Ncols) *reinterpret_cast<uint4*>(lrow + Cfg::OUT_PLANE_BYTES + (j << 1)) = pl;
+            } else {
+              *reinterpret_cast<uint4*>(srow + Cfg::OUT_PLANE_BYTES + ((c ^ (et & 7)) << 4)) = pl;
+            }
+          }
         }
       }
       // accumulator drained: hand the TMEM stage back to the MMA warp
@@ -404,6 +482,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const long long row0 = (long long)m_blk * BLOCK_M;
           const long long rows = (M - row0) < BLOCK_M ? (M - row0) : BLOCK_M;
           bulk_store_1d(dlin + row0 * Ncols, stage_out, (uint32_t)(rows * Ncols * 2));
+          if (X2)
+            bulk_store_1d(reinterpret_cast<bf16*>(x2.dlin_lo) + row0 * Ncols, stage_out + Cfg::OUT_PLANE_BYTES,
+                          (uint32_t)(rows * Ncols * 2));
         } else {
 #pragma unroll
           for (int sub = 0; sub < Cfg::SUBTILES; ++sub) {
@@ -411,6 +492,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (col < Ncols) {
               if (CONV) tma_store_4d(&tmD, stage_out + sub * (BLOCK_M * 128), col, w0, h0, i0);
               else tma_store_2d(&tmD, stage_out + sub * (BLOCK_M * 128), col, m_blk * BLOCK_M);
+              if (X2) {
+                const uint8_t* lo = stage_out + Cfg::OUT_PLANE_BYTES + sub * (BLOCK_M * 128);
+                if (CONV) tma_store_4d(&x2.d, lo, col, w0, h0, i0);
+                else tma_store_2d(&x2.d, lo, col, m_blk * BLOCK_M);
+              }
             }
           }
         }
@@ -459,9 +545,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (!col_ok) rw = r1;
 #pragma unroll 8
             for (; rw < r1; rw += RSPLIT) {
-              const uint2 pk = *reinterpret_cast<const uint2*>(sbase + rw * pitch + (lin ? 0 : ((c ^ (rw & 7)) << 4)));
-              const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk.x));
-              const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk.y));
+              const uint8_t* sp = sbase + rw * pitch + (lin ? 0 : ((c ^ (rw & 7)) << 4));
+              const uint2 pk = *reinterpret_cast<const uint2*>(sp);
+              float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk.x));
+              float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk.y));
+              if (X2) {  // statistics of the full-precision value hi + lo
+                const uint2 pl = *reinterpret_cast<const uint2*>(sp + Cfg::OUT_PLANE_BYTES);
+                const float2 g0 = __half22float2(*reinterpret_cast<const __half2*>(&pl.x));
+                const float2 g1 = __half22float2(*reinterpret_cast<const __half2*>(&pl.y));
+                f0.x += g0.x; f0.y += g0.y; f1.x += g1.x; f1.y += g1.y;
+              }
               s[0] += f0.x; qq[0] = fmaf(f0.x, f0.x, qq[0]);
               s[1] += f0.y; qq[1] = fmaf(f0.y, f0.y, qq[1]);
               s[2] += f1.x; qq[2] = fmaf(f1.x, f1.x, qq[2]);
@@ -507,13 +600,20 @@ int make_map_2d(CUtensorMap* map, const void* ptr, long long rows, long long col
   return ADAMML_OK;
 }
 
-template <int BLOCK_N, bool CONV, bool SHALLOW = false>
+const X2Maps& no_x2() {
+  static X2Maps z;
+  static bool init = false;
+  if (!init) { memset(&z, 0, sizeof(z)); init = true; }
+  return z;
+}
+
+template <int BLOCK_N, bool CONV, bool SHALLOW = false, bool X2 = false>
 int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, const CUtensorMap& tmAdd,
               const ConvMaps& cm, const ConvGeom& geo, const void* addend, long long M, int Ncols, int K, long long ldd, double* stats,
-              long long rpg, cudaStream_t stream, void* dlin = nullptr) {
-  using Cfg = TcCfg<BLOCK_N, SHALLOW>;
+              long long rpg, cudaStream_t stream, void* dlin = nullptr, const X2Maps& x2 = no_x2()) {
+  using Cfg = TcCfg<BLOCK_N, SHALLOW, X2>;
   static bool configured = false;
-  auto kern = tc_gemm_kernel<BLOCK_N, CONV, SHALLOW>;
+  auto kern = tc_gemm_kernel<BLOCK_N, CONV, SHALLOW, X2>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) {
@@ -526,8 +626,8 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap&
   long long tiles = m_blks * ((Ncols + BLOCK_N - 1) / BLOCK_N);
   const int sms = num_sms() * Cfg::CTAS_PER_SM;
   int grid = (int)(tiles < sms ? tiles : sms);
-  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmD, tmAdd, cm, geo, (const bf16*)addend, M, Ncols,
-                                                        K, ldd, stats, rpg, (bf16*)dlin);
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmD, tmAdd, cm, geo, x2, (const bf16*)addend, M,
+                                                        Ncols, K, ldd, stats, rpg, (bf16*)dlin);
   return adamml_check_launch(CONV ? "tc_conv" : "tc_gemm");
 }
 
@@ -553,6 +653,44 @@ void set_tiles(ConvGeom& geo, int Wo, int Ho, int IMGS) {
   geo.tiles_h = (Ho + geo.BH - 1) / geo.BH;
   geo.tiles_i = (IMGS + geo.BI - 1) / geo.BI;
   geo.Ho = Ho; geo.Wo = Wo; geo.IMGS = IMGS;
+}
+
+int make_out_map(CUtensorMap* map, const ConvGeom& geo, const void* y, int Cout) {
+  return make_map_4d(map, (const bf16*)y + ((long long)geo.out_ph * geo.out_W + geo.out_pw) * Cout, Cout, geo.Wo, geo.Ho,
+                     geo.IMGS, (long long)geo.out_s * Cout, (long long)geo.out_s * geo.out_W * Cout,
+                     (long long)geo.out_H * geo.out_W * Cout, geo.BW, geo.BH, geo.BI);
+}
+
+// the four weight planes [4][Ncols][w_ld] (adamml_pack_weight_x2): plane 0 -> tmB, planes 1..3 -> x2.b
+int make_w4_maps(CUtensorMap* tmB, X2Maps& x2, const void* w4, int Ncols, long long w_ld) {
+  const bf16* w = (const bf16*)w4;
+  int rc = make_map_2d(tmB, w, Ncols, w_ld, w_ld, 64);
+  for (int pl = 0; pl < 3 && !rc; ++pl)
+    rc = make_map_2d(&x2.b[pl], w + (long long)(pl + 1) * Ncols * w_ld, Ncols, w_ld, w_ld, 64);
+  return rc;
+}
+
+// x2 variant of run_conv: cm / cm_lo are the tap maps of the hi / lo input planes; w4 the four weight planes
+int run_conv_x2(const ConvGeom& geo, const ConvMaps& cm, const ConvMaps& cm_lo, const void* w4, long long w_ld, void* y,
+                void* y_lo, int Cout, double* stats, cudaStream_t stream) {
+  CUtensorMap tmB, tmD;
+  X2Maps x2;
+  memset(&x2, 0, sizeof(x2));
+  x2.c = cm_lo;
+  int rc = make_w4_maps(&tmB, x2, w4, Cout, w_ld);
+  if (rc) return rc;
+  rc = make_out_map(&tmD, geo, y, Cout);
+  if (rc) return rc;
+  rc = make_out_map(&x2.d, geo, y_lo, Cout);
+  if (rc) return rc;
+  if (stats) {
+    int G = (geo.IMGS + geo.imgs_per_group - 1) / geo.imgs_per_group;
+    cudaMemsetAsync(stats, 0, sizeof(double) * (size_t)G * Cout * 2, stream);
+  }
+  const long long M = (long long)geo.IMGS * geo.Ho * geo.Wo;
+  const int K = geo.ntaps * geo.kb_per_tap * BLOCK_K;
+  return launch_tc<64, true, false, true>(tmB, tmB, tmD, tmD, cm, geo, nullptr, M, Cout, K, Cout, stats, 0, stream,
+                                          nullptr, x2);
 }
 
 // launches the implicit-GEMM kernel for a prepared geometry; w is [Cout][w_ld] bf16, y/addend rows have Cout columns
@@ -581,6 +719,80 @@ int run_conv(const ConvGeom& geo, const ConvMaps& cm, const void* w, long long w
   }
   return dispatch_tc<true>(block_n, tmB, tmB, tmD, tmAdd, cm, geo, addend, (long long)geo.IMGS * geo.Ho * geo.Wo, Cout,
                            geo.ntaps * geo.kb_per_tap * BLOCK_K, Cout, stats, 0, stream);
+}
+
+// geometry + tap tensor maps of an RxS / stride 1|2 convolution over x [IMGS,H,W,Cin] (x_lo: optional lo plane -> cm_lo)
+int conv_setup(ConvGeom& geo, ConvMaps& cm, ConvMaps* cm_lo, const void* x, const void* x_lo, int IMGS, int H, int W,
+               int Cin, int R, int S, int stride, int pad, int Ho, int Wo, int imgs_per_group) {
+  memset(&geo, 0, sizeof(geo));
+  geo.ntaps = R * S;
+  geo.cin = Cin;
+  geo.kb_per_tap = (Cin + BLOCK_K - 1) / BLOCK_K;
+  set_tiles(geo, Wo, Ho, IMGS);
+  geo.out_H = Ho; geo.out_W = Wo; geo.out_s = 1;
+  geo.imgs_per_group = imgs_per_group > 0 ? imgs_per_group : IMGS;
+  // taps: input coordinate = stride*o + (r - pad) = stride*(o + d) + parity
+  bool used[4] = {false, false, false, false};
+  for (int r = 0; r < R; ++r)
+    for (int s_ = 0; s_ < S; ++s_) {
+      int th = r - pad, tw = s_ - pad;
+      int ph = ((th % stride) + stride) % stride, pw = ((tw % stride) + stride) % stride;
+      int t = r * S + s_;
+      geo.tap_koff[t] = t * Cin;
+      geo.tap_map[t] = (signed char)(ph * stride + pw);
+      geo.tap_dh[t] = (signed char)((th - ph) / stride);
+      geo.tap_dw[t] = (signed char)((tw - pw) / stride);
+      used[ph * stride + pw] = true;
+    }
+  memset(&cm, 0, sizeof(cm));
+  if (cm_lo) memset(cm_lo, 0, sizeof(*cm_lo));
+  for (int ph = 0; ph < stride; ++ph)
+    for (int pw = 0; pw < stride; ++pw) {
+      int id = ph * stride + pw;
+      if (!used[id]) continue;
+      int Wd = (W - pw + stride - 1) / stride, Hd = (H - ph + stride - 1) / stride;
+      if (Wd <= 0 || Hd <= 0) { Wd = Wd > 0 ? Wd : 1; Hd = Hd > 0 ? Hd : 1; }
+      const long long off = ((long long)ph * W + pw) * Cin;
+      int rc = make_map_4d(&cm.m[id], (const bf16*)x + off, Cin, Wd, Hd, IMGS, (long long)stride * Cin,
+                           (long long)stride * W * Cin, (long long)H * W * Cin, geo.BW, geo.BH, geo.BI);
+      if (rc) return rc;
+      if (cm_lo) {
+        rc = make_map_4d(&cm_lo->m[id], (const bf16*)x_lo + off, Cin, Wd, Hd, IMGS, (long long)stride * Cin,
+                         (long long)stride * W * Cin, (long long)H * W * Cin, geo.BW, geo.BH, geo.BI);
+        if (rc) return rc;
+      }
+    }
+  return ADAMML_OK;
+}
+
+// geometry of a stride-2 first convolution on the space-to-depth operand (see adamml_tc_stem_conv_bf16)
+int stem_setup(ConvGeom& geo, ConvMaps& cm, ConvMaps* cm_lo, const void* xs, const void* xs_lo, int IMGS, int Hs, int Wp,
+               int Cs, int Ho, int Wo, int taps, int imgs_per_group) {
+  const int VC = taps * Cs;  // virtual channels per position: `taps` consecutive s2d columns
+  memset(&geo, 0, sizeof(geo));
+  geo.ntaps = taps;
+  geo.cin = VC;
+  geo.kb_per_tap = (VC + BLOCK_K - 1) / BLOCK_K;
+  for (int t = 0; t < taps; ++t) {
+    geo.tap_koff[t] = t * VC;
+    geo.tap_map[t] = 0;
+    geo.tap_dh[t] = (signed char)(t - taps / 2);
+    geo.tap_dw[t] = 0;
+  }
+  set_tiles(geo, Wo, Ho, IMGS);
+  geo.out_H = Ho; geo.out_W = Wo; geo.out_s = 1;
+  geo.imgs_per_group = imgs_per_group > 0 ? imgs_per_group : IMGS;
+  memset(&cm, 0, sizeof(cm));
+  // positions 0..Wp-taps: position p covers stored columns p..p+taps-1
+  int rc = make_map_4d(&cm.m[0], xs, VC, Wp - (taps - 1), Hs, IMGS, Cs, (long long)Wp * Cs, (long long)Hs * Wp * Cs,
+                       geo.BW, geo.BH, geo.BI);
+  if (rc) return rc;
+  if (cm_lo) {
+    memset(cm_lo, 0, sizeof(*cm_lo));
+    rc = make_map_4d(&cm_lo->m[0], xs_lo, VC, Wp - (taps - 1), Hs, IMGS, Cs, (long long)Wp * Cs,
+                     (long long)Hs * Wp * Cs, geo.BW, geo.BH, geo.BI);
+  }
+  return rc;
 }
 
 }  // namespace
@@ -675,41 +887,71 @@ int adamml_tc_conv_bf16(const void* x, const void* w, void* y, const void* adden
   ADAMML_REQUIRE(!stats || imgs_per_group > 0, "tc_conv: stats need imgs_per_group");
   ADAMML_REQUIRE(addend_sub == 0 || addend_sub == 1 || addend_sub == 2, "tc_conv: addend_sub must be 0, 1 or 2");
   ConvGeom geo;
-  memset(&geo, 0, sizeof(geo));
-  geo.ntaps = R * S;
-  geo.cin = Cin;
-  geo.kb_per_tap = (Cin + BLOCK_K - 1) / BLOCK_K;
-  set_tiles(geo, Wo, Ho, IMGS);
-  geo.out_H = Ho; geo.out_W = Wo; geo.out_s = 1;
-  if (addend && addend_sub == 2) { geo.addend_sub = 2; geo.add_H = (Ho + 1) / 2; geo.add_W = (Wo + 1) / 2; }
-  geo.imgs_per_group = imgs_per_group > 0 ? imgs_per_group : IMGS;
-  // taps: input coordinate = stride*o + (r - pad) = stride*(o + d) + parity
-  bool used[4] = {false, false, false, false};
-  for (int r = 0; r < R; ++r)
-    for (int s_ = 0; s_ < S; ++s_) {
-      int th = r - pad, tw = s_ - pad;
-      int ph = ((th % stride) + stride) % stride, pw = ((tw % stride) + stride) % stride;
-      int t = r * S + s_;
-      geo.tap_koff[t] = t * Cin;
-      geo.tap_map[t] = (signed char)(ph * stride + pw);
-      geo.tap_dh[t] = (signed char)((th - ph) / stride);
-      geo.tap_dw[t] = (signed char)((tw - pw) / stride);
-      used[ph * stride + pw] = true;
-    }
   ConvMaps cm;
-  memset(&cm, 0, sizeof(cm));
-  const bf16* xb = (const bf16*)x;
-  for (int ph = 0; ph < stride; ++ph)
-    for (int pw = 0; pw < stride; ++pw) {
-      int id = ph * stride + pw;
-      if (!used[id]) continue;
-      int Wd = (W - pw + stride - 1) / stride, Hd = (H - ph + stride - 1) / stride;
-      if (Wd <= 0 || Hd <= 0) { Wd = Wd > 0 ? Wd : 1; Hd = Hd > 0 ? Hd : 1; }
-      int rc = make_map_4d(&cm.m[id], xb + ((long long)ph * W + pw) * Cin, Cin, Wd, Hd, IMGS, (long long)stride * Cin,
-                           (long long)stride * W * Cin, (long long)H * W * Cin, geo.BW, geo.BH, geo.BI);
-      if (rc) return rc;
-    }
+  int rc = conv_setup(geo, cm, nullptr, x, nullptr, IMGS, H, W, Cin, R, S, stride, pad, Ho, Wo, imgs_per_group);
+  if (rc) return rc;
+  if (addend && addend_sub == 2) { geo.addend_sub = 2; geo.add_H = (Ho + 1) / 2; geo.add_W = (Wo + 1) / 2; }
   return run_conv(geo, cm, w, (long long)R * S * Cin, y, addend, Cout, stats, stream);
+}
+
+/* x2 planes: forward convolution of the default precision mode.  x / y are (hi bf16, lo fp16) plane pairs, w4 the
+ * four weight planes of adamml_pack_weight_x2; every K step accumulates x_hi*(b1+b2+b3) + x_lo*fp16(w) in the fp32
+ * TMEM accumulator; fused BN statistics are taken over the full-precision outputs. */
+int adamml_tc_conv_x2(const void* x_hi, const void* x_lo, const void* w4, void* y_hi, void* y_lo, int IMGS, int H,
+                      int W, int Cin, int Cout, int R, int S, int stride, int pad, int Ho, int Wo, double* stats,
+                      int imgs_per_group, cudaStream_t stream) {
+  if (!adamml_tc_conv_supported(Cin, Cout, R, S, stride)) {
+    adamml_set_error("tc_conv_x2: Cin=%d Cout=%d R=%d S=%d stride=%d outside the tcgen05 envelope", Cin, Cout, R, S,
+                     stride);
+    return ADAMML_ERR_UNSUPPORTED;
+  }
+  ADAMML_REQUIRE(Ho == (H + 2 * pad - R) / stride + 1 && Wo == (W + 2 * pad - S) / stride + 1,
+                 "tc_conv_x2: Ho/Wo inconsistent with H/W/R/S/stride/pad");
+  ADAMML_REQUIRE(x_hi && x_lo && w4 && y_hi && y_lo, "tc_conv_x2: every tensor needs all its planes");
+  ADAMML_REQUIRE(((uintptr_t)x_hi % 16) == 0 && ((uintptr_t)x_lo % 16) == 0 && ((uintptr_t)w4 % 16) == 0 &&
+                     ((uintptr_t)y_hi % 16) == 0 && ((uintptr_t)y_lo % 16) == 0,
+                 "tc_conv_x2: operands must be 16-byte aligned");
+  ADAMML_REQUIRE(!stats || imgs_per_group > 0, "tc_conv_x2: stats need imgs_per_group");
+  ConvGeom geo;
+  ConvMaps cm, cm_lo;
+  int rc = conv_setup(geo, cm, &cm_lo, x_hi, x_lo, IMGS, H, W, Cin, R, S, stride, pad, Ho, Wo, imgs_per_group);
+  if (rc) return rc;
+  return run_conv_x2(geo, cm, cm_lo, w4, (long long)R * S * Cin, y_hi, y_lo, Cout, stats, stream);
+}
+
+int adamml_tc_gemm_x2(const void* A_hi, const void* A_lo, const void* B4, void* D_hi, void* D_lo, long long M,
+                      int Ncols, int K, double* stats, long long rows_per_group, cudaStream_t stream) {
+  if (!adamml_tc_supported(M, Ncols, K, K, K, Ncols)) {
+    adamml_set_error("tc_gemm_x2: shape M=%lld N=%d K=%d outside the tcgen05 envelope", M, Ncols, K);
+    return ADAMML_ERR_UNSUPPORTED;
+  }
+  ADAMML_REQUIRE(A_hi && A_lo && B4 && D_hi && D_lo, "tc_gemm_x2: every tensor needs all its planes");
+  ADAMML_REQUIRE(((uintptr_t)A_hi % 16) == 0 && ((uintptr_t)A_lo % 16) == 0 && ((uintptr_t)B4 % 16) == 0 &&
+                     ((uintptr_t)D_hi % 16) == 0 && ((uintptr_t)D_lo % 16) == 0 && ((long long)Ncols * K) % 8 == 0,
+                 "tc_gemm_x2: operands must be 16-byte aligned");
+  ADAMML_REQUIRE(!stats || rows_per_group > 0, "tc_gemm_x2: stats need rows_per_group");
+  const int block_n = 64;
+  CUtensorMap tmA, tmB, tmD;
+  X2Maps x2;
+  memset(&x2, 0, sizeof(x2));
+  int rc = make_map_2d(&tmA, A_hi, M, K, K, BLOCK_M);
+  if (!rc) rc = make_map_2d(&x2.a, A_lo, M, K, K, BLOCK_M);
+  if (!rc) rc = make_w4_maps(&tmB, x2, B4, Ncols, K);
+  if (!rc) rc = make_map_2d(&tmD, D_hi, M, Ncols, Ncols, BLOCK_M);
+  if (!rc) rc = make_map_2d(&x2.d, D_lo, M, Ncols, Ncols, BLOCK_M);
+  if (rc) return rc;
+  if (stats) {
+    long long G = (M + rows_per_group - 1) / rows_per_group;
+    cudaMemsetAsync(stats, 0, sizeof(double) * (size_t)G * Ncols * 2, stream);
+  }
+  ConvMaps cm;
+  ConvGeom geo;
+  memset(&cm, 0, sizeof(cm));
+  memset(&geo, 0, sizeof(geo));
+  void* dlin = (Ncols <= block_n && (Ncols % 64) != 0) ? D_hi : nullptr;
+  x2.dlin_lo = dlin ? D_lo : nullptr;
+  return launch_tc<64, false, false, true>(tmA, tmB, tmD, tmD, cm, geo, nullptr, M, Ncols, K, Ncols, stats,
+                                           rows_per_group, stream, dlin, x2);
 }
 
 /* Data gradient of a stride-2 convolution (resnet.py:100 conv2 of the first Bottleneck of layer2-4) as four
@@ -783,28 +1025,33 @@ int adamml_tc_stem_conv_bf16(const void* xs, const void* w, void* y, int IMGS, i
   ADAMML_REQUIRE(((uintptr_t)xs % 16) == 0 && ((uintptr_t)w % 16) == 0 && ((uintptr_t)y % 16) == 0,
                  "tc_stem_conv: operands must be 16-byte aligned");
   ADAMML_REQUIRE(!stats || imgs_per_group > 0, "tc_stem_conv: stats need imgs_per_group");
-  const int VC = taps * Cs;  // virtual channels per position: `taps` consecutive s2d columns
   ConvGeom geo;
-  memset(&geo, 0, sizeof(geo));
-  geo.ntaps = taps;
-  geo.cin = VC;
-  geo.kb_per_tap = (VC + BLOCK_K - 1) / BLOCK_K;
-  for (int t = 0; t < taps; ++t) {
-    geo.tap_koff[t] = t * VC;
-    geo.tap_map[t] = 0;
-    geo.tap_dh[t] = (signed char)(t - taps / 2);
-    geo.tap_dw[t] = 0;
-  }
-  set_tiles(geo, Wo, Ho, IMGS);
-  geo.out_H = Ho; geo.out_W = Wo; geo.out_s = 1;
-  geo.imgs_per_group = imgs_per_group > 0 ? imgs_per_group : IMGS;
   ConvMaps cm;
-  memset(&cm, 0, sizeof(cm));
-  // positions 0..Wp-taps: position p covers stored columns p..p+taps-1
-  int rc = make_map_4d(&cm.m[0], xs, VC, Wp - (taps - 1), Hs, IMGS, Cs, (long long)Wp * Cs, (long long)Hs * Wp * Cs,
-                       geo.BW, geo.BH, geo.BI);
+  int rc = stem_setup(geo, cm, nullptr, xs, nullptr, IMGS, Hs, Wp, Cs, Ho, Wo, taps, imgs_per_group);
   if (rc) return rc;
-  return run_conv(geo, cm, w, (long long)taps * VC, y, nullptr, Cout, stats, stream);
+  return run_conv(geo, cm, w, (long long)taps * taps * Cs, y, nullptr, Cout, stats, stream);
+}
+
+/* x2 planes of the same first convolutions (operands from adamml_pack_frames_s2d_x2 / adamml_nhwc_to_s2d per plane and
+ * adamml_pack_weight_x2 with stem = 1). */
+int adamml_tc_stem_conv_x2(const void* xs_hi, const void* xs_lo, const void* w4, void* y_hi, void* y_lo, int IMGS,
+                           int Hs, int Wp, int Cs, int Cout, int Ho, int Wo, int taps, double* stats,
+                           int imgs_per_group, cudaStream_t stream) {
+  if (Cs % 8 || Cout % 8 || (taps != 4 && taps != 2) || taps * Cs > 256) {
+    adamml_set_error("tc_stem_conv_x2: Cs=%d Cout=%d taps=%d outside the tcgen05 envelope", Cs, Cout, taps);
+    return ADAMML_ERR_UNSUPPORTED;
+  }
+  ADAMML_REQUIRE(Ho == Hs && Wo + taps - 1 <= Wp, "tc_stem_conv_x2: geometry (Ho == Hs, Wp >= Wo + taps - 1)");
+  ADAMML_REQUIRE(xs_hi && xs_lo && w4 && y_hi && y_lo, "tc_stem_conv_x2: every tensor needs all its planes");
+  ADAMML_REQUIRE(((uintptr_t)xs_hi % 16) == 0 && ((uintptr_t)xs_lo % 16) == 0 && ((uintptr_t)w4 % 16) == 0 &&
+                     ((uintptr_t)y_hi % 16) == 0 && ((uintptr_t)y_lo % 16) == 0,
+                 "tc_stem_conv_x2: operands must be 16-byte aligned");
+  ADAMML_REQUIRE(!stats || imgs_per_group > 0, "tc_stem_conv_x2: stats need imgs_per_group");
+  ConvGeom geo;
+  ConvMaps cm, cm_lo;
+  int rc = stem_setup(geo, cm, &cm_lo, xs_hi, xs_lo, IMGS, Hs, Wp, Cs, Ho, Wo, taps, imgs_per_group);
+  if (rc) return rc;
+  return run_conv_x2(geo, cm, cm_lo, w4, (long long)taps * taps * Cs, y_hi, y_lo, Cout, stats, stream);
 }
 
 }  // extern "C"

@@ -11,6 +11,23 @@ inline int ew_blocks(long long total) {
   return (int)(b < cap ? (b > 0 ? b : 1) : cap);
 }
 
+// four-plane x2 weight operand (see adamml_pack_weight_x2): plane stride n elements
+struct W4Ptr {
+  bf16* p;
+  long long n;
+};
+using ::st_elem;  // keep the plain / x2 overloads of common.cuh visible next to this one
+__device__ __forceinline__ void st_elem(const W4Ptr& w, long long i, float v) {
+  const bf16 b1 = __float2bfloat16_rn(v);
+  const float r1 = v - __bfloat162float(b1);
+  const bf16 b2 = __float2bfloat16_rn(r1);
+  const bf16 b3 = __float2bfloat16_rn(r1 - __bfloat162float(b2));
+  w.p[i] = b1;
+  w.p[w.n + i] = b2;
+  w.p[2 * w.n + i] = b3;
+  reinterpret_cast<__half*>(w.p)[3 * w.n + i] = __float2half_rn(v);
+}
+
 // Input element of the data layer.  fp32 clips arrive normalised.  uint8 clips (decoded frames, the CHW byte
 // tensor ToTorchFormatTensor holds before .float()) are normalised here with the reference's own fp32 arithmetic:
 // x.float().div(255) (utils/video_transforms.py:343) then t.sub_(mean).div_(std) per channel plane (:81-82).
@@ -27,8 +44,8 @@ template <> struct Pair<float> { using type = float2; };
 template <> struct Pair<unsigned char> { using type = uchar2; };
 
 // x: NCHW [N, S*F*C, H, W]  ->  out: NHWC [(s*N+n)*F+f, H, W, Cpad]   (adamml.py:53,65)
-template <typename TIn, typename T>
-__global__ void pack_frames_kernel(const TIn* __restrict__ x, InNorm nm, T* __restrict__ out, int N, int S, int F,
+template <typename TIn, typename MP>
+__global__ void pack_frames_kernel(const TIn* __restrict__ x, InNorm nm, MP out, int N, int S, int F,
                                    int C, int H, int W, int Cpad) {
   long long total = (long long)S * N * F * H * W;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -40,16 +57,16 @@ __global__ void pack_frames_kernel(const TIn* __restrict__ x, InNorm nm, T* __re
     int n = (int)((img / F) % N);
     int s = (int)(img / ((long long)F * N));
     const TIn* src = x + (((long long)n * S * F * C + ((long long)s * F + f) * C) * H + h) * W + w;
-    T* dst = out + idx * Cpad;
-    for (int c = 0; c < C; ++c) dst[c] = from_f32<T>(in_val(src[(long long)c * H * W], nm, c));
-    for (int c = C; c < Cpad; ++c) dst[c] = from_f32<T>(0.f);
+    const MP dst = out + idx * Cpad;
+    for (int c = 0; c < C; ++c) st_elem(dst, c, in_val(src[(long long)c * H * W], nm, c));
+    for (int c = C; c < Cpad; ++c) st_elem(dst, c, 0.f);
   }
 }
 
 // bilinear, align_corners=False, no antialias (F.interpolate at adamml.py:59), keeping
 // frames 0, fstep, 2*fstep, ... of each segment (adamml.py:60-62).
-template <typename TIn, typename T>
-__global__ void resize_frames_kernel(const TIn* __restrict__ x, InNorm nm, T* __restrict__ out, int N, int S, int F,
+template <typename TIn, typename MP>
+__global__ void resize_frames_kernel(const TIn* __restrict__ x, InNorm nm, MP out, int N, int S, int F,
                                      int C, int H, int W, int OH, int OW, int fstep, int Fk, int Cpad) {
   const float sh = (float)H / (float)OH;
   const float sw = (float)W / (float)OW;
@@ -74,7 +91,7 @@ __global__ void resize_frames_kernel(const TIn* __restrict__ x, InNorm nm, T* __
     float lh1 = fminf(fmaxf(hr - (float)h0, 0.f), 1.f), lh0 = 1.f - lh1;
     float lw1 = fminf(fmaxf(wr - (float)w0, 0.f), 1.f), lw0 = 1.f - lw1;
     const TIn* src = x + ((long long)n * S * F * C + ((long long)s * F + f) * C) * H * W;
-    T* dst = out + idx * Cpad;
+    const MP dst = out + idx * Cpad;
     for (int c = 0; c < C; ++c) {
       const TIn* pl = src + (long long)c * H * W;
       float p00 = in_val(pl[(long long)h0 * W + w0], nm, c);
@@ -82,15 +99,15 @@ __global__ void resize_frames_kernel(const TIn* __restrict__ x, InNorm nm, T* __
       float p10 = in_val(pl[(long long)(h0 + hp) * W + w0], nm, c);
       float p11 = in_val(pl[(long long)(h0 + hp) * W + w0 + wp], nm, c);
       float v = lh0 * (lw0 * p00 + lw1 * p01) + lh1 * (lw0 * p10 + lw1 * p11);
-      dst[c] = from_f32<T>(v);
+      st_elem(dst, c, v);
     }
-    for (int c = C; c < Cpad; ++c) dst[c] = from_f32<T>(0.f);
+    for (int c = C; c < Cpad; ++c) st_elem(dst, c, 0.f);
   }
 }
 
 // OIHW fp32 -> OHWI T
-template <typename T>
-__global__ void pack_weight_kernel(const float* __restrict__ src, T* __restrict__ dst, int Cout, int Cin, int R,
+template <typename MP>
+__global__ void pack_weight_kernel(const float* __restrict__ src, MP dst, int Cout, int Cin, int R,
                                    int S, int CinPad) {
   long long total = (long long)Cout * R * S * CinPad;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -100,7 +117,7 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, T* __restrict_
     int r = (int)((idx / ((long long)CinPad * S)) % R);
     int co = (int)(idx / ((long long)CinPad * S * R));
     float v = ci < Cin ? src[(((long long)co * Cin + ci) * R + r) * S + s] : 0.f;
-    dst[idx] = from_f32<T>(v);
+    st_elem(dst, idx, v);
   }
 }
 
@@ -140,9 +157,10 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ src, float* __rest
 // x NCHW fp32 [N, S*F*C, H, W] -> out bf16 [(s*N+n)*F+f, H/2, W/2+4, Cs], stored column ip holds s2d column
 // ip-2 (two zero columns left and right), channel (ph*2+pw)*C + c = x[.., c, 2j+ph, 2i+pw], rest zero.
 // CT/CST > 0: compile-time channel counts, so the pixel is assembled in registers and stored as 16-byte vectors
+// out_lo != nullptr: x2 planes (hi = bf16, lo = fp16 remainder)
 template <typename TIn, int CT, int CST>
-__global__ void pack_frames_s2d_kernel(const TIn* __restrict__ x, InNorm nm, bf16* __restrict__ out, int N, int S,
-                                       int F, int C, int H, int W, int Cs) {
+__global__ void pack_frames_s2d_kernel(const TIn* __restrict__ x, InNorm nm, bf16* __restrict__ out,
+                                       __half* __restrict__ out_lo, int N, int S, int F, int C, int H, int W, int Cs) {
   using P2 = typename Pair<TIn>::type;
   const int Hs = H / 2, Ws = W / 2, Wp = Ws + 4;
   const long long total = (long long)S * N * F * Hs * Wp;
@@ -155,35 +173,51 @@ __global__ void pack_frames_s2d_kernel(const TIn* __restrict__ x, InNorm nm, bf1
     const int n = (int)((img / F) % N);
     const int s = (int)(img / ((long long)F * N));
     bf16* dst = out + idx * Cs;
+    __half* dlo = out_lo ? out_lo + idx * Cs : nullptr;
     const int i = ip - 2;
     if (i < 0 || i >= Ws) {
-      for (int c = 0; c < Cs; c += 8) *reinterpret_cast<uint4*>(dst + c) = make_uint4(0, 0, 0, 0);
+      for (int c = 0; c < Cs; c += 8) {
+        *reinterpret_cast<uint4*>(dst + c) = make_uint4(0, 0, 0, 0);
+        if (dlo) *reinterpret_cast<uint4*>(dlo + c) = make_uint4(0, 0, 0, 0);
+      }
       continue;
     }
     const TIn* src = x + (((long long)n * S * F * C + ((long long)s * F + f) * C) * H + 2 * j) * W + 2 * i;
     if (CT > 0) {
       constexpr int CSV = CST > 0 ? CST : 8;
       __align__(16) bf16 v[CSV];
+      __align__(16) __half vl[CSV];
 #pragma unroll
-      for (int c = 0; c < CSV; ++c) v[c] = __float2bfloat16_rn(0.f);
+      for (int c = 0; c < CSV; ++c) { v[c] = __float2bfloat16_rn(0.f); vl[c] = __float2half_rn(0.f); }
 #pragma unroll
       for (int ph = 0; ph < 2; ++ph)
 #pragma unroll
         for (int c = 0; c < CT; ++c) {
           const P2 t = *reinterpret_cast<const P2*>(src + ((long long)c * H + ph) * W);
-          v[(ph * 2 + 0) * CT + c] = __float2bfloat16_rn(in_val(t.x, nm, c));
-          v[(ph * 2 + 1) * CT + c] = __float2bfloat16_rn(in_val(t.y, nm, c));
+          x2_split(in_val(t.x, nm, c), v[(ph * 2 + 0) * CT + c], vl[(ph * 2 + 0) * CT + c]);
+          x2_split(in_val(t.y, nm, c), v[(ph * 2 + 1) * CT + c], vl[(ph * 2 + 1) * CT + c]);
         }
 #pragma unroll
-      for (int c = 0; c < CSV; c += 8) *reinterpret_cast<uint4*>(dst + c) = *reinterpret_cast<const uint4*>(v + c);
+      for (int c = 0; c < CSV; c += 8) {
+        *reinterpret_cast<uint4*>(dst + c) = *reinterpret_cast<const uint4*>(v + c);
+        if (dlo) *reinterpret_cast<uint4*>(dlo + c) = *reinterpret_cast<const uint4*>(vl + c);
+      }
     } else {
       for (int ph = 0; ph < 2; ++ph)
         for (int c = 0; c < C; ++c) {
           const P2 v = *reinterpret_cast<const P2*>(src + ((long long)c * H + ph) * W);
-          dst[(ph * 2 + 0) * C + c] = __float2bfloat16_rn(in_val(v.x, nm, c));
-          dst[(ph * 2 + 1) * C + c] = __float2bfloat16_rn(in_val(v.y, nm, c));
+          bf16 h0, h1;
+          __half l0, l1;
+          x2_split(in_val(v.x, nm, c), h0, l0);
+          x2_split(in_val(v.y, nm, c), h1, l1);
+          dst[(ph * 2 + 0) * C + c] = h0;
+          dst[(ph * 2 + 1) * C + c] = h1;
+          if (dlo) { dlo[(ph * 2 + 0) * C + c] = l0; dlo[(ph * 2 + 1) * C + c] = l1; }
         }
-      for (int c = 4 * C; c < Cs; ++c) dst[c] = __float2bfloat16_rn(0.f);
+      for (int c = 4 * C; c < Cs; ++c) {
+        dst[c] = __float2bfloat16_rn(0.f);
+        if (dlo) dlo[c] = __float2half_rn(0.f);
+      }
     }
   }
 }
@@ -217,7 +251,8 @@ __global__ void nhwc_to_s2d_kernel(const bf16* __restrict__ x, bf16* __restrict_
 // stride-2 first-conv weight OIHW fp32 [Cout][C][R][R] (R = 7, pad 3 -> T = 4 taps per axis; R = 3, pad 1 -> T = 2)
 // -> bf16 [Cout][T (dh + T/2)][T (dw + T/2)][Cs]: tap (r, s) = (2*dh+ph+pad, 2*dw+pw+pad), channel (ph*2+pw)*C + c;
 // everything else zero.
-__global__ void pack_weight_stem_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int Cout, int C,
+template <typename MP>
+__global__ void pack_weight_stem_kernel(const float* __restrict__ src, MP dst, int Cout, int C,
                                         int Cs, int R, int T) {
   const int pad = R / 2;
   const long long total = (long long)Cout * T * T * Cs;
@@ -233,7 +268,7 @@ __global__ void pack_weight_stem_kernel(const float* __restrict__ src, bf16* __r
       const int r = 2 * (dhi - T / 2) + ph + pad, s_ = 2 * (dwi - T / 2) + pw + pad;
       if (r >= 0 && r < R && s_ >= 0 && s_ < R) v = src[(((long long)co * C + c) * R + r) * R + s_];
     }
-    dst[idx] = __float2bfloat16_rn(v);
+    st_elem(dst, idx, v);
   }
 }
 
@@ -274,41 +309,54 @@ __global__ void cast_kernel(const TI* __restrict__ src, TO* __restrict__ dst, lo
 }  // namespace
 
 template <typename TIn>
-static int pack_frames_any(const TIn* x, InNorm nm, void* out, int N, int S, int F, int C, int H, int W, int Cpad,
-                           int dtype, cudaStream_t stream) {
+static int pack_frames_any(const TIn* x, InNorm nm, void* out, void* out_lo, int N, int S, int F, int C, int H, int W,
+                           int Cpad, int dtype, cudaStream_t stream) {
   ADAMML_REQUIRE(N > 0 && S > 0 && F > 0 && C > 0 && H > 0 && W > 0 && Cpad >= C, "pack_frames: bad dims");
   long long total = (long long)S * N * F * H * W;
+  if (dtype == ADAMML_X2) {
+    ADAMML_REQUIRE(out_lo, "pack_frames: x2 output needs the lo plane");
+    pack_frames_kernel<TIn, X2Ptr><<<ew_blocks(total), 256, 0, stream>>>(x, nm, x2m(out, out_lo), N, S, F, C, H, W, Cpad);
+    return adamml_check_launch("pack_frames");
+  }
   ADAMML_DISPATCH_DTYPE(dtype, T,
-    (pack_frames_kernel<TIn, T><<<ew_blocks(total), 256, 0, stream>>>(x, nm, (T*)out, N, S, F, C, H, W, Cpad)));
+    (pack_frames_kernel<TIn, T*><<<ew_blocks(total), 256, 0, stream>>>(x, nm, (T*)out, N, S, F, C, H, W, Cpad)));
   return adamml_check_launch("pack_frames");
 }
 
 template <typename TIn>
-static int resize_frames_any(const TIn* x, InNorm nm, void* out, int N, int S, int F, int C, int H, int W, int OH,
-                             int OW, int fstep, int Cpad, int dtype, cudaStream_t stream) {
+static int resize_frames_any(const TIn* x, InNorm nm, void* out, void* out_lo, int N, int S, int F, int C, int H, int W,
+                             int OH, int OW, int fstep, int Cpad, int dtype, cudaStream_t stream) {
   ADAMML_REQUIRE(N > 0 && S > 0 && F > 0 && C > 0 && H > 0 && W > 0 && OH > 0 && OW > 0 && fstep > 0 && Cpad >= C,
                  "resize_frames: bad dims");
   int Fk = (F + fstep - 1) / fstep;
   long long total = (long long)S * N * Fk * OH * OW;
+  if (dtype == ADAMML_X2) {
+    ADAMML_REQUIRE(out_lo, "resize_frames: x2 output needs the lo plane");
+    resize_frames_kernel<TIn, X2Ptr><<<ew_blocks(total), 256, 0, stream>>>(x, nm, x2m(out, out_lo), N, S, F, C, H, W,
+                                                                          OH, OW, fstep, Fk, Cpad);
+    return adamml_check_launch("resize_frames");
+  }
   ADAMML_DISPATCH_DTYPE(dtype, T,
-    (resize_frames_kernel<TIn, T><<<ew_blocks(total), 256, 0, stream>>>(x, nm, (T*)out, N, S, F, C, H, W, OH, OW,
-                                                                        fstep, Fk, Cpad)));
+    (resize_frames_kernel<TIn, T*><<<ew_blocks(total), 256, 0, stream>>>(x, nm, (T*)out, N, S, F, C, H, W, OH, OW,
+                                                                         fstep, Fk, Cpad)));
   return adamml_check_launch("resize_frames");
 }
 
 template <typename TIn>
-static int pack_frames_s2d_any(const TIn* x, InNorm nm, void* out, int N, int S, int F, int C, int H, int W, int Cs,
-                               cudaStream_t stream) {
+static int pack_frames_s2d_any(const TIn* x, InNorm nm, void* out, void* out_lo, int N, int S, int F, int C, int H,
+                               int W, int Cs, cudaStream_t stream) {
   ADAMML_REQUIRE(N > 0 && S > 0 && F > 0 && C > 0 && H > 0 && W > 0, "pack_frames_s2d: bad dims");
   ADAMML_REQUIRE(H % 2 == 0 && W % 2 == 0 && Cs % 8 == 0 && Cs >= 4 * C, "pack_frames_s2d: needs even H, W and Cs >= 4C");
   ADAMML_REQUIRE(((uintptr_t)x % (2 * sizeof(TIn))) == 0 && ((uintptr_t)out % 16) == 0,
                  "pack_frames_s2d: unaligned buffers");
   long long total = (long long)S * N * F * (H / 2) * (W / 2 + 4);
+  ADAMML_REQUIRE(((uintptr_t)out_lo % 16) == 0, "pack_frames_s2d: unaligned lo plane");
   bf16* o = (bf16*)out;
+  __half* ol = (__half*)out_lo;
   if (C == 3 && Cs == 16)
-    pack_frames_s2d_kernel<TIn, 3, 16><<<ew_blocks(total), 256, 0, stream>>>(x, nm, o, N, S, F, C, H, W, Cs);
+    pack_frames_s2d_kernel<TIn, 3, 16><<<ew_blocks(total), 256, 0, stream>>>(x, nm, o, ol, N, S, F, C, H, W, Cs);
   else
-    pack_frames_s2d_kernel<TIn, 0, 0><<<ew_blocks(total), 256, 0, stream>>>(x, nm, o, N, S, F, C, H, W, Cs);
+    pack_frames_s2d_kernel<TIn, 0, 0><<<ew_blocks(total), 256, 0, stream>>>(x, nm, o, ol, N, S, F, C, H, W, Cs);
   return adamml_check_launch("pack_frames_s2d");
 }
 
@@ -316,27 +364,27 @@ extern "C" {
 
 int adamml_pack_frames(const float* x, void* out, int N, int S, int F, int C, int H, int W, int Cpad, int dtype,
                        cudaStream_t stream) {
-  return pack_frames_any<float>(x, InNorm{nullptr, nullptr}, out, N, S, F, C, H, W, Cpad, dtype, stream);
+  return pack_frames_any<float>(x, InNorm{nullptr, nullptr}, out, nullptr, N, S, F, C, H, W, Cpad, dtype, stream);
 }
 
 int adamml_pack_frames_u8(const unsigned char* x, const float* mean, const float* stdv, void* out, int N, int S, int F,
                           int C, int H, int W, int Cpad, int dtype, cudaStream_t stream) {
   ADAMML_REQUIRE(mean && stdv, "pack_frames_u8: needs the per-channel mean and std");
-  return pack_frames_any<unsigned char>(x, InNorm{mean, stdv}, out, N, S, F, C, H, W, Cpad, dtype, stream);
+  return pack_frames_any<unsigned char>(x, InNorm{mean, stdv}, out, nullptr, N, S, F, C, H, W, Cpad, dtype, stream);
 }
 
 int adamml_resize_frames(const float* x, void* out, int N, int S, int F, int C, int H, int W, int OH, int OW,
                          int fstep, int Cpad, int dtype, cudaStream_t stream) {
-  return resize_frames_any<float>(x, InNorm{nullptr, nullptr}, out, N, S, F, C, H, W, OH, OW, fstep, Cpad, dtype,
-                                  stream);
+  return resize_frames_any<float>(x, InNorm{nullptr, nullptr}, out, nullptr, N, S, F, C, H, W, OH, OW, fstep, Cpad,
+                                  dtype, stream);
 }
 
 int adamml_resize_frames_u8(const unsigned char* x, const float* mean, const float* stdv, void* out, int N, int S,
                             int F, int C, int H, int W, int OH, int OW, int fstep, int Cpad, int dtype,
                             cudaStream_t stream) {
   ADAMML_REQUIRE(mean && stdv, "resize_frames_u8: needs the per-channel mean and std");
-  return resize_frames_any<unsigned char>(x, InNorm{mean, stdv}, out, N, S, F, C, H, W, OH, OW, fstep, Cpad, dtype,
-                                          stream);
+  return resize_frames_any<unsigned char>(x, InNorm{mean, stdv}, out, nullptr, N, S, F, C, H, W, OH, OW, fstep, Cpad,
+                                          dtype, stream);
 }
 
 int adamml_pack_weight(const float* w_oihw, void* w_ohwi, int Cout, int Cin, int R, int S, int CinPad, int dtype,
@@ -344,7 +392,7 @@ int adamml_pack_weight(const float* w_oihw, void* w_ohwi, int Cout, int Cin, int
   ADAMML_REQUIRE(Cout > 0 && Cin > 0 && R > 0 && S > 0 && CinPad >= Cin, "pack_weight: bad dims");
   long long total = (long long)Cout * R * S * CinPad;
   ADAMML_DISPATCH_DTYPE(dtype, T,
-    pack_weight_kernel<T><<<ew_blocks(total), 256, 0, stream>>>(w_oihw, (T*)w_ohwi, Cout, Cin, R, S, CinPad));
+    pack_weight_kernel<T*><<<ew_blocks(total), 256, 0, stream>>>(w_oihw, (T*)w_ohwi, Cout, Cin, R, S, CinPad));
   return adamml_check_launch("pack_weight");
 }
 
@@ -367,13 +415,66 @@ int adamml_unpack_wgrad(const float* dw_ohwi, float* dw_oihw, int Cout, int Cin,
 
 int adamml_pack_frames_s2d(const float* x, void* out, int N, int S, int F, int C, int H, int W, int Cs,
                            cudaStream_t stream) {
-  return pack_frames_s2d_any<float>(x, InNorm{nullptr, nullptr}, out, N, S, F, C, H, W, Cs, stream);
+  return pack_frames_s2d_any<float>(x, InNorm{nullptr, nullptr}, out, nullptr, N, S, F, C, H, W, Cs, stream);
 }
 
 int adamml_pack_frames_s2d_u8(const unsigned char* x, const float* mean, const float* stdv, void* out, int N, int S,
                               int F, int C, int H, int W, int Cs, cudaStream_t stream) {
   ADAMML_REQUIRE(mean && stdv, "pack_frames_s2d_u8: needs the per-channel mean and std");
-  return pack_frames_s2d_any<unsigned char>(x, InNorm{mean, stdv}, out, N, S, F, C, H, W, Cs, stream);
+  return pack_frames_s2d_any<unsigned char>(x, InNorm{mean, stdv}, out, nullptr, N, S, F, C, H, W, Cs, stream);
+}
+
+/* ---- x2 planes: the data layer of the default precision mode writes hi (bf16) + lo (fp16 remainder) ---- */
+int adamml_pack_frames_x2(const void* x, const float* mean, const float* stdv, void* out_hi, void* out_lo, int N, int S,
+                          int F, int C, int H, int W, int Cpad, int is_u8, cudaStream_t stream) {
+  ADAMML_REQUIRE(!is_u8 || (mean && stdv), "pack_frames_x2: uint8 input needs the per-channel mean and std");
+  if (is_u8)
+    return pack_frames_any<unsigned char>((const unsigned char*)x, InNorm{mean, stdv}, out_hi, out_lo, N, S, F, C, H,
+                                          W, Cpad, ADAMML_X2, stream);
+  return pack_frames_any<float>((const float*)x, InNorm{nullptr, nullptr}, out_hi, out_lo, N, S, F, C, H, W, Cpad,
+                                ADAMML_X2, stream);
+}
+
+int adamml_resize_frames_x2(const void* x, const float* mean, const float* stdv, void* out_hi, void* out_lo, int N,
+                            int S, int F, int C, int H, int W, int OH, int OW, int fstep, int Cpad, int is_u8,
+                            cudaStream_t stream) {
+  ADAMML_REQUIRE(!is_u8 || (mean && stdv), "resize_frames_x2: uint8 input needs the per-channel mean and std");
+  if (is_u8)
+    return resize_frames_any<unsigned char>((const unsigned char*)x, InNorm{mean, stdv}, out_hi, out_lo, N, S, F, C, H,
+                                            W, OH, OW, fstep, Cpad, ADAMML_X2, stream);
+  return resize_frames_any<float>((const float*)x, InNorm{nullptr, nullptr}, out_hi, out_lo, N, S, F, C, H, W, OH, OW,
+                                  fstep, Cpad, ADAMML_X2, stream);
+}
+
+int adamml_pack_frames_s2d_x2(const void* x, const float* mean, const float* stdv, void* out_hi, void* out_lo, int N,
+                              int S, int F, int C, int H, int W, int Cs, int is_u8, cudaStream_t stream) {
+  ADAMML_REQUIRE(out_lo, "pack_frames_s2d_x2: needs the lo plane");
+  ADAMML_REQUIRE(!is_u8 || (mean && stdv), "pack_frames_s2d_x2: uint8 input needs the per-channel mean and std");
+  if (is_u8)
+    return pack_frames_s2d_any<unsigned char>((const unsigned char*)x, InNorm{mean, stdv}, out_hi, out_lo, N, S, F, C,
+                                              H, W, Cs, stream);
+  return pack_frames_s2d_any<float>((const float*)x, InNorm{nullptr, nullptr}, out_hi, out_lo, N, S, F, C, H, W, Cs,
+                                    stream);
+}
+
+/* nn.Conv2d.weight OIHW fp32 -> the FOUR OHWI weight planes of the x2 tensor-core path, plane-major in one buffer
+ * w4 [4][Cout][R][S][CinPad] of 2-byte elements: b1 = bf16(w), b2 = bf16(w - b1), b3 = bf16(w - b1 - b2) (bf16 cascade,
+ * exact to 24 bits) and f = fp16(w).  stem = 1: the space-to-depth first-conv operand (adamml_pack_weight_stem layout,
+ * Cin = C, CinPad = Cs, S = R). */
+int adamml_pack_weight_x2(const float* w_oihw, void* w4, int Cout, int Cin, int R, int S, int CinPad, int stem,
+                          cudaStream_t stream) {
+  ADAMML_REQUIRE(Cout > 0 && Cin > 0 && R > 0 && S > 0 && w4, "pack_weight_x2: bad arguments");
+  if (stem) {
+    ADAMML_REQUIRE(CinPad >= 4 * Cin && (R == 7 || R == 3), "pack_weight_x2: bad stem dims");
+    const int T = (R + 1) / 2;
+    const long long n = (long long)Cout * T * T * CinPad;
+    pack_weight_stem_kernel<W4Ptr><<<ew_blocks(n), 256, 0, stream>>>(w_oihw, W4Ptr{(bf16*)w4, n}, Cout, Cin, CinPad, R, T);
+  } else {
+    ADAMML_REQUIRE(CinPad >= Cin, "pack_weight_x2: CinPad < Cin");
+    const long long n = (long long)Cout * R * S * CinPad;
+    pack_weight_kernel<W4Ptr><<<ew_blocks(n), 256, 0, stream>>>(w_oihw, W4Ptr{(bf16*)w4, n}, Cout, Cin, R, S, CinPad);
+  }
+  return adamml_check_launch("pack_weight_x2");
 }
 
 int adamml_nhwc_to_s2d(const void* x, void* out, long long IMGS, int C, int H, int W, int Cs, int padl, int padr,
@@ -389,8 +490,8 @@ int adamml_pack_weight_stem(const float* w_oihw, void* w_packed, int Cout, int C
                             cudaStream_t stream) {
   ADAMML_REQUIRE(Cout > 0 && C > 0 && Cs >= 4 * C && (R == 7 || R == 3), "pack_weight_stem: bad dims");
   const int T = (R + 1) / 2;
-  pack_weight_stem_kernel<<<ew_blocks((long long)Cout * T * T * Cs), 256, 0, stream>>>(w_oihw, (bf16*)w_packed, Cout,
-                                                                                        C, Cs, R, T);
+  pack_weight_stem_kernel<bf16*><<<ew_blocks((long long)Cout * T * T * Cs), 256, 0, stream>>>(
+      w_oihw, (bf16*)w_packed, Cout, C, Cs, R, T);
   return adamml_check_launch("pack_weight_stem");
 }
 

@@ -117,13 +117,44 @@ template <> struct DwVec<bf16> {
   }
 };
 
+struct X2Raw4 { uint2 hi, lo; };
+template <> struct DwVec<x2_t> {
+  static constexpr int N = 4;
+  typedef X2Raw4 raw;
+  __device__ __forceinline__ static raw zero_raw() { return X2Raw4{make_uint2(0u, 0u), make_uint2(0u, 0u)}; }
+  __device__ __forceinline__ static raw load_raw(const X2CPtr& p) {
+    return X2Raw4{*reinterpret_cast<const uint2*>(p.hi), *reinterpret_cast<const uint2*>(p.lo)};
+  }
+  __device__ __forceinline__ static void unpack(const raw& t, float (&v)[4]) {
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.hi.x));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.hi.y));
+    const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&t.lo.x));
+    const float2 d = __half22float2(*reinterpret_cast<const __half2*>(&t.lo.y));
+    v[0] = a.x + c.x; v[1] = a.y + c.y; v[2] = b.x + d.x; v[3] = b.y + d.y;
+  }
+  __device__ __forceinline__ static void load(const X2CPtr& p, float (&v)[4]) { unpack(load_raw(p), v); }
+  __device__ __forceinline__ static void store(const X2Ptr& p, const float (&v)[4]) {
+    bf16 h[4];
+    __half l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) x2_split(v[i], h[i], l[i]);
+    __nv_bfloat162 h0 = __halves2bfloat162(h[0], h[1]), h1 = __halves2bfloat162(h[2], h[3]);
+    __half2 l0 = __halves2half2(l[0], l[1]), l1 = __halves2half2(l[2], l[3]);
+    uint2 th, tl;
+    th.x = *reinterpret_cast<uint32_t*>(&h0); th.y = *reinterpret_cast<uint32_t*>(&h1);
+    tl.x = *reinterpret_cast<uint32_t*>(&l0); tl.y = *reinterpret_cast<uint32_t*>(&l1);
+    *reinterpret_cast<uint2*>(p.hi) = th;
+    *reinterpret_cast<uint2*>(p.lo) = tl;
+  }
+};
+
 // Stride-1 stencil over a BAND of RH output rows with a rolling 3-row register window: every input vector is
 // loaded once per band (+ 2 halo rows), the 3x3 weights once per thread.  Forward (FLIP = false) and data
 // gradient (FLIP = true, + optional addend).
-template <typename T, bool FLIP, int SW, int RH>
-__global__ void __launch_bounds__(DW_THREADS, 4)
-dw_s1_band_kernel(const T* __restrict__ x, const float* __restrict__ w, T* __restrict__ y,
-                  const T* __restrict__ addend, int IMGS, int H, int W, int C, int strips, int bands) {
+template <typename T, bool FLIP, int SW, int RH, typename CP, typename MP>
+__device__ __forceinline__ void
+dw_s1_band_body(CP x, const float* __restrict__ w, MP y, CP addend, int IMGS, int H, int W, int C, int strips,
+                int bands) {
   typedef DwVec<T> VIO;
   constexpr int V = VIO::N;
   constexpr int NC = SW + 2;
@@ -142,7 +173,7 @@ dw_s1_band_kernel(const T* __restrict__ x, const float* __restrict__ w, T* __res
   const int h1 = h0 + RH < H ? h0 + RH : H;
   float wr[9][V];
   load_w9<V>(w, C, c0, wr);
-  const T* xb = x + (img * H * W) * C + c0;
+  const CP xb = x + ((img * H * W) * C + c0);
   auto load_row = [&](int hi, raw_t (&dst)[NC]) {
     const bool rok = hi >= 0 && hi < H;
 #pragma unroll
@@ -204,11 +235,23 @@ dw_s1_band_kernel(const T* __restrict__ x, const float* __restrict__ w, T* __res
   }
 }
 
+template <typename T, bool FLIP, int SW, int RH>
+__global__ void __launch_bounds__(DW_THREADS, 4)
+dw_s1_band_kernel(const T* __restrict__ x, const float* __restrict__ w, T* __restrict__ y,
+                  const T* __restrict__ addend, int IMGS, int H, int W, int C, int strips, int bands) {
+  dw_s1_band_body<T, FLIP, SW, RH, const T*, T*>(x, w, y, addend, IMGS, H, W, C, strips, bands);
+}
+template <int SW, int RH>
+__global__ void __launch_bounds__(DW_THREADS, 3)
+dw_s1_band_x2_kernel(X2CPtr x, const float* __restrict__ w, X2Ptr y, int IMGS, int H, int W, int C, int strips,
+                     int bands) {
+  dw_s1_band_body<x2_t, false, SW, RH, X2CPtr, X2Ptr>(x, w, y, X2CPtr{nullptr, nullptr}, IMGS, H, W, C, strips, bands);
+}
+
 // Stride-2 forward: strip of SW outputs needs 2*SW+1 input columns per row.
-template <typename T, int SW>
-__global__ void __launch_bounds__(DW_THREADS)
-dw_s2_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w, T* __restrict__ y, int IMGS, int H, int W,
-                 int C, int Ho, int Wo, int strips) {
+template <typename T, int SW, typename CP, typename MP>
+__device__ __forceinline__ void
+dw_s2_fwd_body(CP x, const float* __restrict__ w, MP y, int IMGS, int H, int W, int C, int Ho, int Wo, int strips) {
   constexpr int V = VecIO<T>::N;
   const int cvecs = C / V;
   const long long total = (long long)IMGS * Ho * strips * cvecs;
@@ -232,7 +275,7 @@ dw_s2_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w, T* __rest
   for (int r = 0; r < 3; ++r) {
     const int hi = ho * 2 + r - 1;
     if (hi < 0 || hi >= H) continue;
-    const T* row = x + ((img * H + hi) * W) * C + c0;
+    const CP row = x + (((img * H + hi) * W) * C + c0);
     typename VecIO<T>::raw q[2 * SW + 1];
 #pragma unroll
     for (int j = 0; j < 2 * SW + 1; ++j) {
@@ -261,6 +304,19 @@ dw_s2_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w, T* __rest
     if (wo >= Wo) continue;
     VecIO<T>::store(y + ((img * Ho + ho) * Wo + wo) * C + c0, acc[j]);
   }
+}
+
+template <typename T, int SW>
+__global__ void __launch_bounds__(DW_THREADS)
+dw_s2_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w, T* __restrict__ y, int IMGS, int H, int W,
+                 int C, int Ho, int Wo, int strips) {
+  dw_s2_fwd_body<T, SW, const T*, T*>(x, w, y, IMGS, H, W, C, Ho, Wo, strips);
+}
+template <int SW>
+__global__ void __launch_bounds__(DW_THREADS)
+dw_s2_fwd_x2_kernel(X2CPtr x, const float* __restrict__ w, X2Ptr y, int IMGS, int H, int W, int C, int Ho, int Wo,
+                    int strips) {
+  dw_s2_fwd_body<x2_t, SW, X2CPtr, X2Ptr>(x, w, y, IMGS, H, W, C, Ho, Wo, strips);
 }
 
 // Stride-2 data gradient: one thread per 2x2 input quad (rows 2m, 2m+1; cols 2n, 2n+1) and channel vector;
@@ -554,6 +610,28 @@ int adamml_dwconv_fwd(const void* x, const float* w, void* y, int IMGS, int H, i
     }
   });
   return adamml_check_launch("dwconv_fwd");
+}
+
+/* x2 planes (forward pass of the default precision mode); C % 8 == 0 */
+int adamml_dwconv_fwd_x2(const void* x_hi, const void* x_lo, const float* w, void* y_hi, void* y_lo, int IMGS, int H,
+                         int W, int C, int stride, int Ho, int Wo, cudaStream_t stream) {
+  ADAMML_REQUIRE(stride == 1 || stride == 2, "dwconv: stride must be 1 or 2");
+  ADAMML_REQUIRE(Ho == (H + 2 - 3) / stride + 1 && Wo == (W + 2 - 3) / stride + 1, "dwconv: bad Ho/Wo");
+  ADAMML_REQUIRE(dw_vec_ok<bf16>(C, x_hi, x_lo, y_hi, y_lo), "dwconv_fwd_x2: needs C %% 8 == 0 and aligned planes");
+  if (stride == 1) {
+    constexpr int SW = 2, RH = 16;
+    const int strips = (W + SW - 1) / SW, bands = (H + RH - 1) / RH;
+    const long long total = (long long)IMGS * bands * strips * (C / 4);
+    dw_s1_band_x2_kernel<SW, RH><<<blocks_for(total, DW_THREADS), DW_THREADS, 0, stream>>>(
+        x2c(x_hi, x_lo), w, x2m(y_hi, y_lo), IMGS, H, W, C, strips, bands);
+  } else {
+    constexpr int SW = 2;
+    const int strips = (Wo + SW - 1) / SW;
+    const long long total = (long long)IMGS * Ho * strips * (C / 8);
+    dw_s2_fwd_x2_kernel<SW><<<blocks_for(total, DW_THREADS), DW_THREADS, 0, stream>>>(
+        x2c(x_hi, x_lo), w, x2m(y_hi, y_lo), IMGS, H, W, C, Ho, Wo, strips);
+  }
+  return adamml_check_launch("dwconv_fwd_x2");
 }
 
 int adamml_dwconv_dgrad(const void* dy, const float* w, void* dx, const void* addend, int IMGS, int H, int W, int C,

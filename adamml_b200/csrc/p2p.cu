@@ -12,6 +12,7 @@
 // by the kernel itself, so graph replays keep counting.  Every BN layer owns its own slots, so a slot is only
 // rewritten a whole step (hundreds of flag exchanges) after its last remote read.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -53,8 +54,12 @@ p2p_allreduce_f64_kernel(const unsigned long long* __restrict__ peer_bufs, const
   }
   __syncthreads();
   if (s_fail) {
+    // a peer never arrived: make the failure impossible to miss -- the reduced statistics become NaN (so do the
+    // activations, the loss and every gradient of this step) and err_flag is raised for P2PStats.check()
     if (threadIdx.x == 0) atomicExch(err_flag, 1u);
-    return;  // out keeps garbage; the host checks err_flag at the next synchronisation point
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) out[i] = nan;
+    return;
   }
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     double acc = 0.0;
@@ -76,7 +81,14 @@ int adamml_p2p_allreduce_f64(const unsigned long long* peer_bufs, const unsigned
                              unsigned* epoch_ctr, unsigned* err_flag, cudaStream_t stream) {
   ADAMML_REQUIRE(n > 0 && world > 1 && world <= 64 && rank >= 0 && rank < world && lane >= 0,
                  "p2p_allreduce: bad arguments");
-  const long long timeout_cycles = 20LL * 1000 * 1000 * 1000;  // ~10 s at 2 GHz: a peer that never arrives
+  // how long a rank waits for its peers before it poisons the step (see the kernel): default 120 s at ~2 GHz, i.e.
+  // longer than a checkpoint save or a data-loader stall; ADAMML_B200_P2P_TIMEOUT_S overrides (0 = wait forever and
+  // leave stragglers to the process-group watchdog, like the NCCL path)
+  static const long long timeout_cycles = []() {
+    const char* e = getenv("ADAMML_B200_P2P_TIMEOUT_S");
+    const double sec = e ? atof(e) : 120.0;
+    return sec <= 0.0 ? (long long)0x7fffffffffffffffLL : (long long)(sec * 2.0e9);
+  }();
   p2p_allreduce_f64_kernel<<<1, 1024, 0, stream>>>(peer_bufs, peer_flags, slot_off, out, n, world, rank, lane,
                                                   epoch_ctr, err_flag, timeout_cycles);
   return adamml_check_launch("p2p_allreduce_f64");

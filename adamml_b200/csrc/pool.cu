@@ -138,10 +138,9 @@ __global__ void tpool_bwd_kernel(const T* __restrict__ x, const T* __restrict__ 
 // ---- 16-byte vectorised versions (C % VEC == 0): thread = (pixel, channel vector) ----------------------
 // 3x3/s2/p1 max-pool; optionally records the window position (r*3+s, first maximum in scan order) of
 // every output element so that the backward pass is a pure gather that never re-reads x.
-template <typename T>
-__global__ void __launch_bounds__(256)
-maxpool_fwd_vec_kernel(const T* __restrict__ x, T* __restrict__ y, unsigned char* __restrict__ pos, int IMGS, int H,
-                       int W, int C, int Ho, int Wo) {
+template <typename T, typename CP, typename MP>
+__device__ __forceinline__ void
+maxpool_fwd_vec_body(CP x, MP y, unsigned char* __restrict__ pos, int IMGS, int H, int W, int C, int Ho, int Wo) {
   constexpr int V = VecIO<T>::N;
   const int cvecs = C / V;
   const long long total = (long long)IMGS * Ho * Wo * cvecs;
@@ -191,6 +190,18 @@ maxpool_fwd_vec_kernel(const T* __restrict__ x, T* __restrict__ y, unsigned char
       *reinterpret_cast<unsigned*>(pp) = pk;
     }
   }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+maxpool_fwd_vec_kernel(const T* __restrict__ x, T* __restrict__ y, unsigned char* __restrict__ pos, int IMGS, int H,
+                       int W, int C, int Ho, int Wo) {
+  maxpool_fwd_vec_body<T, const T*, T*>(x, y, pos, IMGS, H, W, C, Ho, Wo);
+}
+__global__ void __launch_bounds__(256)
+maxpool_fwd_vec_x2_kernel(X2CPtr x, X2Ptr y, unsigned char* __restrict__ pos, int IMGS, int H, int W, int C, int Ho,
+                          int Wo) {
+  maxpool_fwd_vec_body<x2_t, X2CPtr, X2Ptr>(x, y, pos, IMGS, H, W, C, Ho, Wo);
 }
 
 // gather backward from recorded positions, one thread per 2x2 input quad (rows 2m, 2m+1; cols 2n, 2n+1) and channel
@@ -258,9 +269,8 @@ maxpool_bwd_pos_kernel(const unsigned char* __restrict__ pos, const T* __restric
 }
 
 // temporal pool k3 s2 p1, one thread per (video, element vector): all TN frames of that position in registers
-template <typename T, int TN>
-__global__ void __launch_bounds__(256)
-tpool_fwd_vec_kernel(const T* __restrict__ x, T* __restrict__ y, long long V_, long long E, int mode_avg) {
+template <typename T, int TN, typename CP, typename MP>
+__device__ __forceinline__ void tpool_fwd_vec_body(CP x, MP y, long long V_, long long E, int mode_avg) {
   constexpr int V = VecIO<T>::N;
   constexpr int TO = (TN + 2 - 3) / 2 + 1;
   const long long evecs = E / V;
@@ -294,6 +304,17 @@ tpool_fwd_vec_kernel(const T* __restrict__ x, T* __restrict__ y, long long V_, l
     }
     VecIO<T>::store(y + (v * TO + to) * E + e, best);
   }
+}
+
+template <typename T, int TN>
+__global__ void __launch_bounds__(256)
+tpool_fwd_vec_kernel(const T* __restrict__ x, T* __restrict__ y, long long V_, long long E, int mode_avg) {
+  tpool_fwd_vec_body<T, TN, const T*, T*>(x, y, V_, E, mode_avg);
+}
+template <int TN>
+__global__ void __launch_bounds__(256)
+tpool_fwd_vec_x2_kernel(X2CPtr x, X2Ptr y, long long V_, long long E, int mode_avg) {
+  tpool_fwd_vec_body<x2_t, TN, X2CPtr, X2Ptr>(x, y, V_, E, mode_avg);
 }
 
 template <typename T, int TN>
@@ -364,14 +385,14 @@ inline bool pool_vec_ok(long long C, const void* a, const void* b = nullptr, con
 }
 
 // y[img][c] = mean over HW. block (32 channels, 8 pixel lanes) per (img, channel tile)
-template <typename T>
-__global__ void avgpool_fwd_kernel(const T* __restrict__ x, float* __restrict__ y, int HW, int C, long long y_ld) {
+template <typename CP>
+__global__ void avgpool_fwd_kernel(CP x, float* __restrict__ y, int HW, int C, long long y_ld) {
   __shared__ float sh[8][33];
   int img = blockIdx.x;
   int c = blockIdx.y * 32 + threadIdx.x;
   float s = 0.f;
   if (c < C)
-    for (int p = threadIdx.y; p < HW; p += 8) s += to_f32(x[((long long)img * HW + p) * C + c]);
+    for (int p = threadIdx.y; p < HW; p += 8) s += ld_elem(x, ((long long)img * HW + p) * C + c);
   sh[threadIdx.y][threadIdx.x] = s;
   __syncthreads();
   if (threadIdx.y == 0 && c < C) {
@@ -478,8 +499,46 @@ int adamml_avgpool_fwd(const void* x, float* y, int IMGS, int HW, int C, long lo
   dim3 block(32, 8);
   if (y_ld <= 0) y_ld = C;
   ADAMML_DISPATCH_DTYPE(dtype, T,
-    avgpool_fwd_kernel<T><<<grid, block, 0, stream>>>((const T*)x, y, HW, C, y_ld));
+    avgpool_fwd_kernel<const T*><<<grid, block, 0, stream>>>((const T*)x, y, HW, C, y_ld));
   return adamml_check_launch("avgpool_fwd");
+}
+
+/* ---- x2 planes (forward pass of the default precision mode); channel counts are multiples of 8 ---- */
+int adamml_maxpool3x3s2_fwd_x2(const void* x_hi, const void* x_lo, void* y_hi, void* y_lo, unsigned char* pos,
+                               int IMGS, int H, int W, int C, int Ho, int Wo, cudaStream_t stream) {
+  ADAMML_REQUIRE(Ho == (H + 2 - 3) / 2 + 1 && Wo == (W + 2 - 3) / 2 + 1, "maxpool: bad Ho/Wo");
+  ADAMML_REQUIRE(pool_vec_ok<bf16>(C, x_hi, x_lo, y_hi) && pool_vec_ok<bf16>(C, y_lo) && ((uintptr_t)pos % 8) == 0,
+                 "maxpool_fwd_x2: needs C %% 8 == 0 and aligned planes");
+  const long long tv = (long long)IMGS * Ho * Wo * (C / 8);
+  maxpool_fwd_vec_x2_kernel<<<(unsigned)((tv + 255) / 256), 256, 0, stream>>>(x2c(x_hi, x_lo), x2m(y_hi, y_lo), pos,
+                                                                               IMGS, H, W, C, Ho, Wo);
+  return adamml_check_launch("maxpool_fwd_x2");
+}
+
+int adamml_tpool_fwd_x2(const void* x_hi, const void* x_lo, void* y_hi, void* y_lo, long long V, int Tn, long long E,
+                        int mode_avg, cudaStream_t stream) {
+  ADAMML_REQUIRE(V > 0 && E > 0, "tpool: empty dims");
+  ADAMML_REQUIRE(Tn == 2 || Tn == 4 || Tn == 8, "tpool_fwd_x2: 2, 4 or 8 frames");
+  ADAMML_REQUIRE(pool_vec_ok<bf16>(E, x_hi, x_lo, y_hi) && pool_vec_ok<bf16>(E, y_lo),
+                 "tpool_fwd_x2: needs E %% 8 == 0 and aligned planes");
+  const long long tv = V * (E / 8);
+  const unsigned vb = (unsigned)((tv + 255) / 256);
+  const X2CPtr x = x2c(x_hi, x_lo);
+  const X2Ptr y = x2m(y_hi, y_lo);
+  if (Tn == 8) tpool_fwd_vec_x2_kernel<8><<<vb, 256, 0, stream>>>(x, y, V, E, mode_avg);
+  else if (Tn == 4) tpool_fwd_vec_x2_kernel<4><<<vb, 256, 0, stream>>>(x, y, V, E, mode_avg);
+  else tpool_fwd_vec_x2_kernel<2><<<vb, 256, 0, stream>>>(x, y, V, E, mode_avg);
+  return adamml_check_launch("tpool_fwd_x2");
+}
+
+int adamml_avgpool_fwd_x2(const void* x_hi, const void* x_lo, float* y, int IMGS, int HW, int C, long long y_ld,
+                          cudaStream_t stream) {
+  ADAMML_REQUIRE(IMGS > 0 && HW > 0 && C > 0, "avgpool: empty dims");
+  dim3 grid(IMGS, ceil_div(C, 32));
+  dim3 block(32, 8);
+  if (y_ld <= 0) y_ld = C;
+  avgpool_fwd_kernel<X2CPtr><<<grid, block, 0, stream>>>(x2c(x_hi, x_lo), y, HW, C, y_ld);
+  return adamml_check_launch("avgpool_fwd_x2");
 }
 
 int adamml_avgpool_bwd(const float* dy, void* dx, int IMGS, int HW, int C, long long dy_ld, int dtype,

@@ -99,13 +99,33 @@ class P2PStats:
             return None
         key = (id(pg), device.index)
         if key not in cls._instances:
+            # every rank must take the SAME path (a rank on NCCL while its peers spin in the peer-memory kernel is a
+            # hang): probe locally, agree with a MIN all-reduce, and only then build the arena; a failure after the
+            # agreement is fatal instead of a silent per-rank fallback
+            why = ""
             try:
-                cls._instances[key] = cls(pg, device)
-            except Exception as e:  # no symmetric memory (no P2P, old driver): NCCL path
-                print(f"[adamml_b200] sync-BN over peer memory unavailable ({type(e).__name__}: {e}); using NCCL",
-                      flush=True)
+                import torch.distributed._symmetric_memory as symm  # noqa: F401
+                ok = torch.cuda.is_available() and dist.get_backend(pg) == "nccl"
+                if not ok:
+                    why = "needs CUDA + an NCCL process group"
+            except Exception as e:  # no symmetric memory in this torch build
+                ok, why = False, f"{type(e).__name__}: {e}"
+            flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=pg)
+            if int(flag.item()) == 0:
+                print(f"[adamml_b200] sync-BN over peer memory unavailable on some rank ({why or 'a peer'}); "
+                      "all ranks use NCCL", flush=True)
                 cls._instances[key] = None
+            else:
+                cls._instances[key] = cls(pg, device)
         return cls._instances[key]
+
+    @classmethod
+    def check_all(cls):
+        """host-side check of every arena (synchronises): call at step / epoch boundaries"""
+        for inst in cls._instances.values():
+            if inst is not None:
+                inst.check()
 
     def slot(self, key, n):
         """-> (offset in doubles, float64 view [n]) of this layer's slot (allocated on first use, 256-byte aligned)"""

@@ -14,12 +14,30 @@ from .dist_utils import P2PStats, allreduce_stats, sync_bn_group
 from .ops import ACT_NONE, ACT_RELU, ACT_RELU6
 
 
+def _bn_key(bn):
+    """slot key of a BatchNorm layer in the peer-memory arena: its index in the model's module order (assigned by
+    assign_bn_keys, identical on every rank) rather than a per-process id()"""
+    return getattr(bn, "_adamml_bn_key", None) or ("id", id(bn))
+
+
+def assign_bn_keys(model):
+    """number the BatchNorm layers of `model` in module order (after convert_sync_batchnorm has replaced them)"""
+    k = 0
+    for m in model.modules():
+        if isinstance(m, torch.nn.modules.batchnorm._BatchNorm):
+            k += 1
+            m._adamml_bn_key = ("bn", k)
+
+
 class Exec:
     """State of one backbone pass."""
 
     def __init__(self, dtype, training, groups, save, param_needs_grad=True, lane=0):
         self.lane = lane  # stream / backbone index: the sync-BN peer-memory exchange keeps one flag row per lane
-        self.dtype = dtype
+        # x2 precision: the FORWARD pass runs on two-plane activations (ops.X2); the tape keeps their bf16 hi planes
+        # and the backward pass is the bf16 engine
+        self.x2 = dtype == ops.PREC_X2
+        self.dtype = torch.bfloat16 if self.x2 else dtype
         self.training = training
         self.G = groups
         self.save = save
@@ -55,8 +73,10 @@ class Exec:
             rec["ss"] = None
         if res_rec:
             res_rec["ss"] = None
+            res_rec["x"], res_rec["z"] = ops.hi_plane(res_rec["x"]), ops.hi_plane(res_rec["z"])
         if self.save:
-            rec.update(out=out, act=act, has_res=res is not None, res_rec=res_rec)
+            rec.update(x=ops.hi_plane(rec["x"]), z=ops.hi_plane(rec["z"]), out=ops.hi_plane(out), act=act,
+                       has_res=res is not None, res_rec=res_rec)
             self.tape.append(rec)
         return out
 
@@ -73,7 +93,7 @@ class Exec:
         p2p = P2PStats.get(pg, w.device) if pg is not None else None
         slot_off = None
         if p2p is not None:  # this rank's partial sums are produced straight into the layer's symmetric slot
-            slot_off, flat = p2p.slot((id(bn), "f"), G * Cout * 2)
+            slot_off, flat = p2p.slot((_bn_key(bn), "f"), G * Cout * 2)
             p2p_sums = flat.view(G, Cout, 2)
         if (not isinstance(x, ops.S2D) and not depthwise and w.shape[1] < 16 and (R, S) == (3, 3)
                 and ops.first_conv_s2d_ok(conv, w.shape[1], x.shape[1], x.shape[2], x.dtype)):
@@ -91,11 +111,12 @@ class Exec:
             wp = ops.pack_weight_dw(w.detach())
             z = ops.dwconv_fwd(x, wp, stride)
         else:
-            wp = ops.pack_weight(w.detach(), self.dtype)
+            wp = ops.pack_weight(w.detach(), ops.PREC_X2 if self.x2 else self.dtype)
             if self.training:
                 sums = p2p_sums if p2p is not None else torch.empty((G, Cout, 2), device=x.device, dtype=torch.float64)
             rows = x.shape[0] * ((x.shape[1] + 2 * pad - R) // stride + 1) * ((x.shape[2] + 2 * pad - S) // stride + 1)
             z, fused = ops.conv_fwd(x, wp, stride, pad, stats=sums, rows_per_group=rows // G)
+            wp = ops.hi_plane(wp)  # the backward pass multiplies by the bf16 weights
         C = z.shape[-1]
         count = z.numel() // C // G
         if self.training:
@@ -106,9 +127,11 @@ class Exec:
                 count = count * p2p.world
             elif pg is not None:
                 count = allreduce_stats(sums, count, pg)
+            if bn.momentum is None:
+                raise NotImplementedError("BatchNorm momentum=None (cumulative moving average) is not on the AdaMML "
+                                          "path (every reference BN uses the default momentum 0.1)")
             mi, ss = ops.bn_finalize(sums, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var,
-                                     count, bn.momentum if bn.momentum is not None else 0.1, bn.eps, C, G, True,
-                                     bn.track_running_stats)
+                                     count, bn.momentum, bn.eps, C, G, True, bn.track_running_stats)
             if bn.num_batches_tracked is not None:
                 bn.num_batches_tracked += G
         else:
@@ -139,7 +162,7 @@ class Exec:
         p2p = P2PStats.get(rec["pg"], z.device) if rec["pg"] is not None else None
         sums_out = slot_off = None
         if p2p is not None:
-            slot_off, flat = p2p.slot((id(bn), "b"), G * C * 2)
+            slot_off, flat = p2p.slot((_bn_key(bn), "b"), G * C * 2)
             sums_out = flat.view(G, C, 2)
         sums = ops.bn_bwd_reduce(dout, out, z, mi, G, act, mask_ss=mask_ss, gm_inplace=inplace, sums_out=sums_out)
         if inplace:
@@ -270,7 +293,7 @@ class Exec:
         if not self.save:
             return ops.maxpool_fwd(x)
         y, pos = ops.maxpool_fwd(x, want_pos=True)
-        self.tape.append(dict(x=x if pos is None else None, pos=pos, shape=tuple(x.shape)))
+        self.tape.append(dict(x=ops.hi_plane(x) if pos is None else None, pos=pos, shape=tuple(x.shape)))
         return y
 
     def maxpool_bwd(self, dy):
@@ -280,7 +303,7 @@ class Exec:
     def tpool(self, x, frames, mode_avg=False):
         y = ops.tpool_fwd(x, frames, mode_avg)
         if self.save:
-            self.tape.append(dict(x=x, frames=frames, avg=mode_avg))
+            self.tape.append(dict(x=ops.hi_plane(x), frames=frames, avg=mode_avg))
         return y
 
     def tpool_bwd(self, dy):
@@ -342,11 +365,15 @@ class BackboneFunction(torch.autograd.Function):
     def backward(ctx, dy):
         ex = ctx.ex
         if ex is None:
+            if getattr(ctx, "consumed", False):
+                raise RuntimeError("Trying to backward through the backbone a second time: its tape (saved "
+                                   "activations) was freed by the first backward; run the forward pass again")
             return (None,) * (4 + len(ctx.params))
         dy = dy.contiguous()
         ctx.net.run_backward(ex, dy)
         grads = tuple(ex.grads.get(p) if need else None for p, need in zip(ctx.params, ctx.needs_input_grad[4:]))
         ctx.ex = None
+        ctx.consumed = True
         return (None, None, None, None) + grads
 
 
@@ -384,8 +411,7 @@ def run_backbones_parallel(jobs):
         s = _side_stream(cur.device, i)
         s.wait_stream(cur)
         with torch.cuda.stream(s):
-            xt = x.t if isinstance(x, ops.S2D) else x
-            xt.record_stream(s)          # allocated on the caller's stream, consumed (and kept on the tape) here
+            x.record_stream(s)           # allocated on the caller's stream, consumed (and kept on the tape) here
             for v in (extra or {}).values():
                 if isinstance(v, torch.Tensor):
                     v.record_stream(s)

@@ -92,6 +92,10 @@ class AdaMML(nn.Module):
         drop=[per main modality [S*N*T', feat]]) replacing the torch RNG draws."""
         S = num_segments if num_segments else self.num_segments
         N = x[0].size(0)
+        if not self.__dict__.get("_bn_keys_done"):  # after a possible convert_sync_batchnorm (train_adamml.py:125-127)
+            from ..engine import assign_bn_keys
+            assign_bn_keys(self)
+            self.__dict__["_bn_keys_done"] = True
         p_x, m_x, S = self.data_layer(x, S)
         dev = x[0].device
         expo = noise["expo"] if noise else None

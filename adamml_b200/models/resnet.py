@@ -15,8 +15,11 @@ _LAYERS = {18: (2, 2, 2, 2), 34: (3, 4, 6, 3), 50: (3, 4, 6, 3), 101: (3, 4, 23,
 
 
 def default_compute_dtype():
+    """ADAMML_B200_PRECISION = x2 (default: two-plane forward, meets the 1e-3 / bit-exact-selection bar) | bf16 (speed
+    mode) | fp32 (exact CUDA-core engine); see ops.PREC_X2."""
     import os
-    return {"bf16": torch.bfloat16, "fp32": torch.float32}[os.environ.get("ADAMML_B200_PRECISION", "bf16")]
+    return {"x2": ops.PREC_X2, "bf16": torch.bfloat16, "fp32": torch.float32}[
+        os.environ.get("ADAMML_B200_PRECISION", "x2")]
 
 
 class _Block(nn.Module):
@@ -125,7 +128,7 @@ class ResNet(nn.Module):
         f = self.orig_num_frames
         c = x.shape[1] // (S * f)
         if ops.stem_s2d_ok(self.conv1, c, x.shape[2], x.shape[3], self.compute_dtype):
-            return ops.pack_frames_s2d(x, S, f, c, norm=norm)
+            return ops.pack_frames_s2d(x, S, f, c, norm=norm, x2=self.compute_dtype == ops.PREC_X2)
         return ops.pack_frames(x, S, f, c, self.compute_dtype, norm=norm)
 
     # ------------------------------------------------------------------ unimodal API (resnet.py:195)

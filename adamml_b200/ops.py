@@ -13,6 +13,82 @@ from ._lib import ACT_NONE, ACT_RELU, ACT_RELU6, call, dtype_code  # noqa: F401
 # "simt" = always the exact CUDA-core engine.
 TC_MODE = "auto"
 
+# Precision modes (the `compute_dtype` of a model):
+#   PREC_X2        default: forward activations / operands as two planes (hi bf16 + lo fp16 remainder, ~20 mantissa
+#                  bits), 4-product tcgen05 GEMMs with fp32 accumulation -> logits within 1e-3 of the reference's fp32
+#                  path and bit-exact policy selections; the backward pass runs on the hi planes in bf16.
+#   torch.bfloat16 speed mode: bf16 storage forward and backward (does NOT meet the 1e-3 bar).
+#   torch.float32  exact CUDA-core engine (fp32 math everywhere).
+PREC_X2 = "x2"
+
+
+class X2:
+    """Two-plane activation (include/adamml_b200.h "x2"): value = hi (bf16) + lo (fp16), both NHWC [IMGS, H, W, C]."""
+    __slots__ = ("hi", "lo")
+    dtype = PREC_X2
+
+    def __init__(self, hi, lo):
+        self.hi, self.lo = hi, lo
+
+    @staticmethod
+    def empty(shape, device):
+        return X2(torch.empty(shape, device=device, dtype=torch.bfloat16),
+                  torch.empty(shape, device=device, dtype=torch.float16))
+
+    @property
+    def shape(self):
+        return self.hi.shape
+
+    @property
+    def device(self):
+        return self.hi.device
+
+    def numel(self):
+        return self.hi.numel()
+
+    def record_stream(self, s):
+        self.hi.record_stream(s)
+        self.lo.record_stream(s)
+
+    def float(self):
+        """fp32 value (tests / fallbacks only)"""
+        return self.hi.float() + self.lo.float()
+
+
+class X2W:
+    """Four-plane weight operand of the x2 tensor-core path (adamml_pack_weight_x2): `planes` is one 2-byte tensor
+    [4, Cout, R, S, Cin]: b1 = bf16(w), b2 = bf16(w - b1), b3 = bf16(w - b1 - b2) and f = fp16(w) (plane 3 holds fp16
+    bits).  planes[0] is the bf16 OHWI operand of the backward pass."""
+    __slots__ = ("planes",)
+
+    def __init__(self, planes):
+        self.planes = planes
+
+    @property
+    def shape(self):
+        return self.planes.shape[1:]
+
+    @property
+    def hi(self):
+        return self.planes[0]
+
+    def cascade(self):
+        """fp64 value of b1 + b2 + b3 (what multiplies the hi plane)"""
+        return self.planes[:3].double().sum(0)
+
+    def f16(self):
+        """fp16(w) (what multiplies the lo plane)"""
+        return self.planes[3].view(torch.float16)
+
+
+def hi_plane(t):
+    """what the backward pass keeps of a forward tensor: the bf16 hi plane of an x2 activation"""
+    if isinstance(t, (X2, X2W)):
+        return t.hi
+    if isinstance(t, S2D) and t.lo is not None:
+        return S2D(t.t, t.C, t.H, t.W, t.R)
+    return t
+
 
 def _chk(t, dtype=None):
     assert t.is_cuda and t.is_contiguous(), "adamml_b200 ops need contiguous CUDA tensors"
@@ -48,6 +124,11 @@ def pack_frames(x, S, F, C, dtype, cpad=None, norm=None):
     N, SFC, H, W = x.shape
     assert SFC == S * F * C, (x.shape, S, F, C)
     cpad = cpad or C
+    if dtype == PREC_X2:
+        out = X2.empty((S * N * F, H, W, cpad), x.device)
+        call("pack_frames_x2", x, nm[0] if nm else None, nm[1] if nm else None, out.hi, out.lo, N, S, F, C, H, W, cpad,
+             int(nm is not None))
+        return out
     out = torch.empty((S * N * F, H, W, cpad), device=x.device, dtype=dtype)
     if nm is None:
         call("pack_frames", x, out, N, S, F, C, H, W, cpad, dtype_code(dtype))
@@ -62,6 +143,11 @@ def resize_frames(x, S, F, C, OH, OW, fstep, dtype, cpad=None, norm=None):
     assert SFC == S * F * C
     cpad = cpad or C
     Fk = (F + fstep - 1) // fstep
+    if dtype == PREC_X2:
+        out = X2.empty((S * N * Fk, OH, OW, cpad), x.device)
+        call("resize_frames_x2", x, nm[0] if nm else None, nm[1] if nm else None, out.hi, out.lo, N, S, F, C, H, W, OH,
+             OW, fstep, cpad, int(nm is not None))
+        return out
     out = torch.empty((S * N * Fk, OH, OW, cpad), device=x.device, dtype=dtype)
     if nm is None:
         call("resize_frames", x, out, N, S, F, C, H, W, OH, OW, fstep, cpad, dtype_code(dtype))
@@ -75,8 +161,9 @@ class S2D:
     [IMGS, H/2, W/2 + pads, Cs] (csrc/data_layer.cu); `R` = filter size (7: ResNet stem, 3: MobileNetV2 first conv),
     `taps` = (R+1)/2 s2d taps per axis; shape reports the logical NHWC input."""
 
-    def __init__(self, t, C, H, W, R):
+    def __init__(self, t, C, H, W, R, lo=None):
         self.t, self.C, self.H, self.W, self.R = t, C, H, W, R
+        self.lo = lo  # x2 mode: fp16 remainder plane of the same shape
         self.Cs = t.shape[-1]
         self.taps = (R + 1) // 2
 
@@ -90,18 +177,30 @@ class S2D:
 
     @property
     def dtype(self):
-        return self.t.dtype
+        return PREC_X2 if self.lo is not None else self.t.dtype
+
+    def record_stream(self, s):
+        self.t.record_stream(s)
+        if self.lo is not None:
+            self.lo.record_stream(s)
+
+
+def _select_rows(t, idx, clips):
+    if t.shape[0] % clips:
+        raise ValueError("select_clips: %d images do not split into %d clips" % (t.shape[0], clips))
+    T = t.shape[0] // clips
+    return t.view(clips, -1).index_select(0, idx).view((idx.numel() * T,) + tuple(t.shape[1:]))
 
 
 def select_clips(x, idx, clips):
     """x: NHWC image batch (or S2D operand) holding `clips` (segment, video) pairs of T consecutive frames each;
     -> the same layout restricted to the pairs listed in idx (int64, ascending)."""
-    t = x.t if isinstance(x, S2D) else x
-    if t.shape[0] % clips:
-        raise ValueError("select_clips: %d images do not split into %d clips" % (t.shape[0], clips))
-    T = t.shape[0] // clips
-    sel = t.view(clips, -1).index_select(0, idx).view((idx.numel() * T,) + tuple(t.shape[1:]))
-    return S2D(sel, x.C, x.H, x.W, x.R) if isinstance(x, S2D) else sel
+    if isinstance(x, X2):
+        return X2(_select_rows(x.hi, idx, clips), _select_rows(x.lo, idx, clips))
+    if isinstance(x, S2D):
+        return S2D(_select_rows(x.t, idx, clips), x.C, x.H, x.W, x.R,
+                   lo=_select_rows(x.lo, idx, clips) if x.lo is not None else None)
+    return _select_rows(x, idx, clips)
 
 
 def first_conv_s2d_ok(conv, C, H, W, dtype):
@@ -109,20 +208,25 @@ def first_conv_s2d_ok(conv, C, H, W, dtype):
     3x3/p1 (MobileNetV2 first conv), even-sized frames, bf16 mode."""
     k = conv.kernel_size
     ok_geom = (k == (7, 7) and conv.padding == (3, 3)) or (k == (3, 3) and conv.padding == (1, 1))
-    return (TC_MODE == "auto" and dtype == torch.bfloat16 and ok_geom and conv.stride == (2, 2) and conv.groups == 1
-            and H % 2 == 0 and W % 2 == 0 and 4 * C <= 64 and conv.out_channels % 8 == 0)
+    return (TC_MODE == "auto" and dtype in (torch.bfloat16, PREC_X2) and ok_geom and conv.stride == (2, 2)
+            and conv.groups == 1 and H % 2 == 0 and W % 2 == 0 and 4 * C <= 64 and conv.out_channels % 8 == 0)
 
 
 stem_s2d_ok = first_conv_s2d_ok
 
 
-def pack_frames_s2d(x, S, F, C, norm=None):
+def pack_frames_s2d(x, S, F, C, norm=None, x2=False):
     """NCHW fp32 (or uint8 + norm) clip -> S2D operand of the 7x7 ResNet stem (two zero columns on either side)."""
     nm = _u8_norm(x, C, norm)
     N, SFC, H, W = x.shape
     assert SFC == S * F * C, (x.shape, S, F, C)
     Cs = ((4 * C + 15) // 16) * 16
     out = torch.empty((S * N * F, H // 2, W // 2 + 4, Cs), device=x.device, dtype=torch.bfloat16)
+    if x2:
+        lo = torch.empty_like(out, dtype=torch.float16)
+        call("pack_frames_s2d_x2", x, nm[0] if nm else None, nm[1] if nm else None, out, lo, N, S, F, C, H, W, Cs,
+             int(nm is not None))
+        return S2D(out, C, H, W, 7, lo=lo)
     if nm is None:
         call("pack_frames_s2d", x, out, N, S, F, C, H, W, Cs)
     else:
@@ -131,25 +235,34 @@ def pack_frames_s2d(x, S, F, C, norm=None):
 
 
 def nhwc_to_s2d(x, R):
-    """NHWC bf16 image batch -> S2D operand of an RxR stride-2 first conv (pad columns: T/2 left, T/2-1 right)."""
-    _chk(x, torch.bfloat16)
+    """NHWC bf16 (or x2) image batch -> S2D operand of an RxR stride-2 first conv (pad columns: T/2 left, T/2-1
+    right).  The kernel is a pure 2-byte re-layout, so an x2 input is converted plane by plane."""
     IMGS, H, W, C = x.shape
     T = (R + 1) // 2
     Cs = ((4 * C + 7) // 8) * 8
     padl, padr = T // 2, T // 2 - 1
-    out = torch.empty((IMGS, H // 2, W // 2 + padl + padr, Cs), device=x.device, dtype=torch.bfloat16)
-    call("nhwc_to_s2d", x, out, IMGS, C, H, W, Cs, padl, padr)
-    return S2D(out, C, H, W, R)
+    planes = []
+    for t in ((x.hi, x.lo) if isinstance(x, X2) else (_chk(x, torch.bfloat16),)):
+        out = torch.empty((IMGS, H // 2, W // 2 + padl + padr, Cs), device=t.device, dtype=t.dtype)
+        call("nhwc_to_s2d", t, out, IMGS, C, H, W, Cs, padl, padr)
+        planes.append(out)
+    return S2D(planes[0], C, H, W, R, lo=planes[1] if len(planes) > 1 else None)
 
 
 def stem_conv_fwd(xs, w_oihw, stats=None, imgs_per_group=0):
     """xs: S2D, w_oihw: fp32 [Cout, C, R, R] parameter -> z bf16 [IMGS, H/2, W/2, Cout] (+ fused BN statistics)."""
     Cout = w_oihw.shape[0]
     T = xs.taps
-    wp = torch.empty((Cout, T, T, xs.Cs), device=xs.device, dtype=torch.bfloat16)
-    call("pack_weight_stem", w_oihw, wp, Cout, xs.C, xs.Cs, xs.R)
     IMGS, Hs, Wp, Cs = xs.t.shape
     Ho, Wo = xs.H // 2, xs.W // 2
+    if xs.lo is not None:  # x2 planes
+        wp = torch.empty((4, Cout, T, T, xs.Cs), device=xs.device, dtype=torch.bfloat16)
+        call("pack_weight_x2", w_oihw, wp, Cout, xs.C, xs.R, xs.R, xs.Cs, 1)
+        z = X2.empty((IMGS, Ho, Wo, Cout), xs.device)
+        call("tc_stem_conv_x2", xs.t, xs.lo, wp, z.hi, z.lo, IMGS, Hs, Wp, Cs, Cout, Ho, Wo, T, stats, imgs_per_group)
+        return z
+    wp = torch.empty((Cout, T, T, xs.Cs), device=xs.device, dtype=torch.bfloat16)
+    call("pack_weight_stem", w_oihw, wp, Cout, xs.C, xs.Cs, xs.R)
     z = torch.empty((IMGS, Ho, Wo, Cout), device=xs.device, dtype=torch.bfloat16)
     call("tc_stem_conv_bf16", xs.t, wp, z, IMGS, Hs, Wp, Cs, Cout, Ho, Wo, T, stats, imgs_per_group)
     return z
@@ -171,6 +284,10 @@ def pack_weight(w, dtype, cin_pad=None):
     _chk(w, torch.float32)
     Cout, Cin, R, S = w.shape
     cin_pad = cin_pad or Cin
+    if dtype == PREC_X2:
+        out = torch.empty((4, Cout, R, S, cin_pad), device=w.device, dtype=torch.bfloat16)
+        call("pack_weight_x2", w, out, Cout, Cin, R, S, cin_pad, 0)
+        return X2W(out)
     if R == 1 and S == 1 and cin_pad == Cin and dtype == torch.float32:
         return w.view(Cout, 1, 1, Cin)
     out = torch.empty((Cout, R, S, cin_pad), device=w.device, dtype=dtype)
@@ -224,6 +341,8 @@ def conv_fwd(x, w, stride, pad, out=None, stats=None, rows_per_group=0):
     If `stats` (double [G,Cout,2]) is given and the tcgen05 engine takes the layer, the BN
     batch statistics are produced by the GEMM epilogue and True is returned as second value.
     """
+    if isinstance(x, X2):
+        return _conv_fwd_x2(x, w, stride, pad, stats, rows_per_group)
     _chk(x); _chk(w, x.dtype)
     IMGS, H, W, Cin = x.shape
     Cout, R, S, Cw = w.shape
@@ -240,6 +359,25 @@ def conv_fwd(x, w, stride, pad, out=None, stats=None, rows_per_group=0):
         return out, stats is not None
     call("simt_conv_fwd", x, w, out, IMGS, H, W, Cin, Cout, R, S, stride, pad, Ho, Wo, 0, 0, 0, dtype_code(x.dtype))
     return out, False
+
+
+def _conv_fwd_x2(x, w, stride, pad, stats, rows_per_group):
+    """x2 forward convolution: x, w are X2 (w from pack_weight(.., PREC_X2)) -> (X2 z, stats fused?)."""
+    IMGS, H, W, Cin = x.shape
+    Cout, R, S, Cw = w.shape
+    assert Cw == Cin and isinstance(w, X2W), (w.shape, x.shape)
+    Ho, Wo = conv_out_hw(H, W, R, S, stride, pad)
+    if Cin % 8 or Cout % 8 or R * S > 49 or stride not in (1, 2) or TC_MODE != "auto":
+        raise NotImplementedError("x2 precision needs tcgen05-shaped dense convolutions (Cin, Cout multiples of 8); "
+                                  "got Cin=%d Cout=%d %dx%d stride %d" % (Cin, Cout, R, S, stride))
+    z = X2.empty((IMGS, Ho, Wo, Cout), x.device)
+    if R == 1 and S == 1 and stride == 1 and pad == 0:
+        call("tc_gemm_x2", x.hi, x.lo, w.planes, z.hi, z.lo, IMGS * H * W, Cout, Cin, stats, rows_per_group)
+    else:
+        ipg = rows_per_group // (Ho * Wo) if stats is not None else 0
+        call("tc_conv_x2", x.hi, x.lo, w.planes, z.hi, z.lo, IMGS, H, W, Cin, Cout, R, S, stride, pad, Ho, Wo, stats,
+             ipg)
+    return z, stats is not None
 
 
 def tc_dgrad_ok(dtype, Cout, Cin, R, S, stride):
@@ -346,10 +484,15 @@ def pack_weight_dw(w):
 
 def dwconv_fwd(x, w, stride):
     """w: tap-major [9, C] (pack_weight_dw)."""
-    _chk(x); _chk(w, torch.float32)
+    _chk(w, torch.float32)
     assert w.shape == (9, x.shape[-1]), "depthwise weights must be tap-major [9, C] (ops.pack_weight_dw)"
     IMGS, H, W, C = x.shape
     Ho, Wo = conv_out_hw(H, W, 3, 3, stride, 1)
+    if isinstance(x, X2):
+        y = X2.empty((IMGS, Ho, Wo, C), x.device)
+        call("dwconv_fwd_x2", x.hi, x.lo, w, y.hi, y.lo, IMGS, H, W, C, stride, Ho, Wo)
+        return y
+    _chk(x)
     y = torch.empty((IMGS, Ho, Wo, C), device=x.device, dtype=x.dtype)
     call("dwconv_fwd", x, w, y, IMGS, H, W, C, stride, Ho, Wo, dtype_code(x.dtype))
     return y
@@ -377,7 +520,10 @@ def bn_stats(z, G, out=None):
     C = z.shape[-1]
     rows = z.numel() // C
     sums = out if out is not None else torch.empty((G, C, 2), device=z.device, dtype=torch.float64)
-    call("bn_stats", z, sums, rows // G, C, G, dtype_code(z.dtype))
+    if isinstance(z, X2):
+        call("bn_stats_x2", z.hi, z.lo, sums, rows // G, C, G)
+    else:
+        call("bn_stats", z, sums, rows // G, C, G, dtype_code(z.dtype))
     return sums
 
 
@@ -393,6 +539,13 @@ def bn_finalize(sums, gamma, beta, running_mean, running_var, count, momentum, e
 def bn_apply(z, scale_shift, G, act, res=None, res_z=None, res_ss=None, out=None):
     C = z.shape[-1]
     rows = z.numel() // C
+    if isinstance(z, X2):
+        if out is None:
+            out = X2.empty(z.shape, z.device)
+        call("bn_apply_x2", z.hi, z.lo, scale_shift, res.hi if res is not None else None,
+             res.lo if res is not None else None, res_z.hi if res_z is not None else None,
+             res_z.lo if res_z is not None else None, res_ss, out.hi, out.lo, rows // G, C, G, act)
+        return out
     if out is None:
         out = torch.empty_like(z)
     call("bn_apply", z, scale_shift, res, res_z, res_ss, out, rows // G, C, G, act, dtype_code(z.dtype))
@@ -446,6 +599,11 @@ def maxpool_fwd(x, want_pos=False):
     """-> y, or (y, pos) with pos = uint8 window position of every maximum (for the gather backward)."""
     IMGS, H, W, C = x.shape
     Ho, Wo = conv_out_hw(H, W, 3, 3, 2, 1)
+    if isinstance(x, X2):
+        y = X2.empty((IMGS, Ho, Wo, C), x.device)
+        pos = torch.empty((IMGS, Ho, Wo, C), device=x.device, dtype=torch.uint8) if want_pos else None
+        call("maxpool3x3s2_fwd_x2", x.hi, x.lo, y.hi, y.lo, pos, IMGS, H, W, C, Ho, Wo)
+        return (y, pos) if want_pos else y
     y = torch.empty((IMGS, Ho, Wo, C), device=x.device, dtype=x.dtype)
     pos = None
     if want_pos and C % (8 if x.dtype == torch.bfloat16 else 4) == 0:
@@ -467,6 +625,10 @@ def tpool_fwd(x, T, mode_avg=False):
     IMGS, H, W, C = x.shape
     V = IMGS // T
     To = (T + 2 - 3) // 2 + 1
+    if isinstance(x, X2):
+        y = X2.empty((V * To, H, W, C), x.device)
+        call("tpool_fwd_x2", x.hi, x.lo, y.hi, y.lo, V, T, H * W * C, int(mode_avg))
+        return y
     y = torch.empty((V * To, H, W, C), device=x.device, dtype=x.dtype)
     call("tpool_fwd", x, y, V, T, H * W * C, int(mode_avg), dtype_code(x.dtype))
     return y
@@ -483,7 +645,10 @@ def avgpool_fwd(x, out=None, out_ld=0):
     IMGS, H, W, C = x.shape
     if out is None:
         out = torch.empty((IMGS, C), device=x.device, dtype=torch.float32)
-    call("avgpool_fwd", x, out, IMGS, H * W, C, out_ld or out.stride(0), dtype_code(x.dtype))
+    if isinstance(x, X2):
+        call("avgpool_fwd_x2", x.hi, x.lo, out, IMGS, H * W, C, out_ld or out.stride(0))
+    else:
+        call("avgpool_fwd", x, out, IMGS, H * W, C, out_ld or out.stride(0), dtype_code(x.dtype))
     return out
 
 

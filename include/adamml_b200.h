@@ -250,6 +250,52 @@ int adamml_fuse_fwd(const float* logits, const float* dec, const float* lf, floa
 int adamml_fuse_bwd(const float* g, const float* logits, const float* dec, const float* lf, float* dlogits,
                     float* ddec, float* dlf, int M, int S, int N, int C, cudaStream_t stream);
 
+/* ---- "x2" forward path: two-plane activations (default precision mode) ----
+ * north_star asks for logits within 1e-3 of the reference's fp32 path and bit-exact policy selections; bf16
+ * storage (8 mantissa bits) misses that by two orders of magnitude on these 50-layer BatchNorm stacks.  In x2 mode
+ * every forward activation, weight operand and conv output is stored as TWO planes, hi = bf16(v) and
+ * lo = fp16(v - hi) (about 20 mantissa bits at bf16 range, 4 bytes per element).  A tcgen05.mma needs both operands
+ * in the same 16-bit format, so the (small) weight operands are packed as FOUR planes `w4` [4][Cout][R][S][Cin]:
+ * the bf16 cascade b1 = bf16(w), b2 = bf16(w - b1), b3 = bf16(w - b1 - b2) and f = fp16(w); every K step issues
+ * x_hi*b1 + x_hi*b2 + x_hi*b3 (bf16 x bf16) + x_lo*f (fp16 x fp16) into one fp32 TMEM accumulator.
+ * The hi planes are ordinary bf16 tensors: they are what the backward pass keeps and reads (bf16 engine above), the
+ * lo planes die with the forward pass.  Same reference call sites as the entry points they mirror; every `_hi` /
+ * `_lo` pair has the shape of the bf16 tensor it replaces, channel counts are multiples of 8. */
+#define ADAMML_X2 2
+int adamml_pack_frames_x2(const void* x, const float* mean, const float* stdv, void* out_hi, void* out_lo, int N, int S,
+                          int F, int C, int H, int W, int Cpad, int is_u8, cudaStream_t stream);
+int adamml_resize_frames_x2(const void* x, const float* mean, const float* stdv, void* out_hi, void* out_lo, int N,
+                            int S, int F, int C, int H, int W, int OH, int OW, int fstep, int Cpad, int is_u8,
+                            cudaStream_t stream);
+int adamml_pack_frames_s2d_x2(const void* x, const float* mean, const float* stdv, void* out_hi, void* out_lo, int N,
+                              int S, int F, int C, int H, int W, int Cs, int is_u8, cudaStream_t stream);
+/* OIHW fp32 -> the four OHWI planes w4 (stem = 1: the space-to-depth first-conv operand, Cin = C, CinPad = Cs,
+ * R = S = 7 | 3) */
+int adamml_pack_weight_x2(const float* w_oihw, void* w4, int Cout, int Cin, int R, int S, int CinPad, int stem,
+                          cudaStream_t stream);
+int adamml_tc_gemm_x2(const void* A_hi, const void* A_lo, const void* B4, void* D_hi, void* D_lo, long long M,
+                      int Ncols, int K, double* stats, long long rows_per_group, cudaStream_t stream);
+int adamml_tc_conv_x2(const void* x_hi, const void* x_lo, const void* w4, void* y_hi, void* y_lo, int IMGS, int H,
+                      int W, int Cin, int Cout, int R, int S, int stride, int pad, int Ho, int Wo, double* stats,
+                      int imgs_per_group, cudaStream_t stream);
+int adamml_tc_stem_conv_x2(const void* xs_hi, const void* xs_lo, const void* w4, void* y_hi, void* y_lo, int IMGS,
+                           int Hs, int Wp, int Cs, int Cout, int Ho, int Wo, int taps, double* stats,
+                           int imgs_per_group, cudaStream_t stream);
+int adamml_dwconv_fwd_x2(const void* x_hi, const void* x_lo, const float* w, void* y_hi, void* y_lo, int IMGS, int H,
+                         int W, int C, int stride, int Ho, int Wo, cudaStream_t stream);
+int adamml_bn_stats_x2(const void* z_hi, const void* z_lo, double* sums, long long rows_per_group, int C, int G,
+                       cudaStream_t stream);
+int adamml_bn_apply_x2(const void* z_hi, const void* z_lo, const float* scale_shift, const void* res_hi,
+                       const void* res_lo, const void* resz_hi, const void* resz_lo, const float* res_scale_shift,
+                       void* out_hi, void* out_lo, long long rows_per_group, int C, int G, int act,
+                       cudaStream_t stream);
+int adamml_maxpool3x3s2_fwd_x2(const void* x_hi, const void* x_lo, void* y_hi, void* y_lo, unsigned char* pos,
+                               int IMGS, int H, int W, int C, int Ho, int Wo, cudaStream_t stream);
+int adamml_tpool_fwd_x2(const void* x_hi, const void* x_lo, void* y_hi, void* y_lo, long long V, int Tn, long long E,
+                        int mode_avg, cudaStream_t stream);
+int adamml_avgpool_fwd_x2(const void* x_hi, const void* x_lo, float* y, int IMGS, int HW, int C, long long y_ld,
+                          cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -32,6 +32,11 @@ CASES = {
     # causality_modeling=None: per-segment FC policy, one Gumbel draw over all rows (policy_net.py:330-339)
     "adamml_rgb_sound_nocausal_train": dict(kind="adamml", modality=["rgb", "sound"], N=2, S=2, hw=64, training=True,
                                             causality=None),
+    # the benchmark's own segment counts: S = 5 in training (5-step LSTM recurrence, 5 sequential running-stat updates,
+    # README.md:89-95) and num_segments = val_num_clips = 10 in validation (utils/utils.py:458, opts.py:122)
+    "adamml_rgb_sound_train_s5": dict(kind="adamml", modality=["rgb", "sound"], N=2, S=5, hw=96, training=True),
+    "adamml_rgb_sound_eval_s10": dict(kind="adamml", modality=["rgb", "sound"], N=2, S=5, S_run=10, hw=96,
+                                      training=False),
 }
 
 

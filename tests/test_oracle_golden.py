@@ -6,7 +6,8 @@ import torch
 from util import O, fingerprint, load_golden, rel
 
 CASES = ["resnet50_rgb_b2", "adamml_rgb_sound_eval", "adamml_rgb_flow_train", "adamml_rgb_sound_flow_train",
-         "adamml_rgb_sound_train", "adamml_rgb_sound_nocausal_train"]
+         "adamml_rgb_sound_train", "adamml_rgb_sound_nocausal_train", "adamml_rgb_sound_train_s5",
+         "adamml_rgb_sound_eval_s10"]
 
 
 @pytest.mark.parametrize("name", CASES)

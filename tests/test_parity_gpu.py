@@ -15,7 +15,8 @@ from util import (O, assert_grads_as_good_as_reference, compare_grads, fingerpri
 pytestmark = pytest.mark.gpu
 
 CASES = ["resnet50_rgb_b2", "adamml_rgb_sound_eval", "adamml_rgb_flow_train", "adamml_rgb_sound_flow_train",
-         "adamml_rgb_sound_train", "adamml_rgb_sound_nocausal_train"]
+         "adamml_rgb_sound_train", "adamml_rgb_sound_nocausal_train", "adamml_rgb_sound_train_s5",
+         "adamml_rgb_sound_eval_s10"]
 LOGIT_TOL = 1e-3
 
 

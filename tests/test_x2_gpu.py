@@ -1,0 +1,314 @@
+"""x2 precision mode (the DEFAULT mode, the one bench.py measures): two-plane forward activations
+(hi bf16 + lo fp16 remainder), 4-product tcgen05 GEMMs, bf16 backward on the hi planes.
+
+Bar (BASELINE.json north_star): logits within 1e-3 relative (max|a-b| / max|b|) of the reference's fp32 path on every
+golden, policy selections bit-exact under a fixed seed.  Kernel-level checks compare every x2 entry point with a
+float64 torch computation on the SAME (plane-rounded) inputs, so only accumulation and output rounding differ."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from util import O, load_golden, namespace, noise_for_model, oracle_run, rel
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_TOL = 1e-3
+CASES = ["resnet50_rgb_b2", "adamml_rgb_sound_eval", "adamml_rgb_flow_train", "adamml_rgb_sound_flow_train",
+         "adamml_rgb_sound_train", "adamml_rgb_sound_nocausal_train", "adamml_rgb_sound_train_s5",
+         "adamml_rgb_sound_eval_s10"]
+
+
+def split(t):
+    """fp32 tensor -> ops.X2 planes (torch restatement of x2_split, csrc/common.cuh)"""
+    from adamml_b200 import ops
+    hi = t.bfloat16()
+    lo = (t - hi.float()).half()
+    return ops.X2(hi.contiguous(), lo.contiguous())
+
+
+def nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def nchw(x):
+    return x.permute(0, 3, 1, 2).contiguous()
+
+
+def err(a, b):
+    a, b = a.double(), b.double()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+# one x2 store rounds to ~2^-20 relative (1e-6).  The fp32 accumulation in TMEM TRUNCATES (no round-to-nearest), so the
+# error of a K-term sum grows ~linearly with K: measured 6e-6 at K = 1152, 1.8e-5 at K = 4608 (layer4's 3x3).
+X2_TOL = 4e-6
+
+
+def x2_tol(K):
+    return max(X2_TOL, 8e-9 * K)
+
+
+@pytest.mark.parametrize("M,N,K", [(1000, 64, 64), (777, 16, 96), (4096, 96, 16), (513, 128, 256), (2048, 256, 64),
+                                   (300, 2048, 512), (129, 24, 144), (640, 1280, 320)])
+def test_tc_gemm_x2(cuda, M, N, K):
+    from adamml_b200 import ops
+    g = torch.Generator().manual_seed(M + N + K)
+    a = split(torch.randn(M, 1, 1, K, generator=g).to(cuda))
+    w = torch.randn(N, K, 1, 1, generator=g).to(cuda) / K ** 0.5
+    wp = ops.pack_weight(w.contiguous(), ops.PREC_X2)
+    G = 2 if M % 2 == 0 else 1
+    sums = torch.empty((G, N, 2), device=cuda, dtype=torch.float64)
+    z, fused = ops.conv_fwd(a, wp, 1, 0, stats=sums, rows_per_group=M // G)
+    assert fused
+    # exactly what the kernel multiplies: hi * (b1 + b2 + b3) + lo * fp16(w), accumulated in fp32
+    ref = (a.hi.double().view(M, K) @ wp.cascade().view(N, K).t()
+           + a.lo.double().view(M, K) @ wp.f16().double().view(N, K).t())
+    assert err(z.float().view(M, N), ref) < X2_TOL
+    # ... and that is the product of the full-precision operands to ~2^-20
+    assert err(z.float().view(M, N), a.float().double().view(M, K) @ w.double().view(N, K).t()) < 1e-5
+    zz = z.float().double().view(G, M // G, N)
+    assert err(sums[..., 0], zz.sum(1)) < 1e-9 + 1e-6
+    assert err(sums[..., 1], (zz * zz).sum(1)) < 1e-6
+    # the bf16 cascade carries the parameter to 24 bits, plane 3 is its fp16 rounding
+    assert err(wp.cascade().view(N, K), w.view(N, K)) < 2e-7
+    assert torch.equal(wp.f16().view(N, K), w.view(N, K).half())
+
+
+@pytest.mark.parametrize("case", [
+    # IMGS,H,W,Cin,Cout,R,stride,pad
+    (4, 14, 14, 64, 64, 3, 1, 1),
+    (3, 15, 13, 32, 48, 3, 2, 1),
+    (2, 28, 28, 128, 128, 3, 2, 1),
+    (2, 14, 14, 128, 256, 1, 2, 0),
+    (2, 7, 7, 512, 512, 3, 1, 1),
+])
+def test_tc_conv_x2(cuda, case):
+    from adamml_b200 import ops
+    IMGS, H, W, Cin, Cout, R, stride, pad = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = split(nhwc(torch.randn(IMGS, Cin, H, W, generator=g)).to(cuda))
+    w = (torch.randn(Cout, Cin, R, R, generator=g) / (Cin * R * R) ** 0.5).to(cuda)
+    wp = ops.pack_weight(w.contiguous(), ops.PREC_X2)
+    G = 2 if IMGS % 2 == 0 else 1
+    sums = torch.empty((G, Cout, 2), device=cuda, dtype=torch.float64)
+    Ho, Wo = ops.conv_out_hw(H, W, R, R, stride, pad)
+    z, fused = ops.conv_fwd(x, wp, stride, pad, stats=sums, rows_per_group=IMGS * Ho * Wo // G)
+    assert fused
+    ref = (F.conv2d(nchw(x.hi.double()), wp.cascade().permute(0, 3, 1, 2), None, stride, pad)  # OHWI -> OIHW
+           + F.conv2d(nchw(x.lo.double()), wp.f16().double().permute(0, 3, 1, 2), None, stride, pad))
+    assert err(nchw(z.float()), ref) < x2_tol(Cin * R * R)
+    assert err(nchw(z.float()), F.conv2d(nchw(x.float().double()), w.double(), None, stride, pad)) < 4e-5
+    zz = z.float().double().view(G, -1, Cout)
+    assert err(sums[..., 0], zz.sum(1)) < 1e-6
+    assert err(sums[..., 1], (zz * zz).sum(1)) < 1e-6
+
+
+@pytest.mark.parametrize("C,R,hw", [(3, 7, 64), (10, 7, 32), (1, 3, 64), (3, 3, 40), (15, 3, 32)])
+def test_first_conv_x2(cuda, C, R, hw):
+    """ResNet stem (7x7/s2/p3 on the s2d operand written by the data layer) and MobileNetV2 first conv (3x3/s2/p1
+    through nhwc_to_s2d) on x2 planes against F.conv2d in float64."""
+    from adamml_b200 import ops
+    g = torch.Generator().manual_seed(C * R)
+    N, S, Fr = 2, 2, 2
+    x = torch.randn(N, S * Fr * C, hw, hw, generator=g).to(cuda)
+    Cout = 64 if R == 7 else 32
+    w = (torch.randn(Cout, C, R, R, generator=g) / (C * R * R) ** 0.5).to(cuda)
+    if R == 7:
+        xs = ops.pack_frames_s2d(x, S, Fr, C, x2=True)
+    else:
+        xs = ops.nhwc_to_s2d(ops.pack_frames(x, S, Fr, C, ops.PREC_X2), 3)
+    sums = torch.empty((S, Cout, 2), device=cuda, dtype=torch.float64)
+    z = ops.stem_conv_fwd(xs, w.contiguous(), stats=sums, imgs_per_group=N * Fr)
+    frames = x.view(N, S, Fr, C, hw, hw).transpose(0, 1).reshape(S * N * Fr, C, hw, hw)
+    fr = split(frames)
+    ref = (F.conv2d(fr.hi.double(), w.double(), None, 2, R // 2)
+           + F.conv2d(fr.lo.double(), w.half().double(), None, 2, R // 2))
+    assert err(nchw(z.float()), ref) < X2_TOL
+    zz = z.float().double().view(S, -1, Cout)
+    assert err(sums[..., 0], zz.sum(1)) < 1e-6
+
+
+def test_bn_apply_and_stats_x2(cuda):
+    from adamml_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    G, rows, C = 2, 500, 96
+    z = split(torch.randn(G * rows, 1, 1, C, generator=g).to(cuda) * 3 + 1)
+    res = split(torch.randn(G * rows, 1, 1, C, generator=g).to(cuda))
+    rz = split(torch.randn(G * rows, 1, 1, C, generator=g).to(cuda))
+    ss = torch.randn(G, C, 2, generator=g).to(cuda)
+    rss = torch.randn(G, C, 2, generator=g).to(cuda)
+    zf, rf, rzf = (t.float().double().view(G, rows, C) for t in (z, res, rz))
+    lin = zf * ss[:, None, :, 0].double() + ss[:, None, :, 1].double()
+    for act, fn in ((ops.ACT_NONE, lambda t: t), (ops.ACT_RELU, torch.relu), (ops.ACT_RELU6, lambda t: t.clamp(0, 6))):
+        out = ops.bn_apply(z, ss, G, act)
+        assert err(out.float().view(G, rows, C), fn(lin)) < 2e-6
+        out = ops.bn_apply(z, ss, G, act, res=res)
+        assert err(out.float().view(G, rows, C), fn(lin + rf)) < 2e-6
+        out = ops.bn_apply(z, ss, G, act, res_z=rz, res_ss=rss)
+        ref = fn(lin + rzf * rss[:, None, :, 0].double() + rss[:, None, :, 1].double())
+        assert err(out.float().view(G, rows, C), ref) < 2e-6
+    sums = ops.bn_stats(z, G)
+    assert err(sums[..., 0], zf.sum(1)) < 1e-6
+    assert err(sums[..., 1], (zf * zf).sum(1)) < 1e-6
+
+
+@pytest.mark.parametrize("stride", [1, 2])
+def test_dwconv_fwd_x2(cuda, stride):
+    from adamml_b200 import ops
+    g = torch.Generator().manual_seed(stride)
+    IMGS, H, W, C = 3, 19, 22, 96
+    x = split(nhwc(torch.randn(IMGS, C, H, W, generator=g)).to(cuda))
+    w = torch.randn(C, 1, 3, 3, generator=g).to(cuda) / 3
+    y = ops.dwconv_fwd(x, ops.pack_weight_dw(w.contiguous()), stride)
+    ref = F.conv2d(nchw(x.float().double()), w.double(), None, stride, 1, 1, C)
+    assert err(nchw(y.float()), ref) < 2e-6
+
+
+def test_pools_x2(cuda):
+    from adamml_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    IMGS, H, W, C = 8, 14, 14, 64
+    xf = nhwc(torch.randn(IMGS, C, H, W, generator=g)).to(cuda)
+    x = split(xf)
+    xr = nchw(x.float())
+    y, pos = ops.maxpool_fwd(x, want_pos=True)
+    assert torch.equal(nchw(y.float()), F.max_pool2d(xr, 3, 2, 1))
+    # recorded positions drive the bf16 backward: same as the positions of a bf16 pool wherever the hi planes decide
+    dy = torch.randn(y.shape, generator=g).to(cuda).bfloat16()
+    dx = ops.maxpool_bwd(None, dy, pos=pos, x_shape=tuple(x.shape))
+    xr2 = xr.clone().requires_grad_(True)
+    F.max_pool2d(xr2, 3, 2, 1).backward(nchw(dy.float()))
+    assert err(nchw(dx.float()), xr2.grad) < 1e-2
+    for T in (2, 4, 8):
+        yt = ops.tpool_fwd(x, T)
+        v = xr.view(IMGS // T, T, C, H, W).transpose(1, 2)
+        ref = F.max_pool3d(v, (3, 1, 1), (2, 1, 1), (1, 0, 0)).transpose(1, 2).reshape(-1, C, H, W)
+        assert torch.equal(nchw(yt.float()), ref)
+    f = ops.avgpool_fwd(x)
+    assert err(f, xr.double().mean((2, 3))) < 1e-6
+
+
+def test_data_layer_x2(cuda):
+    from adamml_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    N, S, Fr, C, hw = 2, 2, 4, 3, 48
+    x = torch.randn(N, S * Fr * C, hw, hw, generator=g).to(cuda)
+    p = ops.pack_frames(x, S, Fr, C, ops.PREC_X2)
+    frames = x.view(N, S, Fr, C, hw, hw).transpose(0, 1).reshape(S * N * Fr, C, hw, hw)
+    assert err(nchw(p.float()), frames) < 2e-6
+    r = ops.resize_frames(x, S, Fr, C, 32, 32, 2, ops.PREC_X2)
+    ref = F.interpolate(x, size=(32, 32), mode="bilinear").view(N, S, Fr, C, 32, 32)[:, :, ::2]
+    ref = ref.transpose(0, 1).reshape(-1, C, 32, 32)
+    assert err(nchw(r.float()), ref) < 2e-6
+    # the planes are exactly the x2 split of the fp32 result
+    r32 = ops.resize_frames(x, S, Fr, C, 32, 32, 2, torch.float32)
+    s = split(r32)
+    assert torch.equal(r.hi, s.hi) and torch.equal(r.lo, s.lo)
+
+
+# ------------------------------------------------------------------------------------------ whole-model parity
+def build(case, cuda, dtype=None):
+    from adamml_b200 import ops
+    from adamml_b200.models import build_model
+    model, arch = build_model(namespace(case, compute_dtype=dtype or ops.PREC_X2))
+    shapes = {k: v.shape for k, v in model.state_dict().items()}
+    model.load_state_dict(O.fill_state_dict(shapes, seed=0), strict=True)
+    return model.to(cuda), arch
+
+
+def run_product(model, case, g_seed, cuda):
+    from test_parity_gpu import run_product as rp
+    return rp(model, case, g_seed, cuda)
+
+
+def cosine(a, b):
+    a, b = a.double().flatten().cpu(), b.double().flatten().cpu()
+    return (a @ b / (a.norm() * b.norm()).clamp_min(1e-300)).item()
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_default_mode_matches_reference_golden(cuda, name):
+    """THE parity gate of the mode bench.py measures: logits within 1e-3 of the reference's recorded logits and
+    policy selections bit-exact, on every golden (incl. the S=5 train / S=10 eval goldens at the benchmark's S)."""
+    from adamml_b200.models.resnet import default_compute_dtype
+    from adamml_b200 import ops
+    assert default_compute_dtype() == ops.PREC_X2, "the default precision mode must be the parity-passing one"
+    g = load_golden(name)
+    case = g["case"]
+    model, arch = build(case, cuda)
+    assert arch == g["arch"]
+    logits, dec, loss = run_product(model, case, g["seed"], cuda)
+    e = rel(logits, g["logits"])
+    print(f"x2 {name}: logits rel {e:.2e}")
+    assert e < LOGIT_TOL
+    if dec is not None:
+        assert torch.equal(dec.detach().cpu(), g["decisions"]), "policy selections must be bit-exact"
+    assert abs(loss.item() - g["loss"].item()) < 1e-3 * max(1.0, abs(g["loss"].item()))
+    if not case["training"]:
+        return
+    loss.backward()
+    torch.cuda.synchronize()
+    sd = model.state_dict()
+    from util import fingerprint
+    for k, fp in g["running_fp"].items():
+        assert rel(fingerprint(sd[k])[1], fp[1]) < 1e-4, k
+    for k, v in g["num_batches_tracked"].items():
+        assert int(sd[k]) == v, k
+
+
+def test_default_mode_gradients_track_oracle(cuda):
+    """Backward of the default mode = bf16 engine on the hi planes of an fp32-class forward.  On a reasonably
+    conditioned case (8 videos) every parameter gradient must point the same way as the fp32 oracle's
+    (per-tensor cosine), and the direction of the whole gradient must agree to bf16 noise."""
+    case = dict(kind="adamml", modality=["rgb", "sound"], N=8, S=2, hw=64, training=True)
+    model, _ = build(case, cuda)
+    logits, dec, loss = run_product(model, case, 5, cuda)
+    loss.backward()
+    shapes = {k: v.shape for k, v in model.state_dict().items()}
+    sd0 = O.fill_state_dict(shapes, seed=0)
+    o_logits, o_dec, g32, _ = oracle_run(case, 5, torch.float32, sd0)
+    assert rel(logits, o_logits) < LOGIT_TOL
+    assert torch.equal(dec.detach().cpu(), o_dec)
+    grads = {k: p.grad for k, p in model.named_parameters()}
+    assert set(grads) == set(g32)
+    # tensors whose true gradient is mathematically zero (e.g. the beta of a linear-bottleneck BN that feeds a
+    # train-mode BN, see util.compare_grads) hold round-off noise on both sides: leave them out of the per-tensor check
+    import statistics as st
+
+    def gkey(k):
+        parts = k.split(".")
+        return ".".join(parts[:parts.index("nets") + 2]) if "nets" in parts else parts[0]
+    med = {}
+    for k, v in g32.items():
+        med.setdefault(gkey(k), []).append(v.abs().max().item())
+    med = {k: st.median(v) for k, v in med.items()}
+    cos = {k: cosine(grads[k], g32[k]) for k in g32
+           if g32[k].numel() > 8 and g32[k].abs().max().item() > 0.02 * med[gkey(k)]}
+    worst = sorted(cos.items(), key=lambda kv: kv[1])[:5]
+    flat_p = torch.cat([grads[k].double().flatten().cpu() for k in sorted(g32)])
+    flat_o = torch.cat([g32[k].double().flatten() for k in sorted(g32)])
+    total = cosine(flat_p, flat_o)
+    import statistics
+    print(f"x2 gradient cosine vs fp32 oracle: whole model {total:.5f}, median tensor "
+          f"{statistics.median(cos.values()):.5f}, worst {worst}")
+    assert total > 0.99
+    assert statistics.median(cos.values()) > 0.99
+    assert sum(1 for v in cos.values() if v < 0.9) <= len(cos) // 20, worst
+
+
+def test_x2_eval_skip_bit_identical(cuda):
+    """decision-driven skipping (AdaMML._forward_selected) on x2 planes: bit-identical to run-everything"""
+    case = dict(kind="adamml", modality=["rgb", "sound"], N=4, S=2, S_run=3, hw=64, training=False)
+    model, _ = build(case, cuda)
+    model.eval()
+    cfg = O.make_cfg(case["modality"], num_segments=case["S"])
+    xs, _ = O.make_inputs(cfg, 4, 3, hw=64)
+    xs = [x.to(cuda) for x in xs]
+    noise = noise_for_model(O.draw_noise(3, cfg, 4, 3, False), cuda)
+    outs = []
+    with torch.no_grad():
+        for skip in (True, False):
+            model.skip_unselected = skip
+            outs.append(model(xs, num_segments=3, noise=noise))
+    assert torch.equal(outs[0][1], outs[1][1])
+    assert torch.equal(outs[0][0], outs[1][0])
