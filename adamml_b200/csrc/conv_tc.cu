@@ -63,7 +63,7 @@ struct X2Maps {
 // X2: the activations and the output are two-plane (hi bf16 + lo fp16) tensors, the weights four-plane (X2Maps); a
 // stage holds [A_hi][A_lo][B1][B2][B3][Bf] and every K step issues A_lo*Bf, A_hi*B3, A_hi*B2, A_hi*B1 into the same
 // fp32 accumulator.
-template <int BLOCK_N, bool SHALLOW = false, bool X2 = false>
+template <int BLOCK_N, bool SHALLOW = false, int X2 = 0>
 struct TcCfg {
   static constexpr int PLANES = X2 ? 2 : 1;              // planes of A and of D
   static constexpr int B_PLANES = X2 ? 4 : 1;
@@ -74,18 +74,25 @@ struct TcCfg {
   static_assert(!SHALLOW || BLOCK_N <= 128, "two CTAs per SM need 2 x (2 x BLOCK_N) <= 512 TMEM columns");
   static_assert(!X2 || (BLOCK_N == 64 && !SHALLOW), "x2: 64-column tiles (64 KB per stage), one CTA per SM");
   // (stage counts that divide by the common K-block counts 1, 2, 4 keep the weight tile resident, see the producer)
-  static constexpr int STAGES = X2 ? 2 : (SHALLOW ? 2 : ((BLOCK_N == 256) ? 3 : (BLOCK_N == 128 ? 4 : 8)));
+  // X2 = 1: reductions of one or two K blocks (2 stages, double-buffered output staging, 8 epilogue warps: the tile is
+  //         all epilogue);
+  // X2 = 2: deep reductions, load / MMA bound (3 stages keep more loads in flight, single output staging buffer);
+  // X2 = 3: 3..8 K blocks under MANY column blocks (the late ResNet 1x1 layers): as 1, but 4 epilogue warps
+  //         (measured: 141 k x 1024 x 256  0.75 ms vs 0.86 ms as X2 = 2 and 0.98 ms as X2 = 1)
+  static constexpr int STAGES = X2 == 2 ? 3 : (X2 ? 2 : (SHALLOW ? 2 : ((BLOCK_N == 256) ? 3 : (BLOCK_N == 128 ? 4 : 8))));
   static constexpr int CTAS_PER_SM = SHALLOW ? 2 : 1;
   // Epilogue warps: wide tiles (256 columns, issue bound) get TWO warps per TMEM lane quarter that split the
   // accumulator columns; narrow tiles are latency bound and run best with one warp per quarter (measured).
-  static constexpr int EPI_WARPS = (BLOCK_N == 256) ? 8 : 4;
+  // (x2 tiles: twice the conversion / statistics work per element -- two warps per quarter hide its latency)
+  // (deep reductions are load / MMA bound: extra epilogue warps only steal issue slots from the control warps)
+  static constexpr int EPI_WARPS = (BLOCK_N == 256 || X2 == 1) ? 8 : 4;
   static constexpr int EPI_THREADS = EPI_WARPS * 32;
   static constexpr int THREADS = 64 + EPI_THREADS;
-  static constexpr bool BACKOFF = (BLOCK_N == 256);  // control warps share SM sub-partitions with epilogue warps
+  static constexpr bool BACKOFF = (BLOCK_N == 256 || X2 == 1);  // control warps share SM sub-partitions with epilogue warps
   static constexpr int SUBTILES = BLOCK_N / 64;              // 64-column (128-byte) output sub-tiles
   // staging tiles of the TMA store: double buffering (store of tile i drains while tile i+1 is staged) measured
   // no faster than a single buffer, which leaves the smem to the operand ring
-  static constexpr int OUT_BUFS = (SHALLOW && BLOCK_N == 64) ? 2 : 1;
+  static constexpr int OUT_BUFS = ((SHALLOW && BLOCK_N == 64) || X2 == 1 || X2 == 3) ? 2 : 1;
   static constexpr int OUT_PLANE_BYTES = SUBTILES * BLOCK_M * 128;
   static constexpr int OUT_TILE_BYTES = PLANES * OUT_PLANE_BYTES;
   static constexpr int OUT_BYTES = OUT_BUFS * OUT_TILE_BYTES;
@@ -139,13 +146,39 @@ struct StatAcc {
   }
 };
 
-template <int BLOCK_N, bool CONV, bool SHALLOW = false, bool X2 = false>
+// Tile order of a persistent CTA.  Default: tiles blockIdx.x, blockIdx.x + grid, ... with the column block fastest
+// (neighbouring CTAs share one A tile through L2).  pin_n (wide layers whose weight block stays resident in the ring,
+// grid a multiple of the column-block count): the CTA keeps ONE column block for its whole life and walks the row
+// blocks c / nb, c / nb + grid / nb, ... -- the weight planes are loaded once per CTA instead of once per tile, and the
+// nb CTAs of a row block still run in step and share its A tile through L2.
+struct TileSched {
+  bool pin;
+  int num_n_blks, num_m_blks;
+  long long num_tiles;
+  __device__ __forceinline__ bool get(int i, int& m_blk, int& n_blk) const {
+    if (pin) {
+      const long long m = (long long)(blockIdx.x / num_n_blks) + (long long)i * (gridDim.x / num_n_blks);
+      if (m >= num_m_blks) return false;
+      m_blk = (int)m;
+      n_blk = (int)(blockIdx.x % num_n_blks);
+      return true;
+    }
+    const long long t = blockIdx.x + (long long)i * gridDim.x;
+    if (t >= num_tiles) return false;
+    n_blk = (int)(t % num_n_blks);
+    m_blk = (int)(t / num_n_blks);
+    return true;
+  }
+};
+
+template <int BLOCK_N, bool CONV, bool SHALLOW = false, int X2 = 0>
 __global__ void __launch_bounds__(TcCfg<BLOCK_N, SHALLOW, X2>::THREADS, TcCfg<BLOCK_N, SHALLOW, X2>::CTAS_PER_SM)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmAdd,
                const __grid_constant__ ConvMaps cmaps, const __grid_constant__ ConvGeom geo,
                const __grid_constant__ X2Maps x2, const bf16* __restrict__ addend, long long M, int Ncols, int K,
-               long long ldd, double* __restrict__ stats, long long rows_per_group, bf16* __restrict__ dlin) {
+               long long ldd, double* __restrict__ stats, long long rows_per_group, bf16* __restrict__ dlin,
+               int pin_n) {
   using Cfg = TcCfg<BLOCK_N, SHALLOW, X2>;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment by pointer arithmetic (keeps the shared address space visible to the compiler: LDS/STS
@@ -167,6 +200,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int num_n_blks = (Ncols + BLOCK_N - 1) / BLOCK_N;
   const long long num_tiles = (long long)num_m_blks * num_n_blks;
   const int num_kb = CONV ? geo.ntaps * geo.kb_per_tap : (K + BLOCK_K - 1) / BLOCK_K;
+  const TileSched sched{pin_n != 0, num_n_blks, num_m_blks, num_tiles};
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < Cfg::STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
@@ -202,11 +236,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // every tile multiplies by the SAME weight tiles, so each slot receives its weight tile once and later tiles
       // load only their A rows.  (Re-fetching the few weight lines per tile from all 148 SMs hot-spots one L2
       // slice: narrow MobileNetV2 layers ran up to 3x slower with the reload.)
-      const bool b_resident = num_n_blks == 1 && (Cfg::STAGES % num_kb) == 0;
+      const bool b_resident = (num_n_blks == 1 || sched.pin) && (Cfg::STAGES % num_kb) == 0;
       int b_loaded = 0;
-      for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int n_blk = (int)(tile % num_n_blks);
-        const int m_blk = (int)(tile / num_n_blks);
+      int n_blk, m_blk;
+      for (int ti = 0; sched.get(ti, m_blk, n_blk); ++ti) {
         int w0 = 0, h0 = 0, i0 = 0;
         if (CONV) {
           w0 = (m_blk % geo.tiles_w) * geo.BW;
@@ -263,7 +296,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    int n_blk_, m_blk_;
+    for (int ti = 0; sched.get(ti, m_blk_, n_blk_); ++ti) {
       ctl_wait<Cfg::BACKOFF>(&tmem_empty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
@@ -331,9 +365,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     int acc = 0, obuf = 0;
     uint32_t acc_phase = 0, add_phase = 0;
-    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int n_blk = (int)(tile % num_n_blks);
-      const int m_blk = (int)(tile / num_n_blks);
+    int n_blk, m_blk;
+    for (int ti = 0; sched.get(ti, m_blk, n_blk); ++ti) {
       uint8_t* stage_out = stage_base + obuf * Cfg::OUT_TILE_BYTES;
       if (Cfg::OUT_BUFS == 2) obuf ^= 1;
       long long arow = 0;
@@ -600,6 +633,15 @@ int make_map_2d(CUtensorMap* map, const void* ptr, long long rows, long long col
   return ADAMML_OK;
 }
 
+// TcCfg variant of an x2 launch (see TcCfg::STAGES); ADAMML_B200_X2_VARIANT=1|2|3 forces one (experiments)
+int x2_variant(int K, int Ncols) {
+  static const int forced = []() { const char* e = getenv("ADAMML_B200_X2_VARIANT"); return e ? atoi(e) : 0; }();
+  if (forced >= 1 && forced <= 3) return forced;
+  if (K <= 2 * BLOCK_K) return 1;
+  if (K <= 8 * BLOCK_K && Ncols >= 4 * 64) return 3;
+  return 2;
+}
+
 const X2Maps& no_x2() {
   static X2Maps z;
   static bool init = false;
@@ -607,7 +649,7 @@ const X2Maps& no_x2() {
   return z;
 }
 
-template <int BLOCK_N, bool CONV, bool SHALLOW = false, bool X2 = false>
+template <int BLOCK_N, bool CONV, bool SHALLOW = false, int X2 = 0>
 int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, const CUtensorMap& tmAdd,
               const ConvMaps& cm, const ConvGeom& geo, const void* addend, long long M, int Ncols, int K, long long ldd, double* stats,
               long long rpg, cudaStream_t stream, void* dlin = nullptr, const X2Maps& x2 = no_x2()) {
@@ -623,11 +665,20 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap&
     configured = true;
   }
   long long m_blks = CONV ? (long long)geo.tiles_w * geo.tiles_h * geo.tiles_i : (M + BLOCK_M - 1) / BLOCK_M;
-  long long tiles = m_blks * ((Ncols + BLOCK_N - 1) / BLOCK_N);
+  const int n_blks = (Ncols + BLOCK_N - 1) / BLOCK_N;
+  long long tiles = m_blks * n_blks;
   const int sms = num_sms() * Cfg::CTAS_PER_SM;
   int grid = (int)(tiles < sms ? tiles : sms);
+  // column-block pinning (TileSched): x2 layers with several column blocks whose weight block fits the ring
+  static const bool pin_on = []() { const char* e = getenv("ADAMML_B200_TC_PIN"); return !(e && e[0] == '0'); }();
+  const int num_kb = CONV ? geo.ntaps * geo.kb_per_tap : (K + BLOCK_K - 1) / BLOCK_K;
+  int pin_n = 0;
+  if (X2 && pin_on && n_blks > 1 && n_blks <= sms && (Cfg::STAGES % num_kb) == 0 && m_blks >= 4LL * (sms / n_blks)) {
+    pin_n = 1;
+    grid = (sms / n_blks) * n_blks;
+  }
   kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmD, tmAdd, cm, geo, x2, (const bf16*)addend, M,
-                                                        Ncols, K, ldd, stats, rpg, (bf16*)dlin);
+                                                        Ncols, K, ldd, stats, rpg, (bf16*)dlin, pin_n);
   return adamml_check_launch(CONV ? "tc_conv" : "tc_gemm");
 }
 
@@ -689,8 +740,15 @@ int run_conv_x2(const ConvGeom& geo, const ConvMaps& cm, const ConvMaps& cm_lo, 
   }
   const long long M = (long long)geo.IMGS * geo.Ho * geo.Wo;
   const int K = geo.ntaps * geo.kb_per_tap * BLOCK_K;
-  return launch_tc<64, true, false, true>(tmB, tmB, tmD, tmD, cm, geo, nullptr, M, Cout, K, Cout, stats, 0, stream,
-                                          nullptr, x2);
+  const int variant = x2_variant(K, Cout);
+  if (variant == 2)
+    return launch_tc<64, true, false, 2>(tmB, tmB, tmD, tmD, cm, geo, nullptr, M, Cout, K, Cout, stats, 0, stream,
+                                         nullptr, x2);
+  if (variant == 3)
+    return launch_tc<64, true, false, 3>(tmB, tmB, tmD, tmD, cm, geo, nullptr, M, Cout, K, Cout, stats, 0, stream,
+                                         nullptr, x2);
+  return launch_tc<64, true, false, 1>(tmB, tmB, tmD, tmD, cm, geo, nullptr, M, Cout, K, Cout, stats, 0, stream,
+                                       nullptr, x2);
 }
 
 // launches the implicit-GEMM kernel for a prepared geometry; w is [Cout][w_ld] bf16, y/addend rows have Cout columns
@@ -950,8 +1008,15 @@ int adamml_tc_gemm_x2(const void* A_hi, const void* A_lo, const void* B4, void* 
   memset(&geo, 0, sizeof(geo));
   void* dlin = (Ncols <= block_n && (Ncols % 64) != 0) ? D_hi : nullptr;
   x2.dlin_lo = dlin ? D_lo : nullptr;
-  return launch_tc<64, false, false, true>(tmA, tmB, tmD, tmD, cm, geo, nullptr, M, Ncols, K, Ncols, stats,
-                                           rows_per_group, stream, dlin, x2);
+  const int variant = x2_variant(K, Ncols);
+  if (variant == 2)
+    return launch_tc<64, false, false, 2>(tmA, tmB, tmD, tmD, cm, geo, nullptr, M, Ncols, K, Ncols, stats,
+                                          rows_per_group, stream, dlin, x2);
+  if (variant == 3)
+    return launch_tc<64, false, false, 3>(tmA, tmB, tmD, tmD, cm, geo, nullptr, M, Ncols, K, Ncols, stats,
+                                          rows_per_group, stream, dlin, x2);
+  return launch_tc<64, false, false, 1>(tmA, tmB, tmD, tmD, cm, geo, nullptr, M, Ncols, K, Ncols, stats,
+                                        rows_per_group, stream, dlin, x2);
 }
 
 /* Data gradient of a stride-2 convolution (resnet.py:100 conv2 of the first Bottleneck of layer2-4) as four

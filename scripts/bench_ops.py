@@ -44,6 +44,48 @@ def gemm(M, N, K, stats, G=5):
     report(f"tc_gemm M={M} N={N} K={K} stats={int(stats)}", ms, 2.0 * M * (N + K), 2.0 * M * N * K)
 
 
+def x2rand(*shape):
+    t = torch.randn(*shape, device=dev, dtype=torch.float32)
+    hi = t.bfloat16()
+    return ops.X2(hi, (t - hi.float()).half())
+
+
+def gemm_x2(M, N, K, stats=True, G=5):
+    a = x2rand(M, 1, 1, K)
+    w = ops.pack_weight(torch.randn(N, K, 1, 1, device=dev) / K ** 0.5, ops.PREC_X2)
+    st = torch.empty(G, N, 2, device=dev, dtype=torch.float64) if stats else None
+    ms = timeit(lambda: ops.conv_fwd(a, w, 1, 0, stats=st, rows_per_group=M // G))
+    report(f"tc_gemm_x2 M={M} N={N} K={K} stats={int(stats)}", ms, 4.0 * M * (N + K), 2.0 * M * N * K)
+
+
+def conv_x2(I, H, W, Ci, Co, R, stride, pad, stats=True, G=5):
+    x = x2rand(I, H, W, Ci)
+    w = ops.pack_weight(torch.randn(Co, Ci, R, R, device=dev) / (Ci * R * R) ** 0.5, ops.PREC_X2)
+    Ho, Wo = ops.conv_out_hw(H, W, R, R, stride, pad)
+    st = torch.empty(G, Co, 2, device=dev, dtype=torch.float64) if stats else None
+    ms = timeit(lambda: ops.conv_fwd(x, w, stride, pad, stats=st, rows_per_group=I * Ho * Wo // G))
+    report(f"tc_conv_x2 I={I} {H}x{W} {Ci}->{Co} {R}x{R} s{stride} stats={int(stats)}", ms,
+           4.0 * (I * H * W * Ci + I * Ho * Wo * Co), 2.0 * I * Ho * Wo * Co * R * R * Ci)
+
+
+def bn_x2(rows, C, G=5, res=False):
+    z = x2rand(rows * G, 1, 1, C)
+    r = x2rand(rows * G, 1, 1, C) if res else None
+    ss = torch.rand(G, C, 2, device=dev)
+    ms = timeit(lambda: ops.bn_apply(z, ss, G, 1, res=r))
+    report(f"bn_apply_x2 rows={rows}x{G} C={C} res={int(res)}", ms, (3.0 if res else 2.0) * 4 * rows * G * C)
+    ms = timeit(lambda: ops.bn_stats(z, G))
+    report(f"bn_stats_x2 rows={rows}x{G} C={C}", ms, 4.0 * rows * G * C)
+
+
+def dw_x2(I, H, C, stride):
+    x = x2rand(I, H, H, C)
+    w = ops.pack_weight_dw(torch.randn(C, 1, 3, 3, device=dev))
+    y = ops.dwconv_fwd(x, w, stride)
+    report(f"dwconv_fwd_x2 I={I} {H}x{H} C={C} s{stride}", timeit(lambda: ops.dwconv_fwd(x, w, stride)),
+           4.0 * (x.numel() + y.numel()), 18.0 * y.numel())
+
+
 def conv(I, H, W, Ci, Co, R, stride, pad, stats, addend=False, G=5):
     x, w = rnd(I, H, W, Ci), rnd(Co, R, R, Ci)
     Ho, Wo = ops.conv_out_hw(H, W, R, R, stride, pad)
@@ -106,6 +148,15 @@ CASES = {
     "wgrad": lambda: [wgrad(2880, 56, 56, 64, 64, 3, 1, 1), wgrad(2880, 56, 56, 256, 64, 1, 1, 0),
                       wgrad(2880, 56, 56, 64, 256, 1, 1, 0), wgrad(1440, 28, 28, 128, 128, 3, 1, 1),
                       wgrad(720, 14, 14, 256, 256, 3, 1, 1), wgrad(360, 7, 7, 512, 2048, 1, 1, 0)],
+    "x2gemm": lambda: [gemm_x2(9031680, 256, 64), gemm_x2(9031680, 64, 256), gemm_x2(9031680, 64, 64),
+                       gemm_x2(1128960, 512, 128), gemm_x2(1128960, 128, 512), gemm_x2(141120, 1024, 256),
+                       gemm_x2(1474560, 144, 24), gemm_x2(5898240, 96, 16), gemm_x2(368640, 192, 32),
+                       gemm_x2(92160, 576, 96), gemm_x2(5898240, 16, 32), gemm_x2(1474560, 24, 144),
+                       gemm_x2(17640, 2048, 512)],
+    "x2conv": lambda: [conv_x2(2880, 56, 56, 64, 64, 3, 1, 1), conv_x2(1440, 28, 28, 128, 128, 3, 1, 1),
+                       conv_x2(720, 14, 14, 256, 256, 3, 1, 1), conv_x2(1440, 56, 56, 256, 512, 1, 2, 0)],
+    "x2bn": lambda: [bn_x2(1806336, 256, res=True), bn_x2(1806336, 64), bn_x2(1843200, 96)],
+    "x2dw": lambda: [dw_x2(1440, 40, 144, 1), dw_x2(360, 128, 96, 2), dw_x2(1440, 80, 32, 1)],
     "bn": lambda: [bn(1806336, 256), bn(1806336, 64), bn(225792, 512), bn(1843200, 96)],
     "dw": lambda: [dw(1440, 40, 144, 1), dw(360, 128, 96, 2), dw(1440, 80, 32, 1)],
 }
