@@ -53,8 +53,17 @@ struct ConvMaps {
 struct X2Maps {
   CUtensorMap a, d;
   CUtensorMap b[3];
+  CUtensorMap add;  // lo plane of a residual addend (fused BN + residual epilogue)
   ConvMaps c;
   void* dlin_lo;
+};
+// Fused epilogue of an inference-mode conv + BatchNorm (+ residual) + ReLU/ReLU6 (resnet.py:96-111,
+// sound_mobilenet_v2.py:33-40, policy_net.py:38-52): with running statistics BN is a per-channel affine map known before
+// the convolution runs, so out = act(acc * scale[c] + shift[c] (+ residual)) leaves the accumulator directly and the
+// pre-BN tensor z never exists.  ss = [Ncols][2] fp32 (scale, shift); act applies after the addend.
+struct EpiSpec {
+  const float* ss;
+  int act;
 };
 
 // SHALLOW: reductions of one or two K blocks (the MobileNetV2 expand / project-gradient GEMMs, K = 16..96).  Their
@@ -178,7 +187,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                const __grid_constant__ ConvMaps cmaps, const __grid_constant__ ConvGeom geo,
                const __grid_constant__ X2Maps x2, const bf16* __restrict__ addend, long long M, int Ncols, int K,
                long long ldd, double* __restrict__ stats, long long rows_per_group, bf16* __restrict__ dlin,
-               int pin_n) {
+               int pin_n, const EpiSpec epi) {
   using Cfg = TcCfg<BLOCK_N, SHALLOW, X2>;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment by pointer arithmetic (keeps the shared address space visible to the compiler: LDS/STS
@@ -219,7 +228,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // dense residual-gradient addend (same pixel lattice as the output): fetched by TMA into the staging tile
-  const bool add_tma = CONV && addend != nullptr && geo.addend_sub != 2;
+  const bool add_tma = addend != nullptr && geo.addend_sub != 2;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -358,7 +367,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     sa_.reset();
     sa_.g = -1;
     sa_.col = 0;
-    int last_n_blk = -1;
+    int last_n_blk = -1, last_ss_blk = -1;
+    float2* ss_s = reinterpret_cast<float2*>(red);  // (scale, shift) of the tile's columns (no statistics in that mode)
     if (stats) {
       for (int j = st; j < BLOCK_N * 2; j += Cfg::EPI_THREADS) red[j] = 0.0;
       epi_bar_sync<Cfg::EPI_THREADS>();
@@ -390,6 +400,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         arow = row;
         row_ok = row < M;
       }
+      if (epi.ss && n_blk != last_ss_blk) {
+        // every thread is past the mid-tile barrier of the previous tile, i.e. done reading the previous block's pairs
+        for (int j = st; j < BLOCK_N; j += Cfg::EPI_THREADS) {
+          const int col = n_blk * BLOCK_N + j;
+          ss_s[j] = col < Ncols ? reinterpret_cast<const float2*>(epi.ss)[col] : make_float2(0.f, 0.f);
+        }
+        last_ss_blk = n_blk;
+      }
       // the staging tile (and row_group) of the previous tile must have been consumed
       if (issuer) {
         if (Cfg::OUT_BUFS == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
@@ -401,11 +419,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           int nsub = 0;
 #pragma unroll
           for (int sub = 0; sub < Cfg::SUBTILES; ++sub) nsub += (n_blk * BLOCK_N + sub * 64 < Ncols) ? 1 : 0;
-          mbar_expect_tx(add_bar, (uint32_t)nsub * (BLOCK_M * 128));
+          mbar_expect_tx(add_bar, (uint32_t)(nsub * Cfg::PLANES) * (BLOCK_M * 128));
 #pragma unroll
           for (int sub = 0; sub < Cfg::SUBTILES; ++sub) {
             const int col = n_blk * BLOCK_N + sub * 64;
-            if (col < Ncols) tma_load_4d(stage_out + sub * (BLOCK_M * 128), &tmAdd, add_bar, col, w0, h0, i0);
+            if (col < Ncols) {
+              uint8_t* dst = stage_out + sub * (BLOCK_M * 128);
+              if (CONV) tma_load_4d(dst, &tmAdd, add_bar, col, w0, h0, i0);
+              else tma_load_2d(dst, &tmAdd, add_bar, col, m_blk * BLOCK_M);
+              if (X2) {
+                if (CONV) tma_load_4d(dst + Cfg::OUT_PLANE_BYTES, &x2.add, add_bar, col, w0, h0, i0);
+                else tma_load_2d(dst + Cfg::OUT_PLANE_BYTES, &x2.add, add_bar, col, m_blk * BLOCK_M);
+              }
+            }
           }
         }
       }
@@ -428,6 +454,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (!row_ok) {  // edge tiles only: rows outside the tensor are staged as zeros (statistics sum them)
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        } else if (epi.ss) {  // fused inference BatchNorm: per-column scale / shift (broadcast smem reads)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float2 p = ss_s[chunk * 32 + j];
+            v[j] = fmaf(v[j], p.x, p.y);
+          }
         }
         if (add_ok && row_ok) {
           const bf16* ap = addend + arow * ldd + col0;
@@ -461,7 +493,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               v[j + 2 * t] += f.x;
               v[j + 2 * t + 1] += f.y;
             }
+            if (X2) {
+              const uint4 pl = *reinterpret_cast<const uint4*>(srow + Cfg::OUT_PLANE_BYTES + ((c ^ (et & 7)) << 4));
+              const __half2* l2 = reinterpret_cast<const __half2*>(&pl);
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                float2 f = __half22float2(l2[t]);
+                v[j + 2 * t] += f.x;
+                v[j + 2 * t + 1] += f.y;
+              }
+            }
           }
+        }
+        if (epi.act != ADAMML_ACT_NONE) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = act_apply(v[j], epi.act);
         }
 #pragma unroll
         for (int j = 0; j < 32; j += 8) {
@@ -652,7 +698,8 @@ const X2Maps& no_x2() {
 template <int BLOCK_N, bool CONV, bool SHALLOW = false, int X2 = 0>
 int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, const CUtensorMap& tmAdd,
               const ConvMaps& cm, const ConvGeom& geo, const void* addend, long long M, int Ncols, int K, long long ldd, double* stats,
-              long long rpg, cudaStream_t stream, void* dlin = nullptr, const X2Maps& x2 = no_x2()) {
+              long long rpg, cudaStream_t stream, void* dlin = nullptr, const X2Maps& x2 = no_x2(),
+              const EpiSpec& epi = EpiSpec{nullptr, ADAMML_ACT_NONE}) {
   using Cfg = TcCfg<BLOCK_N, SHALLOW, X2>;
   static bool configured = false;
   auto kern = tc_gemm_kernel<BLOCK_N, CONV, SHALLOW, X2>;
@@ -678,7 +725,7 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap&
     grid = (sms / n_blks) * n_blks;
   }
   kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmD, tmAdd, cm, geo, x2, (const bf16*)addend, M,
-                                                        Ncols, K, ldd, stats, rpg, (bf16*)dlin, pin_n);
+                                                        Ncols, K, ldd, stats, rpg, (bf16*)dlin, pin_n, epi);
   return adamml_check_launch(CONV ? "tc_conv" : "tc_gemm");
 }
 

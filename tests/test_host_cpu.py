@@ -71,3 +71,64 @@ def test_u8_frames_without_norm_are_rejected():
     x = torch.zeros(1, 3, 4, 4, dtype=torch.uint8)
     with pytest.raises(ValueError):
         ops._u8_norm(x, 3, None)
+
+
+def test_reference_checkpoint_with_module_prefix_loads(tmp_path, model):
+    """Resume / fine-tune compatibility (SURVEY.md §5 checkpoint row): train_adamml.py saves the DDP-wrapped
+    state_dict, i.e. every key carries a `module.` prefix (train_adamml.py:373-383), together with the temperature;
+    the unimodal loader strips that prefix and loads strictly (joint_resnet_mobilenetv2.py:141-155).  A checkpoint
+    file written that way must load into the product model key for key."""
+    from adamml_b200.models import build_model
+    sd = {"module." + k: v.clone() for k, v in model.state_dict().items()}
+    path = tmp_path / "checkpoint.pth.tar"
+    torch.save({"epoch": 3, "arch": "adamml", "state_dict": sd, "temperature": 4.2, "stage": "alternative_training"},
+               path)
+    ckpt = torch.load(path, map_location="cpu")
+    # (a) the reference's resume path: DataParallel / DDP wrapper around the model, load_state_dict(strict)
+    wrapped = torch.nn.DataParallel(model) if False else None  # DataParallel needs a GPU; emulate the wrapper keys
+    m2, _ = build_model(namespace(dict(kind="adamml", modality=["rgb", "sound"], S=2), compute_dtype=torch.bfloat16))
+    holder = torch.nn.Module()
+    holder.module = m2
+    missing, unexpected = holder.load_state_dict(ckpt["state_dict"], strict=True)
+    assert not missing and not unexpected
+    m2.policy_net.set_temperature(ckpt["temperature"])
+    assert m2.policy_net.temperature == 4.2
+    for (k, a), (_, b) in zip(model.state_dict().items(), m2.state_dict().items()):
+        assert torch.equal(a, b), k
+    # (b) the unimodal loader of the main net (joint_resnet_mobilenetv2.py:146-155): per-backbone checkpoint files
+    paths = []
+    for i, net in enumerate(model.main_net.nets):
+        p = tmp_path / f"uni{i}.pth.tar"
+        torch.save({"state_dict": {"module." + k: v for k, v in net.state_dict().items()}}, p)
+        paths.append(str(p))
+    m3, _ = build_model(namespace(dict(kind="adamml", modality=["rgb", "sound"], S=2), compute_dtype=torch.bfloat16,
+                                  unimodality_pretrained=paths))
+    for i, net in enumerate(model.main_net.nets):
+        for (k, a), (_, b) in zip(net.state_dict().items(), m3.main_net.nets[i].state_dict().items()):
+            assert torch.equal(a, b), (i, k)
+
+
+def test_graph_step_guard_sees_host_state_changes(model):
+    """GraphedTrainStep's guard (adamml_b200/graph.py): temperature decay, freeze / unfreeze, train / eval and a
+    Python-float learning rate are baked into captured launches, so each of them must change the snapshot."""
+    from adamml_b200.graph import step_guard
+    opt = torch.optim.SGD(model.main_net.parameters(), 0.01, momentum=0.9)
+    snap = step_guard(model, opt)
+    s0 = snap()
+    assert snap() == s0
+    model.decay_temperature()
+    s1 = snap()
+    assert s1 != s0
+    model.freeze_policy_net()
+    s2 = snap()
+    assert s2 != s1
+    model.unfreeze_policy_net()
+    assert snap() == s1
+    opt.param_groups[0]["lr"] = 0.001
+    s3 = snap()
+    assert s3 != s1
+    was = model.training
+    model.train(not was)
+    assert snap() != s3
+    model.train(was)
+    model.policy_net.set_temperature(5.0)
