@@ -732,10 +732,12 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap&
 template <bool CONV>
 int dispatch_tc(int block_n, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD,
                 const CUtensorMap& tmAdd, const ConvMaps& cm, const ConvGeom& geo, const void* addend, long long M, int Ncols, int K, long long ldd, double* stats,
-                long long rpg, cudaStream_t stream, void* dlin = nullptr) {
+                long long rpg, cudaStream_t stream, void* dlin = nullptr,
+                const EpiSpec& epi = EpiSpec{nullptr, ADAMML_ACT_NONE}) {
 #define ADAMML_TC_CASE(BN) \
   if (block_n == BN)       \
-    return launch_tc<BN, CONV>(tmA, tmB, tmD, tmAdd, cm, geo, addend, M, Ncols, K, ldd, stats, rpg, stream, dlin);
+    return launch_tc<BN, CONV>(tmA, tmB, tmD, tmAdd, cm, geo, addend, M, Ncols, K, ldd, stats, rpg, stream, dlin, \
+                               no_x2(), epi);
   ADAMML_TC_CASE(64)
   ADAMML_TC_CASE(128)
   ADAMML_TC_CASE(256)
@@ -770,7 +772,9 @@ int make_w4_maps(CUtensorMap* tmB, X2Maps& x2, const void* w4, int Ncols, long l
 
 // x2 variant of run_conv: cm / cm_lo are the tap maps of the hi / lo input planes; w4 the four weight planes
 int run_conv_x2(const ConvGeom& geo, const ConvMaps& cm, const ConvMaps& cm_lo, const void* w4, long long w_ld, void* y,
-                void* y_lo, int Cout, double* stats, cudaStream_t stream) {
+                void* y_lo, int Cout, double* stats, cudaStream_t stream,
+                const EpiSpec& epi = EpiSpec{nullptr, ADAMML_ACT_NONE}, const void* res = nullptr,
+                const void* res_lo = nullptr) {
   CUtensorMap tmB, tmD;
   X2Maps x2;
   memset(&x2, 0, sizeof(x2));
@@ -781,6 +785,12 @@ int run_conv_x2(const ConvGeom& geo, const ConvMaps& cm, const ConvMaps& cm_lo, 
   if (rc) return rc;
   rc = make_out_map(&x2.d, geo, y_lo, Cout);
   if (rc) return rc;
+  CUtensorMap tmAdd = tmD;
+  if (res) {
+    rc = make_out_map(&tmAdd, geo, res, Cout);
+    if (!rc) rc = make_out_map(&x2.add, geo, res_lo, Cout);
+    if (rc) return rc;
+  }
   if (stats) {
     int G = (geo.IMGS + geo.imgs_per_group - 1) / geo.imgs_per_group;
     cudaMemsetAsync(stats, 0, sizeof(double) * (size_t)G * Cout * 2, stream);
@@ -789,18 +799,18 @@ int run_conv_x2(const ConvGeom& geo, const ConvMaps& cm, const ConvMaps& cm_lo, 
   const int K = geo.ntaps * geo.kb_per_tap * BLOCK_K;
   const int variant = x2_variant(K, Cout);
   if (variant == 2)
-    return launch_tc<64, true, false, 2>(tmB, tmB, tmD, tmD, cm, geo, nullptr, M, Cout, K, Cout, stats, 0, stream,
-                                         nullptr, x2);
+    return launch_tc<64, true, false, 2>(tmB, tmB, tmD, tmAdd, cm, geo, res, M, Cout, K, Cout, stats, 0, stream,
+                                         nullptr, x2, epi);
   if (variant == 3)
-    return launch_tc<64, true, false, 3>(tmB, tmB, tmD, tmD, cm, geo, nullptr, M, Cout, K, Cout, stats, 0, stream,
-                                         nullptr, x2);
-  return launch_tc<64, true, false, 1>(tmB, tmB, tmD, tmD, cm, geo, nullptr, M, Cout, K, Cout, stats, 0, stream,
-                                       nullptr, x2);
+    return launch_tc<64, true, false, 3>(tmB, tmB, tmD, tmAdd, cm, geo, res, M, Cout, K, Cout, stats, 0, stream,
+                                         nullptr, x2, epi);
+  return launch_tc<64, true, false, 1>(tmB, tmB, tmD, tmAdd, cm, geo, res, M, Cout, K, Cout, stats, 0, stream,
+                                       nullptr, x2, epi);
 }
 
 // launches the implicit-GEMM kernel for a prepared geometry; w is [Cout][w_ld] bf16, y/addend rows have Cout columns
 int run_conv(const ConvGeom& geo, const ConvMaps& cm, const void* w, long long w_ld, void* y, const void* addend,
-             int Cout, double* stats, cudaStream_t stream) {
+             int Cout, double* stats, cudaStream_t stream, const EpiSpec& epi = EpiSpec{nullptr, ADAMML_ACT_NONE}) {
   const int block_n = Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 256);
   CUtensorMap tmB;
   int rc = make_map_2d(&tmB, w, Cout, w_ld, w_ld, block_n);
@@ -823,7 +833,7 @@ int run_conv(const ConvGeom& geo, const ConvMaps& cm, const void* w, long long w
     if (rc) return rc;
   }
   return dispatch_tc<true>(block_n, tmB, tmB, tmD, tmAdd, cm, geo, addend, (long long)geo.IMGS * geo.Ho * geo.Wo, Cout,
-                           geo.ntaps * geo.kb_per_tap * BLOCK_K, Cout, stats, 0, stream);
+                           geo.ntaps * geo.kb_per_tap * BLOCK_K, Cout, stats, 0, stream, nullptr, epi);
 }
 
 // geometry + tap tensor maps of an RxS / stride 1|2 convolution over x [IMGS,H,W,Cin] (x_lo: optional lo plane -> cm_lo)
@@ -915,9 +925,9 @@ int adamml_tc_supported(long long M, int Ncols, int K, long long lda, long long 
   return 1;
 }
 
-int adamml_tc_gemm_bf16(const void* A, const void* B, void* D, long long M, int Ncols, int K, long long lda,
-                        long long ldb, long long ldd, int d_dtype, double* stats, long long rows_per_group,
-                        cudaStream_t stream) {
+static int gemm_bf16_impl(const void* A, const void* B, void* D, long long M, int Ncols, int K, long long lda,
+                          long long ldb, long long ldd, int d_dtype, double* stats, long long rows_per_group,
+                          const EpiSpec& epi, const void* res, cudaStream_t stream) {
   if (lda <= 0) lda = K;
   if (ldb <= 0) ldb = K;
   if (ldd <= 0) ldd = Ncols;
@@ -957,16 +967,38 @@ int adamml_tc_gemm_bf16(const void* A, const void* B, void* D, long long M, int 
   // contiguous output whose rows are not whole 128-byte lines (N = 16, 24, 32, 96, 144, ...): the TMA unit retires
   // about one box row per 4 cycles whatever its width, so the tile is stored as ONE linear bulk copy instead
   static const bool linear_on = []() { const char* e = getenv("ADAMML_B200_TC_LINEAR"); return !(e && e[0] == '0'); }();
-  void* dlin = (linear_on && ldd == Ncols && Ncols <= block_n && (Ncols % 64) != 0) ? D : nullptr;
+  void* dlin = (linear_on && !res && ldd == Ncols && Ncols <= block_n && (Ncols % 64) != 0) ? D : nullptr;
+  CUtensorMap tmAdd = tmD;
+  if (res) {  // residual tile of the fused epilogue: same [M, Ncols] lattice as the output
+    ADAMML_REQUIRE(((uintptr_t)res % 16) == 0, "tc_gemm: residual must be 16-byte aligned");
+    rc = make_map_2d(&tmAdd, res, M, Ncols, ldd, BLOCK_M);
+    if (rc) return rc;
+  }
   if (shallow) {
     if (block_n == 64)
-      return launch_tc<64, false, true>(tmA, tmB, tmD, tmD, cm, geo, nullptr, M, Ncols, K, ldd, stats, rows_per_group,
-                                        stream, dlin);
-    return launch_tc<128, false, true>(tmA, tmB, tmD, tmD, cm, geo, nullptr, M, Ncols, K, ldd, stats, rows_per_group,
-                                       stream, dlin);
+      return launch_tc<64, false, true>(tmA, tmB, tmD, tmAdd, cm, geo, res, M, Ncols, K, ldd, stats, rows_per_group,
+                                        stream, dlin, no_x2(), epi);
+    return launch_tc<128, false, true>(tmA, tmB, tmD, tmAdd, cm, geo, res, M, Ncols, K, ldd, stats, rows_per_group,
+                                       stream, dlin, no_x2(), epi);
   }
-  return dispatch_tc<false>(block_n, tmA, tmB, tmD, tmD, cm, geo, nullptr, M, Ncols, K, ldd, stats, rows_per_group,
-                            stream, dlin);
+  return dispatch_tc<false>(block_n, tmA, tmB, tmD, tmAdd, cm, geo, res, M, Ncols, K, ldd, stats, rows_per_group,
+                            stream, dlin, epi);
+}
+
+int adamml_tc_gemm_bf16(const void* A, const void* B, void* D, long long M, int Ncols, int K, long long lda,
+                        long long ldb, long long ldd, int d_dtype, double* stats, long long rows_per_group,
+                        cudaStream_t stream) {
+  return gemm_bf16_impl(A, B, D, M, Ncols, K, lda, ldb, ldd, d_dtype, stats, rows_per_group,
+                        EpiSpec{nullptr, ADAMML_ACT_NONE}, nullptr, stream);
+}
+
+/* Inference-mode conv + BatchNorm (+ residual) + ReLU/ReLU6 in ONE kernel (resnet.py:96-111 and the MobileNetV2
+ * ConvBNReLU stacks): out = act(A.B^T * scale[c] + shift[c] (+ res)); scale_shift = [Ncols][2] fp32 (the folded
+ * running statistics of adamml_bn_finalize, group 0), res = optional [M, Ncols] tensor, dense strides. */
+int adamml_tc_gemm_bn_act_bf16(const void* A, const void* B, void* D, long long M, int Ncols, int K,
+                               const float* scale_shift, int act, const void* res, cudaStream_t stream) {
+  ADAMML_REQUIRE(scale_shift, "tc_gemm_bn_act: needs the folded BatchNorm scale / shift");
+  return gemm_bf16_impl(A, B, D, M, Ncols, K, 0, 0, 0, ADAMML_BF16, nullptr, 0, EpiSpec{scale_shift, act}, res, stream);
 }
 
 int adamml_tc_conv_supported(int Cin, int Cout, int R, int S, int stride) {
@@ -976,9 +1008,9 @@ int adamml_tc_conv_supported(int Cin, int Cout, int R, int S, int stride) {
   return 1;
 }
 
-int adamml_tc_conv_bf16(const void* x, const void* w, void* y, const void* addend, int IMGS, int H, int W, int Cin,
-                        int Cout, int R, int S, int stride, int pad, int Ho, int Wo, double* stats,
-                        int imgs_per_group, int addend_sub, cudaStream_t stream) {
+static int conv_bf16_impl(const void* x, const void* w, void* y, const void* addend, int IMGS, int H, int W, int Cin,
+                          int Cout, int R, int S, int stride, int pad, int Ho, int Wo, double* stats,
+                          int imgs_per_group, int addend_sub, const EpiSpec& epi, cudaStream_t stream) {
   if (!adamml_tc_conv_supported(Cin, Cout, R, S, stride)) {
     adamml_set_error("tc_conv: Cin=%d Cout=%d R=%d S=%d stride=%d outside the tcgen05 envelope", Cin, Cout, R, S,
                      stride);
@@ -996,15 +1028,31 @@ int adamml_tc_conv_bf16(const void* x, const void* w, void* y, const void* adden
   int rc = conv_setup(geo, cm, nullptr, x, nullptr, IMGS, H, W, Cin, R, S, stride, pad, Ho, Wo, imgs_per_group);
   if (rc) return rc;
   if (addend && addend_sub == 2) { geo.addend_sub = 2; geo.add_H = (Ho + 1) / 2; geo.add_W = (Wo + 1) / 2; }
-  return run_conv(geo, cm, w, (long long)R * S * Cin, y, addend, Cout, stats, stream);
+  return run_conv(geo, cm, w, (long long)R * S * Cin, y, addend, Cout, stats, stream, epi);
+}
+
+int adamml_tc_conv_bf16(const void* x, const void* w, void* y, const void* addend, int IMGS, int H, int W, int Cin,
+                        int Cout, int R, int S, int stride, int pad, int Ho, int Wo, double* stats,
+                        int imgs_per_group, int addend_sub, cudaStream_t stream) {
+  return conv_bf16_impl(x, w, y, addend, IMGS, H, W, Cin, Cout, R, S, stride, pad, Ho, Wo, stats, imgs_per_group,
+                        addend_sub, EpiSpec{nullptr, ADAMML_ACT_NONE}, stream);
+}
+
+int adamml_tc_conv_bn_act_bf16(const void* x, const void* w, void* y, int IMGS, int H, int W, int Cin, int Cout, int R,
+                               int S, int stride, int pad, int Ho, int Wo, const float* scale_shift, int act,
+                               const void* res, cudaStream_t stream) {
+  ADAMML_REQUIRE(scale_shift, "tc_conv_bn_act: needs the folded BatchNorm scale / shift");
+  return conv_bf16_impl(x, w, y, res, IMGS, H, W, Cin, Cout, R, S, stride, pad, Ho, Wo, nullptr, 0, res ? 1 : 0,
+                        EpiSpec{scale_shift, act}, stream);
 }
 
 /* x2 planes: forward convolution of the default precision mode.  x / y are (hi bf16, lo fp16) plane pairs, w4 the
  * four weight planes of adamml_pack_weight_x2; every K step accumulates x_hi*(b1+b2+b3) + x_lo*fp16(w) in the fp32
  * TMEM accumulator; fused BN statistics are taken over the full-precision outputs. */
-int adamml_tc_conv_x2(const void* x_hi, const void* x_lo, const void* w4, void* y_hi, void* y_lo, int IMGS, int H,
-                      int W, int Cin, int Cout, int R, int S, int stride, int pad, int Ho, int Wo, double* stats,
-                      int imgs_per_group, cudaStream_t stream) {
+static int conv_x2_impl(const void* x_hi, const void* x_lo, const void* w4, void* y_hi, void* y_lo, int IMGS, int H,
+                        int W, int Cin, int Cout, int R, int S, int stride, int pad, int Ho, int Wo, double* stats,
+                        int imgs_per_group, const EpiSpec& epi, const void* res_hi, const void* res_lo,
+                        cudaStream_t stream) {
   if (!adamml_tc_conv_supported(Cin, Cout, R, S, stride)) {
     adamml_set_error("tc_conv_x2: Cin=%d Cout=%d R=%d S=%d stride=%d outside the tcgen05 envelope", Cin, Cout, R, S,
                      stride);
@@ -1021,11 +1069,31 @@ int adamml_tc_conv_x2(const void* x_hi, const void* x_lo, const void* w4, void* 
   ConvMaps cm, cm_lo;
   int rc = conv_setup(geo, cm, &cm_lo, x_hi, x_lo, IMGS, H, W, Cin, R, S, stride, pad, Ho, Wo, imgs_per_group);
   if (rc) return rc;
-  return run_conv_x2(geo, cm, cm_lo, w4, (long long)R * S * Cin, y_hi, y_lo, Cout, stats, stream);
+  ADAMML_REQUIRE((!res_hi == !res_lo) && ((uintptr_t)res_hi % 16) == 0 && ((uintptr_t)res_lo % 16) == 0,
+                 "tc_conv_x2: the residual needs both planes, 16-byte aligned");
+  return run_conv_x2(geo, cm, cm_lo, w4, (long long)R * S * Cin, y_hi, y_lo, Cout, stats, stream, epi, res_hi, res_lo);
 }
 
-int adamml_tc_gemm_x2(const void* A_hi, const void* A_lo, const void* B4, void* D_hi, void* D_lo, long long M,
-                      int Ncols, int K, double* stats, long long rows_per_group, cudaStream_t stream) {
+int adamml_tc_conv_x2(const void* x_hi, const void* x_lo, const void* w4, void* y_hi, void* y_lo, int IMGS, int H,
+                      int W, int Cin, int Cout, int R, int S, int stride, int pad, int Ho, int Wo, double* stats,
+                      int imgs_per_group, cudaStream_t stream) {
+  return conv_x2_impl(x_hi, x_lo, w4, y_hi, y_lo, IMGS, H, W, Cin, Cout, R, S, stride, pad, Ho, Wo, stats,
+                      imgs_per_group, EpiSpec{nullptr, ADAMML_ACT_NONE}, nullptr, nullptr, stream);
+}
+
+/* x2 planes of the fused inference epilogue (see adamml_tc_gemm_bn_act_bf16): out = act(conv * scale + shift (+ res)) */
+int adamml_tc_conv_bn_act_x2(const void* x_hi, const void* x_lo, const void* w4, void* y_hi, void* y_lo, int IMGS,
+                             int H, int W, int Cin, int Cout, int R, int S, int stride, int pad, int Ho, int Wo,
+                             const float* scale_shift, int act, const void* res_hi, const void* res_lo,
+                             cudaStream_t stream) {
+  ADAMML_REQUIRE(scale_shift, "tc_conv_bn_act_x2: needs the folded BatchNorm scale / shift");
+  return conv_x2_impl(x_hi, x_lo, w4, y_hi, y_lo, IMGS, H, W, Cin, Cout, R, S, stride, pad, Ho, Wo, nullptr, 0,
+                      EpiSpec{scale_shift, act}, res_hi, res_lo, stream);
+}
+
+static int gemm_x2_impl(const void* A_hi, const void* A_lo, const void* B4, void* D_hi, void* D_lo, long long M,
+                        int Ncols, int K, double* stats, long long rows_per_group, const EpiSpec& epi,
+                        const void* res_hi, const void* res_lo, cudaStream_t stream) {
   if (!adamml_tc_supported(M, Ncols, K, K, K, Ncols)) {
     adamml_set_error("tc_gemm_x2: shape M=%lld N=%d K=%d outside the tcgen05 envelope", M, Ncols, K);
     return ADAMML_ERR_UNSUPPORTED;
@@ -1053,17 +1121,39 @@ int adamml_tc_gemm_x2(const void* A_hi, const void* A_lo, const void* B4, void* 
   ConvGeom geo;
   memset(&cm, 0, sizeof(cm));
   memset(&geo, 0, sizeof(geo));
-  void* dlin = (Ncols <= block_n && (Ncols % 64) != 0) ? D_hi : nullptr;
+  void* dlin = (!res_hi && Ncols <= block_n && (Ncols % 64) != 0) ? D_hi : nullptr;
   x2.dlin_lo = dlin ? D_lo : nullptr;
+  CUtensorMap tmAdd = tmD;
+  if (res_hi) {
+    ADAMML_REQUIRE(res_lo && ((uintptr_t)res_hi % 16) == 0 && ((uintptr_t)res_lo % 16) == 0,
+                   "tc_gemm_x2: the residual needs both planes, 16-byte aligned");
+    rc = make_map_2d(&tmAdd, res_hi, M, Ncols, Ncols, BLOCK_M);
+    if (!rc) rc = make_map_2d(&x2.add, res_lo, M, Ncols, Ncols, BLOCK_M);
+    if (rc) return rc;
+  }
   const int variant = x2_variant(K, Ncols);
   if (variant == 2)
-    return launch_tc<64, false, false, 2>(tmA, tmB, tmD, tmD, cm, geo, nullptr, M, Ncols, K, Ncols, stats,
-                                          rows_per_group, stream, dlin, x2);
+    return launch_tc<64, false, false, 2>(tmA, tmB, tmD, tmAdd, cm, geo, res_hi, M, Ncols, K, Ncols, stats,
+                                          rows_per_group, stream, dlin, x2, epi);
   if (variant == 3)
-    return launch_tc<64, false, false, 3>(tmA, tmB, tmD, tmD, cm, geo, nullptr, M, Ncols, K, Ncols, stats,
-                                          rows_per_group, stream, dlin, x2);
-  return launch_tc<64, false, false, 1>(tmA, tmB, tmD, tmD, cm, geo, nullptr, M, Ncols, K, Ncols, stats,
-                                        rows_per_group, stream, dlin, x2);
+    return launch_tc<64, false, false, 3>(tmA, tmB, tmD, tmAdd, cm, geo, res_hi, M, Ncols, K, Ncols, stats,
+                                          rows_per_group, stream, dlin, x2, epi);
+  return launch_tc<64, false, false, 1>(tmA, tmB, tmD, tmAdd, cm, geo, res_hi, M, Ncols, K, Ncols, stats,
+                                        rows_per_group, stream, dlin, x2, epi);
+}
+
+int adamml_tc_gemm_x2(const void* A_hi, const void* A_lo, const void* B4, void* D_hi, void* D_lo, long long M,
+                      int Ncols, int K, double* stats, long long rows_per_group, cudaStream_t stream) {
+  return gemm_x2_impl(A_hi, A_lo, B4, D_hi, D_lo, M, Ncols, K, stats, rows_per_group,
+                      EpiSpec{nullptr, ADAMML_ACT_NONE}, nullptr, nullptr, stream);
+}
+
+int adamml_tc_gemm_bn_act_x2(const void* A_hi, const void* A_lo, const void* B4, void* D_hi, void* D_lo, long long M,
+                             int Ncols, int K, const float* scale_shift, int act, const void* res_hi,
+                             const void* res_lo, cudaStream_t stream) {
+  ADAMML_REQUIRE(scale_shift, "tc_gemm_bn_act_x2: needs the folded BatchNorm scale / shift");
+  return gemm_x2_impl(A_hi, A_lo, B4, D_hi, D_lo, M, Ncols, K, nullptr, 0, EpiSpec{scale_shift, act}, res_hi, res_lo,
+                      stream);
 }
 
 /* Data gradient of a stride-2 convolution (resnet.py:100 conv2 of the first Bottleneck of layer2-4) as four
@@ -1127,8 +1217,9 @@ int adamml_tc_dgrad_s2_bf16(const void* dy, const void* w_rot, void* dx, int IMG
  * that window is CONTIGUOUS in memory, so it is one TMA box of a tensor map whose W stride (Cs elements) is
  * smaller than its innermost extent (4*Cs elements) — an overlapping, im2col-free view.  K = 16*Cs.
  * w: adamml_pack_weight_stem operand [Cout][4][4*Cs] bf16. */
-int adamml_tc_stem_conv_bf16(const void* xs, const void* w, void* y, int IMGS, int Hs, int Wp, int Cs, int Cout,
-                             int Ho, int Wo, int taps, double* stats, int imgs_per_group, cudaStream_t stream) {
+static int stem_bf16_impl(const void* xs, const void* w, void* y, int IMGS, int Hs, int Wp, int Cs, int Cout, int Ho,
+                          int Wo, int taps, double* stats, int imgs_per_group, const EpiSpec& epi,
+                          cudaStream_t stream) {
   if (Cs % 8 || Cout % 8 || (taps != 4 && taps != 2) || taps * Cs > 256) {
     adamml_set_error("tc_stem_conv: Cs=%d Cout=%d taps=%d outside the tcgen05 envelope", Cs, Cout, taps);
     return ADAMML_ERR_UNSUPPORTED;
@@ -1141,14 +1232,27 @@ int adamml_tc_stem_conv_bf16(const void* xs, const void* w, void* y, int IMGS, i
   ConvMaps cm;
   int rc = stem_setup(geo, cm, nullptr, xs, nullptr, IMGS, Hs, Wp, Cs, Ho, Wo, taps, imgs_per_group);
   if (rc) return rc;
-  return run_conv(geo, cm, w, (long long)taps * taps * Cs, y, nullptr, Cout, stats, stream);
+  return run_conv(geo, cm, w, (long long)taps * taps * Cs, y, nullptr, Cout, stats, stream, epi);
+}
+
+int adamml_tc_stem_conv_bf16(const void* xs, const void* w, void* y, int IMGS, int Hs, int Wp, int Cs, int Cout,
+                             int Ho, int Wo, int taps, double* stats, int imgs_per_group, cudaStream_t stream) {
+  return stem_bf16_impl(xs, w, y, IMGS, Hs, Wp, Cs, Cout, Ho, Wo, taps, stats, imgs_per_group,
+                        EpiSpec{nullptr, ADAMML_ACT_NONE}, stream);
+}
+
+int adamml_tc_stem_conv_bn_act_bf16(const void* xs, const void* w, void* y, int IMGS, int Hs, int Wp, int Cs, int Cout,
+                                    int Ho, int Wo, int taps, const float* scale_shift, int act,
+                                    cudaStream_t stream) {
+  ADAMML_REQUIRE(scale_shift, "tc_stem_conv_bn_act: needs the folded BatchNorm scale / shift");
+  return stem_bf16_impl(xs, w, y, IMGS, Hs, Wp, Cs, Cout, Ho, Wo, taps, nullptr, 0, EpiSpec{scale_shift, act}, stream);
 }
 
 /* x2 planes of the same first convolutions (operands from adamml_pack_frames_s2d_x2 / adamml_nhwc_to_s2d per plane and
  * adamml_pack_weight_x2 with stem = 1). */
-int adamml_tc_stem_conv_x2(const void* xs_hi, const void* xs_lo, const void* w4, void* y_hi, void* y_lo, int IMGS,
-                           int Hs, int Wp, int Cs, int Cout, int Ho, int Wo, int taps, double* stats,
-                           int imgs_per_group, cudaStream_t stream) {
+static int stem_x2_impl(const void* xs_hi, const void* xs_lo, const void* w4, void* y_hi, void* y_lo, int IMGS,
+                        int Hs, int Wp, int Cs, int Cout, int Ho, int Wo, int taps, double* stats,
+                        int imgs_per_group, const EpiSpec& epi, cudaStream_t stream) {
   if (Cs % 8 || Cout % 8 || (taps != 4 && taps != 2) || taps * Cs > 256) {
     adamml_set_error("tc_stem_conv_x2: Cs=%d Cout=%d taps=%d outside the tcgen05 envelope", Cs, Cout, taps);
     return ADAMML_ERR_UNSUPPORTED;
@@ -1163,7 +1267,22 @@ int adamml_tc_stem_conv_x2(const void* xs_hi, const void* xs_lo, const void* w4,
   ConvMaps cm, cm_lo;
   int rc = stem_setup(geo, cm, &cm_lo, xs_hi, xs_lo, IMGS, Hs, Wp, Cs, Ho, Wo, taps, imgs_per_group);
   if (rc) return rc;
-  return run_conv_x2(geo, cm, cm_lo, w4, (long long)taps * taps * Cs, y_hi, y_lo, Cout, stats, stream);
+  return run_conv_x2(geo, cm, cm_lo, w4, (long long)taps * taps * Cs, y_hi, y_lo, Cout, stats, stream, epi);
+}
+
+int adamml_tc_stem_conv_x2(const void* xs_hi, const void* xs_lo, const void* w4, void* y_hi, void* y_lo, int IMGS,
+                           int Hs, int Wp, int Cs, int Cout, int Ho, int Wo, int taps, double* stats,
+                           int imgs_per_group, cudaStream_t stream) {
+  return stem_x2_impl(xs_hi, xs_lo, w4, y_hi, y_lo, IMGS, Hs, Wp, Cs, Cout, Ho, Wo, taps, stats, imgs_per_group,
+                      EpiSpec{nullptr, ADAMML_ACT_NONE}, stream);
+}
+
+int adamml_tc_stem_conv_bn_act_x2(const void* xs_hi, const void* xs_lo, const void* w4, void* y_hi, void* y_lo,
+                                  int IMGS, int Hs, int Wp, int Cs, int Cout, int Ho, int Wo, int taps,
+                                  const float* scale_shift, int act, cudaStream_t stream) {
+  ADAMML_REQUIRE(scale_shift, "tc_stem_conv_bn_act_x2: needs the folded BatchNorm scale / shift");
+  return stem_x2_impl(xs_hi, xs_lo, w4, y_hi, y_lo, IMGS, Hs, Wp, Cs, Cout, Ho, Wo, taps, nullptr, 0,
+                      EpiSpec{scale_shift, act}, stream);
 }
 
 }  // extern "C"

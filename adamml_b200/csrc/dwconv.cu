@@ -26,6 +26,19 @@ __device__ __forceinline__ void load_w9(const float* __restrict__ w, int C, int 
     }
 }
 
+// Fused inference BatchNorm + ReLU/ReLU6 of a depthwise ConvBNReLU (sound_mobilenet_v2.py:58, policy_net.py:66,80): with
+// running statistics BN is a per-channel affine map, applied to the accumulators before the store.  ss = [C][2] fp32
+// (scale, shift) or nullptr.
+template <int V>
+__device__ __forceinline__ void bn_act_vec(float (&a)[V], const float* __restrict__ ss, int c0, int act) {
+  if (!ss) return;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const float2 p = *reinterpret_cast<const float2*>(ss + 2 * (c0 + i));
+    a[i] = act_apply(fmaf(a[i], p.x, p.y), act);
+  }
+}
+
 // Stride-1 stencil shared by forward (FLIP = false) and data gradient (FLIP = true: 180-degree rotated
 // weights, + optional addend).  Strip of SW outputs along W.
 template <typename T, bool FLIP, int SW>
@@ -154,7 +167,7 @@ template <> struct DwVec<x2_t> {
 template <typename T, bool FLIP, int SW, int RH, typename CP, typename MP>
 __device__ __forceinline__ void
 dw_s1_band_body(CP x, const float* __restrict__ w, MP y, CP addend, int IMGS, int H, int W, int C, int strips,
-                int bands) {
+                int bands, const float* __restrict__ ss = nullptr, int act = ADAMML_ACT_NONE) {
   typedef DwVec<T> VIO;
   constexpr int V = VIO::N;
   constexpr int NC = SW + 2;
@@ -215,6 +228,7 @@ dw_s1_band_body(CP x, const float* __restrict__ w, MP y, CP addend, int IMGS, in
 #pragma unroll
         for (int i = 0; i < V; ++i) acc[j][i] += a[i];
       }
+      bn_act_vec<V>(acc[j], ss, c0, act);
       VIO::store(y + o, acc[j]);
     }
   };
@@ -238,20 +252,23 @@ dw_s1_band_body(CP x, const float* __restrict__ w, MP y, CP addend, int IMGS, in
 template <typename T, bool FLIP, int SW, int RH>
 __global__ void __launch_bounds__(DW_THREADS, 4)
 dw_s1_band_kernel(const T* __restrict__ x, const float* __restrict__ w, T* __restrict__ y,
-                  const T* __restrict__ addend, int IMGS, int H, int W, int C, int strips, int bands) {
-  dw_s1_band_body<T, FLIP, SW, RH, const T*, T*>(x, w, y, addend, IMGS, H, W, C, strips, bands);
+                  const T* __restrict__ addend, int IMGS, int H, int W, int C, int strips, int bands,
+                  const float* __restrict__ ss, int act) {
+  dw_s1_band_body<T, FLIP, SW, RH, const T*, T*>(x, w, y, addend, IMGS, H, W, C, strips, bands, ss, act);
 }
 template <int SW, int RH>
 __global__ void __launch_bounds__(DW_THREADS, 3)
 dw_s1_band_x2_kernel(X2CPtr x, const float* __restrict__ w, X2Ptr y, int IMGS, int H, int W, int C, int strips,
-                     int bands) {
-  dw_s1_band_body<x2_t, false, SW, RH, X2CPtr, X2Ptr>(x, w, y, X2CPtr{nullptr, nullptr}, IMGS, H, W, C, strips, bands);
+                     int bands, const float* __restrict__ ss, int act) {
+  dw_s1_band_body<x2_t, false, SW, RH, X2CPtr, X2Ptr>(x, w, y, X2CPtr{nullptr, nullptr}, IMGS, H, W, C, strips, bands,
+                                                       ss, act);
 }
 
 // Stride-2 forward: strip of SW outputs needs 2*SW+1 input columns per row.
 template <typename T, int SW, typename CP, typename MP>
 __device__ __forceinline__ void
-dw_s2_fwd_body(CP x, const float* __restrict__ w, MP y, int IMGS, int H, int W, int C, int Ho, int Wo, int strips) {
+dw_s2_fwd_body(CP x, const float* __restrict__ w, MP y, int IMGS, int H, int W, int C, int Ho, int Wo, int strips,
+               const float* __restrict__ ss, int act) {
   constexpr int V = VecIO<T>::N;
   const int cvecs = C / V;
   const long long total = (long long)IMGS * Ho * strips * cvecs;
@@ -302,6 +319,7 @@ dw_s2_fwd_body(CP x, const float* __restrict__ w, MP y, int IMGS, int H, int W, 
   for (int j = 0; j < SW; ++j) {
     const int wo = w0 + j;
     if (wo >= Wo) continue;
+    bn_act_vec<V>(acc[j], ss, c0, act);
     VecIO<T>::store(y + ((img * Ho + ho) * Wo + wo) * C + c0, acc[j]);
   }
 }
@@ -309,14 +327,14 @@ dw_s2_fwd_body(CP x, const float* __restrict__ w, MP y, int IMGS, int H, int W, 
 template <typename T, int SW>
 __global__ void __launch_bounds__(DW_THREADS)
 dw_s2_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w, T* __restrict__ y, int IMGS, int H, int W,
-                 int C, int Ho, int Wo, int strips) {
-  dw_s2_fwd_body<T, SW, const T*, T*>(x, w, y, IMGS, H, W, C, Ho, Wo, strips);
+                 int C, int Ho, int Wo, int strips, const float* __restrict__ ss, int act) {
+  dw_s2_fwd_body<T, SW, const T*, T*>(x, w, y, IMGS, H, W, C, Ho, Wo, strips, ss, act);
 }
 template <int SW>
 __global__ void __launch_bounds__(DW_THREADS)
 dw_s2_fwd_x2_kernel(X2CPtr x, const float* __restrict__ w, X2Ptr y, int IMGS, int H, int W, int C, int Ho, int Wo,
-                    int strips) {
-  dw_s2_fwd_body<x2_t, SW, X2CPtr, X2Ptr>(x, w, y, IMGS, H, W, C, Ho, Wo, strips);
+                    int strips, const float* __restrict__ ss, int act) {
+  dw_s2_fwd_body<x2_t, SW, X2CPtr, X2Ptr>(x, w, y, IMGS, H, W, C, Ho, Wo, strips, ss, act);
 }
 
 // Stride-2 data gradient: one thread per 2x2 input quad (rows 2m, 2m+1; cols 2n, 2n+1) and channel vector;
@@ -587,34 +605,49 @@ inline unsigned blocks_for(long long total, int threads) { return (unsigned)((to
 
 extern "C" {
 
-int adamml_dwconv_fwd(const void* x, const float* w, void* y, int IMGS, int H, int W, int C, int stride, int Ho,
-                      int Wo, int dtype, cudaStream_t stream) {
+static int dwconv_fwd_impl(const void* x, const float* w, void* y, int IMGS, int H, int W, int C, int stride, int Ho,
+                           int Wo, int dtype, const float* ss, int act, cudaStream_t stream) {
   ADAMML_REQUIRE(stride == 1 || stride == 2, "dwconv: stride must be 1 or 2");
   ADAMML_REQUIRE(Ho == (H + 2 - 3) / stride + 1 && Wo == (W + 2 - 3) / stride + 1, "dwconv: bad Ho/Wo");
   ADAMML_DISPATCH_DTYPE(dtype, T, {
-    if (!dw_vec_ok<T>(C, x, y))
+    if (!dw_vec_ok<T>(C, x, y)) {
+      ADAMML_REQUIRE(!ss, "dwconv: the fused BatchNorm epilogue needs a vectorisable channel count");
       return adamml_dwconv_fwd_scalar(x, w, y, IMGS, H, W, C, stride, Ho, Wo, dtype, stream);
+    }
     const int cvecs = C / VecIO<T>::N;
     if (stride == 1) {
       constexpr int SW = 2, RH = 16;
       const int strips = (W + SW - 1) / SW, bands = (H + RH - 1) / RH;
       const long long total = (long long)IMGS * bands * strips * (C / DwVec<T>::N);
       dw_s1_band_kernel<T, false, SW, RH><<<blocks_for(total, DW_THREADS), DW_THREADS, 0, stream>>>(
-          (const T*)x, w, (T*)y, nullptr, IMGS, H, W, C, strips, bands);
+          (const T*)x, w, (T*)y, nullptr, IMGS, H, W, C, strips, bands, ss, act);
     } else {
       constexpr int SW = 2;
       const int strips = (Wo + SW - 1) / SW;
       const long long total = (long long)IMGS * Ho * strips * cvecs;
-      dw_s2_fwd_kernel<T, SW><<<blocks_for(total, DW_THREADS), DW_THREADS, 0, stream>>>((const T*)x, w, (T*)y, IMGS,
-                                                                                         H, W, C, Ho, Wo, strips);
+      dw_s2_fwd_kernel<T, SW><<<blocks_for(total, DW_THREADS), DW_THREADS, 0, stream>>>(
+          (const T*)x, w, (T*)y, IMGS, H, W, C, Ho, Wo, strips, ss, act);
     }
   });
   return adamml_check_launch("dwconv_fwd");
 }
 
+int adamml_dwconv_fwd(const void* x, const float* w, void* y, int IMGS, int H, int W, int C, int stride, int Ho,
+                      int Wo, int dtype, cudaStream_t stream) {
+  return dwconv_fwd_impl(x, w, y, IMGS, H, W, C, stride, Ho, Wo, dtype, nullptr, ADAMML_ACT_NONE, stream);
+}
+
+/* inference-mode depthwise conv + BatchNorm + ReLU/ReLU6 in one pass: y = act(dwconv(x) * scale[c] + shift[c]) */
+int adamml_dwconv_bn_act_fwd(const void* x, const float* w, void* y, int IMGS, int H, int W, int C, int stride, int Ho,
+                             int Wo, const float* scale_shift, int act, int dtype, cudaStream_t stream) {
+  ADAMML_REQUIRE(scale_shift, "dwconv_bn_act: needs the folded BatchNorm scale / shift");
+  return dwconv_fwd_impl(x, w, y, IMGS, H, W, C, stride, Ho, Wo, dtype, scale_shift, act, stream);
+}
+
 /* x2 planes (forward pass of the default precision mode); C % 8 == 0 */
-int adamml_dwconv_fwd_x2(const void* x_hi, const void* x_lo, const float* w, void* y_hi, void* y_lo, int IMGS, int H,
-                         int W, int C, int stride, int Ho, int Wo, cudaStream_t stream) {
+static int dwconv_fwd_x2_impl(const void* x_hi, const void* x_lo, const float* w, void* y_hi, void* y_lo, int IMGS,
+                              int H, int W, int C, int stride, int Ho, int Wo, const float* ss, int act,
+                              cudaStream_t stream) {
   ADAMML_REQUIRE(stride == 1 || stride == 2, "dwconv: stride must be 1 or 2");
   ADAMML_REQUIRE(Ho == (H + 2 - 3) / stride + 1 && Wo == (W + 2 - 3) / stride + 1, "dwconv: bad Ho/Wo");
   ADAMML_REQUIRE(dw_vec_ok<bf16>(C, x_hi, x_lo, y_hi, y_lo), "dwconv_fwd_x2: needs C %% 8 == 0 and aligned planes");
@@ -623,15 +656,27 @@ int adamml_dwconv_fwd_x2(const void* x_hi, const void* x_lo, const float* w, voi
     const int strips = (W + SW - 1) / SW, bands = (H + RH - 1) / RH;
     const long long total = (long long)IMGS * bands * strips * (C / 4);
     dw_s1_band_x2_kernel<SW, RH><<<blocks_for(total, DW_THREADS), DW_THREADS, 0, stream>>>(
-        x2c(x_hi, x_lo), w, x2m(y_hi, y_lo), IMGS, H, W, C, strips, bands);
+        x2c(x_hi, x_lo), w, x2m(y_hi, y_lo), IMGS, H, W, C, strips, bands, ss, act);
   } else {
     constexpr int SW = 2;
     const int strips = (Wo + SW - 1) / SW;
     const long long total = (long long)IMGS * Ho * strips * (C / 8);
     dw_s2_fwd_x2_kernel<SW><<<blocks_for(total, DW_THREADS), DW_THREADS, 0, stream>>>(
-        x2c(x_hi, x_lo), w, x2m(y_hi, y_lo), IMGS, H, W, C, Ho, Wo, strips);
+        x2c(x_hi, x_lo), w, x2m(y_hi, y_lo), IMGS, H, W, C, Ho, Wo, strips, ss, act);
   }
   return adamml_check_launch("dwconv_fwd_x2");
+}
+
+int adamml_dwconv_fwd_x2(const void* x_hi, const void* x_lo, const float* w, void* y_hi, void* y_lo, int IMGS, int H,
+                         int W, int C, int stride, int Ho, int Wo, cudaStream_t stream) {
+  return dwconv_fwd_x2_impl(x_hi, x_lo, w, y_hi, y_lo, IMGS, H, W, C, stride, Ho, Wo, nullptr, ADAMML_ACT_NONE, stream);
+}
+
+int adamml_dwconv_bn_act_fwd_x2(const void* x_hi, const void* x_lo, const float* w, void* y_hi, void* y_lo, int IMGS,
+                                int H, int W, int C, int stride, int Ho, int Wo, const float* scale_shift, int act,
+                                cudaStream_t stream) {
+  ADAMML_REQUIRE(scale_shift, "dwconv_bn_act_x2: needs the folded BatchNorm scale / shift");
+  return dwconv_fwd_x2_impl(x_hi, x_lo, w, y_hi, y_lo, IMGS, H, W, C, stride, Ho, Wo, scale_shift, act, stream);
 }
 
 int adamml_dwconv_dgrad(const void* dy, const float* w, void* dx, const void* addend, int IMGS, int H, int W, int C,
@@ -647,7 +692,7 @@ int adamml_dwconv_dgrad(const void* dy, const float* w, void* dx, const void* ad
       const int strips = (W + SW - 1) / SW, bands = (H + RH - 1) / RH;
       const long long total = (long long)IMGS * bands * strips * (C / DwVec<T>::N);
       dw_s1_band_kernel<T, true, SW, RH><<<blocks_for(total, DW_THREADS), DW_THREADS, 0, stream>>>(
-          (const T*)dy, w, (T*)dx, (const T*)addend, IMGS, H, W, C, strips, bands);
+          (const T*)dy, w, (T*)dx, (const T*)addend, IMGS, H, W, C, strips, bands, nullptr, ADAMML_ACT_NONE);
     } else {
       const long long total = (long long)IMGS * ((H + 1) / 2) * ((W + 1) / 2) * cvecs;
       dw_s2_dgrad_kernel<T><<<blocks_for(total, DW_THREADS), DW_THREADS, 0, stream>>>(

@@ -14,6 +14,12 @@ from .dist_utils import P2PStats, allreduce_stats, sync_bn_group
 from .ops import ACT_NONE, ACT_RELU, ACT_RELU6
 
 
+# inference: conv + BN (+ residual) + act fused into one kernel (Exec._cba_fused_eval); ADAMML_B200_FUSE_EVAL=0 keeps the
+# conv -> bn_apply pair (tests compare the two)
+import os as _os
+FUSE_EVAL = _os.environ.get("ADAMML_B200_FUSE_EVAL", "1") != "0"
+
+
 def _bn_key(bn):
     """slot key of a BatchNorm layer in the peer-memory arena: its index in the model's module order (assigned by
     assign_bn_keys, identical on every rank) rather than a per-process id()"""
@@ -64,6 +70,10 @@ class Exec:
 
         res_rec: record returned by `conv_bn_stats` for the downsample branch (resnet.py:164-167).
         """
+        if not self.training and not self.save and FUSE_EVAL:
+            out = self._cba_fused_eval(x, conv, bn, act, res, res_rec)
+            if out is not None:
+                return out
         rec = self.conv_bn_stats(x, conv, bn)
         out = ops.bn_apply(rec["z"], rec["ss"], self.G, act, res=res,
                            res_z=res_rec["z"] if res_rec else None, res_ss=res_rec["ss"] if res_rec else None)
@@ -79,6 +89,35 @@ class Exec:
                        has_res=res is not None, res_rec=res_rec)
             self.tape.append(rec)
         return out
+
+    def _cba_fused_eval(self, x, conv, bn, act, res, res_rec):
+        """Inference (running statistics, no tape): conv + BN (+ residual) + ReLU/ReLU6 as ONE kernel — the folded
+        scale / shift, the residual add and the activation run in the epilogue of the convolution (tcgen05 for dense
+        layers, the stencil kernel for depthwise ones); the pre-BN tensor z never exists (resnet.py:96-111).
+        -> None when the layer is outside that envelope (the caller runs conv -> bn_apply)."""
+        w = conv.weight
+        Cout, _, R, S = w.shape
+        stride, pad = conv.stride[0], conv.padding[0]
+        if conv.groups > 1 and (res is not None or res_rec is not None):
+            return None
+        if res_rec is not None:  # BN(downsample) as residual: that branch was not pre-reduced to a plain tensor
+            return None
+        _, ss = ops.bn_finalize(None, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, 1, 0.1,
+                                bn.eps, Cout, 1, False, False)
+        ss = ss[0]
+        if (not isinstance(x, ops.S2D) and conv.groups == 1 and w.shape[1] < 16 and (R, S) == (3, 3)
+                and ops.first_conv_s2d_ok(conv, w.shape[1], x.shape[1], x.shape[2], x.dtype)):
+            x = ops.nhwc_to_s2d(x, 3)
+        if isinstance(x, ops.S2D):
+            return ops.stem_conv_bn_act_fwd(x, w.detach(), ss, act) if res is None else None
+        if conv.groups > 1:
+            if not (conv.groups == conv.in_channels == Cout and R == 3 and pad == 1):
+                return None
+            return ops.dwconv_bn_act_fwd(x, ops.pack_weight_dw(w.detach()), stride, ss, act)
+        if not (self.x2 or self.dtype == torch.bfloat16):
+            return None
+        wp = ops.pack_weight(w.detach(), ops.PREC_X2 if self.x2 else self.dtype)
+        return ops.conv_bn_act_fwd(x, wp, stride, pad, ss, act, res=res)
 
     def conv_bn_stats(self, x, conv, bn):
         """z = conv(x); BN statistics (train) or folded running stats (eval) -> record with z, mi, ss."""
@@ -217,6 +256,11 @@ class Exec:
         a = self.cba(x, blk.conv1, blk.bn1, ACT_RELU)
         a = self.cba(a, blk.conv2, blk.bn2, ACT_RELU)
         if blk.downsample is not None:
+            if not self.training and not self.save and FUSE_EVAL:
+                # inference: the downsample branch is a fused conv + BN kernel of its own, its output the residual
+                idt = self._cba_fused_eval(x, blk.downsample[0], blk.downsample[1], ACT_NONE, None, None)
+                if idt is not None:
+                    return self.cba(a, blk.conv3, blk.bn3, ACT_RELU, res=idt)
             ds = self.conv_bn_stats(x, blk.downsample[0], blk.downsample[1])
             return self.cba(a, blk.conv3, blk.bn3, ACT_RELU, res_rec=ds)
         return self.cba(a, blk.conv3, blk.bn3, ACT_RELU, res=x)
@@ -248,6 +292,10 @@ class Exec:
         """resnet.py:59-74."""
         a = self.cba(x, blk.conv1, blk.bn1, ACT_RELU)
         if blk.downsample is not None:
+            if not self.training and not self.save and FUSE_EVAL:
+                idt = self._cba_fused_eval(x, blk.downsample[0], blk.downsample[1], ACT_NONE, None, None)
+                if idt is not None:
+                    return self.cba(a, blk.conv2, blk.bn2, ACT_RELU, res=idt)
             ds = self.conv_bn_stats(x, blk.downsample[0], blk.downsample[1])
             return self.cba(a, blk.conv2, blk.bn2, ACT_RELU, res_rec=ds)
         return self.cba(a, blk.conv2, blk.bn2, ACT_RELU, res=x)

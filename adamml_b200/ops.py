@@ -380,6 +380,73 @@ def _conv_fwd_x2(x, w, stride, pad, stats, rows_per_group):
     return z, stats is not None
 
 
+# ---------------------------------------------------------------- inference: conv + BN (+ residual) + act, one kernel
+def conv_bn_act_fwd(x, w, stride, pad, ss, act, res=None):
+    """out = act(conv(x, w) * scale + shift (+ res)) in ONE tcgen05 kernel (fused inference epilogue, see the header).
+    x: bf16 NHWC or X2; w from pack_weight in the same mode; ss: fp32 [Cout, 2]; res: tensor of the output's shape.
+    -> None when the layer is outside the tensor-core envelope (the caller then runs the unfused ops)."""
+    IMGS, H, W, Cin = x.shape
+    Cout, R, S, Cw = w.shape
+    assert Cw == Cin, (w.shape, x.shape)
+    Ho, Wo = conv_out_hw(H, W, R, S, stride, pad)
+    _chk(ss, torch.float32)
+    if TC_MODE != "auto" or Cin % 8 or Cout % 8 or R * S > 49 or stride not in (1, 2):
+        return None
+    gemm = R == 1 and S == 1 and stride == 1 and pad == 0
+    if isinstance(x, X2):
+        out = X2.empty((IMGS, Ho, Wo, Cout), x.device)
+        rh, rl = (res.hi, res.lo) if res is not None else (None, None)
+        if gemm:
+            call("tc_gemm_bn_act_x2", x.hi, x.lo, w.planes, out.hi, out.lo, IMGS * H * W, Cout, Cin, ss, act, rh, rl)
+        else:
+            call("tc_conv_bn_act_x2", x.hi, x.lo, w.planes, out.hi, out.lo, IMGS, H, W, Cin, Cout, R, S, stride, pad,
+                 Ho, Wo, ss, act, rh, rl)
+        return out
+    if x.dtype != torch.bfloat16 or (not gemm and Cin < 16):
+        return None
+    _chk(x); _chk(w, torch.bfloat16)
+    out = torch.empty((IMGS, Ho, Wo, Cout), device=x.device, dtype=torch.bfloat16)
+    if gemm:
+        call("tc_gemm_bn_act_bf16", x, w, out, IMGS * H * W, Cout, Cin, ss, act, res)
+    else:
+        call("tc_conv_bn_act_bf16", x, w, out, IMGS, H, W, Cin, Cout, R, S, stride, pad, Ho, Wo, ss, act, res)
+    return out
+
+
+def stem_conv_bn_act_fwd(xs, w_oihw, ss, act):
+    """fused inference epilogue on the space-to-depth first convolutions (see stem_conv_fwd)"""
+    Cout = w_oihw.shape[0]
+    T = xs.taps
+    IMGS, Hs, Wp, Cs = xs.t.shape
+    Ho, Wo = xs.H // 2, xs.W // 2
+    if xs.lo is not None:
+        wp = torch.empty((4, Cout, T, T, xs.Cs), device=xs.device, dtype=torch.bfloat16)
+        call("pack_weight_x2", w_oihw, wp, Cout, xs.C, xs.R, xs.R, xs.Cs, 1)
+        out = X2.empty((IMGS, Ho, Wo, Cout), xs.device)
+        call("tc_stem_conv_bn_act_x2", xs.t, xs.lo, wp, out.hi, out.lo, IMGS, Hs, Wp, Cs, Cout, Ho, Wo, T, ss, act)
+        return out
+    wp = torch.empty((Cout, T, T, xs.Cs), device=xs.device, dtype=torch.bfloat16)
+    call("pack_weight_stem", w_oihw, wp, Cout, xs.C, xs.Cs, xs.R)
+    out = torch.empty((IMGS, Ho, Wo, Cout), device=xs.device, dtype=torch.bfloat16)
+    call("tc_stem_conv_bn_act_bf16", xs.t, wp, out, IMGS, Hs, Wp, Cs, Cout, Ho, Wo, T, ss, act)
+    return out
+
+
+def dwconv_bn_act_fwd(x, w, stride, ss, act):
+    """inference: y = act(dwconv(x) * scale + shift) in one pass; -> None for ragged channel counts"""
+    IMGS, H, W, C = x.shape
+    Ho, Wo = conv_out_hw(H, W, 3, 3, stride, 1)
+    if isinstance(x, X2):
+        y = X2.empty((IMGS, Ho, Wo, C), x.device)
+        call("dwconv_bn_act_fwd_x2", x.hi, x.lo, w, y.hi, y.lo, IMGS, H, W, C, stride, Ho, Wo, ss, act)
+        return y
+    if not vec_channels(x):
+        return None
+    y = torch.empty((IMGS, Ho, Wo, C), device=x.device, dtype=x.dtype)
+    call("dwconv_bn_act_fwd", x, w, y, IMGS, H, W, C, stride, Ho, Wo, ss, act, dtype_code(x.dtype))
+    return y
+
+
 def tc_dgrad_ok(dtype, Cout, Cin, R, S, stride):
     """data gradients that run on the tcgen05 engine (bf16): stride 1, stride-2 RxS (parity classes),
     stride-2 1x1 (compact GEMM, see conv_dgrad_compact)."""

@@ -250,6 +250,25 @@ int adamml_fuse_fwd(const float* logits, const float* dec, const float* lf, floa
 int adamml_fuse_bwd(const float* g, const float* logits, const float* dec, const float* lf, float* dlogits,
                     float* ddec, float* dlf, int M, int S, int N, int C, cudaStream_t stream);
 
+/* ---- inference-mode fused epilogue: conv + BatchNorm (+ residual) + ReLU/ReLU6 in ONE kernel ----
+ * resnet.py:96-111 (Bottleneck: conv -> bn -> relu, conv3 -> bn3 -> += identity -> relu), sound_mobilenet_v2.py:33-40
+ * and policy_net.py:38-52 (ConvBNReLU6).  With running statistics BatchNorm is a per-channel affine map known before
+ * the convolution runs, so out = act(acc * scale[c] + shift[c] (+ res)) leaves the tcgen05 accumulator directly:
+ * the pre-BN tensor is never written and there is no separate BN / add / ReLU pass.  scale_shift = [Cout][2] fp32
+ * (group 0 of adamml_bn_finalize in eval mode); res = optional tensor of the output's shape (fetched by TMA into the
+ * epilogue's staging tile); act applies after the addend.  Training uses batch statistics, which only exist after the
+ * convolution: the train path keeps the fused-statistics epilogue + adamml_bn_apply. */
+int adamml_tc_gemm_bn_act_bf16(const void* A, const void* B, void* D, long long M, int Ncols, int K,
+                               const float* scale_shift, int act, const void* res, cudaStream_t stream);
+int adamml_tc_conv_bn_act_bf16(const void* x, const void* w, void* y, int IMGS, int H, int W, int Cin, int Cout, int R,
+                               int S, int stride, int pad, int Ho, int Wo, const float* scale_shift, int act,
+                               const void* res, cudaStream_t stream);
+int adamml_tc_stem_conv_bn_act_bf16(const void* xs, const void* w, void* y, int IMGS, int Hs, int Wp, int Cs, int Cout,
+                                    int Ho, int Wo, int taps, const float* scale_shift, int act,
+                                    cudaStream_t stream);
+int adamml_dwconv_bn_act_fwd(const void* x, const float* w, void* y, int IMGS, int H, int W, int C, int stride, int Ho,
+                             int Wo, const float* scale_shift, int act, int dtype, cudaStream_t stream);
+
 /* ---- "x2" forward path: two-plane activations (default precision mode) ----
  * north_star asks for logits within 1e-3 of the reference's fp32 path and bit-exact policy selections; bf16
  * storage (8 mantissa bits) misses that by two orders of magnitude on these 50-layer BatchNorm stacks.  In x2 mode
@@ -281,6 +300,19 @@ int adamml_tc_conv_x2(const void* x_hi, const void* x_lo, const void* w4, void* 
 int adamml_tc_stem_conv_x2(const void* xs_hi, const void* xs_lo, const void* w4, void* y_hi, void* y_lo, int IMGS,
                            int Hs, int Wp, int Cs, int Cout, int Ho, int Wo, int taps, double* stats,
                            int imgs_per_group, cudaStream_t stream);
+int adamml_tc_gemm_bn_act_x2(const void* A_hi, const void* A_lo, const void* B4, void* D_hi, void* D_lo, long long M,
+                             int Ncols, int K, const float* scale_shift, int act, const void* res_hi,
+                             const void* res_lo, cudaStream_t stream);
+int adamml_tc_conv_bn_act_x2(const void* x_hi, const void* x_lo, const void* w4, void* y_hi, void* y_lo, int IMGS,
+                             int H, int W, int Cin, int Cout, int R, int S, int stride, int pad, int Ho, int Wo,
+                             const float* scale_shift, int act, const void* res_hi, const void* res_lo,
+                             cudaStream_t stream);
+int adamml_tc_stem_conv_bn_act_x2(const void* xs_hi, const void* xs_lo, const void* w4, void* y_hi, void* y_lo,
+                                  int IMGS, int Hs, int Wp, int Cs, int Cout, int Ho, int Wo, int taps,
+                                  const float* scale_shift, int act, cudaStream_t stream);
+int adamml_dwconv_bn_act_fwd_x2(const void* x_hi, const void* x_lo, const float* w, void* y_hi, void* y_lo, int IMGS,
+                                int H, int W, int C, int stride, int Ho, int Wo, const float* scale_shift, int act,
+                                cudaStream_t stream);
 int adamml_dwconv_fwd_x2(const void* x_hi, const void* x_lo, const float* w, void* y_hi, void* y_lo, int IMGS, int H,
                          int W, int C, int stride, int Ho, int Wo, cudaStream_t stream);
 int adamml_bn_stats_x2(const void* z_hi, const void* z_lo, double* sums, long long rows_per_group, int C, int G,
