@@ -24,7 +24,22 @@ int adamml_check_launch(const char* what) {
   return ADAMML_OK;
 }
 
+static thread_local const int* g_live_n = nullptr;
+static thread_local int g_live_cap = 0;
+
+LiveLimit adamml_live_limit(long long capacity_items) {
+  if (!g_live_n || g_live_cap <= 0 || capacity_items % g_live_cap) return LiveLimit{nullptr, 0};
+  return LiveLimit{g_live_n, (int)(capacity_items / g_live_cap)};
+}
+
 extern "C" {
+
+// see include/adamml_b200.h: device-side work limit of the calling thread's following forward launches
+int adamml_set_live_clips(const int* live_clips, int clip_capacity) {
+  g_live_n = live_clips;
+  g_live_cap = live_clips ? clip_capacity : 0;
+  return ADAMML_OK;
+}
 
 const char* adamml_last_error(void) { return g_err; }
 

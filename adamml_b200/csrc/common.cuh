@@ -32,6 +32,22 @@ int adamml_dwconv_dgrad_scalar(const void* dy, const float* w, void* dx, const v
 int adamml_dwconv_wgrad_scalar(const void* x, const void* dy, float* dw, int IMGS, int H, int W, int C, int stride,
                                int Ho, int Wo, int dtype, cudaStream_t stream);
 
+// Device-side work limit (inference with decision-driven skipping, models/adamml.py:81-86): the batch buffers keep
+// their static capacity, but only the first *n clips hold selected (segment, video) pairs; `unit` = images (or GEMM
+// rows) per clip at this layer.  Kernels read *n on the device and skip every tile / thread beyond it, so the host
+// never learns the count (no D2H copy, no data-dependent launch shape -> the pass is CUDA-graph capturable).
+struct LiveLimit {
+  const int* n;  // nullptr: everything is live
+  int unit;
+};
+// set by adamml_set_live_clips (api.cu, thread local); imgs = static capacity of the op (images or rows)
+LiveLimit adamml_live_limit(long long capacity_items);
+__device__ __forceinline__ long long live_count(const LiveLimit& l, long long cap) {
+  if (!l.n) return cap;
+  const long long v = (long long)(*l.n) * l.unit;
+  return v < cap ? v : cap;
+}
+
 #define ADAMML_REQUIRE(cond, ...)                 \
   do {                                            \
     if (!(cond)) {                                \

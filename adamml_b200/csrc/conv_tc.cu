@@ -64,6 +64,7 @@ struct X2Maps {
 struct EpiSpec {
   const float* ss;
   int act;
+  LiveLimit live = LiveLimit{nullptr, 0};  // inference with skipping: only the first live.n clips are computed
 };
 
 // SHALLOW: reductions of one or two K blocks (the MobileNetV2 expand / project-gradient GEMMs, K = 16..96).  Their
@@ -205,7 +206,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int num_m_blks = CONV ? geo.tiles_w * geo.tiles_h * geo.tiles_i : (int)((M + BLOCK_M - 1) / BLOCK_M);
+  int num_m_blks = CONV ? geo.tiles_w * geo.tiles_h * geo.tiles_i : (int)((M + BLOCK_M - 1) / BLOCK_M);
+  if (epi.live.n) {  // device-side work limit: row blocks are image-major, so the live ones come first
+    if (CONV) {
+      const int ti = (int)((live_count(epi.live, geo.IMGS) + geo.BI - 1) / geo.BI);
+      num_m_blks = geo.tiles_w * geo.tiles_h * ti;
+    } else {
+      num_m_blks = (int)((live_count(epi.live, M) + BLOCK_M - 1) / BLOCK_M);
+    }
+  }
   const int num_n_blks = (Ncols + BLOCK_N - 1) / BLOCK_N;
   const long long num_tiles = (long long)num_m_blks * num_n_blks;
   const int num_kb = CONV ? geo.ntaps * geo.kb_per_tap : (K + BLOCK_K - 1) / BLOCK_K;
@@ -724,8 +733,10 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap&
     pin_n = 1;
     grid = (sms / n_blks) * n_blks;
   }
+  EpiSpec e = epi;
+  if (e.ss && !stats) e.live = adamml_live_limit(CONV ? (long long)geo.IMGS : M);  // inference launches only
   kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmD, tmAdd, cm, geo, x2, (const bf16*)addend, M,
-                                                        Ncols, K, ldd, stats, rpg, (bf16*)dlin, pin_n, epi);
+                                                        Ncols, K, ldd, stats, rpg, (bf16*)dlin, pin_n, e);
   return adamml_check_launch(CONV ? "tc_conv" : "tc_gemm");
 }
 

@@ -225,9 +225,9 @@ __global__ void pack_frames_s2d_kernel(const TIn* __restrict__ x, InNorm nm, bf1
 // NHWC bf16 [IMGS, H, W, C] -> space-to-depth bf16 [IMGS, H/2, W/2 + padl + padr, Cs] (zero pad columns, channel
 // (ph*2+pw)*C + c): operand of the stride-2 first convolutions of the MobileNetV2s on the tensor-core path.
 __global__ void nhwc_to_s2d_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, long long IMGS, int C, int H,
-                                   int W, int Cs, int padl, int padr) {
+                                   int W, int Cs, int padl, int padr, LiveLimit live) {
   const int Hs = H / 2, Ws = W / 2, Wp = Ws + padl + padr;
-  const long long total = IMGS * Hs * Wp;
+  const long long total = live_count(live, IMGS) * Hs * Wp;  // (device-side work limit: inference with skipping)
   const bf16 zero = __float2bfloat16_rn(0.f);
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -482,7 +482,8 @@ int adamml_nhwc_to_s2d(const void* x, void* out, long long IMGS, int C, int H, i
   ADAMML_REQUIRE(IMGS > 0 && C > 0 && H > 0 && W > 0 && padl >= 0 && padr >= 0, "nhwc_to_s2d: bad dims");
   ADAMML_REQUIRE(H % 2 == 0 && W % 2 == 0 && Cs >= 4 * C, "nhwc_to_s2d: needs even H, W and Cs >= 4C");
   long long total = IMGS * (H / 2) * (W / 2 + padl + padr);
-  nhwc_to_s2d_kernel<<<ew_blocks(total), 256, 0, stream>>>((const bf16*)x, (bf16*)out, IMGS, C, H, W, Cs, padl, padr);
+  nhwc_to_s2d_kernel<<<ew_blocks(total), 256, 0, stream>>>((const bf16*)x, (bf16*)out, IMGS, C, H, W, Cs, padl, padr,
+                                                           adamml_live_limit(IMGS));
   return adamml_check_launch("nhwc_to_s2d");
 }
 

@@ -167,7 +167,8 @@ template <> struct DwVec<x2_t> {
 template <typename T, bool FLIP, int SW, int RH, typename CP, typename MP>
 __device__ __forceinline__ void
 dw_s1_band_body(CP x, const float* __restrict__ w, MP y, CP addend, int IMGS, int H, int W, int C, int strips,
-                int bands, const float* __restrict__ ss = nullptr, int act = ADAMML_ACT_NONE) {
+                int bands, const float* __restrict__ ss = nullptr, int act = ADAMML_ACT_NONE,
+                LiveLimit live = LiveLimit{nullptr, 0}) {
   typedef DwVec<T> VIO;
   constexpr int V = VIO::N;
   constexpr int NC = SW + 2;
@@ -182,6 +183,7 @@ dw_s1_band_body(CP x, const float* __restrict__ w, MP y, CP addend, int IMGS, in
   rest /= strips;
   const int h0 = (int)(rest % bands) * RH;
   const long long img = rest / bands;
+  if (img >= live_count(live, IMGS)) return;  // device-side work limit (inference with skipping)
   const int c0 = cv * V;
   const int h1 = h0 + RH < H ? h0 + RH : H;
   float wr[9][V];
@@ -253,22 +255,22 @@ template <typename T, bool FLIP, int SW, int RH>
 __global__ void __launch_bounds__(DW_THREADS, 4)
 dw_s1_band_kernel(const T* __restrict__ x, const float* __restrict__ w, T* __restrict__ y,
                   const T* __restrict__ addend, int IMGS, int H, int W, int C, int strips, int bands,
-                  const float* __restrict__ ss, int act) {
-  dw_s1_band_body<T, FLIP, SW, RH, const T*, T*>(x, w, y, addend, IMGS, H, W, C, strips, bands, ss, act);
+                  const float* __restrict__ ss, int act, LiveLimit live) {
+  dw_s1_band_body<T, FLIP, SW, RH, const T*, T*>(x, w, y, addend, IMGS, H, W, C, strips, bands, ss, act, live);
 }
 template <int SW, int RH>
 __global__ void __launch_bounds__(DW_THREADS, 3)
 dw_s1_band_x2_kernel(X2CPtr x, const float* __restrict__ w, X2Ptr y, int IMGS, int H, int W, int C, int strips,
-                     int bands, const float* __restrict__ ss, int act) {
+                     int bands, const float* __restrict__ ss, int act, LiveLimit live) {
   dw_s1_band_body<x2_t, false, SW, RH, X2CPtr, X2Ptr>(x, w, y, X2CPtr{nullptr, nullptr}, IMGS, H, W, C, strips, bands,
-                                                       ss, act);
+                                                       ss, act, live);
 }
 
 // Stride-2 forward: strip of SW outputs needs 2*SW+1 input columns per row.
 template <typename T, int SW, typename CP, typename MP>
 __device__ __forceinline__ void
 dw_s2_fwd_body(CP x, const float* __restrict__ w, MP y, int IMGS, int H, int W, int C, int Ho, int Wo, int strips,
-               const float* __restrict__ ss, int act) {
+               const float* __restrict__ ss, int act, LiveLimit live) {
   constexpr int V = VecIO<T>::N;
   const int cvecs = C / V;
   const long long total = (long long)IMGS * Ho * strips * cvecs;
@@ -280,6 +282,7 @@ dw_s2_fwd_body(CP x, const float* __restrict__ w, MP y, int IMGS, int H, int W, 
   rest /= strips;
   const int ho = (int)(rest % Ho);
   const long long img = rest / Ho;
+  if (img >= live_count(live, IMGS)) return;
   const int c0 = cv * V;
   float wr[9][V];
   load_w9<V>(w, C, c0, wr);
@@ -327,14 +330,14 @@ dw_s2_fwd_body(CP x, const float* __restrict__ w, MP y, int IMGS, int H, int W, 
 template <typename T, int SW>
 __global__ void __launch_bounds__(DW_THREADS)
 dw_s2_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w, T* __restrict__ y, int IMGS, int H, int W,
-                 int C, int Ho, int Wo, int strips, const float* __restrict__ ss, int act) {
-  dw_s2_fwd_body<T, SW, const T*, T*>(x, w, y, IMGS, H, W, C, Ho, Wo, strips, ss, act);
+                 int C, int Ho, int Wo, int strips, const float* __restrict__ ss, int act, LiveLimit live) {
+  dw_s2_fwd_body<T, SW, const T*, T*>(x, w, y, IMGS, H, W, C, Ho, Wo, strips, ss, act, live);
 }
 template <int SW>
 __global__ void __launch_bounds__(DW_THREADS)
 dw_s2_fwd_x2_kernel(X2CPtr x, const float* __restrict__ w, X2Ptr y, int IMGS, int H, int W, int C, int Ho, int Wo,
-                    int strips, const float* __restrict__ ss, int act) {
-  dw_s2_fwd_body<x2_t, SW, X2CPtr, X2Ptr>(x, w, y, IMGS, H, W, C, Ho, Wo, strips, ss, act);
+                    int strips, const float* __restrict__ ss, int act, LiveLimit live) {
+  dw_s2_fwd_body<x2_t, SW, X2CPtr, X2Ptr>(x, w, y, IMGS, H, W, C, Ho, Wo, strips, ss, act, live);
 }
 
 // Stride-2 data gradient: one thread per 2x2 input quad (rows 2m, 2m+1; cols 2n, 2n+1) and channel vector;
@@ -609,6 +612,7 @@ static int dwconv_fwd_impl(const void* x, const float* w, void* y, int IMGS, int
                            int Wo, int dtype, const float* ss, int act, cudaStream_t stream) {
   ADAMML_REQUIRE(stride == 1 || stride == 2, "dwconv: stride must be 1 or 2");
   ADAMML_REQUIRE(Ho == (H + 2 - 3) / stride + 1 && Wo == (W + 2 - 3) / stride + 1, "dwconv: bad Ho/Wo");
+  const LiveLimit live = ss ? adamml_live_limit(IMGS) : LiveLimit{nullptr, 0};  // inference launches only
   ADAMML_DISPATCH_DTYPE(dtype, T, {
     if (!dw_vec_ok<T>(C, x, y)) {
       ADAMML_REQUIRE(!ss, "dwconv: the fused BatchNorm epilogue needs a vectorisable channel count");
@@ -620,13 +624,13 @@ static int dwconv_fwd_impl(const void* x, const float* w, void* y, int IMGS, int
       const int strips = (W + SW - 1) / SW, bands = (H + RH - 1) / RH;
       const long long total = (long long)IMGS * bands * strips * (C / DwVec<T>::N);
       dw_s1_band_kernel<T, false, SW, RH><<<blocks_for(total, DW_THREADS), DW_THREADS, 0, stream>>>(
-          (const T*)x, w, (T*)y, nullptr, IMGS, H, W, C, strips, bands, ss, act);
+          (const T*)x, w, (T*)y, nullptr, IMGS, H, W, C, strips, bands, ss, act, live);
     } else {
       constexpr int SW = 2;
       const int strips = (Wo + SW - 1) / SW;
       const long long total = (long long)IMGS * Ho * strips * cvecs;
       dw_s2_fwd_kernel<T, SW><<<blocks_for(total, DW_THREADS), DW_THREADS, 0, stream>>>(
-          (const T*)x, w, (T*)y, IMGS, H, W, C, Ho, Wo, strips, ss, act);
+          (const T*)x, w, (T*)y, IMGS, H, W, C, Ho, Wo, strips, ss, act, live);
     }
   });
   return adamml_check_launch("dwconv_fwd");
@@ -651,18 +655,19 @@ static int dwconv_fwd_x2_impl(const void* x_hi, const void* x_lo, const float* w
   ADAMML_REQUIRE(stride == 1 || stride == 2, "dwconv: stride must be 1 or 2");
   ADAMML_REQUIRE(Ho == (H + 2 - 3) / stride + 1 && Wo == (W + 2 - 3) / stride + 1, "dwconv: bad Ho/Wo");
   ADAMML_REQUIRE(dw_vec_ok<bf16>(C, x_hi, x_lo, y_hi, y_lo), "dwconv_fwd_x2: needs C %% 8 == 0 and aligned planes");
+  const LiveLimit live = ss ? adamml_live_limit(IMGS) : LiveLimit{nullptr, 0};
   if (stride == 1) {
     constexpr int SW = 2, RH = 16;
     const int strips = (W + SW - 1) / SW, bands = (H + RH - 1) / RH;
     const long long total = (long long)IMGS * bands * strips * (C / 4);
     dw_s1_band_x2_kernel<SW, RH><<<blocks_for(total, DW_THREADS), DW_THREADS, 0, stream>>>(
-        x2c(x_hi, x_lo), w, x2m(y_hi, y_lo), IMGS, H, W, C, strips, bands, ss, act);
+        x2c(x_hi, x_lo), w, x2m(y_hi, y_lo), IMGS, H, W, C, strips, bands, ss, act, live);
   } else {
     constexpr int SW = 2;
     const int strips = (Wo + SW - 1) / SW;
     const long long total = (long long)IMGS * Ho * strips * (C / 8);
     dw_s2_fwd_x2_kernel<SW><<<blocks_for(total, DW_THREADS), DW_THREADS, 0, stream>>>(
-        x2c(x_hi, x_lo), w, x2m(y_hi, y_lo), IMGS, H, W, C, Ho, Wo, strips, ss, act);
+        x2c(x_hi, x_lo), w, x2m(y_hi, y_lo), IMGS, H, W, C, Ho, Wo, strips, ss, act, live);
   }
   return adamml_check_launch("dwconv_fwd_x2");
 }
@@ -692,7 +697,8 @@ int adamml_dwconv_dgrad(const void* dy, const float* w, void* dx, const void* ad
       const int strips = (W + SW - 1) / SW, bands = (H + RH - 1) / RH;
       const long long total = (long long)IMGS * bands * strips * (C / DwVec<T>::N);
       dw_s1_band_kernel<T, true, SW, RH><<<blocks_for(total, DW_THREADS), DW_THREADS, 0, stream>>>(
-          (const T*)dy, w, (T*)dx, (const T*)addend, IMGS, H, W, C, strips, bands, nullptr, ADAMML_ACT_NONE);
+          (const T*)dy, w, (T*)dx, (const T*)addend, IMGS, H, W, C, strips, bands, nullptr, ADAMML_ACT_NONE,
+          LiveLimit{nullptr, 0});
     } else {
       const long long total = (long long)IMGS * ((H + 1) / 2) * ((W + 1) / 2) * cvecs;
       dw_s2_dgrad_kernel<T><<<blocks_for(total, DW_THREADS), DW_THREADS, 0, stream>>>(

@@ -140,7 +140,8 @@ __global__ void tpool_bwd_kernel(const T* __restrict__ x, const T* __restrict__ 
 // every output element so that the backward pass is a pure gather that never re-reads x.
 template <typename T, typename CP, typename MP>
 __device__ __forceinline__ void
-maxpool_fwd_vec_body(CP x, MP y, unsigned char* __restrict__ pos, int IMGS, int H, int W, int C, int Ho, int Wo) {
+maxpool_fwd_vec_body(CP x, MP y, unsigned char* __restrict__ pos, int IMGS, int H, int W, int C, int Ho, int Wo,
+                     LiveLimit live) {
   constexpr int V = VecIO<T>::N;
   const int cvecs = C / V;
   const long long total = (long long)IMGS * Ho * Wo * cvecs;
@@ -151,6 +152,7 @@ maxpool_fwd_vec_body(CP x, MP y, unsigned char* __restrict__ pos, int IMGS, int 
   const int wo = (int)(pix % Wo);
   const int ho = (int)((pix / Wo) % Ho);
   const long long img = pix / ((long long)Wo * Ho);
+  if (img >= live_count(live, IMGS)) return;  // device-side work limit (inference with skipping)
   typename VecIO<T>::raw q[9];
   bool ok[9];
 #pragma unroll
@@ -195,13 +197,13 @@ maxpool_fwd_vec_body(CP x, MP y, unsigned char* __restrict__ pos, int IMGS, int 
 template <typename T>
 __global__ void __launch_bounds__(256)
 maxpool_fwd_vec_kernel(const T* __restrict__ x, T* __restrict__ y, unsigned char* __restrict__ pos, int IMGS, int H,
-                       int W, int C, int Ho, int Wo) {
-  maxpool_fwd_vec_body<T, const T*, T*>(x, y, pos, IMGS, H, W, C, Ho, Wo);
+                       int W, int C, int Ho, int Wo, LiveLimit live) {
+  maxpool_fwd_vec_body<T, const T*, T*>(x, y, pos, IMGS, H, W, C, Ho, Wo, live);
 }
 __global__ void __launch_bounds__(256)
 maxpool_fwd_vec_x2_kernel(X2CPtr x, X2Ptr y, unsigned char* __restrict__ pos, int IMGS, int H, int W, int C, int Ho,
-                          int Wo) {
-  maxpool_fwd_vec_body<x2_t, X2CPtr, X2Ptr>(x, y, pos, IMGS, H, W, C, Ho, Wo);
+                          int Wo, LiveLimit live) {
+  maxpool_fwd_vec_body<x2_t, X2CPtr, X2Ptr>(x, y, pos, IMGS, H, W, C, Ho, Wo, live);
 }
 
 // gather backward from recorded positions, one thread per 2x2 input quad (rows 2m, 2m+1; cols 2n, 2n+1) and channel
@@ -270,13 +272,15 @@ maxpool_bwd_pos_kernel(const unsigned char* __restrict__ pos, const T* __restric
 
 // temporal pool k3 s2 p1, one thread per (video, element vector): all TN frames of that position in registers
 template <typename T, int TN, typename CP, typename MP>
-__device__ __forceinline__ void tpool_fwd_vec_body(CP x, MP y, long long V_, long long E, int mode_avg) {
+__device__ __forceinline__ void tpool_fwd_vec_body(CP x, MP y, long long V_, long long E, int mode_avg,
+                                                   LiveLimit live) {
   constexpr int V = VecIO<T>::N;
   constexpr int TO = (TN + 2 - 3) / 2 + 1;
   const long long evecs = E / V;
   const long long iv = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (iv >= V_ * evecs) return;
   const long long v = iv / evecs, e = (iv % evecs) * V;
+  if (v >= live_count(live, V_)) return;
   typename VecIO<T>::raw q[TN];
 #pragma unroll
   for (int t = 0; t < TN; ++t) q[t] = VecIO<T>::load_raw(x + (v * TN + t) * E + e);
@@ -308,13 +312,14 @@ __device__ __forceinline__ void tpool_fwd_vec_body(CP x, MP y, long long V_, lon
 
 template <typename T, int TN>
 __global__ void __launch_bounds__(256)
-tpool_fwd_vec_kernel(const T* __restrict__ x, T* __restrict__ y, long long V_, long long E, int mode_avg) {
-  tpool_fwd_vec_body<T, TN, const T*, T*>(x, y, V_, E, mode_avg);
+tpool_fwd_vec_kernel(const T* __restrict__ x, T* __restrict__ y, long long V_, long long E, int mode_avg,
+                     LiveLimit live) {
+  tpool_fwd_vec_body<T, TN, const T*, T*>(x, y, V_, E, mode_avg, live);
 }
 template <int TN>
 __global__ void __launch_bounds__(256)
-tpool_fwd_vec_x2_kernel(X2CPtr x, X2Ptr y, long long V_, long long E, int mode_avg) {
-  tpool_fwd_vec_body<x2_t, TN, X2CPtr, X2Ptr>(x, y, V_, E, mode_avg);
+tpool_fwd_vec_x2_kernel(X2CPtr x, X2Ptr y, long long V_, long long E, int mode_avg, LiveLimit live) {
+  tpool_fwd_vec_body<x2_t, TN, X2CPtr, X2Ptr>(x, y, V_, E, mode_avg, live);
 }
 
 template <typename T, int TN>
@@ -386,9 +391,10 @@ inline bool pool_vec_ok(long long C, const void* a, const void* b = nullptr, con
 
 // y[img][c] = mean over HW. block (32 channels, 8 pixel lanes) per (img, channel tile)
 template <typename CP>
-__global__ void avgpool_fwd_kernel(CP x, float* __restrict__ y, int HW, int C, long long y_ld) {
+__global__ void avgpool_fwd_kernel(CP x, float* __restrict__ y, int HW, int C, long long y_ld, LiveLimit live) {
   __shared__ float sh[8][33];
   int img = blockIdx.x;
+  if (img >= live_count(live, gridDim.x)) return;  // (uniform over the block)
   int c = blockIdx.y * 32 + threadIdx.x;
   float s = 0.f;
   if (c < C)
@@ -424,8 +430,8 @@ int adamml_maxpool3x3s2_fwd(const void* x, void* y, unsigned char* pos, int IMGS
   ADAMML_DISPATCH_DTYPE(dtype, T, {
     if (pool_vec_ok<T>(C, x, y) && ((uintptr_t)pos % 8) == 0) {
       long long tv = total / VecIO<T>::N;
-      maxpool_fwd_vec_kernel<T><<<(unsigned)((tv + 255) / 256), 256, 0, stream>>>((const T*)x, (T*)y, pos, IMGS, H, W,
-                                                                                   C, Ho, Wo);
+      maxpool_fwd_vec_kernel<T><<<(unsigned)((tv + 255) / 256), 256, 0, stream>>>(
+          (const T*)x, (T*)y, pos, IMGS, H, W, C, Ho, Wo, pos ? LiveLimit{nullptr, 0} : adamml_live_limit(IMGS));
     } else {
       ADAMML_REQUIRE(pos == nullptr, "maxpool: position output needs C %% 8 == 0 (bf16) / C %% 4 == 0 (fp32)");
       maxpool_fwd_kernel<T><<<ew_blocks(total), 256, 0, stream>>>((const T*)x, (T*)y, IMGS, H, W, C, Ho, Wo);
@@ -462,9 +468,10 @@ int adamml_tpool_fwd(const void* x, void* y, long long V, int Tn, long long E, i
     const bool vec = pool_vec_ok<T>(E, x, y) && (Tn == 2 || Tn == 4 || Tn == 8);
     const long long tv = V * (E / VecIO<T>::N);
     const unsigned vb = (unsigned)((tv + 255) / 256);
-    if (vec && Tn == 8) tpool_fwd_vec_kernel<T, 8><<<vb, 256, 0, stream>>>((const T*)x, (T*)y, V, E, mode_avg);
-    else if (vec && Tn == 4) tpool_fwd_vec_kernel<T, 4><<<vb, 256, 0, stream>>>((const T*)x, (T*)y, V, E, mode_avg);
-    else if (vec && Tn == 2) tpool_fwd_vec_kernel<T, 2><<<vb, 256, 0, stream>>>((const T*)x, (T*)y, V, E, mode_avg);
+    const LiveLimit live = adamml_live_limit(V);
+    if (vec && Tn == 8) tpool_fwd_vec_kernel<T, 8><<<vb, 256, 0, stream>>>((const T*)x, (T*)y, V, E, mode_avg, live);
+    else if (vec && Tn == 4) tpool_fwd_vec_kernel<T, 4><<<vb, 256, 0, stream>>>((const T*)x, (T*)y, V, E, mode_avg, live);
+    else if (vec && Tn == 2) tpool_fwd_vec_kernel<T, 2><<<vb, 256, 0, stream>>>((const T*)x, (T*)y, V, E, mode_avg, live);
     else tpool_fwd_kernel<T><<<ew_blocks(total), 256, 0, stream>>>((const T*)x, (T*)y, V, Tn, To, E, mode_avg);
   });
   return adamml_check_launch("tpool_fwd");
@@ -499,7 +506,7 @@ int adamml_avgpool_fwd(const void* x, float* y, int IMGS, int HW, int C, long lo
   dim3 block(32, 8);
   if (y_ld <= 0) y_ld = C;
   ADAMML_DISPATCH_DTYPE(dtype, T,
-    avgpool_fwd_kernel<const T*><<<grid, block, 0, stream>>>((const T*)x, y, HW, C, y_ld));
+    avgpool_fwd_kernel<const T*><<<grid, block, 0, stream>>>((const T*)x, y, HW, C, y_ld, adamml_live_limit(IMGS)));
   return adamml_check_launch("avgpool_fwd");
 }
 
@@ -510,8 +517,9 @@ int adamml_maxpool3x3s2_fwd_x2(const void* x_hi, const void* x_lo, void* y_hi, v
   ADAMML_REQUIRE(pool_vec_ok<bf16>(C, x_hi, x_lo, y_hi) && pool_vec_ok<bf16>(C, y_lo) && ((uintptr_t)pos % 8) == 0,
                  "maxpool_fwd_x2: needs C %% 8 == 0 and aligned planes");
   const long long tv = (long long)IMGS * Ho * Wo * (C / 8);
-  maxpool_fwd_vec_x2_kernel<<<(unsigned)((tv + 255) / 256), 256, 0, stream>>>(x2c(x_hi, x_lo), x2m(y_hi, y_lo), pos,
-                                                                               IMGS, H, W, C, Ho, Wo);
+  maxpool_fwd_vec_x2_kernel<<<(unsigned)((tv + 255) / 256), 256, 0, stream>>>(
+      x2c(x_hi, x_lo), x2m(y_hi, y_lo), pos, IMGS, H, W, C, Ho, Wo,
+      pos ? LiveLimit{nullptr, 0} : adamml_live_limit(IMGS));
   return adamml_check_launch("maxpool_fwd_x2");
 }
 
@@ -525,9 +533,10 @@ int adamml_tpool_fwd_x2(const void* x_hi, const void* x_lo, void* y_hi, void* y_
   const unsigned vb = (unsigned)((tv + 255) / 256);
   const X2CPtr x = x2c(x_hi, x_lo);
   const X2Ptr y = x2m(y_hi, y_lo);
-  if (Tn == 8) tpool_fwd_vec_x2_kernel<8><<<vb, 256, 0, stream>>>(x, y, V, E, mode_avg);
-  else if (Tn == 4) tpool_fwd_vec_x2_kernel<4><<<vb, 256, 0, stream>>>(x, y, V, E, mode_avg);
-  else tpool_fwd_vec_x2_kernel<2><<<vb, 256, 0, stream>>>(x, y, V, E, mode_avg);
+  const LiveLimit live = adamml_live_limit(V);
+  if (Tn == 8) tpool_fwd_vec_x2_kernel<8><<<vb, 256, 0, stream>>>(x, y, V, E, mode_avg, live);
+  else if (Tn == 4) tpool_fwd_vec_x2_kernel<4><<<vb, 256, 0, stream>>>(x, y, V, E, mode_avg, live);
+  else tpool_fwd_vec_x2_kernel<2><<<vb, 256, 0, stream>>>(x, y, V, E, mode_avg, live);
   return adamml_check_launch("tpool_fwd_x2");
 }
 
@@ -537,7 +546,7 @@ int adamml_avgpool_fwd_x2(const void* x_hi, const void* x_lo, float* y, int IMGS
   dim3 grid(IMGS, ceil_div(C, 32));
   dim3 block(32, 8);
   if (y_ld <= 0) y_ld = C;
-  avgpool_fwd_kernel<X2CPtr><<<grid, block, 0, stream>>>(x2c(x_hi, x_lo), y, HW, C, y_ld);
+  avgpool_fwd_kernel<X2CPtr><<<grid, block, 0, stream>>>(x2c(x_hi, x_lo), y, HW, C, y_ld, adamml_live_limit(IMGS));
   return adamml_check_launch("avgpool_fwd_x2");
 }
 

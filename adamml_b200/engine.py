@@ -403,7 +403,15 @@ class BackboneFunction(torch.autograd.Function):
     def forward(ctx, net, x, groups, extra, *params):
         need = bool(extra.get("_save")) and any(ctx.needs_input_grad[4:])
         ex = Exec(net.compute_dtype, net.training, groups, save=need, lane=int(extra.get("_lane", 0)))
-        y = net.run_forward(ex, x, extra)
+        live = extra.get("_live")  # (count tensor, clip capacity): inference with device-side skipping
+        if live is not None:
+            assert not need and not net.training, "the device-side work limit is an inference-only feature"
+            ops.set_live_clips(live[0], live[1])
+        try:
+            y = net.run_forward(ex, x, extra)
+        finally:
+            if live is not None:
+                ops.set_live_clips(None, 0)
         ctx.ex = ex if need else None
         ctx.net = net
         ctx.params = params

@@ -32,8 +32,12 @@ class AdaMML(nn.Module):
         self.update_main_net = True
         self.compute_dtype = compute_dtype or default_compute_dtype()
         # inference: run the main backbones only on the (segment, video) pairs the policy selected (see forward)
-        self.skip_unselected = os.environ.get("ADAMML_B200_EVAL_SKIP", "1") != "0"
-        self.last_selected_fraction = None
+        # ADAMML_B200_EVAL_SKIP: "device" (default; compaction and work limit on the device, no host sync, the pass is
+        # CUDA-graph capturable), "host" (decisions read back, data-dependent batch shape), "0" (run everything)
+        mode = os.environ.get("ADAMML_B200_EVAL_SKIP", "device")
+        self.skip_unselected = mode != "0"
+        self.skip_mode = "host" if mode in ("host", "1") else "device"
+        self._sel_state = None
         if rng_policy:
             self.freeze_policy_net()
             del self.policy_net.fcs
@@ -132,11 +136,44 @@ class AdaMML(nn.Module):
         return (self.skip_unselected and not torch.is_grad_enabled()
                 and not any(mod.training for mod in self.main_net.modules()))
 
+    @property
+    def last_selected_fraction(self):
+        """share of (segment, video, modality) pairs the last skipping pass ran (reads the device counts lazily)"""
+        st = self._sel_state
+        if st is None:
+            return None
+        if isinstance(st, tuple):
+            counts, total = st
+            self._sel_state = st = sum(int(c.item()) for c in counts) / float(total)
+        return st
+
+    @last_selected_fraction.setter
+    def last_selected_fraction(self, v):
+        self._sel_state = v
+
+    def _forward_selected_device(self, m_x, S, N, decisions):
+        """Skipping without a host round trip: compaction, gather, work limit and scatter all run on the device
+        (csrc/gating.cu); shapes are static, so the pass can be captured into a CUDA graph."""
+        dec = decisions.detach().float().contiguous()           # [S, M, N]
+        SN = S * N
+        jobs, meta = [], []
+        for m, (net, x) in enumerate(zip(self.main_net.nets, m_x)):
+            idx, count = ops.select_compact(dec, m)
+            jobs.append((net, ops.gather_clips(x, idx, count, SN), 1, dict(_live=(count, SN))))
+            meta.append((idx, count))
+        outs = run_backbones_parallel(jobs)
+        per_mod = [ops.scatter_rows(y.contiguous(), idx, count, SN) for y, (idx, count) in zip(outs, meta)]
+        self._sel_state = ([c for _, c in meta], SN * len(m_x))
+        logits = self.main_net(None, decisions, S, N, per_mod=per_mod)
+        return logits, decisions.permute(2, 0, 1)
+
     def _forward_selected(self, p_jobs, m_x, S, N, expo, decisions):
         if decisions is None:
             feats = run_backbones_parallel(p_jobs)
             decisions, _ = self.policy_net(None, S, N, expo=expo, feats=feats)
             del feats
+        if self.skip_mode == "device":
+            return self._forward_selected_device(m_x, S, N, decisions)
         dev = decisions.device
         dec_host = decisions.detach().to("cpu", torch.float32)            # [S, M, N]; the one D2H sync of the pass
         SN = S * N

@@ -203,6 +203,50 @@ def select_clips(x, idx, clips):
     return _select_rows(x, idx, clips)
 
 
+# ---------------------------------------------------------------- device-side gating (inference with skipping)
+def select_compact(decisions, m):
+    """decisions fp32 [S, M, N] (0/1) -> (idx int32 [S*N] ascending pair indices s*N+n of modality m, count int32 [1]),
+    both on the device: nothing is read back."""
+    S, M, N = decisions.shape
+    _chk(decisions, torch.float32)
+    idx = torch.empty(S * N, device=decisions.device, dtype=torch.int32)
+    count = torch.empty(1, device=decisions.device, dtype=torch.int32)
+    call("select_compact", decisions, S, M, N, m, idx, count)
+    return idx, count
+
+
+def _gather_plane(t, idx, count, clips):
+    if t.shape[0] % clips:
+        raise ValueError("gather_clips: %d images do not split into %d clips" % (t.shape[0], clips))
+    out = torch.empty_like(t)
+    call("gather_rows", t, out, idx, count, t.numel() // clips * t.element_size(), clips)
+    return out
+
+
+def gather_clips(x, idx, count, clips):
+    """device-side counterpart of select_clips: the clips listed in idx[:count] move to the front of a buffer of the
+    SAME static shape (the tail is left uninitialised: the live limit keeps every kernel away from it)."""
+    if isinstance(x, X2):
+        return X2(_gather_plane(x.hi, idx, count, clips), _gather_plane(x.lo, idx, count, clips))
+    if isinstance(x, S2D):
+        return S2D(_gather_plane(x.t, idx, count, clips), x.C, x.H, x.W, x.R,
+                   lo=_gather_plane(x.lo, idx, count, clips) if x.lo is not None else None)
+    return _gather_plane(x, idx, count, clips)
+
+
+def scatter_rows(y, idx, count, rows_out):
+    """y fp32 [K, C] (rows >= count are garbage) -> [rows_out, C] with out[idx[j]] = y[j], zeros elsewhere"""
+    _chk(y, torch.float32)
+    out = torch.empty((rows_out, y.shape[1]), device=y.device, dtype=torch.float32)
+    call("scatter_rows_f32", y, idx, count, out, rows_out, y.shape[1])
+    return out
+
+
+def set_live_clips(count, capacity):
+    """arm / disarm (count=None) the device-side work limit of the following inference launches of this thread"""
+    _lib.lib().cdll.adamml_set_live_clips(count.data_ptr() if count is not None else None, int(capacity))
+
+
 def first_conv_s2d_ok(conv, C, H, W, dtype):
     """stride-2 first convolutions that run on tcgen05 through the space-to-depth view: 7x7/p3 (ResNet stem) and
     3x3/p1 (MobileNetV2 first conv), even-sized frames, bf16 mode."""

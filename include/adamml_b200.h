@@ -269,6 +269,24 @@ int adamml_tc_stem_conv_bn_act_bf16(const void* xs, const void* w, void* y, int 
 int adamml_dwconv_bn_act_fwd(const void* x, const float* w, void* y, int IMGS, int H, int W, int C, int stride, int Ho,
                              int Wo, const float* scale_shift, int act, int dtype, cudaStream_t stream);
 
+/* ---- device-side gating: inference with decision-driven skipping, no host round trip ----
+ * The reference runs every main backbone on every (segment, video) pair and multiplies its logits by the policy's 0/1
+ * decision (models/adamml.py:81-86, joint_resnet_mobilenetv2.py:92-94).  With running-statistic BatchNorm an unselected
+ * pair contributes exactly zero, so it is skipped -- on the device: adamml_select_compact turns the decisions
+ * [S][M][N] of modality m into the ascending list idx[] of selected pairs p = s*N + n and their number *count;
+ * adamml_gather_rows moves those clips to the front of a static-capacity batch buffer; adamml_set_live_clips arms a
+ * (thread-local) work limit that the following inference launches of the calling thread honour by reading *count on
+ * the device (tcgen05 tile loops, depthwise / pooling / s2d threads beyond the live prefix exit); adamml_scatter_rows_f32
+ * puts the logits back (zeros elsewhere).  Nothing depends on the count on the host, so the pass captures into a CUDA
+ * graph.  adamml_set_live_clips(NULL, 0) disarms the limit. */
+int adamml_select_compact(const float* decisions, int S, int M, int N, int m, int* idx, int* count,
+                          cudaStream_t stream);
+int adamml_gather_rows(const void* src, void* dst, const int* idx, const int* count, long long row_bytes, int capacity,
+                       cudaStream_t stream);
+int adamml_scatter_rows_f32(const float* y, const int* idx, const int* count, float* out, int rows_out, int C,
+                            cudaStream_t stream);
+int adamml_set_live_clips(const int* live_clips, int clip_capacity);
+
 /* ---- "x2" forward path: two-plane activations (default precision mode) ----
  * north_star asks for logits within 1e-3 of the reference's fp32 path and bit-exact policy selections; bf16
  * storage (8 mantissa bits) misses that by two orders of magnitude on these 50-layer BatchNorm stacks.  In x2 mode

@@ -1,8 +1,9 @@
 #!/usr/bin/env python
 """Inference throughput with decision-driven skipping: eval-mode AdaMML forward at
-N=72 clips, S=10 segments (the reference's test-time setting, utils/utils.py:427-507), RGB+Audio, bf16.
-Times the run-everything path (what the reference computes) and the selected-only path on the same inputs.
-Usage: python scripts/bench_eval_skip.py [N] [S]"""
+N=72 clips, S=10 segments (the reference's test-time setting, utils/utils.py:427-507), RGB+Audio.
+Times the run-everything path (what the reference computes) and the selected-only path on the same inputs, in the
+default x2 precision mode (or bf16 / with the fused inference epilogue off for comparison).
+Usage: python scripts/bench_eval_skip.py [N] [S] [x2|bf16] [fuse=1|0]"""
 import json
 import os
 import sys
@@ -18,6 +19,11 @@ from adamml_b200.models import build_model  # noqa: E402
 def main():
     N = int(sys.argv[1]) if len(sys.argv) > 1 else 72
     S = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+    prec = sys.argv[3] if len(sys.argv) > 3 else "x2"
+    from adamml_b200 import engine, ops
+    if len(sys.argv) > 4:
+        engine.FUSE_EVAL = sys.argv[4] != "0"
+    dtype = {"x2": ops.PREC_X2, "bf16": torch.bfloat16}[prec]
     dev = torch.device("cuda:0")
     torch.cuda.set_device(dev)
     results = []
@@ -29,7 +35,7 @@ def main():
                              imagenet_pretrained=False, modality=["rgb", "sound"], input_channels=[3, 1],
                              dataset="kinetics-sounds", dense_sampling=False, lr_scheduler="cosine", sync_bn=False,
                              batch_size=N, prefix="", epochs=1,
-                             compute_dtype=torch.bfloat16)
+                             compute_dtype=dtype)
         torch.manual_seed(0)
         model, _ = build_model(ns)
         model = model.to(dev).eval()
@@ -43,7 +49,8 @@ def main():
             with torch.no_grad():
                 return model([rgb, snd], num_segments=S)
 
-        row = {"policy": "rng>%.2f" % thr if rng_policy else "lstm (random init)", "N": N, "S": S}
+        row = {"policy": "rng>%.2f" % thr if rng_policy else "lstm (random init)", "N": N, "S": S, "precision": prec,
+               "fused_epilogue": engine.FUSE_EVAL}
         for skip in (False, True):
             for _ in range(3):
                 run(skip)

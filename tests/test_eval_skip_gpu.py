@@ -46,11 +46,15 @@ def _inputs(dev, modality, N, S):
     return xs
 
 
-@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("mode", ["device", "host"])
+@pytest.mark.parametrize("dtype", ["x2", torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("modality", [["rgb", "sound"], ["rgb", "sound", "flow", "rgbdiff"]])
-def test_selected_only_equals_run_everything(cuda, modality, dtype):
+def test_selected_only_equals_run_everything(cuda, modality, dtype, mode):
+    """mode "device": compaction / gather / work limit / scatter on the device, no host sync (csrc/gating.cu);
+    mode "host": decisions read back, data-dependent batch shape."""
     N, S = 5, 3
     model = _model(cuda, modality, dtype)
+    model.skip_mode = mode
     M = model.num_modality
     xs = _inputs(cuda, modality, N, S)
     g = torch.Generator(device=cuda).manual_seed(11)
@@ -70,14 +74,16 @@ def test_selected_only_equals_run_everything(cuda, modality, dtype):
     assert err < 1e-5, err
 
 
+@pytest.mark.parametrize("mode", ["device", "host"])
 @pytest.mark.parametrize("thr,expect", [(1.5, 0.0), (-1.0, 1.0), (0.5, None)])
-def test_rng_policy_extremes(cuda, thr, expect):
+def test_rng_policy_extremes(cuda, thr, expect, mode):
     """rng_policy (adamml.py:38-40,76-78): nothing selected -> exactly zero logits without any main launch;
     everything selected -> the plain path; mixed -> equals run-everything on the same random decisions."""
     from adamml_b200 import _lib
     N, S = 4, 3
     modality = ["rgb", "sound"]
     model = _model(cuda, modality, torch.bfloat16, rng_policy=True, rng_threshold=thr)
+    model.skip_mode = mode
     xs = _inputs(cuda, modality, N, S)
     with torch.no_grad():
         model.skip_unselected = False
@@ -95,7 +101,8 @@ def test_rng_policy_extremes(cuda, thr, expect):
         assert model.last_selected_fraction == expect
     if expect == 0.0:
         assert logits.abs().max() == 0 and ref_logits.abs().max() == 0
-        assert launches < 0.1 * full_launches, (launches, full_launches)
+        if mode == "host":  # (device mode issues the same launches; their tile loops / threads find nothing live)
+            assert launches < 0.1 * full_launches, (launches, full_launches)
     err = ((logits - ref_logits).abs().max() / ref_logits.abs().max().clamp_min(1e-30)).item()
     assert err < 1e-5, err
 
@@ -115,3 +122,37 @@ def test_training_or_grad_mode_never_skips(cuda):
     model.main_net.nets[0].bn1.train()                # a single BN left in train mode is enough to disable it
     with torch.no_grad():
         assert not model._can_skip()
+
+
+def test_device_skip_pass_is_graph_capturable(cuda):
+    """NS3: with the gating on the device nothing in the inference pass depends on the host knowing the decisions, so
+    data layer + policy + compaction + gated main nets + fusion capture into ONE CUDA graph; replays on new inputs /
+    new Gumbel noise must reproduce the eager pass bit for bit (different selections, same launches)."""
+    N, S = 4, 3
+    modality = ["rgb", "sound"]
+    model = _model(cuda, modality, "x2")
+    model.skip_mode = "device"
+    M = model.num_modality
+    xs = _inputs(cuda, modality, N, S)
+    g = torch.Generator(device=cuda).manual_seed(21)
+    expo = torch.empty(S, M * N, 2, device=cuda).exponential_(generator=g)
+    with torch.no_grad():
+        for _ in range(2):  # warm-up (lazy allocations, bn key assignment)
+            model(xs, noise=dict(expo=expo))
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            g_logits, g_dec = model(xs, noise=dict(expo=expo))
+        seen = set()
+        for trial in range(3):
+            for x in xs:
+                x.copy_(torch.randn(x.shape, device=cuda, generator=g) * (1 + trial))
+            expo.copy_(torch.empty_like(expo).exponential_(generator=g))
+            graph.replay()
+            torch.cuda.synchronize()
+            r_logits, r_dec = g_logits.clone(), g_dec.clone()
+            e_logits, e_dec = model(xs, noise=dict(expo=expo))
+            assert torch.equal(r_dec, e_dec)
+            assert torch.equal(r_logits, e_logits), (r_logits - e_logits).abs().max()
+            seen.add(tuple(r_dec.flatten().tolist()))
+        assert len(seen) > 1, "the replays never changed the selection: the test would not exercise the gating"
