@@ -12,6 +12,10 @@
 namespace {
 
 constexpr int DW_THREADS = 128;
+#ifndef ADAMML_DW_FWD_PACKED
+#define ADAMML_DW_FWD_PACKED 1
+#endif
+constexpr bool DW_FWD_PACKED = ADAMML_DW_FWD_PACKED != 0;  // packed FFMA2 in the forward / dgrad stencils (wgrad: always)
 
 // weights are TAP-MAJOR fp32 [9][C] (adamml_pack_weight_dw): a thread's V channels of one tap are one or two
 // 16-byte loads, coalesced across the warp
@@ -36,6 +40,25 @@ __device__ __forceinline__ void bn_act_vec(float (&a)[V], const float* __restric
   for (int i = 0; i < V; ++i) {
     const float2 p = *reinterpret_cast<const float2*>(ss + 2 * (c0 + i));
     a[i] = act_apply(fmaf(a[i], p.x, p.y), act);
+  }
+}
+
+// acc += a * b over V channels with the packed FFMA2 of sm_100 (fma.rn.f32x2: two fp32 FMAs per issued instruction;
+// same IEEE results as two fmaf): the depthwise stencils are issue bound, not HBM bound
+template <int V, bool PACKED = true>
+__device__ __forceinline__ void fma_vec(float (&acc)[V], const float (&a)[V], const float (&b)[V]) {
+  static_assert(V % 2 == 0, "channel vectors hold an even number of channels");
+  if constexpr (!PACKED) {  // (A/B switch: measured within 3 % of the packed form on the forward / dgrad stencils)
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc[i] = fmaf(a[i], b[i], acc[i]);
+  } else {
+#pragma unroll
+  for (int i = 0; i < V; i += 2) {
+    const float2 r = __ffma2_rn(make_float2(a[i], a[i + 1]), make_float2(b[i], b[i + 1]),
+                                make_float2(acc[i], acc[i + 1]));
+    acc[i] = r.x;
+    acc[i + 1] = r.y;
+  }
   }
 }
 
@@ -73,7 +96,7 @@ dw_s1_kernel(const T* __restrict__ x, const float* __restrict__ w, T* __restrict
 #pragma unroll
     for (int j = 0; j < SW + 2; ++j) {
       const int wi = w0 + j - 1;
-      if (wi >= 0 && wi < W) q[j] = VecIO<T>::load_raw(row + (long long)wi * C);
+      if (wi >= 0 && wi < W) q[j] = VecIO<T>::load_raw(row + wi * C);
     }
 #pragma unroll
     for (int j = 0; j < SW + 2; ++j) {
@@ -191,10 +214,11 @@ dw_s1_band_body(CP x, const float* __restrict__ w, MP y, CP addend, int IMGS, in
   const CP xb = x + ((img * H * W) * C + c0);
   auto load_row = [&](int hi, raw_t (&dst)[NC]) {
     const bool rok = hi >= 0 && hi < H;
+    const int rbase = (hi * W + w0 - 1) * C;  // 32-bit offsets inside one image (checked by the launcher)
 #pragma unroll
     for (int j = 0; j < NC; ++j) {
       const int wi = w0 + j - 1;
-      dst[j] = (rok && wi >= 0 && wi < W) ? VIO::load_raw(xb + ((long long)hi * W + wi) * C) : VIO::zero_raw();
+      dst[j] = (rok && wi >= 0 && wi < W) ? VIO::load_raw(xb + (rbase + j * C)) : VIO::zero_raw();
     }
   };
   auto emit = [&](int ho, const raw_t (&ra)[NC], const raw_t (&rb)[NC], const raw_t (&rc)[NC]) {
@@ -214,8 +238,7 @@ dw_s1_band_body(CP x, const float* __restrict__ w, MP y, CP addend, int IMGS, in
           const int o = j - s;
           if (o < 0 || o >= SW) continue;
           const int t = FLIP ? (2 - r) * 3 + (2 - s) : r * 3 + s;
-#pragma unroll
-          for (int i = 0; i < V; ++i) acc[o][i] = fmaf(v[i], wr[t][i], acc[o][i]);
+          fma_vec<V, DW_FWD_PACKED>(acc[o], v, wr[t]);
         }
       }
     }
@@ -223,7 +246,7 @@ dw_s1_band_body(CP x, const float* __restrict__ w, MP y, CP addend, int IMGS, in
     for (int j = 0; j < SW; ++j) {
       const int wo = w0 + j;
       if (wo >= W) continue;
-      const long long o = ((img * H + ho) * W + wo) * C + c0;
+      const long long o = img * ((long long)H * W * C) + ((ho * W + wo) * C + c0);  // (32-bit inside the image)
       if (addend) {
         float a[V];
         VIO::load(addend + o, a);
@@ -300,7 +323,7 @@ dw_s2_fwd_body(CP x, const float* __restrict__ w, MP y, int IMGS, int H, int W, 
 #pragma unroll
     for (int j = 0; j < 2 * SW + 1; ++j) {
       const int wi = w0 * 2 + j - 1;
-      if (wi >= 0 && wi < W) q[j] = VecIO<T>::load_raw(row + (long long)wi * C);
+      if (wi >= 0 && wi < W) q[j] = VecIO<T>::load_raw(row + wi * C);
     }
 #pragma unroll
     for (int j = 0; j < 2 * SW + 1; ++j) {
@@ -313,8 +336,7 @@ dw_s2_fwd_body(CP x, const float* __restrict__ w, MP y, int IMGS, int H, int W, 
         if ((j - s) & 1) continue;
         const int o = (j - s) / 2;
         if (j - s < 0 || o >= SW) continue;
-#pragma unroll
-        for (int i = 0; i < V; ++i) acc[o][i] = fmaf(v[i], wr[r * 3 + s][i], acc[o][i]);
+        fma_vec<V, DW_FWD_PACKED>(acc[o], v, wr[r * 3 + s]);
       }
     }
   }
@@ -395,8 +417,7 @@ dw_s2_dgrad_kernel(const T* __restrict__ dy, const float* __restrict__ w, T* __r
           if ((q + 1 - s) & 1) continue;
           if (q + 1 - s < 0) continue;
           const int b = (q + 1 - s) / 2;
-#pragma unroll
-          for (int i = 0; i < V; ++i) acc[i] = fmaf(g[a][b][i], wr[r * 3 + s][i], acc[i]);
+          fma_vec<V, DW_FWD_PACKED>(acc, g[a][b], wr[r * 3 + s]);
         }
       }
       const long long o = ((img * H + hi) * W + wi) * C + c0;
@@ -454,7 +475,7 @@ dw_wgrad_vec_kernel(const T* __restrict__ x, const T* __restrict__ dy, float* __
 #pragma unroll
         for (int j = 0; j < NC; ++j) {
           const int wi = w0 * STRIDE + j - 1;
-          if (wi >= 0 && wi < W) q[j] = VecIO<T>::load_raw(row + (long long)wi * C);
+          if (wi >= 0 && wi < W) q[j] = VecIO<T>::load_raw(row + wi * C);
         }
 #pragma unroll
         for (int j = 0; j < NC; ++j) {
@@ -467,8 +488,7 @@ dw_wgrad_vec_kernel(const T* __restrict__ x, const T* __restrict__ dy, float* __
             if (j - s < 0 || ((j - s) % STRIDE) != 0) continue;
             const int o = (j - s) / STRIDE;
             if (o >= SW) continue;
-#pragma unroll
-            for (int i = 0; i < V; ++i) acc[r * 3 + s][i] = fmaf(g[o][i], v[i], acc[r * 3 + s][i]);
+            fma_vec<V>(acc[r * 3 + s], g[o], v);
           }
         }
       }
@@ -523,17 +543,19 @@ dw_wgrad_band_kernel(const T* __restrict__ x, const T* __restrict__ dy, float* _
       const T* gb = dy + (img * H * W) * C + c0;
       auto load_x = [&](int hi, raw_t (&dst)[NC]) {
         const bool rok = hi >= 0 && hi < H;
+        const int rbase = (hi * W + w0 - 1) * C;
 #pragma unroll
         for (int j = 0; j < NC; ++j) {
           const int wi = w0 + j - 1;
-          dst[j] = (rok && wi >= 0 && wi < W) ? VIO::load_raw(xb + ((long long)hi * W + wi) * C) : VIO::zero_raw();
+          dst[j] = (rok && wi >= 0 && wi < W) ? VIO::load_raw(xb + (rbase + j * C)) : VIO::zero_raw();
         }
       };
       auto load_g = [&](int ho, raw_t (&dst)[SW]) {
         const bool rok = ho < h1;
+        const int rbase = (ho * W + w0) * C;
 #pragma unroll
         for (int j = 0; j < SW; ++j)
-          dst[j] = (rok && w0 + j < W) ? VIO::load_raw(gb + ((long long)ho * W + w0 + j) * C) : VIO::zero_raw();
+          dst[j] = (rok && w0 + j < W) ? VIO::load_raw(gb + (rbase + j * C)) : VIO::zero_raw();
       };
       auto emit = [&](const raw_t (&g)[SW], const raw_t (&ra)[NC], const raw_t (&rb)[NC], const raw_t (&rc)[NC]) {
         float gv[SW][V];
@@ -549,8 +571,7 @@ dw_wgrad_band_kernel(const T* __restrict__ x, const T* __restrict__ dy, float* _
             for (int s_ = 0; s_ < 3; ++s_) {
               const int o = j - s_;
               if (o < 0 || o >= SW) continue;
-#pragma unroll
-              for (int i = 0; i < V; ++i) acc[r * 3 + s_][i] = fmaf(gv[o][i], v[i], acc[r * 3 + s_][i]);
+              fma_vec<V>(acc[r * 3 + s_], gv[o], v);
             }
           }
         }
@@ -611,6 +632,7 @@ extern "C" {
 static int dwconv_fwd_impl(const void* x, const float* w, void* y, int IMGS, int H, int W, int C, int stride, int Ho,
                            int Wo, int dtype, const float* ss, int act, cudaStream_t stream) {
   ADAMML_REQUIRE(stride == 1 || stride == 2, "dwconv: stride must be 1 or 2");
+  ADAMML_REQUIRE((long long)H * W * C < (1LL << 31), "dwconv: one image must stay below 2^31 elements");
   ADAMML_REQUIRE(Ho == (H + 2 - 3) / stride + 1 && Wo == (W + 2 - 3) / stride + 1, "dwconv: bad Ho/Wo");
   const LiveLimit live = ss ? adamml_live_limit(IMGS) : LiveLimit{nullptr, 0};  // inference launches only
   ADAMML_DISPATCH_DTYPE(dtype, T, {

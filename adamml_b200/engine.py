@@ -50,6 +50,14 @@ class Exec:
         self.param_needs_grad = param_needs_grad
         self.tape = []
         self.grads = {}  # parameter -> gradient tensor (filled by bwd)
+        self.nbt = []    # num_batches_tracked buffers of the BatchNorm layers this pass ran in train mode
+
+    def finish_forward(self):
+        """num_batches_tracked += S for every train-mode BatchNorm of the pass (the reference's S sequential segment
+        calls each add 1) as one multi-tensor launch instead of one tiny kernel per layer"""
+        if self.nbt:
+            torch._foreach_add_(self.nbt, self.G)
+            self.nbt = []
 
     # ------------------------------------------------------------------ helpers
     def _acc(self, p, g):
@@ -172,7 +180,7 @@ class Exec:
             mi, ss = ops.bn_finalize(sums, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var,
                                      count, bn.momentum, bn.eps, C, G, True, bn.track_running_stats)
             if bn.num_batches_tracked is not None:
-                bn.num_batches_tracked += G
+                self.nbt.append(bn.num_batches_tracked)  # advanced by G in ONE multi-tensor launch (finish_forward)
         else:
             mi, ss = ops.bn_finalize(None, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, 1,
                                      0.1, bn.eps, C, G, False, False)
@@ -409,6 +417,7 @@ class BackboneFunction(torch.autograd.Function):
             ops.set_live_clips(live[0], live[1])
         try:
             y = net.run_forward(ex, x, extra)
+            ex.finish_forward()
         finally:
             if live is not None:
                 ops.set_live_clips(None, 0)

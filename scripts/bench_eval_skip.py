@@ -68,6 +68,28 @@ def main():
                 row["selected_fraction"] = round(model.last_selected_fraction, 3)
                 row["decision_mean"] = round(out[1].mean().item(), 3)
         row["speedup"] = round(row["full"]["ms"] / row["skip"]["ms"], 3)
+        row["skip_mode"] = model.skip_mode
+        if model.skip_mode == "device" and not rng_policy:
+            # the device-gated pass has no host sync: capture it once, replay it with one launch
+            model.skip_unselected = True
+            expo = model.policy_net.draw_gumbel_noise(S, N, dev)
+            with torch.no_grad():
+                model([rgb, snd], num_segments=S, noise=dict(expo=expo))
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    model([rgb, snd], num_segments=S, noise=dict(expo=expo))
+            for _ in range(2):
+                graph.replay()
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(reps):
+                graph.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / reps
+            row["skip_graph"] = {"ms": round(ms, 2), "clips_per_s": round(N / ms * 1e3, 1)}
+            del graph
         print(json.dumps(row), flush=True)
         results.append(row)
         del model, rgb, snd
