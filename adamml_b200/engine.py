@@ -18,6 +18,17 @@ from .ops import ACT_NONE, ACT_RELU, ACT_RELU6
 # conv -> bn_apply pair (tests compare the two)
 import os as _os
 FUSE_EVAL = _os.environ.get("ADAMML_B200_FUSE_EVAL", "1") != "0"
+# training memory: ADAMML_B200_RECOMPUTE=1 does not keep the post-activation output of layers WITHOUT a residual input
+# for the backward pass; the consumer's weight gradient rebuilds it from the saved pre-BN tensor (one extra bf16
+# bn_apply pass per such layer in backward).  Measured RGB+Audio N=72: see DESIGN.md §4.
+RECOMPUTE = _os.environ.get("ADAMML_B200_RECOMPUTE", "0") != "0"
+
+
+class _ShapeOnly:
+    """stand-in for a forward tensor that was not kept and is needed only for its shape (frozen weights)"""
+
+    def __init__(self, shape):
+        self.shape = torch.Size(shape)
 
 
 def _bn_key(bn):
@@ -51,6 +62,7 @@ class Exec:
         self.tape = []
         self.grads = {}  # parameter -> gradient tensor (filled by bwd)
         self.nbt = []    # num_batches_tracked buffers of the BatchNorm layers this pass ran in train mode
+        self.recompute = RECOMPUTE and dtype != torch.float32
 
     def finish_forward(self):
         """num_batches_tracked += S for every train-mode BatchNorm of the pass (the reference's S sequential segment
@@ -82,19 +94,28 @@ class Exec:
             out = self._cba_fused_eval(x, conv, bn, act, res, res_rec)
             if out is not None:
                 return out
+        x_src = getattr(x, "_adamml_src", None) if self.save else None  # x is a recomputable activation (see below)
         rec = self.conv_bn_stats(x, conv, bn)
         out = ops.bn_apply(rec["z"], rec["ss"], self.G, act, res=res,
                            res_z=res_rec["z"] if res_rec else None, res_ss=res_rec["ss"] if res_rec else None)
+        # recompute mode: the output of a layer without residual input is act(z * scale + shift) of tensors the tape
+        # keeps anyway, so it is not saved; a consumer that needs it for its weight gradient rebuilds it (bf16)
+        lazy = (self.save and self.recompute and res is None and res_rec is None
+                and ops.vec_channels(ops.hi_plane(rec["z"])))
         # the forward scale/shift of a layer without residual input is kept (tiny): backward recomputes the
         # ReLU/ReLU6 mask from z with it instead of streaming `out` again
-        if res is not None or res_rec is not None or act == ACT_NONE:
+        if res is not None or res_rec is not None or (act == ACT_NONE and not lazy):
             rec["ss"] = None
         if res_rec:
             res_rec["ss"] = None
             res_rec["x"], res_rec["z"] = ops.hi_plane(res_rec["x"]), ops.hi_plane(res_rec["z"])
         if self.save:
-            rec.update(x=ops.hi_plane(rec["x"]), z=ops.hi_plane(rec["z"]), out=ops.hi_plane(out), act=act,
-                       has_res=res is not None, res_rec=res_rec)
+            if x_src is not None and rec["x"] is x:   # (not re-laid out into an s2d operand)
+                rec.update(x=None, x_lazy=x_src, x_shape=tuple(x.shape))
+            rec.update(x=ops.hi_plane(rec["x"]), z=ops.hi_plane(rec["z"]), out=None if lazy else ops.hi_plane(out),
+                       act=act, has_res=res is not None, res_rec=res_rec)
+            if lazy:
+                out._adamml_src = dict(z=rec["z"], ss=rec["ss"], act=act, G=self.G)
             self.tape.append(rec)
         return out
 
@@ -230,6 +251,12 @@ class Exec:
             dres = dout
         dx = None
         x = rec["x"]
+        if x is None and rec.get("x_lazy") is not None:
+            if need_w:  # rebuild the producer's output from its saved pre-BN tensor (recompute mode)
+                src = rec["x_lazy"]
+                x = ops.bn_apply(src["z"], src["ss"], src["G"], src["act"])
+            else:
+                x = _ShapeOnly(rec["x_shape"])
         stride, pad = conv.stride[0], conv.padding[0]
         if rec["stem"]:
             assert not need_dx, "the s2d stem has no data gradient (its input is data)"

@@ -24,11 +24,12 @@ PREC_X2 = "x2"
 
 class X2:
     """Two-plane activation (include/adamml_b200.h "x2"): value = hi (bf16) + lo (fp16), both NHWC [IMGS, H, W, C]."""
-    __slots__ = ("hi", "lo")
+    __slots__ = ("hi", "lo", "_adamml_src")
     dtype = PREC_X2
 
     def __init__(self, hi, lo):
         self.hi, self.lo = hi, lo
+        self._adamml_src = None
 
     @staticmethod
     def empty(shape, device):

@@ -355,6 +355,9 @@ def run_gpu_arm(a):
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     modality = a.modality.split(",")
     S, N = a.segments, a.batch
+    if a.recompute:
+        from adamml_b200 import engine
+        engine.RECOMPUTE = True
     torch.manual_seed(0)
     model, _ = build_model(namespace(modality, S, a.precision))
     model = model.to(dev).train()
@@ -529,6 +532,7 @@ def run_gpu_arm(a):
         "config": {"workload": f"AdaMML {'+'.join(modality)} S={S} F=8 224^2, batch {N}/GPU, "
                                f"fwd+loss+bwd+Adam(policy)+SGD(main)", "batch_per_gpu": N, "segments": S,
                    "sync_bn": sync_bn, "parallelism": f"dp{world}", "cuda_graph": use_graph,
+                   "recompute_activations": bool(a.recompute),
                    "l2": "inputs (1.8 GB/step) and activations exceed the 126 MB L2; no explicit flush",
                    "peak_mem_gib": round(peak_mem, 1)},
         "e2e": {"value": clips / (ms_e2e / 1e3), "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
@@ -600,6 +604,9 @@ def main():
                                                             "captured CUDA graph per step")
     ap.add_argument("--u8-input", action="store_true", help="visual modalities as uint8 frames: 4x less H2D traffic, "
                     "scaling + mean/std normalisation inside the data-layer kernels")
+    ap.add_argument("--recompute", action="store_true", help="do not keep the outputs of layers without residual input "
+                    "for backward (rebuilt from the saved pre-BN tensors): -35 %% activation memory for one extra bf16 "
+                    "BN-apply pass per such layer; lets the two-ResNet configs run at batch 72")
     ap.add_argument("--dump-calls", default=None, help="write one JSON line per C-ABI call of one step (op, ms, args)")
     a = ap.parse_args()
     if a.warmup < 3 and a.impl == "ours":

@@ -312,3 +312,37 @@ def test_x2_eval_skip_bit_identical(cuda):
             outs.append(model(xs, num_segments=3, noise=noise))
     assert torch.equal(outs[0][1], outs[1][1])
     assert torch.equal(outs[0][0], outs[1][0])
+
+
+@pytest.mark.parametrize("mode", ["x2", "bf16"])
+def test_recompute_mode_same_gradients_less_memory(cuda, mode):
+    """ADAMML_B200_RECOMPUTE: outputs of layers without residual input are not kept for backward; the consumer's
+    weight gradient rebuilds them from the saved pre-BN tensor.  Same logits / selections (forward is untouched),
+    gradients equal to bf16 rounding, and a clearly smaller peak."""
+    from adamml_b200 import engine, ops
+    case = dict(kind="adamml", modality=["rgb", "sound"], N=4, S=2, hw=64, training=True)
+    res = {}
+    old = engine.RECOMPUTE
+    try:
+        for rc in (False, True):
+            engine.RECOMPUTE = rc
+            model, _ = build(case, cuda, dtype=ops.PREC_X2 if mode == "x2" else torch.bfloat16)
+            torch.cuda.synchronize()
+            torch.cuda.reset_peak_memory_stats()
+            base = torch.cuda.memory_allocated()
+            logits, dec, loss = run_product(model, case, 5, cuda)
+            fwd_peak = torch.cuda.max_memory_allocated() - base
+            held = torch.cuda.memory_allocated() - base          # what the tape keeps alive for backward
+            loss.backward()
+            torch.cuda.synchronize()
+            res[rc] = (logits.detach(), dec.detach(), {k: p.grad.clone() for k, p in model.named_parameters()}, held,
+                       fwd_peak)
+            del model, logits, dec, loss
+    finally:
+        engine.RECOMPUTE = old
+    assert torch.equal(res[True][0], res[False][0]) and torch.equal(res[True][1], res[False][1])
+    from util import compare_grads
+    bad = compare_grads(res[True][2], res[False][2], tol=3e-2)
+    assert len(bad) <= len(res[True][2]) // 50, bad[:5]
+    print(f"{mode}: tape memory {res[False][3] / 2**20:.0f} -> {res[True][3] / 2**20:.0f} MiB")
+    assert res[True][3] < 0.8 * res[False][3]
