@@ -1,5 +1,4 @@
 #!/bin/bash
-# scratch GPU job (run as: gpurun -- 'bash scripts/_job.sh')
 mkdir -p gpurun_out
-timeout 500 python bench.py --steps 5 --warmup 3 --modality rgb,flow,rgbdiff --batch 64 --recompute --u8-input --no-cpu-baseline > gpurun_out/r2_bench_cfg3_rgb_flow_N64_1gpu.log 2> gpurun_out/cfg3.err; tail -c 300 gpurun_out/cfg3.err; cut -c1-200 gpurun_out/r2_bench_cfg3_rgb_flow_N64_1gpu.log; grep -o '"peak_mem_gib": [0-9.]*' gpurun_out/r2_bench_cfg3_rgb_flow_N64_1gpu.log
-timeout 500 python bench.py --steps 5 --warmup 3 --modality rgb,sound,flow,rgbdiff --batch 48 --recompute --u8-input --no-cpu-baseline > gpurun_out/r2_bench_cfg4_N48_1gpu.log 2> gpurun_out/cfg4.err; tail -c 300 gpurun_out/cfg4.err; cut -c1-200 gpurun_out/r2_bench_cfg4_N48_1gpu.log; grep -o '"peak_mem_gib": [0-9.]*' gpurun_out/r2_bench_cfg4_N48_1gpu.log
+bash scripts/run_sanitizers.sh 240 2>&1 | tee gpurun_out/r2_sanitizer_summary.txt
+timeout 300 python bench.py --steps 6 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/r2_bench_1gpu_nograph.log 2> gpurun_out/nograph.err; tail -c 200 gpurun_out/nograph.err; cut -c1-220 gpurun_out/r2_bench_1gpu_nograph.log

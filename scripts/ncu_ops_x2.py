@@ -27,35 +27,47 @@ def x2rand(*shape):
 
 G, rows = 5, 1806336
 M = rows * G
-# layer1 conv3 (64 -> 256) forward, x2, with fused BN statistics
-a64 = x2rand(M, 1, 1, 64)
-w = ops.pack_weight(torch.randn(256, 64, 1, 1, device=dev) / 8, ops.PREC_X2)
-st = torch.empty(G, 256, 2, device=dev, dtype=torch.float64)
-z, _ = ops.conv_fwd(a64, w, 1, 0, stats=st, rows_per_group=rows)
-# bn3 + identity + ReLU, x2
-res = x2rand(M, 1, 1, 256)
-ss = torch.rand(G, 256, 2, device=dev)
-out = ops.bn_apply(z, ss, G, 1, res=res)
-del res
-# layer1 conv2 (3x3, 64 -> 64) forward, x2
-x3 = x2rand(2880, 56, 56, 64)
-w3 = ops.pack_weight(torch.randn(64, 64, 3, 3, device=dev) / 24, ops.PREC_X2)
-st3 = torch.empty(G, 64, 2, device=dev, dtype=torch.float64)
-ops.conv_fwd(x3, w3, 1, 1, stats=st3, rows_per_group=rows)
-del x3
-# a MobileNetV2 depthwise forward, x2
-xd = x2rand(1440, 40, 40, 144)
-ops.dwconv_fwd(xd, ops.pack_weight_dw(torch.randn(144, 1, 3, 3, device=dev)), 1)
-del xd
-# backward (bf16 on the hi planes): BN reduce / apply of the residual layer, weight gradient of conv3
-dout = rnd(M, 256)
-mi = torch.rand(G, 256, 2, device=dev) + 0.5
-gamma = torch.rand(256, device=dev) + 0.5
-zh, oh = z.hi.view(M, 256), out.hi.view(M, 256)
-sums = ops.bn_bwd_reduce(dout, oh, zh, mi, G, 1)
-dz, _ = ops.bn_bwd_apply(dout, oh, zh, mi, gamma, sums, G, rows, 1, True)
-dw = torch.empty(256, 1, 1, 64, device=dev, dtype=torch.float32)
-_lib.call("tc_wgrad_bf16", a64.hi.view(2880, 56, 56, 64), dz.view(2880, 56, 56, 256), dw, 2880, 56, 56, 64, 256, 1, 1, 1,
-          0, 56, 56)
+which = sys.argv[1] if len(sys.argv) > 1 else "all"
+
+
+def want(k):
+    return which in ("all", k)
+
+
+if want("gemm") or want("bn") or want("bwd"):
+    # layer1 conv3 (64 -> 256) forward, x2, with fused BN statistics
+    a64 = x2rand(M, 1, 1, 64)
+    w = ops.pack_weight(torch.randn(256, 64, 1, 1, device=dev) / 8, ops.PREC_X2)
+    st = torch.empty(G, 256, 2, device=dev, dtype=torch.float64)
+    z, _ = ops.conv_fwd(a64, w, 1, 0, stats=st, rows_per_group=rows)
+if want("bn") or want("bwd"):
+    # bn3 + identity + ReLU, x2
+    res = x2rand(M, 1, 1, 256)
+    ss = torch.rand(G, 256, 2, device=dev)
+    out = ops.bn_apply(z, ss, G, 1, res=res)
+    del res
+if want("conv"):
+    # layer1 conv2 (3x3, 64 -> 64) forward, x2
+    x3 = x2rand(2880, 56, 56, 64)
+    w3 = ops.pack_weight(torch.randn(64, 64, 3, 3, device=dev) / 24, ops.PREC_X2)
+    st3 = torch.empty(G, 64, 2, device=dev, dtype=torch.float64)
+    ops.conv_fwd(x3, w3, 1, 1, stats=st3, rows_per_group=rows)
+    del x3
+if want("dw"):
+    # a MobileNetV2 depthwise forward, x2
+    xd = x2rand(1440, 40, 40, 144)
+    ops.dwconv_fwd(xd, ops.pack_weight_dw(torch.randn(144, 1, 3, 3, device=dev)), 1)
+    del xd
+if want("bwd"):
+    # backward (bf16 on the hi planes): BN reduce / apply of the residual layer, weight gradient of conv3
+    dout = rnd(M, 256)
+    mi = torch.rand(G, 256, 2, device=dev) + 0.5
+    gamma = torch.rand(256, device=dev) + 0.5
+    zh, oh = z.hi.view(M, 256), out.hi.view(M, 256)
+    sums = ops.bn_bwd_reduce(dout, oh, zh, mi, G, 1)
+    dz, _ = ops.bn_bwd_apply(dout, oh, zh, mi, gamma, sums, G, rows, 1, True)
+    dw = torch.empty(256, 1, 1, 64, device=dev, dtype=torch.float32)
+    _lib.call("tc_wgrad_bf16", a64.hi.view(2880, 56, 56, 64), dz.view(2880, 56, 56, 256), dw, 2880, 56, 56, 64, 256, 1,
+              1, 1, 0, 56, 56)
 torch.cuda.synchronize()
 print("done")
