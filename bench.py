@@ -370,8 +370,14 @@ def run_gpu_arm(a):
         net = model
         if not use_graph:  # eager mode: the reference's DDP wrap (train_adamml.py:129)
             net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=True)
-    p_opt = torch.optim.Adam(model.policy_net.parameters(), 0.01, weight_decay=1e-4, capturable=use_graph)
-    opt = torch.optim.SGD(model.main_net.parameters(), 0.01, momentum=0.9, weight_decay=1e-4)
+    if a.torch_tail:   # the reference's own tail: torch CE / policy loss / optimizers (train_adamml.py:250-257)
+        p_opt = torch.optim.Adam(model.policy_net.parameters(), 0.01, weight_decay=1e-4, capturable=use_graph)
+        opt = torch.optim.SGD(model.main_net.parameters(), 0.01, momentum=0.9, weight_decay=1e-4)
+    else:              # same update rules, one multi-tensor launch per optimizer (adamml_b200/optim.py, §8 f2)
+        from adamml_b200.optim import FusedAdam, FusedSGD, loss_tail
+        p_opt = FusedAdam(model.policy_net.parameters(), 0.01, weight_decay=1e-4)
+        opt = FusedSGD(model.main_net.parameters(), 0.01, momentum=0.9, weight_decay=1e-4)
+        cw_dev = torch.ones(model.num_modality, device=dev)
     cost_weights = [1.0] * model.num_modality
     params = list(model.parameters())
 
@@ -385,7 +391,10 @@ def run_gpu_arm(a):
         p_opt.zero_grad(set_to_none=True)
         opt.zero_grad(set_to_none=True)
         out, sel = net(xs)
-        loss = F.cross_entropy(out, y) + policy_loss(sel, cost_weights, 10.0, out, y)
+        if a.torch_tail:
+            loss = F.cross_entropy(out, y) + policy_loss(sel, cost_weights, 10.0, out, y)
+        else:
+            loss = loss_tail(out, y, sel, cw_dev, 10.0, True)
         loss.backward()
         if world > 1 and use_graph:  # DDP's gradient averaging as one flat NCCL all-reduce inside the graph
             from adamml_b200.dist_utils import allreduce_grads
@@ -534,7 +543,7 @@ def run_gpu_arm(a):
         "config": {"workload": f"AdaMML {'+'.join(modality)} S={S} F=8 224^2, batch {N}/GPU, "
                                f"fwd+loss+bwd+Adam(policy)+SGD(main)", "batch_per_gpu": N, "segments": S,
                    "sync_bn": sync_bn, "parallelism": f"dp{world}", "cuda_graph": use_graph,
-                   "recompute_activations": bool(a.recompute),
+                   "recompute_activations": bool(a.recompute), "fused_tail": not a.torch_tail,
                    "l2": "inputs (1.8 GB/step) and activations exceed the 126 MB L2; no explicit flush",
                    "peak_mem_gib": round(peak_mem, 1)},
         "e2e": {"value": clips / (ms_e2e / 1e3), "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
@@ -606,6 +615,8 @@ def main():
                                                             "captured CUDA graph per step")
     ap.add_argument("--u8-input", action="store_true", help="visual modalities as uint8 frames: 4x less H2D traffic, "
                     "scaling + mean/std normalisation inside the data-layer kernels")
+    ap.add_argument("--torch-tail", action="store_true", help="CE / policy loss / Adam / SGD as the reference's torch "
+                    "code instead of the fused loss kernel + multi-tensor optimizers (same update rules)")
     ap.add_argument("--recompute", action="store_true", help="do not keep the outputs of layers without residual input "
                     "for backward (rebuilt from the saved pre-BN tensors): -35 %% activation memory for one extra bf16 "
                     "BN-apply pass per such layer; lets the two-ResNet configs run at batch 72")

@@ -269,6 +269,26 @@ int adamml_tc_stem_conv_bn_act_bf16(const void* xs, const void* w, void* y, int 
 int adamml_dwconv_bn_act_fwd(const void* x, const float* w, void* y, int IMGS, int H, int W, int C, int stride, int Ho,
                              int Wo, const float* scale_shift, int act, int dtype, cudaStream_t stream);
 
+/* ---- train-step tail (utils/utils.py:362-400, train_adamml.py:250-257) ----
+ * adamml_loss_tail: cross-entropy + 'blockdrop' policy loss (utils/utils.py:166-184, including its [N] x [N,1]
+ * broadcast) and both gradients in one launch.  logits [N][C] fp32, target int64 [N], selection [N][S][M] fp32,
+ * cost_weights fp32 [M]; loss fp32 [1], dlogits [N][C], dselection [N][S][M] (gradients of the loss itself).
+ * adamml_sgd_multi / adamml_adam_multi: torch.optim.SGD (momentum, dampening 0, L2 weight decay) / torch.optim.Adam
+ * (bias correction, L2 weight decay, no amsgrad) over ALL tensors of a parameter group in one launch.  table = device
+ * array [2 + states][n_tensors] of addresses (param, grad, momentum | exp_avg, exp_avg_sq), sizes [n_tensors] element
+ * counts, chunk_tensor / chunk_start [n_chunks] = the tensor and element offset each block of adamml_opt_chunk()
+ * elements works on.  The Adam step counter `step` (int64 [1]) lives on the device and is advanced by the call. */
+int adamml_loss_tail(const float* logits, const long long* target, const float* selection, const float* cost_weights,
+                     float gamma, int use_policy, int N, int C, int S, int M, float* loss, float* dlogits,
+                     float* dselection, cudaStream_t stream);
+int adamml_sgd_multi(const unsigned long long* table, const long long* sizes, const int* chunk_tensor,
+                     const long long* chunk_start, int n_tensors, int n_chunks, float lr, float momentum,
+                     float weight_decay, cudaStream_t stream);
+int adamml_adam_multi(const unsigned long long* table, const long long* sizes, const int* chunk_tensor,
+                      const long long* chunk_start, int n_tensors, int n_chunks, float lr, float beta1, float beta2,
+                      float eps, float weight_decay, long long* step, cudaStream_t stream);
+int adamml_opt_chunk(void);
+
 /* ---- device-side gating: inference with decision-driven skipping, no host round trip ----
  * The reference runs every main backbone on every (segment, video) pair and multiplies its logits by the policy's 0/1
  * decision (models/adamml.py:81-86, joint_resnet_mobilenetv2.py:92-94).  With running-statistic BatchNorm an unselected

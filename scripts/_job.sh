@@ -1,4 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-bash scripts/run_sanitizers.sh 240 2>&1 | tee gpurun_out/r2_sanitizer_summary.txt
-timeout 300 python bench.py --steps 6 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/r2_bench_1gpu_nograph.log 2> gpurun_out/nograph.err; tail -c 200 gpurun_out/nograph.err; cut -c1-220 gpurun_out/r2_bench_1gpu_nograph.log
+timeout 300 python -m pytest tests/test_train_tail_gpu.py -q 2>&1 | tail -15
+timeout 400 python bench.py --steps 8 --warmup 3 --no-cpu-baseline > gpurun_out/bench_x2_fusedtail.log 2> gpurun_out/ft.err; tail -c 300 gpurun_out/ft.err; cut -c1-200 gpurun_out/bench_x2_fusedtail.log
+timeout 400 python bench.py --steps 8 --warmup 3 --no-cpu-baseline --torch-tail > gpurun_out/bench_x2_torchtail.log 2> gpurun_out/tt.err; tail -c 300 gpurun_out/tt.err; cut -c1-200 gpurun_out/bench_x2_torchtail.log
