@@ -175,13 +175,17 @@ struct TileSched {
     }
     const long long t = blockIdx.x + (long long)i * gridDim.x;
     if (t >= num_tiles) return false;
-    n_blk = (int)(t % num_n_blks);
-    m_blk = (int)(t / num_n_blks);
+    const unsigned tu = (unsigned)t, q = tu / (unsigned)num_n_blks;  // (tile counts stay far below 2^31)
+    n_blk = (int)(tu - q * (unsigned)num_n_blks);
+    m_blk = (int)q;
     return true;
   }
 };
 
-template <int BLOCK_N, bool CONV, bool SHALLOW = false, int X2 = 0>
+// EPI: the fused inference epilogue (EpiSpec: BatchNorm scale / shift, activation, x2 residual planes, device-side work
+// limit) is compiled in only for the inference instantiations -- the training kernels keep their lean epilogue (with the
+// code compiled in but unused, the x2 training GEMMs ran 12-20 % slower: 168 instead of 136 registers per thread).
+template <int BLOCK_N, bool CONV, bool SHALLOW = false, int X2 = 0, bool EPI = false>
 __global__ void __launch_bounds__(TcCfg<BLOCK_N, SHALLOW, X2>::THREADS, TcCfg<BLOCK_N, SHALLOW, X2>::CTAS_PER_SM)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmAdd,
@@ -207,7 +211,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int lane = threadIdx.x & 31;
 
   int num_m_blks = CONV ? geo.tiles_w * geo.tiles_h * geo.tiles_i : (int)((M + BLOCK_M - 1) / BLOCK_M);
-  if (epi.live.n) {  // device-side work limit: row blocks are image-major, so the live ones come first
+  if (EPI && epi.live.n) {  // device-side work limit: row blocks are image-major, so the live ones come first
     if (CONV) {
       const int ti = (int)((live_count(epi.live, geo.IMGS) + geo.BI - 1) / geo.BI);
       num_m_blks = geo.tiles_w * geo.tiles_h * ti;
@@ -237,7 +241,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // dense residual-gradient addend (same pixel lattice as the output): fetched by TMA into the staging tile
-  const bool add_tma = addend != nullptr && geo.addend_sub != 2;
+  // (x2 launches only carry an addend -- the residual planes -- in the fused inference epilogue)
+  const bool add_tma = (X2 ? EPI : true) && addend != nullptr && geo.addend_sub != 2;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -409,7 +414,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         arow = row;
         row_ok = row < M;
       }
-      if (epi.ss && n_blk != last_ss_blk) {
+      if (EPI && epi.ss && n_blk != last_ss_blk) {
         // every thread is past the mid-tile barrier of the previous tile, i.e. done reading the previous block's pairs
         for (int j = st; j < BLOCK_N; j += Cfg::EPI_THREADS) {
           const int col = n_blk * BLOCK_N + j;
@@ -463,7 +468,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (!row_ok) {  // edge tiles only: rows outside the tensor are staged as zeros (statistics sum them)
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = 0.f;
-        } else if (epi.ss) {  // fused inference BatchNorm: per-column scale / shift (broadcast smem reads)
+        } else if (EPI && epi.ss) {  // fused inference BatchNorm: per-column scale / shift (broadcast smem reads)
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const float2 p = ss_s[chunk * 32 + j];
@@ -502,7 +507,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               v[j + 2 * t] += f.x;
               v[j + 2 * t + 1] += f.y;
             }
-            if (X2) {
+            if (X2 && EPI) {
               const uint4 pl = *reinterpret_cast<const uint4*>(srow + Cfg::OUT_PLANE_BYTES + ((c ^ (et & 7)) << 4));
               const __half2* l2 = reinterpret_cast<const __half2*>(&pl);
 #pragma unroll
@@ -514,7 +519,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
         }
-        if (epi.act != ADAMML_ACT_NONE) {
+        if (EPI && epi.act != ADAMML_ACT_NONE) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = act_apply(v[j], epi.act);
         }
@@ -619,7 +624,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             } else {
               const long long row0 = (long long)m_blk * BLOCK_M;
               if (row0 + r0 >= M) break;
-              g = (row0 + r0) / rows_per_group;
+              // (M < 2^31 for every launch, see adamml_tc_supported: 32-bit division instead of the ~80-instruction
+              // 64-bit one, executed by every epilogue thread for every tile)
+              g = (long long)((unsigned)(row0 + r0) / (unsigned)rows_per_group);
               const long long e = (g + 1) * rows_per_group - row0;
               r1 = e < BLOCK_M ? (int)e : BLOCK_M;
             }
@@ -704,14 +711,14 @@ const X2Maps& no_x2() {
   return z;
 }
 
-template <int BLOCK_N, bool CONV, bool SHALLOW = false, int X2 = 0>
-int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, const CUtensorMap& tmAdd,
+template <int BLOCK_N, bool CONV, bool SHALLOW, int X2, bool EPI>
+int launch_tc_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, const CUtensorMap& tmAdd,
               const ConvMaps& cm, const ConvGeom& geo, const void* addend, long long M, int Ncols, int K, long long ldd, double* stats,
               long long rpg, cudaStream_t stream, void* dlin = nullptr, const X2Maps& x2 = no_x2(),
               const EpiSpec& epi = EpiSpec{nullptr, ADAMML_ACT_NONE}) {
   using Cfg = TcCfg<BLOCK_N, SHALLOW, X2>;
   static bool configured = false;
-  auto kern = tc_gemm_kernel<BLOCK_N, CONV, SHALLOW, X2>;
+  auto kern = tc_gemm_kernel<BLOCK_N, CONV, SHALLOW, X2, EPI>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) {
@@ -734,10 +741,22 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap&
     grid = (sms / n_blks) * n_blks;
   }
   EpiSpec e = epi;
-  if (e.ss && !stats) e.live = adamml_live_limit(CONV ? (long long)geo.IMGS : M);  // inference launches only
+  if (EPI && e.ss && !stats) e.live = adamml_live_limit(CONV ? (long long)geo.IMGS : M);  // inference launches only
   kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmD, tmAdd, cm, geo, x2, (const bf16*)addend, M,
                                                         Ncols, K, ldd, stats, rpg, (bf16*)dlin, pin_n, e);
   return adamml_check_launch(CONV ? "tc_conv" : "tc_gemm");
+}
+
+template <int BLOCK_N, bool CONV, bool SHALLOW = false, int X2 = 0>
+int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, const CUtensorMap& tmAdd,
+              const ConvMaps& cm, const ConvGeom& geo, const void* addend, long long M, int Ncols, int K, long long ldd,
+              double* stats, long long rpg, cudaStream_t stream, void* dlin = nullptr, const X2Maps& x2 = no_x2(),
+              const EpiSpec& epi = EpiSpec{nullptr, ADAMML_ACT_NONE}) {
+  if (epi.ss)
+    return launch_tc_impl<BLOCK_N, CONV, SHALLOW, X2, true>(tmA, tmB, tmD, tmAdd, cm, geo, addend, M, Ncols, K, ldd,
+                                                            stats, rpg, stream, dlin, x2, epi);
+  return launch_tc_impl<BLOCK_N, CONV, SHALLOW, X2, false>(tmA, tmB, tmD, tmAdd, cm, geo, addend, M, Ncols, K, ldd,
+                                                           stats, rpg, stream, dlin, x2, epi);
 }
 
 template <bool CONV>

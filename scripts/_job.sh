@@ -1,5 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_train_tail_gpu.py -q 2>&1 | tail -15
-timeout 400 python bench.py --steps 8 --warmup 3 --no-cpu-baseline > gpurun_out/bench_x2_fusedtail.log 2> gpurun_out/ft.err; tail -c 300 gpurun_out/ft.err; cut -c1-200 gpurun_out/bench_x2_fusedtail.log
-timeout 400 python bench.py --steps 8 --warmup 3 --no-cpu-baseline --torch-tail > gpurun_out/bench_x2_torchtail.log 2> gpurun_out/tt.err; tail -c 300 gpurun_out/tt.err; cut -c1-200 gpurun_out/bench_x2_torchtail.log
+timeout 400 python -m pytest tests/test_x2_gpu.py tests/test_kernels_gpu.py tests/test_fused_eval_gpu.py tests/test_eval_skip_gpu.py -q -k "tc_ or fused or bn_act or first_conv or skip or selected or rng" 2>&1 | tail -3
+timeout 300 python scripts/bench_ops.py x2gemm > gpurun_out/ops_x2gemm_v4.log 2>&1; cat gpurun_out/ops_x2gemm_v4.log
