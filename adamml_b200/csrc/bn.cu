@@ -317,8 +317,8 @@ __global__ void __launch_bounds__(EW_THREADS, 2)
 bn_stats_rows_x2_kernel(X2CPtr a, double* __restrict__ sums, long long rows_per_group, int C, int cpb, int k,
                         int blocks_per_group) {
   constexpr int V = 8;
-  constexpr int UN = 2;
-  constexpr int CH = 8;
+  constexpr int UN = 4;  // 8 independent 16-byte loads in flight per thread: one tensor only, so the memory-level
+  constexpr int CH = 4;  // parallelism has to come from the unroll (2 -> 4: measured below)
   extern __shared__ double shd[];
   const int cl = threadIdx.x % cpb, rl = threadIdx.x / cpb;
   const int c0 = (blockIdx.y * cpb + cl) * V;
@@ -707,7 +707,13 @@ int adamml_bn_stats_x2(const void* z_hi, const void* z_lo, double* sums, long lo
   ADAMML_REQUIRE(C % 8 == 0 && vec_ok<bf16>(C, z_hi, z_lo), "bn_stats_x2: needs C %% 8 == 0 and aligned planes");
   cudaMemsetAsync(sums, 0, sizeof(double) * (size_t)G * C * 2, stream);
   const RowGeom rg = row_geom<x2_t>(C);
-  const int bpg = reduce_bpg(rg, rows_per_group, G);
+  // persistent over row chunks, ~8 blocks per SM in total (a single-tensor stream needs more resident warps than the
+  // three-tensor backward reduction to cover the HBM latency)
+  const long long chunk_rows = (long long)rg.k * 4 * 4;
+  const long long chunks = (rows_per_group + chunk_rows - 1) / chunk_rows;
+  long long want = (8LL * num_sms_ew() + (long long)G * rg.cchunks - 1) / ((long long)G * rg.cchunks);
+  if (want < 1) want = 1;
+  const int bpg = (int)(chunks < want ? chunks : want);
   const size_t sm = sizeof(double) * rg.threads * 2 * 8;
   dim3 vg((unsigned)(bpg * (long long)G), rg.cchunks);
   bn_stats_rows_x2_kernel<<<vg, rg.threads, sm, stream>>>(x2c(z_hi, z_lo), sums, rows_per_group, C, rg.cpb, rg.k, bpg);

@@ -229,7 +229,11 @@ def run_reference_arm(a):
 # the algorithmic bytes of that launch: measured traffic == algorithmic traffic to within 1-2 % for the streaming
 # kernels, 1.2x for the weight-gradient kernel (dy is re-read per 128-row M tile).
 NCU_TRAFFIC_RATIO = {"bn_bwd_reduce": 14.014 / 13.873, "bn_bwd_apply": 18.479 / 18.498, "bn_apply": 9.205 / 9.249,
-                     "tc_gemm_bf16": 5.722 / 5.780, "tc_wgrad_bf16": 6.941 / 5.780}
+                     "tc_gemm_bf16": 5.722 / 5.780, "tc_wgrad_bf16": 6.941 / 5.780,
+                     # round 2, profiles/r2_ncu_ops_x2_N72.txt: 9 M x 256 x 64 x2 GEMM reads its A planes 1.57x (the four
+                     # column-block CTAs of a row block drift apart), 3x3 x2 conv and bn_apply_x2 move the algorithmic bytes
+                     "tc_gemm_x2": (3.638 + 9.195) / 11.561, "bn_apply_x2": (18.497 + 9.216) / 27.745,
+                     "tc_conv_x2": (2.315 + 2.276) / 4.624}
 
 
 def kernel_work(name, a):
@@ -568,9 +572,9 @@ def run_gpu_arm(a):
             ratio = NCU_TRAFFIC_RATIO.get(name)
             out["roofline"] = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
                                "frac": ach / pk["hbm"], "traffic": (by / cnt) * ratio if ratio else None,
-                               "traffic_source": "ncu --set full capture profiles/r1_ncu_ops_N72.txt (measured / "
-                                                 "algorithmic DRAM bytes of the largest launch), applied to the mean "
-                                                 "launch" if ratio else None,
+                               "traffic_source": "ncu --set full captures profiles/r2_ncu_ops_x2_N72.txt / "
+                                                 "r1_ncu_ops_N72.txt (measured / algorithmic DRAM bytes of the largest "
+                                                 "launch), applied to the mean launch" if ratio else None,
                                "peak_source": pk["src"],
                                "algorithmic_bytes_per_launch": by / cnt, "launches_per_step": cnt,
                                "avg_launch_ms": t_ms / cnt, "share_of_step": t_ms / total,
