@@ -387,6 +387,61 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int j = st; j < BLOCK_N * 2; j += Cfg::EPI_THREADS) red[j] = 0.0;
       epi_bar_sync<Cfg::EPI_THREADS>();
     }
+    // Register-resident statistics (shallow x2 training GEMMs: the tile is all epilogue, and re-reading the staged
+    // tile for the column sums cost more issue slots than the conversion itself).  A thread owns ONE accumulator row
+    // slot and a FIXED 32-column chunk for its whole life (one column block per CTA: a single block or pinned
+    // scheduling), so sum / sum of squares are 2 x 16 packed fp32 FMAs per tile on the values it converts anyway; the
+    // cross-row reduction (warp butterfly -> shared fp64 -> one global fp64 atomic per column) runs only when the BN
+    // group changes or after RS_TILES tiles (bounds the fp32 partial sums).  Tiles that straddle two BN groups take
+    // the staged-tile path below.
+    constexpr bool REGSTATS = (X2 == 1) && !CONV && !EPI;
+    constexpr int RS_N = REGSTATS ? 16 : 1;
+    constexpr int RS_TILES = 32;
+    float2 rsS[RS_N], rsQ[RS_N];
+#pragma unroll
+    for (int j = 0; j < RS_N; ++j) { rsS[j] = make_float2(0.f, 0.f); rsQ[j] = make_float2(0.f, 0.f); }
+    long long rs_g = -1;
+    int rs_tiles = 0;
+    const bool rs_on = REGSTATS && stats != nullptr && (num_n_blks == 1 || sched.pin);
+    const int rs_nblk = sched.pin ? (int)(blockIdx.x % num_n_blks) : 0;
+    auto rs_flush = [&]() {
+      if constexpr (REGSTATS) {
+        float s[32], qv[32];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          s[2 * j] = rsS[j].x; s[2 * j + 1] = rsS[j].y;
+          qv[2 * j] = rsQ[j].x; qv[2 * j + 1] = rsQ[j].y;
+          rsS[j] = make_float2(0.f, 0.f);
+          rsQ[j] = make_float2(0.f, 0.f);
+        }
+        // halving butterfly over the warp's 32 rows: afterwards lane l holds the sums of column l of the chunk
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+          const bool up = (lane & off) != 0;
+#pragma unroll
+          for (int i = 0; i < off; ++i) {
+            const float ss_ = up ? s[i] : s[i + off], ks = up ? s[i + off] : s[i];
+            const float sq_ = up ? qv[i] : qv[i + off], kq = up ? qv[i + off] : qv[i];
+            s[i] = ks + __shfl_xor_sync(0xffffffffu, ss_, off);
+            qv[i] = kq + __shfl_xor_sync(0xffffffffu, sq_, off);
+          }
+        }
+        const int cl = chalf * 32 + lane;
+        if (rs_nblk * BLOCK_N + cl < Ncols) {
+          atomicAdd(red + cl * 2 + 0, (double)s[0]);
+          atomicAdd(red + cl * 2 + 1, (double)qv[0]);
+        }
+        epi_bar_sync<Cfg::EPI_THREADS>();
+        for (int j = st; j < BLOCK_N * 2; j += Cfg::EPI_THREADS) {
+          const double v = red[j];
+          if (v != 0.0) {
+            atomicAdd(stats + (rs_g * Ncols + rs_nblk * BLOCK_N + (j >> 1)) * 2 + (j & 1), v);
+            red[j] = 0.0;
+          }
+        }
+        epi_bar_sync<Cfg::EPI_THREADS>();
+      }
+    };
     int acc = 0, obuf = 0;
     uint32_t acc_phase = 0, add_phase = 0;
     int n_blk, m_blk;
@@ -421,6 +476,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           ss_s[j] = col < Ncols ? reinterpret_cast<const float2*>(epi.ss)[col] : make_float2(0.f, 0.f);
         }
         last_ss_blk = n_blk;
+      }
+      bool rs_tile = false;
+      if (REGSTATS && rs_on) {
+        const long long row0 = (long long)m_blk * BLOCK_M;
+        const long long rlast = (row0 + BLOCK_M <= M ? row0 + BLOCK_M : M) - 1;
+        const unsigned g0 = (unsigned)row0 / (unsigned)rows_per_group, g1 = (unsigned)rlast / (unsigned)rows_per_group;
+        rs_tile = g0 == g1;
+        if (rs_tile) {
+          if ((long long)g0 != rs_g || rs_tiles == RS_TILES) {  // (uniform over the epilogue threads: a collective)
+            if (rs_g >= 0) rs_flush();
+            rs_g = g0;
+            rs_tiles = 0;
+          }
+          ++rs_tiles;
+        }
       }
       // the staging tile (and row_group) of the previous tile must have been consumed
       if (issuer) {
@@ -523,6 +593,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = act_apply(v[j], epi.act);
         }
+        if (REGSTATS && rs_tile) {
+#pragma unroll
+          for (int j = 0; j < RS_N; ++j) {
+            const float2 vv = make_float2(v[(2 * j) & 31], v[(2 * j + 1) & 31]);
+            rsS[j] = __ffma2_rn(vv, make_float2(1.f, 1.f), rsS[j]);
+            rsQ[j] = __ffma2_rn(vv, vv, rsQ[j]);
+          }
+        }
 #pragma unroll
         for (int j = 0; j < 32; j += 8) {
           __nv_bfloat162 p0 = __floats2bfloat162_rn(v[j], v[j + 1]);
@@ -595,7 +673,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
-      if (stats) {
+      if (stats && !rs_tile) {
         if (n_blk != last_n_blk) {
           sa_.template flush<BLOCK_N, Cfg::EPI_THREADS>(stats, Ncols, red, last_n_blk * BLOCK_N, st);
           last_n_blk = n_blk;
@@ -663,6 +741,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
     if (stats) sa_.template flush<BLOCK_N, Cfg::EPI_THREADS>(stats, Ncols, red, last_n_blk * BLOCK_N, st);
+    if (REGSTATS && rs_on && rs_g >= 0) rs_flush();
     if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 

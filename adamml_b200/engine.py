@@ -263,10 +263,15 @@ class Exec:
             if need_w:
                 self._acc(conv.weight, ops.stem_wgrad(x, dz, conv.out_channels))
         elif rec["depthwise"]:
-            if need_w:
-                self._acc(conv.weight, ops.dwconv_wgrad(x, dz, stride))
-            if need_dx:
-                dx = ops.dwconv_dgrad(dz, rec["w"], tuple(x.shape), stride, addend=addend)
+            if need_w and need_dx and addend is None and ops.dwconv_bwd_ok(x, dz, stride):
+                # both gradients from one pass over dz and x (TMA-staged tiles, csrc/dwconv_bwd.cu)
+                dx, dw = ops.dwconv_bwd(x, dz, rec["w"], stride)
+                self._acc(conv.weight, dw)
+            else:
+                if need_w:
+                    self._acc(conv.weight, ops.dwconv_wgrad(x, dz, stride))
+                if need_dx:
+                    dx = ops.dwconv_dgrad(dz, rec["w"], tuple(x.shape), stride, addend=addend)
         else:
             w = rec["w"]
             if need_w:

@@ -4,6 +4,8 @@ Every function takes/returns torch CUDA tensors whose storage comes from torch's
 allocator; all arithmetic happens inside libadamml_b200.so.  Activations are NHWC
 `[IMGS, H, W, C]` tensors (fp32 or bf16); weights for the dense engines are OHWI.
 """
+import os
+
 import torch
 
 from . import _lib
@@ -615,6 +617,28 @@ def dwconv_dgrad(dy, w, x_shape, stride, addend=None):
     dx = torch.empty(x_shape, device=dy.device, dtype=dy.dtype)
     call("dwconv_dgrad", dy, w, dx, addend, IMGS, H, W, C, stride, dy.shape[1], dy.shape[2], dtype_code(dy.dtype))
     return dx
+
+
+DW_FUSED_BWD = os.environ.get("ADAMML_B200_DW_FUSED_BWD", "1") != "0"
+
+
+def dwconv_bwd_ok(x, dy, stride):
+    """the fused TMA-tile backward (csrc/dwconv_bwd.cu) handles bf16 tensors with C % 16 == 0"""
+    return (DW_FUSED_BWD and isinstance(x, torch.Tensor) and x.dtype == torch.bfloat16 and dy.dtype == torch.bfloat16
+            and x.shape[-1] % 16 == 0 and stride in (1, 2))
+
+
+def dwconv_bwd(x, dy, w, stride):
+    """-> (dx, dw): data gradient (bf16 NHWC) and fp32 weight gradient in torch's [C,1,3,3] layout from ONE pass
+    over dy and x.  w: tap-major [9, C] (pack_weight_dw)."""
+    _chk(x); _chk(dy, x.dtype); _chk(w, torch.float32)
+    IMGS, H, W, C = x.shape
+    dx = torch.empty((IMGS, H, W, C), device=x.device, dtype=x.dtype)
+    dwt = torch.empty((9, C), device=x.device, dtype=torch.float32)
+    call("dwconv_bwd", x, dy, w, dx, dwt, IMGS, H, W, C, stride, dy.shape[1], dy.shape[2])
+    dw = torch.empty((C, 1, 3, 3), device=x.device, dtype=torch.float32)
+    call("unpack_wgrad_dw", dwt, dw, C)
+    return dx, dw
 
 
 def dwconv_wgrad(x, dy, stride):

@@ -151,6 +151,12 @@ int adamml_dwconv_dgrad(const void* dy, const float* w, void* dx, const void* ad
                         int stride, int Ho, int Wo, int dtype, cudaStream_t stream);
 int adamml_dwconv_wgrad(const void* x, const void* dy, float* dw, int IMGS, int H, int W, int C, int stride, int Ho,
                         int Wo, int dtype, cudaStream_t stream);
+/* Fused depthwise backward (bf16 NHWC, TMA-staged tiles): dx = conv_transpose(dy, w) AND dw (fp32 tap-major [9][C],
+ * overwritten) from ONE pass over dy and x -- the autograd of the same call sites.  adamml_dwconv_bwd_supported -> 1
+ * when the shape is handled (C % 16 == 0), else the two calls above are used. */
+int adamml_dwconv_bwd_supported(int IMGS, int H, int W, int C, int stride);
+int adamml_dwconv_bwd(const void* x, const void* dy, const float* w, void* dx, float* dw, int IMGS, int H, int W, int C,
+                      int stride, int Ho, int Wo, cudaStream_t stream);
 
 /* ---- BatchNorm2d (+ReLU/ReLU6, + residual) with per-segment groups ----
  * nn.BatchNorm2d at resnet.py:50,53,82-86,139,166 ; sound_mobilenet_v2.py:37,62 ; policy_net.py:41,50,67-85

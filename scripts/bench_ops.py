@@ -132,7 +132,62 @@ def dw(I, H, C, stride):
     report(f"dwconv_wgrad I={I} {H}x{H} C={C} s{stride}", timeit(lambda: ops.dwconv_wgrad(x, dy, stride)), by)
 
 
+_FLUSH = None
+
+
+def timeit_cold(fn, reps=6, warm=2):
+    """per-launch CUDA-event time with the 126 MB L2 flushed (256 MB written) before every launch: the small late
+    layers would otherwise be timed L2-resident"""
+    global _FLUSH
+    if _FLUSH is None:
+        _FLUSH = torch.empty(256 << 20, device=dev, dtype=torch.uint8)
+    for _ in range(warm):
+        fn()
+    tot = 0.0
+    for _ in range(reps):
+        _FLUSH.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        tot += e0.elapsed_time(e1)
+    return tot / reps
+
+
+# every depthwise layer shape of the N=72 RGB+Audio step: (IMGS, H, C, stride, launches per step)
+DW_SHAPES = [(360, 128, 96, 2, 2), (1440, 80, 96, 2, 1), (360, 64, 144, 1, 2), (360, 128, 32, 1, 2),
+             (1440, 40, 144, 1, 1), (360, 16, 384, 1, 8), (360, 32, 192, 1, 4), (1440, 80, 32, 1, 1),
+             (1440, 20, 192, 1, 2), (360, 16, 576, 1, 4), (360, 64, 144, 2, 2), (1440, 40, 144, 2, 1),
+             (360, 8, 960, 1, 6), (720, 10, 384, 1, 4), (720, 10, 576, 1, 2), (360, 32, 192, 2, 2),
+             (360, 16, 576, 2, 2), (360, 5, 960, 1, 3), (720, 20, 192, 2, 1), (360, 10, 576, 2, 1)]
+
+
+def dw_bwd_all():
+    """separate dgrad + wgrad launches vs the fused TMA-tile backward, L2 flushed, summed over one step"""
+    sep_tot = fus_tot = 0.0
+    for I, H, C, stride, n in DW_SHAPES:
+        x = rnd(I, H, H, C)
+        w = ops.pack_weight_dw(torch.randn(C, 1, 3, 3, device=dev))
+        Ho = (H - 1) // stride + 1
+        dy = rnd(I, Ho, Ho, C)
+        by = 2.0 * (2 * x.numel() + dy.numel())
+
+        def sep():
+            ops.dwconv_dgrad(dy, w, tuple(x.shape), stride)
+            ops.dwconv_wgrad(x, dy, stride)
+        t_sep = timeit_cold(sep)
+        t_fus = timeit_cold(lambda: ops.dwconv_bwd(x, dy, w, stride))
+        sep_tot += n * t_sep
+        fus_tot += n * t_fus
+        print(f"dw_bwd I={I} {H}x{H} C={C} s{stride} x{n}: separate {t_sep:7.3f} ms  fused {t_fus:7.3f} ms "
+              f"({by / t_fus / 1e6:6.0f} GB/s, {by / t_fus / 1e6 / HBM * 100:5.1f}% hbm)", flush=True)
+        del x, dy
+    print(f"dw_bwd per step: separate {sep_tot:.2f} ms -> fused {fus_tot:.2f} ms", flush=True)
+
+
 CASES = {
+    "dwbwd": dw_bwd_all,
     "gemm": lambda: [gemm(9031680, 256, 64, True), gemm(9031680, 256, 64, False), gemm(9031680, 64, 256, True),
                      gemm(9031680, 64, 64, True), gemm(4515840, 128, 256, True), gemm(1128960, 512, 128, True),
                      gemm(9216000, 96, 16, True), gemm(2304000, 24, 144, True), gemm(282240, 1024, 256, True),

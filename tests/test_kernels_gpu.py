@@ -159,6 +159,40 @@ def test_dwconv(cuda, case, dtype):
     assert relerr(dw, w.grad) < 5e-5
 
 
+# fused depthwise backward on TMA tiles (csrc/dwconv_bwd.cu): every channel-chunk width (64 | 48 | 32 | 16), both
+# strides, row-tile heights 8 | 5 (stride 1) and 4 | 5 (stride 2), ragged widths / heights, several tiles per CTA,
+# images-per-tile > 1 and image counts that do not fill the last tile
+DW_BWD_CASES = [(2, 16, 16, 32, 1), (3, 15, 17, 96, 2), (2, 8, 8, 960, 1), (1, 10, 10, 144, 2), (3, 10, 10, 576, 1),
+                (5, 5, 5, 960, 1), (2, 40, 40, 144, 1), (1, 128, 128, 32, 1), (2, 64, 64, 96, 2), (7, 20, 20, 192, 2),
+                (3, 33, 19, 16, 1), (2, 21, 35, 48, 2), (9, 16, 16, 384, 1), (40, 8, 8, 64, 1), (37, 10, 10, 64, 2),
+                (2, 80, 80, 96, 2), (300, 16, 16, 128, 1)]
+
+
+@pytest.mark.parametrize("case", DW_BWD_CASES)
+def test_dwconv_bwd_fused(cuda, case):
+    """dx and dw of ONE adamml_dwconv_bwd launch vs torch autograd (fp32 math on the bf16-rounded operands) and vs
+    the separate dgrad / wgrad kernels."""
+    from adamml_b200 import ops
+    IMGS, H, W, C, stride = case
+    g = torch.Generator(device="cpu").manual_seed(sum(case))
+    x = torch.randn(IMGS, C, H, W, generator=g).to(cuda).bfloat16().float()
+    w = torch.randn(C, 1, 3, 3, generator=g).to(cuda) / 3
+    x.requires_grad_(True); w.requires_grad_(True)
+    y_ref = F.conv2d(x, w, None, stride, 1, groups=C)
+    dy = torch.randn(y_ref.shape, generator=g).to(cuda).bfloat16().float()
+    y_ref.backward(dy)
+    xn, dyn = nhwc(x.detach()).bfloat16(), nhwc(dy).bfloat16()
+    wd = ops.pack_weight_dw(w.detach().contiguous())
+    assert ops.dwconv_bwd_ok(xn, dyn, stride)
+    dx, dw = ops.dwconv_bwd(xn, dyn, wd, stride)
+    assert relerr(nchw(dx), x.grad) < TOL[torch.bfloat16]
+    assert relerr(dw, w.grad) < 5e-5
+    dx2 = ops.dwconv_dgrad(dyn, wd, tuple(xn.shape), stride)
+    # same products, different summation order: equal up to one bf16 rounding of a few elements
+    assert relerr(dx.float(), dx2.float()) < 2 ** -7
+    assert (dx != dx2).float().mean().item() < 0.02
+
+
 @pytest.mark.parametrize("act", [0, 1, 2])
 @pytest.mark.parametrize("residual", ["none", "plain", "bn"])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])

@@ -48,8 +48,11 @@ def x2_tol(K):
     return max(X2_TOL, 8e-9 * K)
 
 
+# (the last four run the shallow kernel with ONE column block per CTA -- single block or pinned scheduling -- i.e. the
+# register-resident statistics: group boundaries inside a tile, > 32 tiles per CTA and group, ragged last tile)
 @pytest.mark.parametrize("M,N,K", [(1000, 64, 64), (777, 16, 96), (4096, 96, 16), (513, 128, 256), (2048, 256, 64),
-                                   (300, 2048, 512), (129, 24, 144), (640, 1280, 320)])
+                                   (300, 2048, 512), (129, 24, 144), (640, 1280, 320), (40000, 96, 16),
+                                   (80002, 256, 64), (76800, 64, 128), (1515520, 64, 64)])
 def test_tc_gemm_x2(cuda, M, N, K):
     from adamml_b200 import ops
     g = torch.Generator().manual_seed(M + N + K)
