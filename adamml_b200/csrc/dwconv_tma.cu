@@ -1,4 +1,5 @@
-// Depthwise 3x3 backward on TMA-staged tiles: data gradient AND weight gradient in ONE pass (bf16 NHWC).
+// Depthwise 3x3 on TMA-staged tiles: (1) backward -- data gradient AND weight gradient in ONE pass (bf16 NHWC);
+// (2) x2 training forward, stride 1, with the train-mode BatchNorm statistics of its output fused (dw_fwd_x2_s1_kernel).
 //
 // Reference call sites: autograd of the 3x3 `groups=hidden_dim` convolutions of every InvertedResidual
 // (models/sound_mobilenet_v2.py:58, models/policy_net.py:66,80).  The two gradients read the same dy neighbourhood:
@@ -272,6 +273,158 @@ dw_bwd_s2_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant
   reduce_dw(dW, reinterpret_cast<float*>(stages), g, cp, pos, active, c0, dWg);
 }
 
+// ---- x2 training forward, stride 1, + BatchNorm statistics ---------------------------------------------------------
+// z = dwconv3x3(x) on two-plane activations (hi bf16 + lo fp16, common.cuh), written as two planes, and
+// sums[g][c] = (sum z, sum z^2) per BN group g = img / imgs_per_group in the same pass (models/sound_mobilenet_v2.py:58,62;
+// policy_net.py:66-67,80-81 in train mode): the separate bn_stats_x2 pass over z disappears.  Same tile scheme as the
+// backward: both planes of the x tile (with halo) arrive by TMA, a thread owns a channel pair and a 2-column strip,
+// joins hi + lo ONCE per loaded value into a rolling fp32 window, 9 packed FMAs per output pair.  A tile never
+// straddles two BN groups (BI divides imgs_per_group), so the per-thread fp32 partial sums are flushed (shared-memory
+// reduction -> one fp64 atomic per channel and CTA) only when the CTA's group changes or every FWD_FLUSH_TILES tiles.
+constexpr int FWD_FLUSH_TILES = 32;
+
+__device__ __forceinline__ float2 ld_x2(const bf16* hi, const __half* lo) {
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(hi));
+  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(lo));
+  return make_float2(a.x + b.x, a.y + b.y);
+}
+__device__ __forceinline__ void st_x2(bf16* hi, __half* lo, float2 v) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(v.x, v.y);
+  const float2 hf = __bfloat1622float2(h);
+  float rx = v.x - hf.x, ry = v.y - hf.y;
+  rx = rx == rx ? rx : 0.f;  // inf - inf: keep the non-finite value in hi only (x2_split)
+  ry = ry == ry ? ry : 0.f;
+  *reinterpret_cast<__nv_bfloat162*>(hi) = h;
+  *reinterpret_cast<__half2*>(lo) = __floats2half2_rn(rx, ry);
+}
+
+template <int TH, int CB>
+__global__ void __launch_bounds__(DWB_THREADS, 2)
+dw_fwd_x2_s1_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__ CUtensorMap tmLo,
+                    const float* __restrict__ w, bf16* __restrict__ y_hi, __half* __restrict__ y_lo,
+                    double* __restrict__ sums, int imgs_per_group, const __grid_constant__ DwGeom g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+  float* red = reinterpret_cast<float*>(smem + 128);  // [npos][2][CB] statistics partials
+  uint8_t* stages = smem + 128 + 4096;
+  const int stage_bytes = 2 * g.dy_bytes;  // (dy_bytes = one halo-tile plane)
+
+  const int cp = threadIdx.x % (CB / 2), pos = threadIdx.x / (CB / 2);
+  const bool active = pos < g.npos;
+  const int half_tw = g.TW >> 1;
+  const int jp = pos % half_tw, bi = pos / half_tw;
+  const int chunk = blockIdx.x % g.chunks;
+  const int c0 = chunk * CB;
+  const int cta = blockIdx.x / g.chunks, ncta = gridDim.x / g.chunks;
+  const int sp_tiles = g.tiles_w * g.tiles_h * g.tiles_i;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmHi)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmLo)) : "memory");
+  }
+  __syncthreads();
+
+  auto issue = [&](int s, int stage) {  // one thread
+    const int wt = s % g.tiles_w, ht = (s / g.tiles_w) % g.tiles_h, it = s / (g.tiles_w * g.tiles_h);
+    uint8_t* dst = stages + stage * stage_bytes;
+    mbar_expect_tx(&full[stage], (uint32_t)(2 * g.BI * (TH + 2) * (g.TW + 2) * CB * 2));
+    tma_load_4d(dst, &tmHi, &full[stage], c0, wt * g.TW - 1, ht * TH - 1, it * g.BI);
+    tma_load_4d(dst + g.dy_bytes, &tmLo, &full[stage], c0, wt * g.TW - 1, ht * TH - 1, it * g.BI);
+  };
+
+  float2 wr[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+    wr[t] = active ? *reinterpret_cast<const float2*>(w + (long long)t * g.C + c0 + 2 * cp) : make_float2(0.f, 0.f);
+  float2 S = make_float2(0.f, 0.f), Q = make_float2(0.f, 0.f);
+  int cur_g = -1, since_flush = 0;
+  auto flush = [&]() {  // collective of the CTA
+    if (active) {
+      *reinterpret_cast<float2*>(red + (pos * 2 + 0) * CB + 2 * cp) = S;
+      *reinterpret_cast<float2*>(red + (pos * 2 + 1) * CB + 2 * cp) = Q;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * CB; i += DWB_THREADS) {
+      const int k = i / CB, c = i - k * CB;
+      double a = 0.0;
+      for (int p = 0; p < g.npos; ++p) a += (double)red[(p * 2 + k) * CB + c];
+      atomicAdd(sums + ((long long)cur_g * g.C + c0 + c) * 2 + k, a);
+    }
+    __syncthreads();
+    S = make_float2(0.f, 0.f);
+    Q = make_float2(0.f, 0.f);
+    since_flush = 0;
+  };
+
+  if (threadIdx.x == 0 && cta < sp_tiles) issue(cta, 0);
+  const int pitch = (g.TW + 2) * CB;  // elements per tile row
+  int it_ = 0;
+  for (int s = cta; s < sp_tiles; s += ncta, ++it_) {
+    const int stage = it_ & 1;
+    if (threadIdx.x == 0 && s + ncta < sp_tiles) issue(s + ncta, stage ^ 1);
+    const int wt = s % g.tiles_w, ht = (s / g.tiles_w) % g.tiles_h, ti = s / (g.tiles_w * g.tiles_h);
+    if (sums) {
+      const int tg = (ti * g.BI) / imgs_per_group;
+      if (tg != cur_g || since_flush == FWD_FLUSH_TILES) {
+        if (cur_g >= 0) flush();
+        cur_g = tg;
+      }
+      ++since_flush;
+    }
+    mbar_wait(&full[stage], (uint32_t)((it_ >> 1) & 1));
+    if (active) {
+      const int off = ((bi * (TH + 2)) * (g.TW + 2) + 2 * jp) * CB + 2 * cp;
+      const bf16* hiS = reinterpret_cast<const bf16*>(stages + stage * stage_bytes) + off;
+      const __half* loS = reinterpret_cast<const __half*>(stages + stage * stage_bytes + g.dy_bytes) + off;
+      const int img = ti * g.BI + bi, h0 = ht * TH, wc = wt * g.TW + 2 * jp;
+      const bool ok0 = img < g.IMGS && wc < g.W, ok1 = img < g.IMGS && wc + 1 < g.W;
+      const long long o0 = (((long long)img * g.H + h0) * g.W + wc) * g.C + c0 + 2 * cp;
+      float2 X[3][4];  // rolling window: x rows h-1, h, h+1 (mod 3) x columns wc-1 .. wc+2
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        X[0][j] = ld_x2(hiS + j * CB, loS + j * CB);
+        X[1][j] = ld_x2(hiS + pitch + j * CB, loS + pitch + j * CB);
+      }
+#pragma unroll
+      for (int h = 0; h < TH; ++h) {
+        float2(&Xn)[4] = X[(h + 2) % 3];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) Xn[j] = ld_x2(hiS + (h + 2) * pitch + j * CB, loS + (h + 2) * pitch + j * CB);
+        float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          float2(&Xr)[4] = X[(h + r) % 3];  // x row h + r - 1
+#pragma unroll
+          for (int s_ = 0; s_ < 3; ++s_) {
+            a0 = __ffma2_rn(Xr[s_], wr[r * 3 + s_], a0);      // x column wc + s - 1  ->  window index s
+            a1 = __ffma2_rn(Xr[s_ + 1], wr[r * 3 + s_], a1);
+          }
+        }
+        if (h0 + h < g.H) {
+          const long long o = o0 + (long long)h * g.W * g.C;
+          if (ok0) {
+            st_x2(y_hi + o, y_lo + o, a0);
+            S = __ffma2_rn(a0, make_float2(1.f, 1.f), S);
+            Q = __ffma2_rn(a0, a0, Q);
+          }
+          if (ok1) {
+            st_x2(y_hi + o + g.C, y_lo + o + g.C, a1);
+            S = __ffma2_rn(a1, make_float2(1.f, 1.f), S);
+            Q = __ffma2_rn(a1, a1, Q);
+          }
+        }
+      }
+    }
+    __syncthreads();  // the stage may be refilled by the next iteration's TMA
+  }
+  if (sums && cur_g >= 0) flush();
+}
+
+
 // 4D map over an NHWC bf16 tensor, dims {C, W, H, IMGS}, box {CB, bw, bh, bi}, no swizzle, out-of-bounds = zeros
 int make_dw_map(CUtensorMap* map, const void* ptr, int C, int W, int H, int IMGS, int CB, int bw, int bh, int bi) {
   EncodeTiledFn enc = get_encode_fn();
@@ -292,6 +445,33 @@ int make_dw_map(CUtensorMap* map, const void* ptr, int C, int W, int H, int IMGS
 }
 
 inline int pad128(int v) { return (v + 127) & ~127; }
+
+constexpr int DW_SMEM_LIMIT = 110 * 1024;  // two CTAs per SM
+
+// Positions of a tile = column units (column pairs | quad columns) x images, at most DWB_THREADS / CP of them.  Fewest
+// tiles wins (a tile costs one pass of every thread over its rows), then the wider one (narrower halo), among the
+// shapes whose two-stage ring fits DW_SMEM_LIMIT.  group_imgs > 0: images per tile divide it (a tile never straddles
+// two BatchNorm groups).  smem_of(u, bi) -> dynamic shared memory of the kernel for that tile shape.
+template <typename F>
+bool pick_dw_tile(int units, int IMGS, int max_pos, int group_imgs, F smem_of, int* out_u, int* out_bi) {
+  long long best = -1;
+  for (int u = 1; u <= max_pos && u <= 64; ++u) {
+    int bi = max_pos / u;
+    if (bi > 16) bi = 16;
+    if (bi > IMGS) bi = IMGS;
+    if (group_imgs > 0) {
+      if (bi > group_imgs) bi = group_imgs;
+      while (bi > 1 && group_imgs % bi) --bi;
+    }
+    while (bi > 1 && smem_of(u, bi) > DW_SMEM_LIMIT) --bi;
+    if (group_imgs > 0)
+      while (bi > 1 && group_imgs % bi) --bi;
+    if (bi < 1 || smem_of(u, bi) > DW_SMEM_LIMIT) continue;
+    const long long t = (long long)((units + u - 1) / u) * ((IMGS + bi - 1) / bi);
+    if (best < 0 || t < best || (t == best && u > *out_u)) { best = t; *out_u = u; *out_bi = bi; }
+  }
+  return best >= 0;
+}
 
 }  // namespace
 
@@ -320,18 +500,18 @@ int adamml_dwconv_bwd(const void* x, const void* dy, const float* w, void* dx, f
   g.CP = g.CB / 2;
   g.chunks = C / g.CB;
   const int max_pos = DWB_THREADS / g.CP;
-  // positions per tile = column units x images: fewest tiles wins, then the narrower halo
-  const int units = stride == 1 ? (W + 1) / 2 : (W + 1) / 2;  // column pairs (s1) | quad columns (s2)
-  long long best = -1;
+  const int units = (W + 1) / 2;  // column pairs (stride 1) | quad columns (stride 2)
+  const int TH1 = (H % 8 != 0 && H % 5 == 0) ? 5 : 8;
+  const int Hq_ = (H + 1) / 2;
+  const int TH2 = (Hq_ % 4 != 0 && Hq_ % 5 == 0) ? 5 : 4;
+  const int CBv = g.CB;
+  auto smem_of = [&](int u, int bi) {
+    if (stride == 1)
+      return 2 * (pad128(bi * (TH1 + 2) * (2 * u + 2) * CBv * 2) + pad128(bi * TH1 * 2 * u * CBv * 2)) + 256;
+    return 2 * (pad128(bi * (TH2 + 1) * (u + 1) * CBv * 2) + pad128(bi * 4 * TH2 * u * CBv * 2)) + 256;
+  };
   int best_u = 1, best_bi = 1;
-  for (int u = 1; u <= max_pos && u <= 64; ++u) {
-    int bi = max_pos / u;
-    if (bi > IMGS) bi = IMGS;
-    if (bi < 1) bi = 1;
-    if (bi > 16) bi = 16;
-    const long long t = (long long)((units + u - 1) / u) * ((IMGS + bi - 1) / bi);
-    if (best < 0 || t < best || (t == best && u > best_u)) { best = t; best_u = u; best_bi = bi; }
-  }
+  ADAMML_REQUIRE(pick_dw_tile(units, IMGS, max_pos, 0, smem_of, &best_u, &best_bi), "dwconv_bwd: no tile shape fits");
   g.BI = best_bi;
   g.npos = best_u * best_bi;
   g.tiles_i = (IMGS + g.BI - 1) / g.BI;
@@ -340,7 +520,7 @@ int adamml_dwconv_bwd(const void* x, const void* dy, const float* w, void* dx, f
   cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)C * 9, stream);
   const int sms2 = num_sms() * 2;
   if (stride == 1) {
-    const int TH = (H % 8 != 0 && H % 5 == 0) ? 5 : 8;
+    const int TH = TH1;
     g.TW = best_u * 2;
     g.tiles_w = (W + g.TW - 1) / g.TW;
     g.tiles_h = (H + TH - 1) / TH;
@@ -361,13 +541,13 @@ int adamml_dwconv_bwd(const void* x, const void* dy, const float* w, void* dx, f
     DWB_PICK(8, 64) DWB_PICK(8, 48) DWB_PICK(8, 32) DWB_PICK(8, 16)
     DWB_PICK(5, 64) DWB_PICK(5, 48) DWB_PICK(5, 32) DWB_PICK(5, 16)
 #undef DWB_PICK
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM_LIMIT);
     if (e != cudaSuccess) { adamml_set_error("dwconv_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return ADAMML_ERR_CUDA; }
-    ADAMML_REQUIRE(smem <= 110 * 1024, "dwconv_bwd: tile does not fit shared memory (%d bytes)", smem);
+    ADAMML_REQUIRE(smem <= DW_SMEM_LIMIT, "dwconv_bwd: tile does not fit shared memory (%d bytes)", smem);
     kern<<<grid, DWB_THREADS, smem, stream>>>(tmDy, tmX, w, (bf16*)dx, dw, g);
   } else {
-    const int Hq = (H + 1) / 2;
-    const int TH = (Hq % 4 != 0 && Hq % 5 == 0) ? 5 : 4;
+    const int Hq = Hq_;
+    const int TH = TH2;
     g.TW = best_u;
     g.tiles_w = (units + g.TW - 1) / g.TW;
     g.tiles_h = (Hq + TH - 1) / TH;
@@ -388,12 +568,73 @@ int adamml_dwconv_bwd(const void* x, const void* dy, const float* w, void* dx, f
     DWB_PICK(4, 64) DWB_PICK(4, 48) DWB_PICK(4, 32) DWB_PICK(4, 16)
     DWB_PICK(5, 64) DWB_PICK(5, 48) DWB_PICK(5, 32) DWB_PICK(5, 16)
 #undef DWB_PICK
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM_LIMIT);
     if (e != cudaSuccess) { adamml_set_error("dwconv_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return ADAMML_ERR_CUDA; }
-    ADAMML_REQUIRE(smem <= 110 * 1024, "dwconv_bwd: tile does not fit shared memory (%d bytes)", smem);
+    ADAMML_REQUIRE(smem <= DW_SMEM_LIMIT, "dwconv_bwd: tile does not fit shared memory (%d bytes)", smem);
     kern<<<grid, DWB_THREADS, smem, stream>>>(tmDy, tmX, w, (bf16*)dx, dw, g);
   }
   return adamml_check_launch("dwconv_bwd");
+}
+
+/* x2 training forward of a depthwise 3x3 / stride 1 / pad 1 conv on TMA tiles with the BatchNorm statistics of its
+ * output fused: z (two planes) = dwconv(x), sums[G][C][2] (double; overwritten; may be NULL) = per-group (sum, sum of
+ * squares) of z, group = img / imgs_per_group.  adamml_dwconv_fwd_stats_x2_supported -> 1 when the shape is handled. */
+int adamml_dwconv_fwd_stats_x2_supported(int IMGS, int H, int W, int C, int stride) {
+  return stride == 1 && adamml_dwconv_bwd_supported(IMGS, H, W, C, stride);
+}
+
+int adamml_dwconv_fwd_stats_x2(const void* x_hi, const void* x_lo, const float* w, void* y_hi, void* y_lo,
+                               double* sums, int IMGS, int H, int W, int C, int imgs_per_group, cudaStream_t stream) {
+  ADAMML_REQUIRE(adamml_dwconv_fwd_stats_x2_supported(IMGS, H, W, C, 1), "dwconv_fwd_stats_x2: unsupported shape");
+  ADAMML_REQUIRE(((uintptr_t)x_hi % 16) == 0 && ((uintptr_t)x_lo % 16) == 0 && ((uintptr_t)y_hi % 16) == 0 &&
+                     ((uintptr_t)y_lo % 16) == 0, "dwconv_fwd_stats_x2: planes must be 16-byte aligned");
+  if (imgs_per_group <= 0) imgs_per_group = IMGS;
+  ADAMML_REQUIRE(!sums || IMGS % imgs_per_group == 0, "dwconv_fwd_stats_x2: IMGS must be a multiple of imgs_per_group");
+  DwGeom g;
+  memset(&g, 0, sizeof(g));
+  g.IMGS = IMGS; g.H = H; g.W = W; g.C = C; g.Ho = H; g.Wo = W;
+  g.CB = (C % 64 == 0) ? 64 : ((C % 48 == 0) ? 48 : ((C % 32 == 0) ? 32 : 16));
+  g.CP = g.CB / 2;
+  g.chunks = C / g.CB;
+  const int max_pos = DWB_THREADS / g.CP;
+  const int units = (W + 1) / 2;
+  const int TH = (H % 8 != 0 && H % 5 == 0) ? 5 : 8;
+  const int CBv = g.CB;
+  auto smem_of = [&](int u, int bi) { return 4 * pad128(bi * (TH + 2) * (2 * u + 2) * CBv * 2) + 4096 + 256; };
+  int best_u = 1, best_bi = 1;
+  ADAMML_REQUIRE(pick_dw_tile(units, IMGS, max_pos, imgs_per_group, smem_of, &best_u, &best_bi),
+                 "dwconv_fwd_stats_x2: no tile shape fits");
+  g.BI = best_bi;
+  g.npos = best_u * best_bi;
+  g.tiles_i = (IMGS + g.BI - 1) / g.BI;
+  g.TW = best_u * 2;
+  g.tiles_w = (W + g.TW - 1) / g.TW;
+  g.tiles_h = (H + TH - 1) / TH;
+  g.dy_bytes = pad128(g.BI * (TH + 2) * (g.TW + 2) * g.CB * 2);
+  g.x_bytes = 0;
+  CUtensorMap tmHi, tmLo;
+  int rc = make_dw_map(&tmHi, x_hi, C, W, H, IMGS, g.CB, g.TW + 2, TH + 2, g.BI);
+  if (rc) return rc;
+  rc = make_dw_map(&tmLo, x_lo, C, W, H, IMGS, g.CB, g.TW + 2, TH + 2, g.BI);
+  if (rc) return rc;
+  if (sums) cudaMemsetAsync(sums, 0, sizeof(double) * (size_t)(IMGS / imgs_per_group) * C * 2, stream);
+  const int smem = 2 * (2 * g.dy_bytes) + 4096 + 256;
+  ADAMML_REQUIRE(smem <= DW_SMEM_LIMIT, "dwconv_fwd_stats_x2: tile does not fit shared memory (%d bytes)", smem);
+  const long long sp = (long long)g.tiles_w * g.tiles_h * g.tiles_i;
+  const int sms2 = num_sms() * 2;
+  long long per = sms2 / g.chunks > 0 ? sms2 / g.chunks : 1;
+  if (per > sp) per = sp;
+  const int grid = (int)per * g.chunks;
+  typedef void (*KernFn)(const CUtensorMap, const CUtensorMap, const float*, bf16*, __half*, double*, int, const DwGeom);
+  KernFn kern = nullptr;
+#define DWF_PICK(THV, CBV) if (TH == THV && g.CB == CBV) kern = dw_fwd_x2_s1_kernel<THV, CBV>;
+  DWF_PICK(8, 64) DWF_PICK(8, 48) DWF_PICK(8, 32) DWF_PICK(8, 16)
+  DWF_PICK(5, 64) DWF_PICK(5, 48) DWF_PICK(5, 32) DWF_PICK(5, 16)
+#undef DWF_PICK
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM_LIMIT);
+  if (e != cudaSuccess) { adamml_set_error("dwconv_fwd_stats_x2: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return ADAMML_ERR_CUDA; }
+  kern<<<grid, DWB_THREADS, smem, stream>>>(tmHi, tmLo, w, (bf16*)y_hi, (__half*)y_lo, sums, imgs_per_group, g);
+  return adamml_check_launch("dwconv_fwd_stats_x2");
 }
 
 }  // extern "C"

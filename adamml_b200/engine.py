@@ -177,7 +177,11 @@ class Exec:
         elif depthwise:
             assert conv.groups == conv.in_channels == Cout and R == 3 and pad == 1
             wp = ops.pack_weight_dw(w.detach())
-            z = ops.dwconv_fwd(x, wp, stride)
+            if self.training:
+                sums = p2p_sums if p2p is not None else torch.empty((G, Cout, 2), device=x.device, dtype=torch.float64)
+                z, fused = ops.dwconv_fwd_stats(x, wp, stride, sums, x.shape[0] // G)
+            else:
+                z = ops.dwconv_fwd(x, wp, stride)
         else:
             wp = ops.pack_weight(w.detach(), ops.PREC_X2 if self.x2 else self.dtype)
             if self.training:
@@ -189,7 +193,7 @@ class Exec:
         count = z.numel() // C // G
         if self.training:
             if not fused:
-                sums = ops.bn_stats(z, G, out=p2p_sums if p2p is not None else None)
+                sums = ops.bn_stats(z, G, out=sums)
             if p2p is not None:
                 sums = p2p.allreduce(slot_off, G * C * 2, self.lane).view(G, C, 2)
                 count = count * p2p.world
@@ -264,7 +268,7 @@ class Exec:
                 self._acc(conv.weight, ops.stem_wgrad(x, dz, conv.out_channels))
         elif rec["depthwise"]:
             if need_w and need_dx and addend is None and ops.dwconv_bwd_ok(x, dz, stride):
-                # both gradients from one pass over dz and x (TMA-staged tiles, csrc/dwconv_bwd.cu)
+                # both gradients from one pass over dz and x (TMA-staged tiles, csrc/dwconv_tma.cu)
                 dx, dw = ops.dwconv_bwd(x, dz, rec["w"], stride)
                 self._acc(conv.weight, dw)
             else:

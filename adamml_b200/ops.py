@@ -612,6 +612,24 @@ def dwconv_fwd(x, w, stride):
     return y
 
 
+DW_TMA_FWD = os.environ.get("ADAMML_B200_DW_TMA_FWD", "1") != "0"
+
+
+def dwconv_fwd_stats(x, w, stride, stats, imgs_per_group):
+    """Training forward of a depthwise conv with the BatchNorm statistics of its output: -> (z, fused).  x2 planes /
+    stride 1 / C % 16 == 0 run the TMA-tile kernel that fills `stats` ([G, C, 2] float64: sum, sum of squares per
+    group of imgs_per_group images) in the same pass (csrc/dwconv_tma.cu); otherwise fused is False and the caller
+    runs bn_stats over z."""
+    IMGS, H, W, C = x.shape
+    if DW_TMA_FWD and isinstance(x, X2) and stride == 1 and C % 16 == 0 and stats is not None:
+        _chk(w, torch.float32)
+        assert w.shape == (9, C) and stats.dtype == torch.float64 and IMGS % imgs_per_group == 0
+        y = X2.empty((IMGS, H, W, C), x.device)
+        call("dwconv_fwd_stats_x2", x.hi, x.lo, w, y.hi, y.lo, stats, IMGS, H, W, C, imgs_per_group)
+        return y, True
+    return dwconv_fwd(x, w, stride), False
+
+
 def dwconv_dgrad(dy, w, x_shape, stride, addend=None):
     IMGS, H, W, C = x_shape
     dx = torch.empty(x_shape, device=dy.device, dtype=dy.dtype)
@@ -623,7 +641,7 @@ DW_FUSED_BWD = os.environ.get("ADAMML_B200_DW_FUSED_BWD", "1") != "0"
 
 
 def dwconv_bwd_ok(x, dy, stride):
-    """the fused TMA-tile backward (csrc/dwconv_bwd.cu) handles bf16 tensors with C % 16 == 0"""
+    """the fused TMA-tile backward (csrc/dwconv_tma.cu) handles bf16 tensors with C % 16 == 0"""
     return (DW_FUSED_BWD and isinstance(x, torch.Tensor) and x.dtype == torch.bfloat16 and dy.dtype == torch.bfloat16
             and x.shape[-1] % 16 == 0 and stride in (1, 2))
 

@@ -359,6 +359,12 @@ int adamml_dwconv_bn_act_fwd_x2(const void* x_hi, const void* x_lo, const float*
                                 cudaStream_t stream);
 int adamml_dwconv_fwd_x2(const void* x_hi, const void* x_lo, const float* w, void* y_hi, void* y_lo, int IMGS, int H,
                          int W, int C, int stride, int Ho, int Wo, cudaStream_t stream);
+/* x2 training forward of a depthwise 3x3 / stride-1 conv on TMA-staged tiles with the train-mode BatchNorm statistics
+ * of its output fused (sound_mobilenet_v2.py:58,62 ; policy_net.py:66-67,80-81): sums = double [G][C][2] (sum, sum of
+ * squares) per group = img / imgs_per_group, overwritten; NULL = no statistics. */
+int adamml_dwconv_fwd_stats_x2_supported(int IMGS, int H, int W, int C, int stride);
+int adamml_dwconv_fwd_stats_x2(const void* x_hi, const void* x_lo, const float* w, void* y_hi, void* y_lo,
+                               double* sums, int IMGS, int H, int W, int C, int imgs_per_group, cudaStream_t stream);
 int adamml_bn_stats_x2(const void* z_hi, const void* z_lo, double* sums, long long rows_per_group, int C, int G,
                        cudaStream_t stream);
 int adamml_bn_apply_x2(const void* z_hi, const void* z_lo, const float* scale_shift, const void* res_hi,

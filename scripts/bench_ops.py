@@ -186,7 +186,33 @@ def dw_bwd_all():
     print(f"dw_bwd per step: separate {sep_tot:.2f} ms -> fused {fus_tot:.2f} ms", flush=True)
 
 
+def dw_fwd_all():
+    """x2 training forward of the stride-1 depthwise layers: register-window kernel + bn_stats_x2 pass vs the TMA-tile
+    kernel with fused statistics, L2 flushed, summed over one step"""
+    old_tot = new_tot = 0.0
+    for I, H, C, stride, n in DW_SHAPES:
+        if stride != 1:
+            continue
+        x = x2rand(I, H, H, C)
+        w = ops.pack_weight_dw(torch.randn(C, 1, 3, 3, device=dev))
+        sums = torch.empty(5, C, 2, device=dev, dtype=torch.float64)
+        by = 4.0 * 2 * x.hi.numel()
+
+        def old():
+            z = ops.dwconv_fwd(x, w, 1)
+            ops.bn_stats(z, 5, out=sums)
+        t_old = timeit_cold(old)
+        t_new = timeit_cold(lambda: ops.dwconv_fwd_stats(x, w, 1, sums, I // 5))
+        old_tot += n * t_old
+        new_tot += n * t_new
+        print(f"dw_fwd_x2 I={I} {H}x{H} C={C} s1 x{n}: fwd + bn_stats {t_old:7.3f} ms  fused {t_new:7.3f} ms "
+              f"({by / t_new / 1e6:6.0f} GB/s, {by / t_new / 1e6 / HBM * 100:5.1f}% hbm)", flush=True)
+        del x
+    print(f"dw_fwd_x2 (stride 1) per step: fwd + bn_stats {old_tot:.2f} ms -> fused {new_tot:.2f} ms", flush=True)
+
+
 CASES = {
+    "dwfwd": dw_fwd_all,
     "dwbwd": dw_bwd_all,
     "gemm": lambda: [gemm(9031680, 256, 64, True), gemm(9031680, 256, 64, False), gemm(9031680, 64, 256, True),
                      gemm(9031680, 64, 64, True), gemm(4515840, 128, 256, True), gemm(1128960, 512, 128, True),

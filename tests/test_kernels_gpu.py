@@ -159,13 +159,13 @@ def test_dwconv(cuda, case, dtype):
     assert relerr(dw, w.grad) < 5e-5
 
 
-# fused depthwise backward on TMA tiles (csrc/dwconv_bwd.cu): every channel-chunk width (64 | 48 | 32 | 16), both
+# fused depthwise backward on TMA tiles (csrc/dwconv_tma.cu): every channel-chunk width (64 | 48 | 32 | 16), both
 # strides, row-tile heights 8 | 5 (stride 1) and 4 | 5 (stride 2), ragged widths / heights, several tiles per CTA,
 # images-per-tile > 1 and image counts that do not fill the last tile
 DW_BWD_CASES = [(2, 16, 16, 32, 1), (3, 15, 17, 96, 2), (2, 8, 8, 960, 1), (1, 10, 10, 144, 2), (3, 10, 10, 576, 1),
                 (5, 5, 5, 960, 1), (2, 40, 40, 144, 1), (1, 128, 128, 32, 1), (2, 64, 64, 96, 2), (7, 20, 20, 192, 2),
                 (3, 33, 19, 16, 1), (2, 21, 35, 48, 2), (9, 16, 16, 384, 1), (40, 8, 8, 64, 1), (37, 10, 10, 64, 2),
-                (2, 80, 80, 96, 2), (300, 16, 16, 128, 1)]
+                (2, 80, 80, 96, 2), (300, 16, 16, 128, 1), (720, 10, 10, 384, 1), (90, 10, 10, 576, 2)]
 
 
 @pytest.mark.parametrize("case", DW_BWD_CASES)

@@ -131,6 +131,31 @@ def test_first_conv_x2(cuda, C, R, hw):
     assert err(sums[..., 0], zz.sum(1)) < 1e-6
 
 
+@pytest.mark.parametrize("case", [(4, 16, 16, 32), (6, 8, 8, 960), (4, 10, 10, 576), (10, 5, 5, 960), (2, 40, 40, 144),
+                                  (2, 128, 128, 32), (4, 33, 19, 16), (6, 21, 35, 48), (12, 16, 16, 384),
+                                  (40, 8, 8, 64), (600, 16, 16, 128), (720, 10, 10, 384)])
+def test_dwconv_fwd_stats_x2(cuda, case):
+    """x2 depthwise stride-1 training forward on TMA tiles with fused BatchNorm statistics: z against a float64
+    depthwise conv of the joined planes and against the register-window kernel; sums against float64 sums of z."""
+    from adamml_b200 import ops
+    IMGS, H, W, C = case
+    G = 2
+    g = torch.Generator().manual_seed(sum(case))
+    x = split(nhwc(torch.randn(IMGS, C, H, W, generator=g) + 0.25).to(cuda))
+    w = (torch.randn(C, 1, 3, 3, generator=g) / 3).to(cuda)
+    wd = ops.pack_weight_dw(w.contiguous())
+    sums = torch.full((G, C, 2), float("nan"), device=cuda, dtype=torch.float64)
+    z, fused = ops.dwconv_fwd_stats(x, wd, 1, sums, IMGS // G)
+    assert fused
+    ref = F.conv2d(nchw(x.float().double()), w.double(), None, 1, 1, groups=C)
+    assert err(nchw(z.float()), ref) < X2_TOL
+    z_old = ops.dwconv_fwd(x, wd, 1)
+    assert err(z.float(), z_old.float()) < X2_TOL
+    zz = z.float().double().view(G, -1, C)
+    assert err(sums[..., 0], zz.sum(1)) < 1e-6
+    assert err(sums[..., 1], (zz * zz).sum(1)) < 1e-6
+
+
 def test_bn_apply_and_stats_x2(cuda):
     from adamml_b200 import ops
     g = torch.Generator().manual_seed(3)
