@@ -222,7 +222,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int num_n_blks = (Ncols + BLOCK_N - 1) / BLOCK_N;
   const long long num_tiles = (long long)num_m_blks * num_n_blks;
   const int num_kb = CONV ? geo.ntaps * geo.kb_per_tap : (K + BLOCK_K - 1) / BLOCK_K;
-  const TileSched sched{pin_n != 0, num_n_blks, num_m_blks, num_tiles};
+  const TileSched sched{(pin_n & 1) != 0, num_n_blks, num_m_blks, num_tiles};
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < Cfg::STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
@@ -242,7 +242,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_slot;
   // dense residual-gradient addend (same pixel lattice as the output): fetched by TMA into the staging tile
   // (x2 launches only carry an addend -- the residual planes -- in the fused inference epilogue)
-  const bool add_tma = (X2 ? EPI : true) && addend != nullptr && geo.addend_sub != 2;
+  // (x2 training launches never carry an addend: their epilogue is compiled without the addend paths)
+  constexpr bool HAS_ADD = !X2 || EPI;
+  const bool add_tma = HAS_ADD && addend != nullptr && geo.addend_sub != 2;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -402,6 +404,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int j = 0; j < RS_N; ++j) { rsS[j] = make_float2(0.f, 0.f); rsQ[j] = make_float2(0.f, 0.f); }
     long long rs_g = -1;
     int rs_tiles = 0;
+    long long rs_gcur = 0, rs_gend = rows_per_group;  // group of the current tile's first row and its end row (the
+                                                       // tiles of a CTA come in increasing row order: no division)
     const bool rs_on = REGSTATS && stats != nullptr && (num_n_blks == 1 || sched.pin);
     const int rs_nblk = sched.pin ? (int)(blockIdx.x % num_n_blks) : 0;
     auto rs_flush = [&]() {
@@ -449,7 +453,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint8_t* stage_out = stage_base + obuf * Cfg::OUT_TILE_BYTES;
       if (Cfg::OUT_BUFS == 2) obuf ^= 1;
       long long arow = 0;
-      bool row_ok, add_ok = addend != nullptr && !add_tma;
+      bool row_ok, add_ok = HAS_ADD && addend != nullptr && !add_tma;
       int w0 = 0, h0 = 0, i0 = 0;
       if (CONV) {
         w0 = (m_blk % geo.tiles_w) * geo.BW;
@@ -480,13 +484,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       bool rs_tile = false;
       if (REGSTATS && rs_on) {
         const long long row0 = (long long)m_blk * BLOCK_M;
-        const long long rlast = (row0 + BLOCK_M <= M ? row0 + BLOCK_M : M) - 1;
-        const unsigned g0 = (unsigned)row0 / (unsigned)rows_per_group, g1 = (unsigned)rlast / (unsigned)rows_per_group;
-        rs_tile = g0 == g1;
+        const long long rend = row0 + BLOCK_M <= M ? row0 + BLOCK_M : M;
+        while (row0 >= rs_gend) { ++rs_gcur; rs_gend += rows_per_group; }
+        rs_tile = rend <= rs_gend;  // the whole tile lies in group rs_gcur
         if (rs_tile) {
-          if ((long long)g0 != rs_g || rs_tiles == RS_TILES) {  // (uniform over the epilogue threads: a collective)
+          if (rs_gcur != rs_g || rs_tiles == RS_TILES) {  // (uniform over the epilogue threads: a collective)
             if (rs_g >= 0) rs_flush();
-            rs_g = g0;
+            rs_g = rs_gcur;
             rs_tiles = 0;
           }
           ++rs_tiles;
@@ -498,7 +502,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       }
       epi_bar_sync<Cfg::EPI_THREADS>();
-      if (add_tma) {
+      if (HAS_ADD && add_tma) {
         if (issuer) {
           int nsub = 0;
 #pragma unroll
@@ -521,7 +525,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      if (add_tma) {
+      if (HAS_ADD && add_tma) {
         mbar_wait(add_bar, add_phase);
         add_phase ^= 1;
       }
@@ -545,7 +549,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             v[j] = fmaf(v[j], p.x, p.y);
           }
         }
-        if (add_ok && row_ok) {
+        if (HAS_ADD && add_ok && row_ok) {
           const bf16* ap = addend + arow * ldd + col0;
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
@@ -565,7 +569,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // linear mode (dlin): plain row-major rows of Ncols elements, the image of the contiguous output tile
         uint8_t* srow = stage_out + (chunk >> 1) * (BLOCK_M * 128) + et * 128;
         uint8_t* lrow = stage_out + (size_t)et * (size_t)(Ncols * 2) + chunk * 64;
-        if (add_tma && row_ok) {
+        if (HAS_ADD && add_tma && row_ok) {
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
             const int c = (chunk & 1) * 4 + (j >> 3);
@@ -639,7 +643,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
       // accumulator drained: hand the TMEM stage back to the MMA warp
-      tc_fence_before();
+      // (every lane has executed tcgen05.wait::ld, so its TMEM reads are complete; the before_thread_sync fence in
+      // front of the arrive compiles to a MEMBAR.ALL.CTA in the per-tile critical chain -- pin_n bit 1 drops it)
+      if (!(pin_n & 2)) tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -819,6 +825,8 @@ int launch_tc_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
     pin_n = 1;
     grid = (sms / n_blks) * n_blks;
   }
+  static const bool nofence = []() { const char* e = getenv("ADAMML_B200_TC_NOFENCE"); return e && e[0] == '1'; }();
+  if (nofence) pin_n |= 2;
   EpiSpec e = epi;
   if (EPI && e.ss && !stats) e.live = adamml_live_limit(CONV ? (long long)geo.IMGS : M);  // inference launches only
   kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmD, tmAdd, cm, geo, x2, (const bf16*)addend, M,

@@ -1,5 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -8 | cut -c1-300
-timeout 300 python scripts/bench_ops.py dwfwd 2>&1 | tee gpurun_out/dwfwd.log | tail -4
-timeout 600 python bench.py 2>&1 | tail -2 > gpurun_out/bench_a.log; tail -c 3000 gpurun_out/bench_a.log
+timeout 600 python -m pytest tests/test_x2_gpu.py -q -x -k "tc_gemm_x2" 2>&1 | tail -3
+echo "--- fence (default)"; timeout 300 python scripts/bench_ops.py x2gemm 2>&1 | tee gpurun_out/x2gemm_b.log
+echo "--- no fence"; ADAMML_B200_TC_NOFENCE=1 timeout 300 python scripts/bench_ops.py x2gemm 2>&1 | tee gpurun_out/x2gemm_nofence.log
+ADAMML_B200_TC_NOFENCE=1 timeout 600 python -m pytest tests/test_x2_gpu.py -q -x -k "tc_gemm_x2 or tc_conv_x2" 2>&1 | tail -3
