@@ -303,6 +303,12 @@ def kernel_work(name, a):
     if name == "dwconv_fwd_x2":
         I, H, W, C, st, Ho, Wo = a[5:12]
         return 2.0 * 9 * I * Ho * Wo * C, 4.0 * float(I * H * W * C + I * Ho * Wo * C)
+    if name == "dwconv_fwd_stats_x2":   # (x_hi, x_lo, w, y_hi, y_lo, sums, IMGS, H, W, C, imgs_per_group): stride 1
+        I, H, W, C = a[6:10]
+        return 2.0 * 9 * I * H * W * C, 4.0 * float(2 * I * H * W * C)
+    if name == "dwconv_bwd":            # (x, dy, w, dx, dw, IMGS, H, W, C, stride, Ho, Wo): reads x + dy, writes dx
+        I, H, W, C, st, Ho, Wo = a[5:12]
+        return 2.0 * 18 * I * Ho * Wo * C, 2.0 * float(2 * I * H * W * C + I * Ho * Wo * C)
     if name == "maxpool3x3s2_fwd_x2":
         I, H, W, C, Ho, Wo = a[5:11]
         return 0.0, 4.0 * float(I * H * W * C + I * Ho * Wo * C) + I * Ho * Wo * C

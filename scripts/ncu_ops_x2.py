@@ -54,10 +54,17 @@ if want("conv"):
     ops.conv_fwd(x3, w3, 1, 1, stats=st3, rows_per_group=rows)
     del x3
 if want("dw"):
-    # a MobileNetV2 depthwise forward, x2
+    # MobileNetV2 depthwise layers on TMA-staged tiles (csrc/dwconv_tma.cu): x2 stride-1 forward with fused BatchNorm
+    # statistics, and the fused data + weight gradient at stride 1 and stride 2 (bf16)
+    wd = ops.pack_weight_dw(torch.randn(144, 1, 3, 3, device=dev))
     xd = x2rand(1440, 40, 40, 144)
-    ops.dwconv_fwd(xd, ops.pack_weight_dw(torch.randn(144, 1, 3, 3, device=dev)), 1)
+    std = torch.empty(G, 144, 2, device=dev, dtype=torch.float64)
+    ops.dwconv_fwd_stats(xd, wd, 1, std, 1440 // G)
+    ops.dwconv_bwd(xd.hi, rnd(1440, 40, 40, 144), wd, 1)
     del xd
+    wd2 = ops.pack_weight_dw(torch.randn(96, 1, 3, 3, device=dev))
+    ops.dwconv_bwd(rnd(1440, 80, 80, 96), rnd(1440, 40, 40, 96), wd2, 2)
+    ops.dwconv_fwd(x2rand(1440, 80, 80, 96), wd2, 2)
 if want("bwd"):
     # backward (bf16 on the hi planes): BN reduce / apply of the residual layer, weight gradient of conv3
     dout = rnd(M, 256)
