@@ -7,6 +7,7 @@
 // images are ordered segment-major, group g = img / imgs_per_group, statistics are kept per
 // (group, channel) and running stats receive the S momentum updates in segment order.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -601,11 +602,19 @@ inline void stream_geom(const RowGeom& rg, long long rows_per_group, int* rows_p
   *bpg = (int)((rows_per_group + rpb - 1) / rpb);
   *rows_per_block = (int)rpb;
 }
-// persistent reduction launch: ~4 blocks per SM in total
-inline int reduce_bpg(const RowGeom& rg, long long rows_per_group, int G) {
-  long long chunk_rows = (long long)rg.k * EW_UNROLL * 4;
+// persistent reduction launch: exactly ONE wave of resident blocks.  (The grid used to be a fixed 4 blocks per SM; at
+// 128 registers only 2 x 256 threads are resident per SM, so 595 equal-work blocks ran as 296 + 296 + 3: a third round
+// for three blocks.)  `kern` / smem: the kernel about to be launched, for the occupancy query.
+template <typename K>
+inline int reduce_bpg(K kern, size_t smem, const RowGeom& rg, long long rows_per_group, int G, int chunk_iters = 4) {
+  long long chunk_rows = (long long)rg.k * EW_UNROLL * chunk_iters;
   long long chunks = (rows_per_group + chunk_rows - 1) / chunk_rows;
-  long long want = (4LL * num_sms_ew() + (long long)G * rg.cchunks - 1) / ((long long)G * rg.cchunks);
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, rg.threads, smem) != cudaSuccess || per_sm < 1)
+    per_sm = 2;
+  static const int forced = []() { const char* e = getenv("ADAMML_B200_BN_REDUCE_BPSM"); return e ? atoi(e) : 0; }();
+  if (forced > 0) per_sm = forced;  // (experiments: 4 = the former fixed grid)
+  long long want = ((long long)per_sm * num_sms_ew()) / ((long long)G * rg.cchunks);
   if (want < 1) want = 1;
   return (int)(chunks < want ? chunks : want);
 }
@@ -628,8 +637,8 @@ int adamml_bn_stats(const void* z, double* sums, long long rows_per_group, int C
   ADAMML_DISPATCH_DTYPE(dtype, T, {
     if (vec_ok<T>(C, z)) {
       const RowGeom rg = row_geom<T>(C);
-      const int bpg = reduce_bpg(rg, rows_per_group, G);
       const size_t sm = sizeof(double) * rg.threads * 2 * VecIO<T>::N;
+      const int bpg = reduce_bpg(bn_reduce_rows_kernel<T, 0, false>, sm, rg, rows_per_group, G);
       dim3 vg((unsigned)(bpg * (long long)G), rg.cchunks);
       bn_reduce_rows_kernel<T, 0, false><<<vg, rg.threads, sm, stream>>>((const T*)z, nullptr, nullptr, nullptr, nullptr, sums,
                                                                   nullptr, rows_per_group, C, rg.cpb, rg.k, bpg, 0);
@@ -709,12 +718,8 @@ int adamml_bn_stats_x2(const void* z_hi, const void* z_lo, double* sums, long lo
   const RowGeom rg = row_geom<x2_t>(C);
   // persistent over row chunks, ~8 blocks per SM in total (a single-tensor stream needs more resident warps than the
   // three-tensor backward reduction to cover the HBM latency)
-  const long long chunk_rows = (long long)rg.k * 4 * 4;
-  const long long chunks = (rows_per_group + chunk_rows - 1) / chunk_rows;
-  long long want = (8LL * num_sms_ew() + (long long)G * rg.cchunks - 1) / ((long long)G * rg.cchunks);
-  if (want < 1) want = 1;
-  const int bpg = (int)(chunks < want ? chunks : want);
   const size_t sm = sizeof(double) * rg.threads * 2 * 8;
+  const int bpg = reduce_bpg(bn_stats_rows_x2_kernel, sm, rg, rows_per_group, G);  // (chunk = k * 4 * 4 rows)
   dim3 vg((unsigned)(bpg * (long long)G), rg.cchunks);
   bn_stats_rows_x2_kernel<<<vg, rg.threads, sm, stream>>>(x2c(z_hi, z_lo), sums, rows_per_group, C, rg.cpb, rg.k, bpg);
   return adamml_check_launch("bn_stats_x2");
@@ -730,10 +735,12 @@ int adamml_bn_bwd_reduce(const void* dout, const void* out, const void* z, const
   ADAMML_DISPATCH_DTYPE(dtype, T, {
     if (vec_ok<T>(C, dout, out, z)) {
       const RowGeom rg = row_geom<T>(C);
-      const int bpg = reduce_bpg(rg, rows_per_group, G);
       const size_t sm = sizeof(double) * rg.threads * 2 * VecIO<T>::N;
+      const bool maskz = mask_scale_shift && act != ADAMML_ACT_NONE;
+      const int bpg = maskz ? reduce_bpg(bn_reduce_rows_kernel<T, 1, true>, sm, rg, rows_per_group, G)
+                            : reduce_bpg(bn_reduce_rows_kernel<T, 1, false>, sm, rg, rows_per_group, G);
       dim3 vg((unsigned)(bpg * (long long)G), rg.cchunks);
-      if (mask_scale_shift && act != ADAMML_ACT_NONE)
+      if (maskz)
         bn_reduce_rows_kernel<T, 1, true><<<vg, rg.threads, sm, stream>>>((const T*)dout, nullptr, (const T*)z,
                                                                           mean_invstd, mask_scale_shift, sums,
                                                                           (T*)gm_out, rows_per_group, C, rg.cpb, rg.k,

@@ -211,7 +211,24 @@ def dw_fwd_all():
     print(f"dw_fwd_x2 (stride 1) per step: fwd + bn_stats {old_tot:.2f} ms -> fused {new_tot:.2f} ms", flush=True)
 
 
+def bn_bwd_reduce_cases():
+    """the two shapes of the BatchNorm backward reduction: residual layers (dout, out, z -> masked gradient written in
+    place) and layers whose ReLU mask is recomputed from z (dout, z)"""
+    for rows, C in [(1806336, 256), (225792, 512), (28224, 1024), (1806336, 64), (225792, 128), (294912, 144),
+                    (1179648, 96)]:
+        G = 5
+        z, dout, out = rnd(rows * G, C), rnd(rows * G, C), rnd(rows * G, C)
+        mi = torch.rand(G, C, 2, device=dev) + 0.5
+        ss = torch.rand(G, C, 2, device=dev)
+        ms = timeit_cold(lambda: ops.bn_bwd_reduce(dout, out, z, mi, G, 1, gm_inplace=True))
+        report(f"bn_bwd_reduce residual (3 reads + gm write) rows={rows}x{G} C={C}", ms, 4.0 * 2 * rows * G * C)
+        ms = timeit_cold(lambda: ops.bn_bwd_reduce(dout, None, z, mi, G, 1, mask_ss=ss))
+        report(f"bn_bwd_reduce mask from z (2 reads)         rows={rows}x{G} C={C}", ms, 2.0 * 2 * rows * G * C)
+        del z, dout, out
+
+
 CASES = {
+    "bnbwdred": bn_bwd_reduce_cases,
     "dwfwd": dw_fwd_all,
     "dwbwd": dw_bwd_all,
     "gemm": lambda: [gemm(9031680, 256, 64, True), gemm(9031680, 256, 64, False), gemm(9031680, 64, 256, True),
