@@ -619,6 +619,21 @@ inline int reduce_bpg(K kern, size_t smem, const RowGeom& rg, long long rows_per
   return (int)(chunks < want ? chunks : want);
 }
 
+// (sum gm, sum gm * out) -> (sum gm, sum gm * xhat) for a layer out = act(z * scale + shift): wherever the activation
+// passes the gradient, out IS z * scale + shift, so sum gm * z = (sum gm * out - shift * sum gm) / scale.
+__global__ void bn_sums_from_out_kernel(const double* __restrict__ raw, const float* __restrict__ ss,
+                                        const float* __restrict__ mean_invstd, double* __restrict__ sums, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double A = raw[2 * i], B = raw[2 * i + 1];
+  const double sc = (double)ss[2 * i], sh = (double)ss[2 * i + 1];
+  const double mean = (double)mean_invstd[2 * i], invstd = (double)mean_invstd[2 * i + 1];
+  // scale == 0 (gamma == 0): the output carries no information about z; dz = gamma * (...) is zero anyway
+  const double gz = sc != 0.0 ? (B - sh * A) / sc : mean * A;
+  sums[2 * i] = A;
+  sums[2 * i + 1] = invstd * (gz - mean * A);
+}
+
 inline int ew_blocks(long long total) {
   long long b = (total + 255) / 256;
   long long cap = 148LL * 32;
@@ -794,6 +809,17 @@ int adamml_bn_bwd_apply(const void* dout, const void* out, const void* z, const 
     }
   });
   return adamml_check_launch("bn_bwd_apply");
+}
+
+/* raw [G][C][2] = (sum gm, sum gm * out) accumulated by adamml_dwconv_bwd's fused reduction -> sums [G][C][2] =
+ * (sum gm, sum gm * xhat), the layout adamml_bn_bwd_reduce produces; scale_shift / mean_invstd: the layer's forward
+ * [G][C][2] coefficients.  raw and sums may alias. */
+int adamml_bn_sums_from_out(const double* raw, const float* scale_shift, const float* mean_invstd, double* sums, int C,
+                            int G, cudaStream_t stream) {
+  ADAMML_REQUIRE(raw && scale_shift && mean_invstd && sums && C > 0 && G > 0, "bn_sums_from_out: bad arguments");
+  const int n = C * G;
+  bn_sums_from_out_kernel<<<(n + 255) / 256, 256, 0, stream>>>(raw, scale_shift, mean_invstd, sums, n);
+  return adamml_check_launch("bn_sums_from_out");
 }
 
 int adamml_bn_param_grad(const double* sums, float* dgamma, float* dbeta, int C, int G, int accumulate,

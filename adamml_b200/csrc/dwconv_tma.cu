@@ -43,6 +43,50 @@ __device__ __forceinline__ void st_bf2(bf16* p, float2 v) {
   *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(v.x, v.y);
 }
 
+// Optional fused BatchNorm-backward REDUCTION of the layer that produced x (the expand / first conv in front of the
+// depthwise conv: x = act(bn(z)), no residual): that layer's backward needs gm = dx * act'(x) and, per BN group and
+// channel, sum gm and sum gm * xhat.  The kernel already holds dx and x at every position, and wherever act' = 1 the
+// saved output IS the normalised value (x = z * scale + shift), so it stores gm instead of dx and accumulates
+// (sum gm, sum gm * x); adamml_bn_sums_from_out (bn.cu) turns those into (sum gm, sum gm * xhat).  The separate
+// bn_bwd_reduce pass over (dx, z) disappears.  A tile never straddles two BN groups (BI divides imgs_per_group).
+struct PreReduce {
+  double* sums;  // raw [G][C][2] = (sum gm, sum gm * x), zeroed by the launcher; nullptr = off
+  int imgs_per_group;
+  int act;
+};
+constexpr int PRE_FLUSH_TILES = 32;
+constexpr int DW_RED_BYTES = 4096;  // [positions][2][CB] fp32 partials of a statistics flush
+
+// ACT (compile time): ADAMML_ACT_RELU | ADAMML_ACT_RELU6 (the mask is evaluated on the stored output, act_pass)
+template <int ACT>
+__device__ __forceinline__ float2 pre_mask(float2 a, float2 x, float2& A, float2& B) {
+  const bool p0 = ACT == ADAMML_ACT_RELU6 ? (x.x > 0.f && x.x < 6.f) : (x.x > 0.f);
+  const bool p1 = ACT == ADAMML_ACT_RELU6 ? (x.y > 0.f && x.y < 6.f) : (x.y > 0.f);
+  const float2 gm = make_float2(p0 ? a.x : 0.f, p1 ? a.y : 0.f);
+  A = __ffma2_rn(gm, make_float2(1.f, 1.f), A);
+  B = __ffma2_rn(gm, x, B);
+  return gm;
+}
+// collective of the CTA: per-thread (A, B) partials -> shared memory -> one fp64 atomic per channel and value
+template <int CB>
+__device__ __forceinline__ void pre_flush(float2& A, float2& B, float* red, int npos, int cp, int pos, bool active,
+                                          double* __restrict__ sums, long long grp, int C, int c0) {
+  if (active) {
+    *reinterpret_cast<float2*>(red + (pos * 2 + 0) * CB + 2 * cp) = A;
+    *reinterpret_cast<float2*>(red + (pos * 2 + 1) * CB + 2 * cp) = B;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * CB; i += blockDim.x) {
+    const int k = i / CB, c = i - k * CB;
+    double a = 0.0;
+    for (int p = 0; p < npos; ++p) a += (double)red[(p * 2 + k) * CB + c];
+    atomicAdd(sums + (grp * C + c0 + c) * 2 + k, a);
+  }
+  __syncthreads();
+  A = make_float2(0.f, 0.f);
+  B = make_float2(0.f, 0.f);
+}
+
 // shared-memory reduction of the per-thread weight-gradient accumulators over the positions of the CTA, then one
 // fp32 atomic per (tap, channel)
 __device__ __forceinline__ void reduce_dw(const float2 (&dW)[9], float* red, const DwGeom& g, int cp, int pos,
@@ -62,16 +106,20 @@ __device__ __forceinline__ void reduce_dw(const float2 (&dW)[9], float* red, con
   }
 }
 
-template <int TH, int CB>
+template <int TH, int CB, int PRE>
 __global__ void __launch_bounds__(DWB_THREADS, 2)
 dw_bwd_s1_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUtensorMap tmX,
                  const float* __restrict__ w, bf16* __restrict__ dx, float* __restrict__ dWg,
-                 const __grid_constant__ DwGeom g) {
+                 const __grid_constant__ DwGeom g, const PreReduce pre) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);
-  uint8_t* stages = smem + 128;
+  float* red = reinterpret_cast<float*>(smem + 128);
+  uint8_t* stages = smem + 128 + DW_RED_BYTES;
   const int stage_bytes = g.dy_bytes + g.x_bytes;
+  float2 pA = make_float2(0.f, 0.f), pB = make_float2(0.f, 0.f);
+  long long pre_g = -1;
+  int pre_tiles = 0;
 
   const int cp = threadIdx.x % (CB / 2), pos = threadIdx.x / (CB / 2);
   const bool active = pos < g.npos;
@@ -112,6 +160,15 @@ dw_bwd_s1_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant
   for (int s = cta; s < sp_tiles; s += ncta, ++it_) {
     const int stage = it_ & 1;
     if (threadIdx.x == 0 && s + ncta < sp_tiles) issue(s + ncta, stage ^ 1);
+    if (PRE) {
+      const long long tg = ((s / (g.tiles_w * g.tiles_h)) * g.BI) / pre.imgs_per_group;
+      if (tg != pre_g || pre_tiles == PRE_FLUSH_TILES) {
+        if (pre_g >= 0) pre_flush<CB>(pA, pB, red, g.npos, cp, pos, active, pre.sums, pre_g, g.C, c0);
+        pre_g = tg;
+        pre_tiles = 0;
+      }
+      ++pre_tiles;
+    }
     mbar_wait(&full[stage], (uint32_t)((it_ >> 1) & 1));
     if (active) {
       const int wt = s % g.tiles_w, ht = (s / g.tiles_w) % g.tiles_h, ti = s / (g.tiles_w * g.tiles_h);
@@ -121,7 +178,8 @@ dw_bwd_s1_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant
                        ((bi * TH) * g.TW + 2 * jp) * CB + 2 * cp;
       const int img = ti * g.BI + bi, h0 = ht * TH, wc = wt * g.TW + 2 * jp;
       const bool ok0 = img < g.IMGS && wc < g.W, ok1 = img < g.IMGS && wc + 1 < g.W;
-      bf16* dxp = dx + (((long long)img * g.H + h0) * g.W + wc) * g.C + c0 + 2 * cp;
+      bf16* dxr = dx + (((long long)img * g.H + h0) * g.W + wc) * g.C + c0 + 2 * cp;
+      const long long row_stride = (long long)g.W * g.C;
       float2 D[3][4];  // rolling window: dy rows h-1, h, h+1 (mod 3) x columns wc-1 .. wc+2
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -149,29 +207,38 @@ dw_bwd_s1_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant
             dW[r * 3 + s_] = __ffma2_rn(x1, d1, dW[r * 3 + s_]);
           }
         }
-        if (h0 + h < g.H) {
-          if (ok0) st_bf2(dxp + (long long)h * g.W * g.C, a0);
-          if (ok1) st_bf2(dxp + (long long)h * g.W * g.C + g.C, a1);
-        }
+        // (x is zero outside the image -- TMA fill -- so the activation mask already drops those positions from the
+        // fused sums; only the stores are predicated)
+        const float2 o0 = PRE ? pre_mask<PRE>(a0, x0, pA, pB) : a0;
+        const float2 o1 = PRE ? pre_mask<PRE>(a1, x1, pA, pB) : a1;
+        const bool rok = h0 + h < g.H;
+        if (rok && ok0) st_bf2(dxr, o0);
+        if (rok && ok1) st_bf2(dxr + g.C, o1);
+        dxr += row_stride;
       }
     }
     __syncthreads();  // the stage may be refilled by the next iteration's TMA
   }
+  if (PRE && pre_g >= 0) pre_flush<CB>(pA, pB, red, g.npos, cp, pos, active, pre.sums, pre_g, g.C, c0);
   reduce_dw(dW, reinterpret_cast<float*>(stages), g, cp, pos, active, c0, dWg);
 }
 
 // stride 2: thread = (channel pair, quad column n, image); tile = TH quad rows x TW quad columns; dy tile has one
 // extra row / column (dy[m+1], dy[n+1]), x tile is [2 TH][2 TW]
-template <int TH, int CB>
+template <int TH, int CB, int PRE>
 __global__ void __launch_bounds__(DWB_THREADS, 2)
 dw_bwd_s2_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUtensorMap tmX,
                  const float* __restrict__ w, bf16* __restrict__ dx, float* __restrict__ dWg,
-                 const __grid_constant__ DwGeom g) {
+                 const __grid_constant__ DwGeom g, const PreReduce pre) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);
-  uint8_t* stages = smem + 128;
+  float* red = reinterpret_cast<float*>(smem + 128);
+  uint8_t* stages = smem + 128 + DW_RED_BYTES;
   const int stage_bytes = g.dy_bytes + g.x_bytes;
+  float2 pA = make_float2(0.f, 0.f), pB = make_float2(0.f, 0.f);
+  long long pre_g = -1;
+  int pre_tiles = 0;
 
   const int cp = threadIdx.x % (CB / 2), pos = threadIdx.x / (CB / 2);
   const bool active = pos < g.npos;
@@ -211,6 +278,15 @@ dw_bwd_s2_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant
   for (int s = cta; s < sp_tiles; s += ncta, ++it_) {
     const int stage = it_ & 1;
     if (threadIdx.x == 0 && s + ncta < sp_tiles) issue(s + ncta, stage ^ 1);
+    if (PRE) {
+      const long long tg = ((s / (g.tiles_w * g.tiles_h)) * g.BI) / pre.imgs_per_group;
+      if (tg != pre_g || pre_tiles == PRE_FLUSH_TILES) {
+        if (pre_g >= 0) pre_flush<CB>(pA, pB, red, g.npos, cp, pos, active, pre.sums, pre_g, g.C, c0);
+        pre_g = tg;
+        pre_tiles = 0;
+      }
+      ++pre_tiles;
+    }
     mbar_wait(&full[stage], (uint32_t)((it_ >> 1) & 1));
     if (active) {
       const int wt = s % g.tiles_w, ht = (s / g.tiles_w) % g.tiles_h, ti = s / (g.tiles_w * g.tiles_h);
@@ -220,7 +296,8 @@ dw_bwd_s2_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant
                        ((bi * 2 * TH) * 2 * g.TW + 2 * n) * CB + 2 * cp;
       const int img = ti * g.BI + bi, hq = ht * TH, wc = (wt * g.TW + n) * 2;
       const bool ok0 = img < g.IMGS && wc < g.W, ok1 = img < g.IMGS && wc + 1 < g.W;
-      bf16* dxp = dx + (((long long)img * g.H + 2 * hq) * g.W + wc) * g.C + c0 + 2 * cp;
+      bf16* dxr = dx + (((long long)img * g.H + 2 * hq) * g.W + wc) * g.C + c0 + 2 * cp;
+      const long long row_stride = (long long)g.W * g.C;
       float2 D[2][2];  // dy rows m, m+1 (mod 2) x columns n, n+1
       D[0][0] = ld_bf2(dyS);
       D[0][1] = ld_bf2(dyS + CB);
@@ -257,19 +334,21 @@ dw_bwd_s2_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant
         dW[6] = __ffma2_rn(x11, D0[1], dW[6]);
         dW[8] = __ffma2_rn(x11, D0[0], dW[8]);
         const int h = 2 * (hq + m);
-        bf16* o = dxp + (long long)(2 * m) * g.W * g.C;
-        if (h < g.H) {
-          if (ok0) st_bf2(o, a00);
-          if (ok1) st_bf2(o + g.C, a01);
-        }
-        if (h + 1 < g.H) {
-          if (ok0) st_bf2(o + (long long)g.W * g.C, a10);
-          if (ok1) st_bf2(o + (long long)g.W * g.C + g.C, a11);
-        }
+        const float2 o00 = PRE ? pre_mask<PRE>(a00, x00, pA, pB) : a00;
+        const float2 o01 = PRE ? pre_mask<PRE>(a01, x01, pA, pB) : a01;
+        const float2 o10 = PRE ? pre_mask<PRE>(a10, x10, pA, pB) : a10;
+        const float2 o11 = PRE ? pre_mask<PRE>(a11, x11, pA, pB) : a11;
+        const bool r0 = h < g.H, r1 = h + 1 < g.H;
+        if (r0 && ok0) st_bf2(dxr, o00);
+        if (r0 && ok1) st_bf2(dxr + g.C, o01);
+        if (r1 && ok0) st_bf2(dxr + row_stride, o10);
+        if (r1 && ok1) st_bf2(dxr + row_stride + g.C, o11);
+        dxr += 2 * row_stride;
       }
     }
     __syncthreads();
   }
+  if (PRE && pre_g >= 0) pre_flush<CB>(pA, pB, red, g.npos, cp, pos, active, pre.sums, pre_g, g.C, c0);
   reduce_dw(dW, reinterpret_cast<float*>(stages), g, cp, pos, active, c0, dWg);
 }
 
@@ -487,12 +566,20 @@ int adamml_dwconv_bwd_supported(int IMGS, int H, int W, int C, int stride) {
 
 /* Depthwise 3x3 (pad 1) backward, bf16 NHWC: dx = conv_transpose(dy, w) and dw = the weight gradient (fp32 tap-major
  * [9][C], overwritten) from ONE pass over dy and x.  w: fp32 tap-major [9][C] (adamml_pack_weight_dw). */
-int adamml_dwconv_bwd(const void* x, const void* dy, const float* w, void* dx, float* dw, int IMGS, int H, int W, int C,
-                      int stride, int Ho, int Wo, cudaStream_t stream) {
+int adamml_dwconv_bwd(const void* x, const void* dy, const float* w, void* dx, float* dw, double* pre_sums,
+                      int pre_imgs_per_group, int pre_act, int IMGS, int H, int W, int C, int stride, int Ho, int Wo,
+                      cudaStream_t stream) {
   ADAMML_REQUIRE(adamml_dwconv_bwd_supported(IMGS, H, W, C, stride), "dwconv_bwd: unsupported shape (C %% 16, stride)");
   ADAMML_REQUIRE(Ho == (H + 2 - 3) / stride + 1 && Wo == (W + 2 - 3) / stride + 1, "dwconv_bwd: bad Ho/Wo");
   ADAMML_REQUIRE(((uintptr_t)x % 16) == 0 && ((uintptr_t)dy % 16) == 0 && ((uintptr_t)dx % 16) == 0,
                  "dwconv_bwd: tensors must be 16-byte aligned");
+  PreReduce pre{pre_sums, pre_imgs_per_group > 0 ? pre_imgs_per_group : IMGS, pre_act};
+  if (pre_sums) {
+    ADAMML_REQUIRE(pre_act == ADAMML_ACT_RELU || pre_act == ADAMML_ACT_RELU6,
+                   "dwconv_bwd: the fused producer reduction needs a ReLU / ReLU6 producer");
+    ADAMML_REQUIRE(IMGS % pre.imgs_per_group == 0, "dwconv_bwd: IMGS must be a multiple of pre_imgs_per_group");
+    cudaMemsetAsync(pre_sums, 0, sizeof(double) * (size_t)(IMGS / pre.imgs_per_group) * C * 2, stream);
+  }
   DwGeom g;
   memset(&g, 0, sizeof(g));
   g.IMGS = IMGS; g.H = H; g.W = W; g.C = C; g.Ho = Ho; g.Wo = Wo;
@@ -507,11 +594,12 @@ int adamml_dwconv_bwd(const void* x, const void* dy, const float* w, void* dx, f
   const int CBv = g.CB;
   auto smem_of = [&](int u, int bi) {
     if (stride == 1)
-      return 2 * (pad128(bi * (TH1 + 2) * (2 * u + 2) * CBv * 2) + pad128(bi * TH1 * 2 * u * CBv * 2)) + 256;
-    return 2 * (pad128(bi * (TH2 + 1) * (u + 1) * CBv * 2) + pad128(bi * 4 * TH2 * u * CBv * 2)) + 256;
+      return 2 * (pad128(bi * (TH1 + 2) * (2 * u + 2) * CBv * 2) + pad128(bi * TH1 * 2 * u * CBv * 2)) + 256 + DW_RED_BYTES;
+    return 2 * (pad128(bi * (TH2 + 1) * (u + 1) * CBv * 2) + pad128(bi * 4 * TH2 * u * CBv * 2)) + 256 + DW_RED_BYTES;
   };
   int best_u = 1, best_bi = 1;
-  ADAMML_REQUIRE(pick_dw_tile(units, IMGS, max_pos, 0, smem_of, &best_u, &best_bi), "dwconv_bwd: no tile shape fits");
+  ADAMML_REQUIRE(pick_dw_tile(units, IMGS, max_pos, pre_sums ? pre.imgs_per_group : 0, smem_of, &best_u, &best_bi),
+                 "dwconv_bwd: no tile shape fits");
   g.BI = best_bi;
   g.npos = best_u * best_bi;
   g.tiles_i = (IMGS + g.BI - 1) / g.BI;
@@ -530,21 +618,26 @@ int adamml_dwconv_bwd(const void* x, const void* dy, const float* w, void* dx, f
     if (rc) return rc;
     rc = make_dw_map(&tmX, x, C, W, H, IMGS, g.CB, g.TW, TH, g.BI);
     if (rc) return rc;
-    const int smem = 2 * (g.dy_bytes + g.x_bytes) + 256;
+    const int smem = 2 * (g.dy_bytes + g.x_bytes) + 256 + DW_RED_BYTES;
     const long long sp = (long long)g.tiles_w * g.tiles_h * g.tiles_i;
     long long per = sms2 / g.chunks > 0 ? sms2 / g.chunks : 1;
     if (per > sp) per = sp;
     const int grid = (int)per * g.chunks;
-    typedef void (*KernFn)(const CUtensorMap, const CUtensorMap, const float*, bf16*, float*, const DwGeom);
+    typedef void (*KernFn)(const CUtensorMap, const CUtensorMap, const float*, bf16*, float*, const DwGeom,
+                           const PreReduce);
     KernFn kern = nullptr;
-#define DWB_PICK(THV, CBV) if (TH == THV && g.CB == CBV) kern = dw_bwd_s1_kernel<THV, CBV>;
+#define DWB_PICK(THV, CBV)                                                                              \
+  if (TH == THV && g.CB == CBV)                                                                         \
+    kern = !pre_sums ? dw_bwd_s1_kernel<THV, CBV, 0>                                                    \
+                     : (pre_act == ADAMML_ACT_RELU6 ? dw_bwd_s1_kernel<THV, CBV, ADAMML_ACT_RELU6>     \
+                                                    : dw_bwd_s1_kernel<THV, CBV, ADAMML_ACT_RELU>);
     DWB_PICK(8, 64) DWB_PICK(8, 48) DWB_PICK(8, 32) DWB_PICK(8, 16)
     DWB_PICK(5, 64) DWB_PICK(5, 48) DWB_PICK(5, 32) DWB_PICK(5, 16)
 #undef DWB_PICK
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM_LIMIT);
     if (e != cudaSuccess) { adamml_set_error("dwconv_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return ADAMML_ERR_CUDA; }
     ADAMML_REQUIRE(smem <= DW_SMEM_LIMIT, "dwconv_bwd: tile does not fit shared memory (%d bytes)", smem);
-    kern<<<grid, DWB_THREADS, smem, stream>>>(tmDy, tmX, w, (bf16*)dx, dw, g);
+    kern<<<grid, DWB_THREADS, smem, stream>>>(tmDy, tmX, w, (bf16*)dx, dw, g, pre);
   } else {
     const int Hq = Hq_;
     const int TH = TH2;
@@ -557,21 +650,26 @@ int adamml_dwconv_bwd(const void* x, const void* dy, const float* w, void* dx, f
     if (rc) return rc;
     rc = make_dw_map(&tmX, x, C, W, H, IMGS, g.CB, 2 * g.TW, 2 * TH, g.BI);
     if (rc) return rc;
-    const int smem = 2 * (g.dy_bytes + g.x_bytes) + 256;
+    const int smem = 2 * (g.dy_bytes + g.x_bytes) + 256 + DW_RED_BYTES;
     const long long sp = (long long)g.tiles_w * g.tiles_h * g.tiles_i;
     long long per = sms2 / g.chunks > 0 ? sms2 / g.chunks : 1;
     if (per > sp) per = sp;
     const int grid = (int)per * g.chunks;
-    typedef void (*KernFn)(const CUtensorMap, const CUtensorMap, const float*, bf16*, float*, const DwGeom);
+    typedef void (*KernFn)(const CUtensorMap, const CUtensorMap, const float*, bf16*, float*, const DwGeom,
+                           const PreReduce);
     KernFn kern = nullptr;
-#define DWB_PICK(THV, CBV) if (TH == THV && g.CB == CBV) kern = dw_bwd_s2_kernel<THV, CBV>;
+#define DWB_PICK(THV, CBV)                                                                              \
+  if (TH == THV && g.CB == CBV)                                                                         \
+    kern = !pre_sums ? dw_bwd_s2_kernel<THV, CBV, 0>                                                    \
+                     : (pre_act == ADAMML_ACT_RELU6 ? dw_bwd_s2_kernel<THV, CBV, ADAMML_ACT_RELU6>     \
+                                                    : dw_bwd_s2_kernel<THV, CBV, ADAMML_ACT_RELU>);
     DWB_PICK(4, 64) DWB_PICK(4, 48) DWB_PICK(4, 32) DWB_PICK(4, 16)
     DWB_PICK(5, 64) DWB_PICK(5, 48) DWB_PICK(5, 32) DWB_PICK(5, 16)
 #undef DWB_PICK
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM_LIMIT);
     if (e != cudaSuccess) { adamml_set_error("dwconv_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return ADAMML_ERR_CUDA; }
     ADAMML_REQUIRE(smem <= DW_SMEM_LIMIT, "dwconv_bwd: tile does not fit shared memory (%d bytes)", smem);
-    kern<<<grid, DWB_THREADS, smem, stream>>>(tmDy, tmX, w, (bf16*)dx, dw, g);
+    kern<<<grid, DWB_THREADS, smem, stream>>>(tmDy, tmX, w, (bf16*)dx, dw, g, pre);
   }
   return adamml_check_launch("dwconv_bwd");
 }

@@ -22,6 +22,9 @@ FUSE_EVAL = _os.environ.get("ADAMML_B200_FUSE_EVAL", "1") != "0"
 # for the backward pass; the consumer's weight gradient rebuilds it from the saved pre-BN tensor (one extra bf16
 # bn_apply pass per such layer in backward).  Measured RGB+Audio N=72: see DESIGN.md §4.
 RECOMPUTE = _os.environ.get("ADAMML_B200_RECOMPUTE", "0") != "0"
+# backward of a depthwise conv also reduces the BatchNorm gradient sums of the layer that produced its input
+# (csrc/dwconv_tma.cu PreReduce); ADAMML_B200_DW_FUSE_PRE=0 keeps the separate bn_bwd_reduce pass (tests compare)
+DW_FUSE_PRE = _os.environ.get("ADAMML_B200_DW_FUSE_PRE", "1") != "0"
 
 
 class _ShapeOnly:
@@ -236,7 +239,14 @@ class Exec:
         if p2p is not None:
             slot_off, flat = p2p.slot((_bn_key(bn), "b"), G * C * 2)
             sums_out = flat.view(G, C, 2)
-        sums = ops.bn_bwd_reduce(dout, out, z, mi, G, act, mask_ss=mask_ss, gm_inplace=inplace, sums_out=sums_out)
+        pre = rec.pop("pre_reduced", None)
+        if pre is not None:
+            # the depthwise backward kernel that produced dout already masked it and reduced (sum gm, sum gm * out)
+            # (ops.dwconv_bwd pre=...): no pass over (dout, z) here
+            sums = ops.bn_sums_from_out(pre, rec["ss"], mi, out=sums_out)
+            out, act, want_dres, mask_ss = None, ACT_NONE, False, None
+        else:
+            sums = ops.bn_bwd_reduce(dout, out, z, mi, G, act, mask_ss=mask_ss, gm_inplace=inplace, sums_out=sums_out)
         if inplace:
             rec["dout_masked"] = True
             out, act, want_dres = None, ACT_NONE, False
@@ -268,8 +278,16 @@ class Exec:
                 self._acc(conv.weight, ops.stem_wgrad(x, dz, conv.out_channels))
         elif rec["depthwise"]:
             if need_w and need_dx and addend is None and ops.dwconv_bwd_ok(x, dz, stride):
-                # both gradients from one pass over dz and x (TMA-staged tiles, csrc/dwconv_tma.cu)
-                dx, dw = ops.dwconv_bwd(x, dz, rec["w"], stride)
+                # both gradients from one pass over dz and x (TMA-staged tiles, csrc/dwconv_tma.cu); when x is the
+                # output of a plain conv + BN + act layer, that layer's BN-backward reduction rides along
+                prev = self._dw_producer(rec, x)
+                pre = None
+                if prev is not None:
+                    raw = torch.empty((G, C, 2), device=x.device, dtype=torch.float64)
+                    pre = (raw, x.shape[0] // G, prev["act"])
+                dx, dw = ops.dwconv_bwd(x, dz, rec["w"], stride, pre=pre)
+                if prev is not None:
+                    prev["pre_reduced"] = raw
                 self._acc(conv.weight, dw)
             else:
                 if need_w:
@@ -293,6 +311,26 @@ class Exec:
                 dx = ops.conv_dgrad(dz, w, tuple(x.shape), stride, pad, addend=addend, w_rot=w_rot,
                                     addend_sub=addend_sub)
         return dx, dres, False
+
+    def _dw_producer(self, rec, x):
+        """The tape record of the layer whose output is the input x of the depthwise layer `rec`, when its
+        BatchNorm-backward reduction can be fused into the depthwise backward kernel: a conv + BN + ReLU/ReLU6 layer
+        without residual input whose forward scale / shift was kept (cba), directly below `rec` on the tape."""
+        if not DW_FUSE_PRE or not self.tape:
+            return None
+        prev = self.tape[-1]
+        if prev.get("bn") is None or prev.get("has_res") or prev.get("res_rec") is not None:
+            return None
+        if prev.get("act", ACT_NONE) == ACT_NONE or prev.get("ss") is None or prev.get("pre_reduced") is not None:
+            return None
+        if prev.get("out") is not None:
+            same = prev["out"] is rec["x"]
+        else:  # recompute mode: x was rebuilt from the producer's saved pre-BN tensor
+            lz = rec.get("x_lazy")
+            same = lz is not None and lz["z"] is prev["z"]
+        if not same or tuple(prev["z"].shape) != tuple(x.shape) or x.shape[0] % self.G:
+            return None
+        return prev
 
     # ------------------------------------------------------------------ ResNet blocks
     def bottleneck(self, x, blk):

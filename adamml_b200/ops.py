@@ -646,17 +646,32 @@ def dwconv_bwd_ok(x, dy, stride):
             and x.shape[-1] % 16 == 0 and stride in (1, 2))
 
 
-def dwconv_bwd(x, dy, w, stride):
+def dwconv_bwd(x, dy, w, stride, pre=None):
     """-> (dx, dw): data gradient (bf16 NHWC) and fp32 weight gradient in torch's [C,1,3,3] layout from ONE pass
-    over dy and x.  w: tap-major [9, C] (pack_weight_dw)."""
+    over dy and x.  w: tap-major [9, C] (pack_weight_dw).
+    pre = (raw_sums [G, C, 2] float64, imgs_per_group, act): also fuse the BatchNorm-backward reduction of the layer
+    that produced x = act(bn(z)): dx comes back masked (dx * act'(x)) and raw_sums holds (sum gm, sum gm * x) per
+    group and channel (-> bn_sums_from_out)."""
     _chk(x); _chk(dy, x.dtype); _chk(w, torch.float32)
     IMGS, H, W, C = x.shape
     dx = torch.empty((IMGS, H, W, C), device=x.device, dtype=x.dtype)
     dwt = torch.empty((9, C), device=x.device, dtype=torch.float32)
-    call("dwconv_bwd", x, dy, w, dx, dwt, IMGS, H, W, C, stride, dy.shape[1], dy.shape[2])
+    raw, ipg, act = pre if pre is not None else (None, 0, ACT_NONE)
+    if raw is not None:
+        assert raw.dtype == torch.float64 and raw.is_contiguous() and IMGS % ipg == 0
+        assert tuple(raw.shape) == (IMGS // ipg, C, 2)
+    call("dwconv_bwd", x, dy, w, dx, dwt, raw, ipg, act, IMGS, H, W, C, stride, dy.shape[1], dy.shape[2])
     dw = torch.empty((C, 1, 3, 3), device=x.device, dtype=torch.float32)
     call("unpack_wgrad_dw", dwt, dw, C)
     return dx, dw
+
+
+def bn_sums_from_out(raw, scale_shift, mean_invstd, out=None):
+    """(sum gm, sum gm * out) of dwconv_bwd's fused reduction -> (sum gm, sum gm * xhat) as bn_bwd_reduce returns"""
+    G, C, _ = raw.shape
+    sums = out if out is not None else raw
+    call("bn_sums_from_out", raw, scale_shift, mean_invstd, sums, C, G)
+    return sums
 
 
 def dwconv_wgrad(x, dy, stride):

@@ -155,8 +155,16 @@ int adamml_dwconv_wgrad(const void* x, const void* dy, float* dw, int IMGS, int 
  * overwritten) from ONE pass over dy and x -- the autograd of the same call sites.  adamml_dwconv_bwd_supported -> 1
  * when the shape is handled (C % 16 == 0), else the two calls above are used. */
 int adamml_dwconv_bwd_supported(int IMGS, int H, int W, int C, int stride);
-int adamml_dwconv_bwd(const void* x, const void* dy, const float* w, void* dx, float* dw, int IMGS, int H, int W, int C,
-                      int stride, int Ho, int Wo, cudaStream_t stream);
+int adamml_dwconv_bwd(const void* x, const void* dy, const float* w, void* dx, float* dw, double* pre_sums,
+                      int pre_imgs_per_group, int pre_act, int IMGS, int H, int W, int C, int stride, int Ho, int Wo,
+                      cudaStream_t stream);
+/* pre_sums != NULL fuses the BatchNorm-backward REDUCTION of the layer that produced x = act(bn(z)) (the expand / first
+ * conv in front of the depthwise conv, no residual): dx is written already masked (gm = dx * act'(x), pre_act = that
+ * layer's activation) and pre_sums [G][C][2] (double, overwritten) = per BN group (img / pre_imgs_per_group) and
+ * channel (sum gm, sum gm * x); adamml_bn_sums_from_out converts them to the (sum gm, sum gm * xhat) that
+ * adamml_bn_bwd_reduce would have produced from (dx, z) in a separate pass. */
+int adamml_bn_sums_from_out(const double* raw, const float* scale_shift, const float* mean_invstd, double* sums, int C,
+                            int G, cudaStream_t stream);
 
 /* ---- BatchNorm2d (+ReLU/ReLU6, + residual) with per-segment groups ----
  * nn.BatchNorm2d at resnet.py:50,53,82-86,139,166 ; sound_mobilenet_v2.py:37,62 ; policy_net.py:41,50,67-85

@@ -165,7 +165,7 @@ DW_SHAPES = [(360, 128, 96, 2, 2), (1440, 80, 96, 2, 1), (360, 64, 144, 1, 2), (
 
 def dw_bwd_all():
     """separate dgrad + wgrad launches vs the fused TMA-tile backward, L2 flushed, summed over one step"""
-    sep_tot = fus_tot = 0.0
+    sep_tot = fus_tot = pre_tot = 0.0
     for I, H, C, stride, n in DW_SHAPES:
         x = rnd(I, H, H, C)
         w = ops.pack_weight_dw(torch.randn(C, 1, 3, 3, device=dev))
@@ -178,12 +178,17 @@ def dw_bwd_all():
             ops.dwconv_wgrad(x, dy, stride)
         t_sep = timeit_cold(sep)
         t_fus = timeit_cold(lambda: ops.dwconv_bwd(x, dy, w, stride))
+        raw = torch.empty(5, C, 2, device=dev, dtype=torch.float64)
+        t_pre = timeit_cold(lambda: ops.dwconv_bwd(x, dy, w, stride, pre=(raw, I // 5, 2)))
         sep_tot += n * t_sep
         fus_tot += n * t_fus
+        pre_tot += n * t_pre
         print(f"dw_bwd I={I} {H}x{H} C={C} s{stride} x{n}: separate {t_sep:7.3f} ms  fused {t_fus:7.3f} ms "
-              f"({by / t_fus / 1e6:6.0f} GB/s, {by / t_fus / 1e6 / HBM * 100:5.1f}% hbm)", flush=True)
+              f"({by / t_fus / 1e6:6.0f} GB/s, {by / t_fus / 1e6 / HBM * 100:5.1f}% hbm)  + producer BN reduce "
+              f"{t_pre:7.3f} ms", flush=True)
         del x, dy
-    print(f"dw_bwd per step: separate {sep_tot:.2f} ms -> fused {fus_tot:.2f} ms", flush=True)
+    print(f"dw_bwd per step: separate {sep_tot:.2f} ms -> fused {fus_tot:.2f} ms -> with the producer's BN reduction "
+          f"{pre_tot:.2f} ms", flush=True)
 
 
 def dw_fwd_all():

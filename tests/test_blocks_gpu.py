@@ -180,6 +180,76 @@ def test_inverted_residual(cuda, variant, cfg):
         assert relerr(ex.grads[p], want[k]) < 1e-3, k
 
 
+@pytest.mark.parametrize("variant", ["sound", "policy"])
+@pytest.mark.parametrize("cfg", [(32, 16, 1, 1), (16, 24, 2, 6), (24, 24, 1, 6), (64, 96, 1, 6)])
+@pytest.mark.parametrize("recompute", [False, True])
+def test_inverted_residual_x2_fused_producer_reduce(cuda, variant, cfg, recompute):
+    """Default-mode (x2 forward, bf16 backward) MobileNetV2 block: the depthwise backward kernel that also reduces
+    the BatchNorm gradient sums of the expand layer (engine.DW_FUSE_PRE) against the separate bn_bwd_reduce pass,
+    and both against a float64 torch run."""
+    from adamml_b200 import engine, ops
+    from adamml_b200.engine import Exec
+    import copy
+    import importlib
+    policy_net = importlib.import_module("adamml_b200.models.policy_net")
+    sound_mobilenet_v2 = importlib.import_module("adamml_b200.models.sound_mobilenet_v2")
+    inp, oup, stride, t = cfg
+    g = torch.Generator().manual_seed(7)
+    blk = (sound_mobilenet_v2._InvertedResidual if variant == "sound" else policy_net._InvertedResidual)(inp, oup,
+                                                                                                      stride, t)
+    randomize(blk, g)
+    blk = blk.to(cuda).train()
+    use_res = blk.use_res_connect if variant == "sound" else blk.identity
+    G, ipg, H = 2, 6, 20
+    x = torch.randn(G * ipg, inp, H, H, generator=g).to(cuda)
+    blk64 = copy.deepcopy(blk).double()
+    x64 = x.double().requires_grad_(True)
+    ref = torch.cat([(xs + blk64.conv(xs)) if use_res else blk64.conv(xs) for xs in x64.chunk(G)])
+    dy = torch.randn(ref.shape, generator=g).to(cuda)
+    ref.backward(dy.double())
+    want = {k: p.grad.clone() for k, p in blk64.named_parameters()}
+    xn = nhwc(x)
+    hi = xn.bfloat16()
+    res = {}
+    old = engine.DW_FUSE_PRE
+    try:
+        for fuse in (True, False):
+            engine.DW_FUSE_PRE = fuse
+            ex = Exec(ops.PREC_X2, True, G, save=True)
+            ex.recompute = recompute
+            n0 = _lib_launches()
+            out = ex.inverted_residual(ops.X2(hi, (xn - hi.float()).half()), blk.layers(), use_res)
+            dx = ex.inverted_residual_bwd(nhwc(dy).bfloat16())
+            assert not ex.tape
+            res[fuse] = (out.float(), dx.float(), {k: ex.grads[p].clone() for k, p in blk.named_parameters()},
+                         _lib_launches() - n0)
+    finally:
+        engine.DW_FUSE_PRE = old
+    assert relerr(nchw(res[True][0]), ref) < 1e-4
+    assert torch.equal(res[True][0], res[False][0])
+    assert t == 1 or res[True][3] == res[False][3]   # bn_bwd_reduce (+ memset) replaced by bn_sums_from_out
+    # fused vs separate reduction: the fused kernel takes the ReLU6 mask from the saved OUTPUT (like torch's
+    # hardtanh_backward), the separate pass recomputes it from the bf16 pre-BN tensor -- the ~0.1 % of elements within
+    # one bf16 rounding of a threshold differ; vs float64 the bf16 backward is judged in the rms sense
+    def rms(a, b):
+        a, b = a.double(), b.double()
+        return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+    # (on this random data a BN gradient is a zero-mean sum: 0.1 % flipped masks move it by sqrt(0.001 / 0.5) ~ 5 %,
+    # so the two variants are each held to the float64 result, the fused one to no more than the separate one + 20 %)
+    e_f, e_s = rms(nchw(res[True][1]), x64.grad), rms(nchw(res[False][1]), x64.grad)
+    print(f"dx: fused {e_f:.4f} separate {e_s:.4f} fused-vs-separate {rms(res[True][1], res[False][1]):.4f}")
+    assert e_f < 0.15 and e_f < 1.2 * e_s + 5e-3   # (whole-model bf16 gradient cosine is 0.99: tests/test_x2_gpu.py)
+    for k in want:
+        e_f, e_s = rms(res[True][2][k], want[k]), rms(res[False][2][k], want[k])
+        print(f"{k}: fused {e_f:.4f} separate {e_s:.4f} fused-vs-separate {rms(res[True][2][k], res[False][2][k]):.4f}")
+        assert e_f < 0.15 and e_f < 1.2 * e_s + 5e-3, k
+
+
+def _lib_launches():
+    from adamml_b200 import _lib
+    return _lib.launch_count()
+
+
 def test_small_resnet_end_to_end(cuda):
     """ResNet-18-style net (BasicBlocks, 3 temporal pools, head) fwd+bwd vs torch, 12 videos x 8 frames.
     Layer4 sees only 48 values per BN channel, so gradients are judged against a float64 torch run with the

@@ -193,6 +193,44 @@ def test_dwconv_bwd_fused(cuda, case):
     assert (dx != dx2).float().mean().item() < 0.02
 
 
+@pytest.mark.parametrize("case", [(4, 16, 16, 32, 1, 2), (6, 15, 17, 96, 2, 2), (4, 8, 8, 960, 1, 1),
+                                  (10, 10, 10, 144, 2, 2), (12, 10, 10, 576, 1, 2), (10, 5, 5, 960, 1, 1),
+                                  (4, 40, 40, 144, 1, 2), (6, 64, 64, 96, 2, 2), (80, 8, 8, 64, 1, 2),
+                                  (600, 16, 16, 128, 1, 1), (330, 12, 12, 48, 2, 2)])
+def test_dwconv_bwd_fused_producer_reduce(cuda, case):
+    """adamml_dwconv_bwd with the fused BatchNorm-backward reduction of the layer that produced x = act(bn(z)):
+    dx comes back masked, and bn_sums_from_out of the raw sums equals what bn_bwd_reduce computes from (dx, z) in
+    a separate pass (same mask source: the saved output)."""
+    from adamml_b200 import ops
+    IMGS, H, W, C, stride, act = case
+    G = 2
+    g = torch.Generator(device="cpu").manual_seed(sum(case))
+    z = (torch.randn(IMGS, H, W, C, generator=g) * 1.5 + 0.3).to(cuda).bfloat16()
+    ss = torch.stack([torch.rand(G, C, generator=g) + 0.5, torch.randn(G, C, generator=g)], dim=-1).to(cuda)
+    mi = torch.stack([torch.randn(G, C, generator=g) * 0.3, torch.rand(G, C, generator=g) + 0.5], dim=-1).to(cuda)
+    x = ops.bn_apply(z, ss, G, act)                       # the producer's saved output (bf16)
+    Ho, Wo = ops.conv_out_hw(H, W, 3, 3, stride, 1)
+    dy = torch.randn(IMGS, Ho, Wo, C, generator=g).to(cuda).bfloat16()
+    wd = ops.pack_weight_dw((torch.randn(C, 1, 3, 3, generator=g) / 3).to(cuda).contiguous())
+    dx0, dw0 = ops.dwconv_bwd(x, dy, wd, stride)
+    raw = torch.full((G, C, 2), float("nan"), device=cuda, dtype=torch.float64)
+    gm, dw1 = ops.dwconv_bwd(x, dy, wd, stride, pre=(raw, IMGS // G, act))
+    assert relerr(dw1, dw0) < 1e-5   # (fp32 atomics across CTAs: same products, order not fixed)
+    xf = x.float()
+    keep = (xf > 0) & (xf < 6) if act == 2 else (xf > 0)
+    assert torch.equal(gm, torch.where(keep, dx0, torch.zeros_like(dx0)))
+    # raw sums: fp32 products of the UNROUNDED gradient, so compare against the rounded one at bf16-sum accuracy
+    gmd, xd = gm.double().view(G, -1, C), xf.double().view(G, -1, C)
+    assert relerr(raw[..., 0], gmd.sum(1)) < 5e-3
+    assert relerr(raw[..., 1], (gmd * xd).sum(1)) < 5e-3
+    sums = ops.bn_sums_from_out(raw.clone(), ss, mi)
+    want = ops.bn_bwd_reduce(dx0.clone(), x, z, mi, G, act)
+    assert relerr(sums[..., 0], want[..., 0]) < 5e-3
+    # sum gm * xhat: z is only known through the bf16 output here (one extra rounding per element)
+    scale = (gmd.abs() * ((z.double().view(G, -1, C) - mi[..., 0].double().unsqueeze(1)) * mi[..., 1].double().unsqueeze(1)).abs()).sum(1)
+    assert ((sums[..., 1] - want[..., 1]).abs() / scale.clamp_min(1e-30)).max().item() < 4e-3
+
+
 @pytest.mark.parametrize("act", [0, 1, 2])
 @pytest.mark.parametrize("residual", ["none", "plain", "bn"])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
