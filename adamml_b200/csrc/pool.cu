@@ -138,10 +138,18 @@ __global__ void tpool_bwd_kernel(const T* __restrict__ x, const T* __restrict__ 
 // ---- 16-byte vectorised versions (C % VEC == 0): thread = (pixel, channel vector) ----------------------
 // 3x3/s2/p1 max-pool; optionally records the window position (r*3+s, first maximum in scan order) of
 // every output element so that the backward pass is a pure gather that never re-reads x.
+// PreBN (training stem, resnet.py:197-200): x is the PRE-BatchNorm tensor z and every window element goes through
+// act(z * scale + shift) (per BN group = img / imgs_per_group and channel) on its way into the maximum, so the
+// full-resolution post-activation tensor -- which nothing but this pool reads -- is never written.
+struct PreBN {
+  const float* ss;  // [G][C][2] (scale, shift); nullptr = plain max-pool
+  int imgs_per_group;
+  int act;
+};
 template <typename T, typename CP, typename MP>
 __device__ __forceinline__ void
 maxpool_fwd_vec_body(CP x, MP y, unsigned char* __restrict__ pos, int IMGS, int H, int W, int C, int Ho, int Wo,
-                     LiveLimit live) {
+                     LiveLimit live, PreBN pre = PreBN{nullptr, 1, ADAMML_ACT_NONE}) {
   constexpr int V = VecIO<T>::N;
   const int cvecs = C / V;
   const long long total = (long long)IMGS * Ho * Wo * cvecs;
@@ -169,11 +177,24 @@ maxpool_fwd_vec_body(CP x, MP y, unsigned char* __restrict__ pos, int IMGS, int 
   int bp[V];
 #pragma unroll
   for (int i = 0; i < V; ++i) { best[i] = -INFINITY; bp[i] = 0; }
+  float sc[V], sh[V];
+  if (pre.ss) {
+    const float* p = pre.ss + ((img / pre.imgs_per_group) * C + cv * V) * 2;
+#pragma unroll
+    for (int i = 0; i < V; i += 2) {
+      const float4 f = *reinterpret_cast<const float4*>(p + 2 * i);
+      sc[i] = f.x; sh[i] = f.y; sc[i + 1] = f.z; sh[i + 1] = f.w;
+    }
+  }
 #pragma unroll
   for (int t = 0; t < 9; ++t) {
     if (ok[t]) {
       float v[V];
       VecIO<T>::unpack(q[t], v);
+      if (pre.ss) {
+#pragma unroll
+        for (int i = 0; i < V; ++i) v[i] = act_apply(fmaf(v[i], sc[i], sh[i]), pre.act);
+      }
 #pragma unroll
       for (int i = 0; i < V; ++i)
         if (v[i] > best[i] || v[i] != v[i]) { best[i] = v[i]; bp[i] = t; }
@@ -204,6 +225,11 @@ __global__ void __launch_bounds__(256)
 maxpool_fwd_vec_x2_kernel(X2CPtr x, X2Ptr y, unsigned char* __restrict__ pos, int IMGS, int H, int W, int C, int Ho,
                           int Wo, LiveLimit live) {
   maxpool_fwd_vec_body<x2_t, X2CPtr, X2Ptr>(x, y, pos, IMGS, H, W, C, Ho, Wo, live);
+}
+__global__ void __launch_bounds__(256)
+bn_act_maxpool_fwd_vec_x2_kernel(X2CPtr z, X2Ptr y, unsigned char* __restrict__ pos, int IMGS, int H, int W, int C,
+                                 int Ho, int Wo, PreBN pre) {
+  maxpool_fwd_vec_body<x2_t, X2CPtr, X2Ptr>(z, y, pos, IMGS, H, W, C, Ho, Wo, LiveLimit{nullptr, 0}, pre);
 }
 
 // gather backward from recorded positions, one thread per 2x2 input quad (rows 2m, 2m+1; cols 2n, 2n+1) and channel
@@ -521,6 +547,22 @@ int adamml_maxpool3x3s2_fwd_x2(const void* x_hi, const void* x_lo, void* y_hi, v
       x2c(x_hi, x_lo), x2m(y_hi, y_lo), pos, IMGS, H, W, C, Ho, Wo,
       pos ? LiveLimit{nullptr, 0} : adamml_live_limit(IMGS));
   return adamml_check_launch("maxpool_fwd_x2");
+}
+
+/* training stem (resnet.py:197-200): y = maxpool3x3s2(act(z * scale + shift)) straight from the pre-BatchNorm planes z;
+ * scale_shift = float [G][C][2] of adamml_bn_finalize, group = img / imgs_per_group.  pos as adamml_maxpool3x3s2_fwd. */
+int adamml_bn_act_maxpool3x3s2_fwd_x2(const void* z_hi, const void* z_lo, const float* scale_shift, int imgs_per_group,
+                                      int act, void* y_hi, void* y_lo, unsigned char* pos, int IMGS, int H, int W,
+                                      int C, int Ho, int Wo, cudaStream_t stream) {
+  ADAMML_REQUIRE(Ho == (H + 2 - 3) / 2 + 1 && Wo == (W + 2 - 3) / 2 + 1, "bn_act_maxpool: bad Ho/Wo");
+  ADAMML_REQUIRE(scale_shift && imgs_per_group > 0 && IMGS % imgs_per_group == 0, "bn_act_maxpool: bad BN groups");
+  ADAMML_REQUIRE(pool_vec_ok<bf16>(C, z_hi, z_lo, y_hi) && pool_vec_ok<bf16>(C, y_lo) && ((uintptr_t)pos % 8) == 0 &&
+                     ((uintptr_t)scale_shift % 16) == 0,
+                 "bn_act_maxpool_fwd_x2: needs C %% 8 == 0 and aligned planes");
+  const long long tv = (long long)IMGS * Ho * Wo * (C / 8);
+  bn_act_maxpool_fwd_vec_x2_kernel<<<(unsigned)((tv + 255) / 256), 256, 0, stream>>>(
+      x2c(z_hi, z_lo), x2m(y_hi, y_lo), pos, IMGS, H, W, C, Ho, Wo, PreBN{scale_shift, imgs_per_group, act});
+  return adamml_check_launch("bn_act_maxpool_fwd_x2");
 }
 
 int adamml_tpool_fwd_x2(const void* x_hi, const void* x_lo, void* y_hi, void* y_lo, long long V, int Tn, long long E,

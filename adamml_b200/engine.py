@@ -25,6 +25,8 @@ RECOMPUTE = _os.environ.get("ADAMML_B200_RECOMPUTE", "0") != "0"
 # backward of a depthwise conv also reduces the BatchNorm gradient sums of the layer that produced its input
 # (csrc/dwconv_tma.cu PreReduce); ADAMML_B200_DW_FUSE_PRE=0 keeps the separate bn_bwd_reduce pass (tests compare)
 DW_FUSE_PRE = _os.environ.get("ADAMML_B200_DW_FUSE_PRE", "1") != "0"
+# training stem of the ResNets: BN + ReLU applied inside the max-pool kernel (Exec.cba_maxpool); =0 keeps bn_apply + pool
+FUSE_STEM_POOL = _os.environ.get("ADAMML_B200_FUSE_STEM_POOL", "1") != "0"
 
 
 class _ShapeOnly:
@@ -121,6 +123,21 @@ class Exec:
                 out._adamml_src = dict(z=rec["z"], ss=rec["ss"], act=act, G=self.G)
             self.tape.append(rec)
         return out
+
+    def cba_maxpool(self, x, conv, bn, act):
+        """ResNet stem: maxpool3x3s2(act(bn(conv(x)))) (resnet.py:197-200).  Default-mode training: BN + ReLU are
+        applied inside the pooling kernel on the pre-BN planes, so the full-resolution post-activation tensor (which
+        only the pool reads; backward takes the mask from z and the pool's recorded positions) is never written."""
+        Cout = conv.out_channels
+        if not (FUSE_STEM_POOL and self.training and self.save and self.x2 and act != ACT_NONE and Cout % 8 == 0):
+            return self.maxpool(self.cba(x, conv, bn, act))
+        rec = self.conv_bn_stats(x, conv, bn)
+        z = rec["z"]
+        y, pos = ops.bn_act_maxpool_fwd(z, rec["ss"], self.G, act)
+        rec.update(x=ops.hi_plane(rec["x"]), z=ops.hi_plane(z), out=None, act=act, has_res=False, res_rec=None)
+        self.tape.append(rec)
+        self.tape.append(dict(x=None, pos=pos, shape=tuple(z.shape)))
+        return y
 
     def _cba_fused_eval(self, x, conv, bn, act, res, res_rec):
         """Inference (running statistics, no tape): conv + BN (+ residual) + ReLU/ReLU6 as ONE kernel — the folded

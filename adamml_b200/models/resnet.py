@@ -97,8 +97,7 @@ class ResNet(nn.Module):
     def run_forward(self, ex, x, extra):
         """x: NHWC [G*videos*frames, H, W, C] -> logits [G*videos, classes] (resnet.py:195-223)."""
         frames = self.orig_num_frames
-        a = ex.cba(x, self.conv1, self.bn1, ACT_RELU)
-        a = ex.maxpool(a)
+        a = ex.cba_maxpool(x, self.conv1, self.bn1, ACT_RELU)
         for li in range(4):
             for blk in getattr(self, f"layer{li + 1}"):
                 a = ex.bottleneck(a, blk) if blk.bottleneck else ex.basicblock(a, blk)

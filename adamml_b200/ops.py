@@ -781,6 +781,17 @@ def maxpool_fwd(x, want_pos=False):
     return (y, pos) if want_pos else y
 
 
+def bn_act_maxpool_fwd(z, scale_shift, G, act):
+    """x2 training stem: (maxpool3x3s2(act(z * scale + shift)), pos) from the pre-BN planes in one pass"""
+    assert isinstance(z, X2)
+    IMGS, H, W, C = z.shape
+    Ho, Wo = conv_out_hw(H, W, 3, 3, 2, 1)
+    y = X2.empty((IMGS, Ho, Wo, C), z.device)
+    pos = torch.empty((IMGS, Ho, Wo, C), device=z.device, dtype=torch.uint8)
+    call("bn_act_maxpool3x3s2_fwd_x2", z.hi, z.lo, scale_shift, IMGS // G, act, y.hi, y.lo, pos, IMGS, H, W, C, Ho, Wo)
+    return y, pos
+
+
 def maxpool_bwd(x, dy, pos=None, x_shape=None):
     """dx from either the forward input x or the recorded positions (then x may be None, pass x_shape)."""
     IMGS, H, W, C = x_shape if x is None else x.shape

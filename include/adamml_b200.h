@@ -379,6 +379,11 @@ int adamml_bn_apply_x2(const void* z_hi, const void* z_lo, const float* scale_sh
                        const void* res_lo, const void* resz_hi, const void* resz_lo, const float* res_scale_shift,
                        void* out_hi, void* out_lo, long long rows_per_group, int C, int G, int act,
                        cudaStream_t stream);
+/* training stem: maxpool3x3s2(act(bn(z))) from the pre-BN planes in one pass (resnet.py:197-200: bn1, relu, maxpool);
+ * the full-resolution post-activation tensor is never written */
+int adamml_bn_act_maxpool3x3s2_fwd_x2(const void* z_hi, const void* z_lo, const float* scale_shift, int imgs_per_group,
+                                      int act, void* y_hi, void* y_lo, unsigned char* pos, int IMGS, int H, int W,
+                                      int C, int Ho, int Wo, cudaStream_t stream);
 int adamml_maxpool3x3s2_fwd_x2(const void* x_hi, const void* x_lo, void* y_hi, void* y_lo, unsigned char* pos,
                                int IMGS, int H, int W, int C, int Ho, int Wo, cudaStream_t stream);
 int adamml_tpool_fwd_x2(const void* x_hi, const void* x_lo, void* y_hi, void* y_lo, long long V, int Tn, long long E,

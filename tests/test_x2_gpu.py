@@ -156,6 +156,59 @@ def test_dwconv_fwd_stats_x2(cuda, case):
     assert err(sums[..., 1], (zz * zz).sum(1)) < 1e-6
 
 
+@pytest.mark.parametrize("case", [(4, 16, 16, 64, 1), (6, 15, 17, 24, 2), (2, 112, 112, 64, 1)])
+def test_bn_act_maxpool_x2(cuda, case):
+    """training stem: maxpool(act(bn(z))) straight from the pre-BN planes == bn_apply_x2 followed by the x2 max-pool
+    (rounding to the planes is monotonic, so the pooled VALUES are identical; only ties may pick another position)"""
+    from adamml_b200 import ops
+    IMGS, H, W, C, act = case
+    G = 2
+    g = torch.Generator().manual_seed(sum(case))
+    z = split(nhwc(torch.randn(IMGS, C, H, W, generator=g) * 1.5).to(cuda))
+    ss = torch.stack([torch.randn(G, C, generator=g), torch.randn(G, C, generator=g)], dim=-1).to(cuda)
+    y, pos = ops.bn_act_maxpool_fwd(z, ss, G, act)
+    y0, pos0 = ops.maxpool_fwd(ops.bn_apply(z, ss, G, act), want_pos=True)
+    # (same values; a value half a bf16 ulp above its hi plane may be re-split as (hi + ulp, -ulp / 2) by the second pass)
+    assert torch.equal(y.float(), y0.float())
+    assert (pos != pos0).float().mean().item() < 0.02   # ties after rounding (ReLU zeros): any maximal position is valid
+    # positions really point at a maximum of the window
+    o = nchw(ops.bn_apply(z, ss, G, act).float())
+    ref = F.max_pool2d(o, 3, 2, 1)
+    assert err(nchw(y.float()), ref) < X2_TOL
+
+
+def test_resnet_stem_pool_fusion_same_step(cuda):
+    """whole ResNet in the default mode with the stem's BN + ReLU applied inside the max-pool kernel vs bn_apply + pool:
+    identical logits, gradients equal up to tie-breaking among equal maxima"""
+    import importlib
+    from adamml_b200 import engine, ops
+    ResNet = importlib.import_module("adamml_b200.models.resnet").ResNet
+    g = torch.Generator().manual_seed(3)
+    net = ResNet(18, 8, num_classes=17, dropout=0.5, input_channels=3, compute_dtype=ops.PREC_X2).to(cuda).train()
+    x = torch.randn(6, 24, 64, 64, generator=g).to(cuda)
+    mask = torch.empty(6, 512).bernoulli_(0.5, generator=g).div_(0.5).to(cuda)
+    dy = torch.randn(6, 17, generator=g).to(cuda)
+    res = {}
+    old = engine.FUSE_STEM_POOL
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    try:
+        for fuse in (True, False):
+            engine.FUSE_STEM_POOL = fuse
+            net.load_state_dict(sd)
+            net.zero_grad(set_to_none=True)
+            y = net(x, drop_mask=mask)
+            y.backward(dy)
+            res[fuse] = (y.detach().clone(), {k: p.grad.clone() for k, p in net.named_parameters()})
+    finally:
+        engine.FUSE_STEM_POOL = old
+    # (equal pooled values can come as different plane pairs -- (hi, +ulp/2) vs (hi + ulp, -ulp/2) -- and the lo plane
+    # multiplies the fp16 copy of the weights: logits agree to the x2 rounding level, not bit for bit)
+    assert err(res[True][0], res[False][0]) < 2e-4
+    for k, gr in res[True][1].items():
+        a, b = gr.double(), res[False][1][k].double()
+        assert ((a - b).norm() / b.norm().clamp_min(1e-30)).item() < 5e-2, k
+
+
 def test_bn_apply_and_stats_x2(cuda):
     from adamml_b200 import ops
     g = torch.Generator().manual_seed(3)
