@@ -234,11 +234,12 @@ inline int num_sms_ew() {
 }
 
 // out = act( z*scale+shift  [+ res]  [+ res_z*res_scale+res_shift] )
-template <typename T, typename CP, typename MP>
+// RESZ = false: compiled without the BN(downsample) residual branch (its 16 coefficient registers)
+template <typename T, typename CP, typename MP, bool RESZ = true>
 __device__ __forceinline__ void
-bn_apply_rows_body(CP z, const float* __restrict__ ss, CP res, CP res_z, const float* __restrict__ res_ss, MP out,
+bn_apply_rows_body(CP z, const float* __restrict__ ss, CP res, CP res_z_, const float* __restrict__ res_ss, MP out,
                    long long rows_per_group, int C, int cpb, int k, int rows_per_block, int blocks_per_group,
-                   int act) {
+                   int act, unsigned char* __restrict__ mask_bits = nullptr) {
   constexpr int V = VecIO<T>::N;
   const int cl = threadIdx.x % cpb, rl = threadIdx.x / cpb;
   const int c0 = (blockIdx.y * cpb + cl) * V;
@@ -248,14 +249,15 @@ bn_apply_rows_body(CP z, const float* __restrict__ ss, CP res, CP res_z, const f
   const long long r0 = (long long)bg * rows_per_block;
   long long r1 = r0 + rows_per_block;
   if (r1 > rows_per_group) r1 = rows_per_group;
-  float sc[V], sh[V], rsc[V], rsh[V];
+  const CP res_z = RESZ ? res_z_ : CP{};
+  float sc[V], sh[V], rsc[RESZ ? V : 1], rsh[RESZ ? V : 1];
 #pragma unroll
   for (int i = 0; i < V; ++i) {
     const float2 p = *reinterpret_cast<const float2*>(ss + ((long long)g * C + c0 + i) * 2);
     sc[i] = p.x; sh[i] = p.y;
-    rsc[i] = 0.f; rsh[i] = 0.f;
+    if (RESZ) { rsc[i] = 0.f; rsh[i] = 0.f; }
   }
-  if (res_z) {
+  if (RESZ && res_z) {
 #pragma unroll
     for (int i = 0; i < V; ++i) {
       const float2 p = *reinterpret_cast<const float2*>(res_ss + ((long long)g * C + c0 + i) * 2);
@@ -281,14 +283,18 @@ bn_apply_rows_body(CP z, const float* __restrict__ ss, CP res, CP res_z, const f
         float vo[V], vz[V], vr[V];
         VecIO<T>::unpack(qz[u], vz);
         if (res || res_z) VecIO<T>::unpack(qr[u], vr);
+        unsigned m = 0;  // 1-bit activation mask of the 8 channels: what the backward reduction of a residual layer
+                         // reads instead of streaming `out` again
 #pragma unroll
         for (int i = 0; i < V; ++i) {
           float v = fmaf(vz[i], sc[i], sh[i]);
           if (res) v += vr[i];
-          else if (res_z) v += fmaf(vr[i], rsc[i], rsh[i]);
+          else if (RESZ && res_z) v += fmaf(vr[i], rsc[RESZ ? i : 0], rsh[RESZ ? i : 0]);
           vo[i] = act_apply(v, act);
+          m |= act_pass(vo[i], act) ? (1u << i) : 0u;
         }
         VecIO<T>::store(out + base + rr * C, vo);
+        if (V == 8 && mask_bits) mask_bits[(base + rr * C) >> 3] = (unsigned char)m;
       }
     }
   }
@@ -304,12 +310,13 @@ bn_apply_rows_kernel(const T* __restrict__ z, const float* __restrict__ ss, cons
                                       blocks_per_group, act);
 }
 // x2 planes (forward pass of the default precision mode)
-__global__ void __launch_bounds__(EW_THREADS)
+template <bool RESZ>
+__global__ void __launch_bounds__(EW_THREADS, 2)
 bn_apply_rows_x2_kernel(X2CPtr z, const float* __restrict__ ss, X2CPtr res, X2CPtr res_z,
                         const float* __restrict__ res_ss, X2Ptr out, long long rows_per_group, int C, int cpb, int k,
-                        int rows_per_block, int blocks_per_group, int act) {
-  bn_apply_rows_body<x2_t, X2CPtr, X2Ptr>(z, ss, res, res_z, res_ss, out, rows_per_group, C, cpb, k, rows_per_block,
-                                          blocks_per_group, act);
+                        int rows_per_block, int blocks_per_group, int act, unsigned char* __restrict__ mask_bits) {
+  bn_apply_rows_body<x2_t, X2CPtr, X2Ptr, RESZ>(z, ss, res, res_z, res_ss, out, rows_per_group, C, cpb, k,
+                                                rows_per_block, blocks_per_group, act, mask_bits);
 }
 
 // sums[g][c][0] += sum z ; sums[g][c][1] += sum z^2 over x2 planes (depthwise-conv outputs: their BN statistics are
@@ -385,7 +392,7 @@ __global__ void __launch_bounds__(EW_THREADS, 2)
 bn_reduce_rows_kernel(const T* a /*z | dout (may alias gm_out)*/, const T* __restrict__ out, const T* __restrict__ z,
                       const float* __restrict__ mean_invstd, const float* __restrict__ mss,
                       double* __restrict__ sums, T* gm_out, long long rows_per_group, int C, int cpb, int k,
-                      int blocks_per_group, int act) {
+                      int blocks_per_group, int act, const unsigned char* __restrict__ mask_bits = nullptr) {
   constexpr int V = VecIO<T>::N;
   // the wide (fp64) accumulators live in the thread's shared-memory slot, not in registers: that leaves room for
   // 4 independent 16-byte loads per tensor in flight at <= 128 registers (2 CTAs / SM) — the kernel is
@@ -425,6 +432,7 @@ bn_reduce_rows_kernel(const T* a /*z | dout (may alias gm_out)*/, const T* __res
       for (int i = 0; i < V; ++i) { s[i] = 0; q[i] = 0; }
       for (long long r = rc + rl; r < r1; r += (long long)k * UN) {
         typename VecIO<T>::raw qa[UN], qz[UN], qo[UN];
+        unsigned mb[UN];  // 1-bit masks written by the forward bn_apply (residual layers): 1 byte instead of 16
 #pragma unroll
         for (int u = 0; u < UN; ++u) {
           const long long rr = r + (long long)u * k;
@@ -432,7 +440,10 @@ bn_reduce_rows_kernel(const T* a /*z | dout (may alias gm_out)*/, const T* __res
             qa[u] = VecIO<T>::load_raw(a + base + rr * C);
             if (MODE == 1) {
               qz[u] = VecIO<T>::load_raw(z + base + rr * C);
-              if (act != ADAMML_ACT_NONE && !MASKZ) qo[u] = VecIO<T>::load_raw(out + base + rr * C);
+              if (act != ADAMML_ACT_NONE && !MASKZ) {
+                if (V == 8 && mask_bits) mb[u] = mask_bits[(base + rr * C) >> 3];
+                else qo[u] = VecIO<T>::load_raw(out + base + rr * C);
+              }
             }
           }
         }
@@ -448,6 +459,9 @@ bn_reduce_rows_kernel(const T* a /*z | dout (may alias gm_out)*/, const T* __res
                 if (MASKZ) {
 #pragma unroll
                   for (int i = 0; i < V; ++i) vo[i] = fmaf(vz[i], msc[i], msh[i]);
+                } else if (V == 8 && mask_bits) {  // (a value act_pass accepts for ReLU and ReLU6 alike | rejects)
+#pragma unroll
+                  for (int i = 0; i < V; ++i) vo[i] = ((mb[u] >> i) & 1u) ? 1.f : 0.f;
                 } else {
                   VecIO<T>::unpack(qo[u], vo);
                 }
@@ -708,7 +722,7 @@ int adamml_bn_apply(const void* z, const float* scale_shift, const void* res, co
 int adamml_bn_apply_x2(const void* z_hi, const void* z_lo, const float* scale_shift, const void* res_hi,
                        const void* res_lo, const void* resz_hi, const void* resz_lo, const float* res_scale_shift,
                        void* out_hi, void* out_lo, long long rows_per_group, int C, int G, int act,
-                       cudaStream_t stream) {
+                       unsigned char* mask_bits, cudaStream_t stream) {
   ADAMML_REQUIRE(rows_per_group > 0 && C > 0 && G > 0, "bn_apply_x2: empty dims");
   ADAMML_REQUIRE(!resz_hi || res_scale_shift, "bn_apply_x2: res_z needs res_scale_shift");
   ADAMML_REQUIRE(z_hi && z_lo && out_hi && out_lo && (!res_hi == !res_lo) && (!resz_hi == !resz_lo),
@@ -719,9 +733,14 @@ int adamml_bn_apply_x2(const void* z_hi, const void* z_lo, const float* scale_sh
   int rpb, bpg;
   stream_geom(rg, rows_per_group, &rpb, &bpg);
   dim3 vg((unsigned)(bpg * (long long)G), rg.cchunks);
-  bn_apply_rows_x2_kernel<<<vg, rg.threads, 0, stream>>>(x2c(z_hi, z_lo), scale_shift, x2c(res_hi, res_lo),
-                                                        x2c(resz_hi, resz_lo), res_scale_shift, x2m(out_hi, out_lo),
-                                                        rows_per_group, C, rg.cpb, rg.k, rpb, bpg, act);
+  if (resz_hi)
+    bn_apply_rows_x2_kernel<true><<<vg, rg.threads, 0, stream>>>(
+        x2c(z_hi, z_lo), scale_shift, x2c(res_hi, res_lo), x2c(resz_hi, resz_lo), res_scale_shift, x2m(out_hi, out_lo),
+        rows_per_group, C, rg.cpb, rg.k, rpb, bpg, act, mask_bits);
+  else
+    bn_apply_rows_x2_kernel<false><<<vg, rg.threads, 0, stream>>>(
+        x2c(z_hi, z_lo), scale_shift, x2c(res_hi, res_lo), x2c(resz_hi, resz_lo), res_scale_shift, x2m(out_hi, out_lo),
+        rows_per_group, C, rg.cpb, rg.k, rpb, bpg, act, mask_bits);
   return adamml_check_launch("bn_apply_x2");
 }
 
@@ -742,10 +761,12 @@ int adamml_bn_stats_x2(const void* z_hi, const void* z_lo, double* sums, long lo
 
 int adamml_bn_bwd_reduce(const void* dout, const void* out, const void* z, const float* mean_invstd,
                          const float* mask_scale_shift, double* sums, void* gm_out, long long rows_per_group, int C,
-                         int G, int act, int dtype, cudaStream_t stream) {
+                         int G, int act, int dtype, const unsigned char* mask_bits, cudaStream_t stream) {
   ADAMML_REQUIRE(rows_per_group > 0 && C > 0 && G > 0, "bn_bwd_reduce: empty dims");
-  ADAMML_REQUIRE(act == ADAMML_ACT_NONE || out || mask_scale_shift,
-                 "bn_bwd_reduce: activation mask needs the saved output or the forward scale/shift");
+  ADAMML_REQUIRE(act == ADAMML_ACT_NONE || out || mask_scale_shift || mask_bits,
+                 "bn_bwd_reduce: activation mask needs the saved output, its 1-bit mask or the forward scale/shift");
+  ADAMML_REQUIRE(!mask_bits || (dtype == ADAMML_BF16 && C % 8 == 0),
+                 "bn_bwd_reduce: 1-bit masks come with bf16 tensors of C %% 8 == 0");
   cudaMemsetAsync(sums, 0, sizeof(double) * (size_t)G * C * 2, stream);
   ADAMML_DISPATCH_DTYPE(dtype, T, {
     if (vec_ok<T>(C, dout, out, z)) {
@@ -763,10 +784,11 @@ int adamml_bn_bwd_reduce(const void* dout, const void* out, const void* z, const
       else
         bn_reduce_rows_kernel<T, 1, false><<<vg, rg.threads, sm, stream>>>((const T*)dout, (const T*)out, (const T*)z,
                                                                            mean_invstd, nullptr, sums, (T*)gm_out,
-                                                                           rows_per_group, C, rg.cpb, rg.k, bpg, act);
+                                                                           rows_per_group, C, rg.cpb, rg.k, bpg, act,
+                                                                           mask_bits);
     } else {
       ADAMML_REQUIRE(act == ADAMML_ACT_NONE || out, "bn_bwd_reduce: ragged channel count needs the saved output");
-      ADAMML_REQUIRE(!gm_out, "bn_bwd_reduce: gm_out needs a vectorisable channel count");
+      ADAMML_REQUIRE(!gm_out && !mask_bits, "bn_bwd_reduce: gm_out / mask_bits need a vectorisable channel count");
       int bpg = ceil_div(rows_per_group, ROWS_PER_BLOCK);
       dim3 grid((unsigned)(bpg * (long long)G), ceil_div(C, 32));
       dim3 block(32, 8);

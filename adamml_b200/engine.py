@@ -27,6 +27,8 @@ RECOMPUTE = _os.environ.get("ADAMML_B200_RECOMPUTE", "0") != "0"
 DW_FUSE_PRE = _os.environ.get("ADAMML_B200_DW_FUSE_PRE", "1") != "0"
 # training stem of the ResNets: BN + ReLU applied inside the max-pool kernel (Exec.cba_maxpool); =0 keeps bn_apply + pool
 FUSE_STEM_POOL = _os.environ.get("ADAMML_B200_FUSE_STEM_POOL", "1") != "0"
+# residual layers keep a 1-bit ReLU mask of their output for the BatchNorm backward reduction (=0: it re-reads `out`)
+MASK_BITS = _os.environ.get("ADAMML_B200_MASK_BITS", "1") != "0"
 
 
 class _ShapeOnly:
@@ -101,8 +103,17 @@ class Exec:
                 return out
         x_src = getattr(x, "_adamml_src", None) if self.save else None  # x is a recomputable activation (see below)
         rec = self.conv_bn_stats(x, conv, bn)
+        # residual layers: the backward reduction needs the activation mask of the OUTPUT (it cannot be recomputed from
+        # z alone); bn_apply writes it as 1 bit per element so that pass does not stream the 16-bit output again
+        bits = None
+        z_ = rec["z"]
+        if (MASK_BITS and self.save and self.x2 and act != ACT_NONE and (res is not None or res_rec is not None)
+                and isinstance(z_, ops.X2) and z_.shape[-1] % 8 == 0):
+            bits = torch.empty((z_.hi.numel() // 8,), device=z_.hi.device, dtype=torch.uint8)
         out = ops.bn_apply(rec["z"], rec["ss"], self.G, act, res=res,
-                           res_z=res_rec["z"] if res_rec else None, res_ss=res_rec["ss"] if res_rec else None)
+                           res_z=res_rec["z"] if res_rec else None, res_ss=res_rec["ss"] if res_rec else None,
+                           mask_bits=bits)
+        rec["mask_bits"] = bits
         # recompute mode: the output of a layer without residual input is act(z * scale + shift) of tensors the tape
         # keeps anyway, so it is not saved; a consumer that needs it for its weight gradient rebuilds it (bf16)
         lazy = (self.save and self.recompute and res is None and res_rec is None
@@ -263,7 +274,9 @@ class Exec:
             sums = ops.bn_sums_from_out(pre, rec["ss"], mi, out=sums_out)
             out, act, want_dres, mask_ss = None, ACT_NONE, False, None
         else:
-            sums = ops.bn_bwd_reduce(dout, out, z, mi, G, act, mask_ss=mask_ss, gm_inplace=inplace, sums_out=sums_out)
+            bits = rec.get("mask_bits") if (out is not None and out is rec.get("out")) else None
+            sums = ops.bn_bwd_reduce(dout, out, z, mi, G, act, mask_ss=mask_ss, gm_inplace=inplace, sums_out=sums_out,
+                                     mask_bits=bits)
         if inplace:
             rec["dout_masked"] = True
             out, act, want_dres = None, ACT_NONE, False

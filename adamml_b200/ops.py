@@ -705,16 +705,21 @@ def bn_finalize(sums, gamma, beta, running_mean, running_var, count, momentum, e
     return mean_invstd, scale_shift
 
 
-def bn_apply(z, scale_shift, G, act, res=None, res_z=None, res_ss=None, out=None):
+def bn_apply(z, scale_shift, G, act, res=None, res_z=None, res_ss=None, out=None, mask_bits=None):
+    """mask_bits (x2 only): uint8 [rows, C // 8] that receives the 1-bit activation mask of every output element
+    (read by bn_bwd_reduce instead of the saved output)."""
     C = z.shape[-1]
     rows = z.numel() // C
     if isinstance(z, X2):
         if out is None:
             out = X2.empty(z.shape, z.device)
+        if mask_bits is not None:
+            assert mask_bits.dtype == torch.uint8 and mask_bits.numel() == rows * (C // 8) and C % 8 == 0
         call("bn_apply_x2", z.hi, z.lo, scale_shift, res.hi if res is not None else None,
              res.lo if res is not None else None, res_z.hi if res_z is not None else None,
-             res_z.lo if res_z is not None else None, res_ss, out.hi, out.lo, rows // G, C, G, act)
+             res_z.lo if res_z is not None else None, res_ss, out.hi, out.lo, rows // G, C, G, act, mask_bits)
         return out
+    assert mask_bits is None
     if out is None:
         out = torch.empty_like(z)
     call("bn_apply", z, scale_shift, res, res_z, res_ss, out, rows // G, C, G, act, dtype_code(z.dtype))
@@ -733,15 +738,15 @@ def vec_channels(t):
     return t.shape[-1] % (8 if t.dtype == torch.bfloat16 else 4) == 0
 
 
-def bn_bwd_reduce(dout, out, z, mean_invstd, G, act, mask_ss=None, gm_inplace=False, sums_out=None):
+def bn_bwd_reduce(dout, out, z, mean_invstd, G, act, mask_ss=None, gm_inplace=False, sums_out=None, mask_bits=None):
     """mask_ss: forward scale/shift [G,C,2] of a layer without residual input -> the ReLU/ReLU6 mask is recomputed
     from z and `out` is not read.  gm_inplace: dout is overwritten with the masked gradient dout * act'(out), which
     is also the gradient of a residual input; the following bn_bwd_apply then runs with act = NONE."""
     C = z.shape[-1]
     rows = z.numel() // C
     sums = sums_out if sums_out is not None else torch.empty((G, C, 2), device=z.device, dtype=torch.float64)
-    call("bn_bwd_reduce", dout, out, z, mean_invstd, _mask_ss(z, mask_ss), sums, dout if gm_inplace else None,
-         rows // G, C, G, act, dtype_code(z.dtype))
+    call("bn_bwd_reduce", dout, None if mask_bits is not None else out, z, mean_invstd, _mask_ss(z, mask_ss), sums,
+         dout if gm_inplace else None, rows // G, C, G, act, dtype_code(z.dtype), mask_bits)
     return sums
 
 

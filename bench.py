@@ -271,7 +271,7 @@ def kernel_work(name, a):
     if name == "bn_bwd_reduce":   # (dout, out, z, mi, mask_ss, sums, gm_out, rpg, C, G, act, dtype)
         n = a[7] * a[8] * a[9]
         return 0.0, (2 if a[11] == 1 else 4) * n * (2.0 + (1 if (a[10] and T(1) and not T(4)) else 0)
-                                                    + (1 if T(6) else 0))
+                                                    + (1 if T(6) else 0) + (1.0 / 16 if len(a) > 12 and T(12) else 0))
     if name == "bn_bwd_apply":    # (dout, out, z, mi, gamma, mask_ss, sums, dz, dres, rpg, C, G, count, act, training, dtype)
         n = a[9] * a[10] * a[11]
         need_z = T(7) or (T(5) and a[13])
@@ -297,7 +297,7 @@ def kernel_work(name, a):
         return 2.0 * I * Ho * Wo * Co * 16 * Cs, 4.0 * (I * Hs * Wp * Cs + I * Ho * Wo * Co)
     if name == "bn_apply_x2":
         n = a[10] * a[11] * a[12]
-        return 0.0, 4.0 * n * (2.0 + (1 if T(3) or T(5) else 0))
+        return 0.0, 4.0 * n * (2.0 + (1 if T(3) or T(5) else 0)) + (n / 8.0 if len(a) > 14 and T(14) else 0.0)
     if name == "bn_stats_x2":
         return 0.0, 4.0 * float(a[3] * a[4] * a[5])
     if name == "dwconv_fwd_x2":

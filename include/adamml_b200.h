@@ -185,7 +185,9 @@ int adamml_bn_apply(const void* z, const float* scale_shift, const void* res, co
  * bn_bwd_apply (and the residual branch, whose gradient IS gm) run with act = NONE and never read `out`. */
 int adamml_bn_bwd_reduce(const void* dout, const void* out, const void* z, const float* mean_invstd,
                          const float* mask_scale_shift, double* sums, void* gm_out, long long rows_per_group, int C,
-                         int G, int act, int dtype, cudaStream_t stream);
+                         int G, int act, int dtype, const unsigned char* mask_bits, cudaStream_t stream);
+/* (mask_bits: optional [rows][C/8] bytes written by adamml_bn_apply_x2 -- bit i of a byte = activation passes the
+ * gradient at channel 8*j + i; when given, `out` is not read: 1 bit instead of 16 per element on residual layers) */
 int adamml_bn_bwd_apply(const void* dout, const void* out, const void* z, const float* mean_invstd,
                         const float* gamma, const float* mask_scale_shift, const double* sums, void* dz, void* dres,
                         long long rows_per_group, int C, int G, double count, int act, int training, int dtype,
@@ -378,7 +380,7 @@ int adamml_bn_stats_x2(const void* z_hi, const void* z_lo, double* sums, long lo
 int adamml_bn_apply_x2(const void* z_hi, const void* z_lo, const float* scale_shift, const void* res_hi,
                        const void* res_lo, const void* resz_hi, const void* resz_lo, const float* res_scale_shift,
                        void* out_hi, void* out_lo, long long rows_per_group, int C, int G, int act,
-                       cudaStream_t stream);
+                       unsigned char* mask_bits, cudaStream_t stream);
 /* training stem: maxpool3x3s2(act(bn(z))) from the pre-BN planes in one pass (resnet.py:197-200: bn1, relu, maxpool);
  * the full-resolution post-activation tensor is never written */
 int adamml_bn_act_maxpool3x3s2_fwd_x2(const void* z_hi, const void* z_lo, const float* scale_shift, int imgs_per_group,

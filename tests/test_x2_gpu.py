@@ -209,6 +209,39 @@ def test_resnet_stem_pool_fusion_same_step(cuda):
         assert ((a - b).norm() / b.norm().clamp_min(1e-30)).item() < 5e-2, k
 
 
+@pytest.mark.parametrize("act", [1, 2])
+@pytest.mark.parametrize("C", [64, 24, 1024])
+def test_bn_mask_bits(cuda, act, C):
+    """residual layers: bn_apply_x2 writes a 1-bit activation mask per output element; bn_bwd_reduce with the bits
+    (instead of the saved output) gives the same sums and the same in-place masked gradient"""
+    from adamml_b200 import ops
+    G, rows = 2, 515
+    g = torch.Generator().manual_seed(C + act)
+    z = split((torch.randn(G * rows, 1, 1, C, generator=g) * 2).to(cuda))
+    res = split((torch.randn(G * rows, 1, 1, C, generator=g) * 2).to(cuda))
+    ss = torch.stack([torch.rand(G, C, generator=g) + 0.5, torch.randn(G, C, generator=g)], dim=-1).to(cuda)
+    mi = torch.stack([torch.randn(G, C, generator=g) * 0.3, torch.rand(G, C, generator=g) + 0.5], dim=-1).to(cuda)
+    bits = torch.full((G * rows * C // 8,), 0xAA, device=cuda, dtype=torch.uint8)
+    out = ops.bn_apply(z, ss, G, act, res=res, mask_bits=bits)
+    out0 = ops.bn_apply(z, ss, G, act, res=res)
+    assert torch.equal(out.hi, out0.hi) and torch.equal(out.lo, out0.lo)
+    o = out.float().view(-1, C // 8, 8)
+    keep = ((o > 0) & (o < 6)) if act == 2 else (o > 0)
+    want = (keep.to(torch.int32) << torch.arange(8, device=cuda, dtype=torch.int32)).sum(-1).to(torch.uint8).view(-1)
+    assert torch.equal(bits, want)
+    dout = torch.randn(G * rows, 1, 1, C, generator=g).to(cuda).bfloat16()
+    d1, d2 = dout.clone(), dout.clone()
+    # (reference: the mask taken from the x2 value, as the bits are; the hi plane alone differs only where it rounds to 6)
+    s2 = ops.bn_bwd_reduce(d2, out.hi, z.hi, mi, G, act, gm_inplace=True)
+    s1 = ops.bn_bwd_reduce(d1, None, z.hi, mi, G, act, gm_inplace=True, mask_bits=bits)
+    gm_want = torch.where(keep.view(dout.shape), dout, torch.zeros_like(dout))
+    assert torch.equal(d1, gm_want)
+    same = (d1 == d2).float().mean().item()
+    assert same > 0.995
+    if same == 1.0:
+        assert err(s1, s2) < 1e-12
+
+
 def test_bn_apply_and_stats_x2(cuda):
     from adamml_b200 import ops
     g = torch.Generator().manual_seed(3)
