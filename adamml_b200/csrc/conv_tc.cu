@@ -817,11 +817,18 @@ int launch_tc_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
   long long tiles = m_blks * n_blks;
   const int sms = num_sms() * Cfg::CTAS_PER_SM;
   int grid = (int)(tiles < sms ? tiles : sms);
-  // column-block pinning (TileSched): x2 layers with several column blocks whose weight block fits the ring
-  static const bool pin_on = []() { const char* e = getenv("ADAMML_B200_TC_PIN"); return !(e && e[0] == '0'); }();
+  // column-block pinning (TileSched): x2 layers with several column blocks -- when the weight block fits the ring it
+  // stays resident; with fused statistics pinning pays even when it does not: a CTA that changes its column block
+  // every tile flushes its statistics every tile (shared fp64 CAS atomics + 128 global fp64 atomics in the epilogue
+  // chain; ncu on 141 k x 1024 x 256: 61 % of the shared-memory wavefronts were conflict replays of that flush,
+  // 0.84 -> 0.52 ms pinned; 1x1/s2 256 -> 512 at 56x56: 2.90 -> 1.89 ms), a pinned CTA only when the BatchNorm group
+  // changes.  (Column-block counts that divide the grid -- 2, 4 -- never changed block and are unaffected.)
+  // ADAMML_B200_TC_PIN=1: resident case only, 0: off.
+  static const int pin_mode = []() { const char* e = getenv("ADAMML_B200_TC_PIN"); return e ? atoi(e) : 2; }();
   const int num_kb = CONV ? geo.ntaps * geo.kb_per_tap : (K + BLOCK_K - 1) / BLOCK_K;
   int pin_n = 0;
-  if (X2 && pin_on && n_blks > 1 && n_blks <= sms && (Cfg::STAGES % num_kb) == 0 && m_blks >= 4LL * (sms / n_blks)) {
+  const bool pin_fit = (Cfg::STAGES % num_kb) == 0 || (pin_mode >= 2 && stats != nullptr);
+  if (X2 && pin_mode > 0 && n_blks > 1 && n_blks <= sms && pin_fit && m_blks >= 4LL * (sms / n_blks)) {
     pin_n = 1;
     grid = (sms / n_blks) * n_blks;
   }

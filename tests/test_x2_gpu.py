@@ -52,7 +52,10 @@ def x2_tol(K):
 # register-resident statistics: group boundaries inside a tile, > 32 tiles per CTA and group, ragged last tile)
 @pytest.mark.parametrize("M,N,K", [(1000, 64, 64), (777, 16, 96), (4096, 96, 16), (513, 128, 256), (2048, 256, 64),
                                    (300, 2048, 512), (129, 24, 144), (640, 1280, 320), (40000, 96, 16),
-                                   (80002, 256, 64), (76800, 64, 128), (1515520, 64, 64)])
+                                   (80002, 256, 64), (76800, 64, 128), (1515520, 64, 64),
+                                   # several column blocks whose weight block does NOT fit the ring: pinned for the
+                                   # statistics alone (one flush per BatchNorm group instead of one per tile)
+                                   (20002, 1024, 256), (9000, 2048, 512)])
 def test_tc_gemm_x2(cuda, M, N, K):
     from adamml_b200 import ops
     g = torch.Generator().manual_seed(M + N + K)
@@ -84,6 +87,9 @@ def test_tc_gemm_x2(cuda, M, N, K):
     (2, 28, 28, 128, 128, 3, 2, 1),
     (2, 14, 14, 128, 256, 1, 2, 0),
     (2, 7, 7, 512, 512, 3, 1, 1),
+    # enough row blocks for column-block pinning (non-resident weights): 3x3 with 2 column blocks, 1x1/s2 with 8
+    (64, 28, 28, 128, 128, 3, 1, 1),
+    (48, 28, 28, 128, 512, 1, 2, 0),
 ])
 def test_tc_conv_x2(cuda, case):
     from adamml_b200 import ops
