@@ -106,7 +106,15 @@ struct TcCfg {
   static constexpr int OUT_PLANE_BYTES = SUBTILES * BLOCK_M * 128;
   static constexpr int OUT_TILE_BYTES = PLANES * OUT_PLANE_BYTES;
   static constexpr int OUT_BYTES = OUT_BUFS * OUT_TILE_BYTES;
-  static constexpr int TMEM_COLS = 2 * BLOCK_N;
+  // WIDE (deep-reduction x2 variants): the three bf16 weight planes b1 | b2 | b3 lie back to back in a stage, so
+  // x_hi multiplies them as ONE 192-column MMA into three accumulator column groups and x_lo * fp16(w) goes into a
+  // fourth; the epilogue adds the four groups (small terms first).  Per K step the tensor core then reads
+  // (4 + 6) + (4 + 2) = 16 KB of operands from shared memory instead of 4 x (4 + 2) = 24 KB: these kernels are bound
+  // by the SM's 128 B/clk shared-memory port (TMA fills + operand reads), not by the MMA rate (ncu: tensor pipe 42 %
+  // active on the 3x3 64 -> 64 layer, MMA warp never waiting for loads).
+  static constexpr bool WIDE = X2 >= 2;
+  static constexpr int ACC_COLS = WIDE ? 4 * BLOCK_N : BLOCK_N;  // TMEM columns of one accumulator stage
+  static constexpr int TMEM_COLS = 2 * ACC_COLS;
   static constexpr int RED_BYTES = BLOCK_N * 2 * 8;  // per-CTA fp64 column sums, combined before the global atomics
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + OUT_BYTES + 1024 /*align slack*/ + 1024 /*barriers*/ + RED_BYTES;
 };
@@ -325,7 +333,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int ti = 0; sched.get(ti, m_blk_, n_blk_); ++ti) {
       ctl_wait<Cfg::BACKOFF>(&tmem_empty[acc], acc_phase ^ 1);
       tc_fence_after();
-      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * Cfg::ACC_COLS);
       for (int kb = 0; kb < num_kb; ++kb) {
         ctl_wait<Cfg::BACKOFF>(&full_bar[stage], phase);
         tc_fence_after();
@@ -339,14 +347,27 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint64_t db2 = make_smem_desc_sw128(sb + Cfg::B_BYTES);
             const uint64_t db3 = make_smem_desc_sw128(sb + 2 * Cfg::B_BYTES);
             const uint64_t dbf = make_smem_desc_sw128(sb + 3 * Cfg::B_BYTES);
+            if (Cfg::WIDE && !(pin_n & 8)) {
+              // x_hi * [b1 | b2 | b3] -> columns [0, 3 BLOCK_N), x_lo * fp16(w) -> columns [3 BLOCK_N, 4 BLOCK_N)
+              const uint32_t idesc_w = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((3 * BLOCK_N) >> 3) << 17) |
+                                       ((uint32_t)(BLOCK_M >> 4) << 24);
 #pragma unroll
-            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-              const uint64_t o = (uint64_t)(k * 2);
-              // small terms first: lo * fp16(w), hi * b3, hi * b2, hi * b1
-              umma_bf16(tmem_d, da_lo + o, dbf + o, idesc_f16, (kb > 0 || k > 0) ? 1u : 0u);
-              umma_bf16(tmem_d, da + o, db3 + o, idesc, 1u);
-              umma_bf16(tmem_d, da + o, db2 + o, idesc, 1u);
-              umma_bf16(tmem_d, da + o, db + o, idesc, 1u);
+              for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                const uint64_t o = (uint64_t)(k * 2);
+                const uint32_t accum = (kb > 0 || k > 0) ? 1u : 0u;
+                umma_bf16(tmem_d + 3 * BLOCK_N, da_lo + o, dbf + o, idesc_f16, accum);
+                umma_bf16(tmem_d, da + o, db + o, idesc_w, accum);
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                const uint64_t o = (uint64_t)(k * 2);
+                // small terms first: lo * fp16(w), hi * b3, hi * b2, hi * b1
+                umma_bf16(tmem_d, da_lo + o, dbf + o, idesc_f16, (kb > 0 || k > 0) ? 1u : 0u);
+                umma_bf16(tmem_d, da + o, db3 + o, idesc, 1u);
+                umma_bf16(tmem_d, da + o, db2 + o, idesc, 1u);
+                umma_bf16(tmem_d, da + o, db + o, idesc, 1u);
+              }
             }
           } else {
 #pragma unroll
@@ -534,11 +555,27 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int chunk = chalf * CHUNKS_PER_WARP; chunk < (chalf + 1) * CHUNKS_PER_WARP; ++chunk) {
         const int col0 = n_blk * BLOCK_N + chunk * 32;
         if (col0 >= Ncols) break;  // warp-uniform
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + chunk * 32), r);
         float v[32];
+        const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * Cfg::ACC_COLS + chunk * 32);
+        if (Cfg::WIDE && !(pin_n & 8)) {
+          // four accumulator groups: ((x_lo * f + x_hi * b3) + x_hi * b2) + x_hi * b1
+          uint32_t r0[32], r1[32];
+          tmem_ld_32x32b_x32_nowait(tacc + 3 * BLOCK_N, r0);
+          tmem_ld_32x32b_x32_nowait(tacc + 2 * BLOCK_N, r1);
+          tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]) + __uint_as_float(r1[j]);
+          tmem_ld_32x32b_x32_nowait(tacc + BLOCK_N, r0);
+          tmem_ld_32x32b_x32_nowait(tacc, r1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = (v[j] + __uint_as_float(r0[j])) + __uint_as_float(r1[j]);
+        } else {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(tacc, r);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        }
         if (!row_ok) {  // edge tiles only: rows outside the tensor are staged as zeros (statistics sum them)
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = 0.f;
@@ -834,6 +871,9 @@ int launch_tc_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
   }
   static const bool nofence = []() { const char* e = getenv("ADAMML_B200_TC_NOFENCE"); return e && e[0] == '1'; }();
   if (nofence) pin_n |= 2;
+  // (bit 3: the WIDE variants fall back to four 64-column MMAs per K step -- A/B experiments)
+  static const bool nowide = []() { const char* e = getenv("ADAMML_B200_X2_WIDE"); return e && e[0] == '0'; }();
+  if (nowide) pin_n |= 8;
   EpiSpec e = epi;
   if (EPI && e.ss && !stats) e.live = adamml_live_limit(CONV ? (long long)geo.IMGS : M);  // inference launches only
   kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmD, tmAdd, cm, geo, x2, (const bf16*)addend, M,
