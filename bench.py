@@ -479,6 +479,22 @@ def run_gpu_arm(a):
         prof = sorted(agg.items(), key=lambda kv: -kv[1][0])
 
     run_step = lambda: step(dx, dy)  # noqa: E731
+    if not use_graph:
+        # eager launches: the host enqueues step i+1 only when step i has finished on the device -- what the
+        # reference's loop does by reading loss.item() every step (utils/utils.py:385-388).  Unbounded run-ahead keeps
+        # the tapes of several steps alive at 119 GiB each, the caching allocator falls into its free-and-retry path
+        # (device-wide syncs) and the step measured 324 ms instead of the 290 ms of the same launches under the
+        # per-step loss read (e2e).
+        done_ev = []
+
+        def run_step():
+            if len(done_ev) >= 1:
+                done_ev.pop(0).synchronize()
+            loss = step(dx, dy)
+            ev = torch.cuda.Event()
+            ev.record()
+            done_ev.append(ev)
+            return loss
     if use_graph:
         from adamml_b200.graph import GraphedTrainStep, step_guard
         p_opt.zero_grad(set_to_none=True)
