@@ -118,12 +118,16 @@ class AdaMML(nn.Module):
         if drop_masks is None:
             drop_masks = self.main_net.draw_drop_masks(S, N, dev)
         m_jobs = self.main_net.backbone_jobs(m_x, S, drop_masks)
-        # every backbone of the step (policy + main) is independent until the policy head / late fusion
-        outs = run_backbones_parallel(p_jobs + m_jobs)
+        # every backbone of the step (policy + main) is independent until the policy head / late fusion.  The main
+        # backbones are enqueued FIRST: their millisecond-scale kernels keep the device busy while the host issues the
+        # hundreds of microsecond-scale launches of the policy nets (eager mode; inside a captured graph the order
+        # is irrelevant)
+        outs = run_backbones_parallel(m_jobs + p_jobs)
+        n_main = len(m_jobs)
         del p_x, m_x, p_jobs, m_jobs
         if not self.rng_policy:
-            decisions, _ = self.policy_net(None, S, N, expo=expo, feats=outs[:len(self.policy_net.joint_net.nets)])
-            outs = outs[len(self.policy_net.joint_net.nets):]
+            decisions, _ = self.policy_net(None, S, N, expo=expo, feats=outs[n_main:])
+        outs = outs[:n_main]
         logits = self.main_net(None, decisions, S, N, per_mod=outs)
         return logits, decisions.permute(2, 0, 1)
 
