@@ -221,25 +221,21 @@ maxpool_fwd_vec_kernel(const T* __restrict__ x, T* __restrict__ y, unsigned char
                        int W, int C, int Ho, int Wo, LiveLimit live) {
   maxpool_fwd_vec_body<T, const T*, T*>(x, y, pos, IMGS, H, W, C, Ho, Wo, live);
 }
-__global__ void __launch_bounds__(256)
-maxpool_fwd_vec_x2_kernel(X2CPtr x, X2Ptr y, unsigned char* __restrict__ pos, int IMGS, int H, int W, int C, int Ho,
-                          int Wo, LiveLimit live) {
-  maxpool_fwd_vec_body<x2_t, X2CPtr, X2Ptr>(x, y, pos, IMGS, H, W, C, Ho, Wo, live);
-}
-// Training stem: one window ROW (3 taps = 6 x 16 bytes) in flight per thread instead of the whole window, so the kernel
-// fits 2-3 blocks per SM without spilling (the whole-window body needs 135 registers -> ONE 256-thread block per SM,
-// ncu: 12 % warps active, 6.46 ms for 12.1 GB = 29 % of the copy peak).
-template <int MINB>
-__global__ void __launch_bounds__(256, MINB)  // (IMGS * Ho < 2^31 rows, Wo * C / 8 < 2^31: checked by the launcher)
-bn_act_maxpool_fwd_vec_x2_kernel(X2CPtr z, X2Ptr y, unsigned char* __restrict__ pos, int IMGS, int H, int W, int C,
-                                 int Ho, int Wo, PreBN pre) {
-  // one output row (img, ho) per block: the row decode is block-uniform and 32-bit, the per-thread decode one small
-  // division -- with a flat index the five 64-bit divisions cost as many instructions as the nine taps
+// x2 max-pool (plain, or the training stem's maxpool(act(z * scale + shift))): one window ROW (3 taps = 6 x 16 bytes) in
+// flight per thread instead of the whole window, so the kernel fits 3 blocks per SM without spilling (the whole-window
+// body needs 135 registers -> ONE 256-thread block per SM; ncu: 12 % warps active, 6.46 ms for 12.1 GB at the N=72 stem
+// shape), and one output row (img, ho) per block: the row decode is block-uniform and 32-bit, the per-thread decode one
+// small division -- with a flat index the five 64-bit divisions cost as many instructions as the nine taps.
+// 6.46 -> 3.11 ms.  (IMGS * Ho < 2^31 rows, Wo * C / 8 < 2^31: checked by the launcher)
+__global__ void __launch_bounds__(256, 3)
+maxpool_rows_x2_kernel(X2CPtr z, X2Ptr y, unsigned char* __restrict__ pos, int IMGS, int H, int W, int C, int Ho, int Wo,
+                       LiveLimit live, PreBN pre) {
   constexpr int V = 8;
   const int cvecs = C / V;
   const unsigned rowid = blockIdx.x;
   const int ho = (int)(rowid % (unsigned)Ho);
   const long long img = rowid / (unsigned)Ho;
+  if (img >= live_count(live, IMGS)) return;  // device-side work limit (inference with skipping)
   const unsigned it = threadIdx.x + blockIdx.y * blockDim.x;
   if (it >= (unsigned)(Wo * cvecs)) return;
   const int wo = (int)(it / (unsigned)cvecs);
@@ -248,8 +244,8 @@ bn_act_maxpool_fwd_vec_x2_kernel(X2CPtr z, X2Ptr y, unsigned char* __restrict__ 
   float best[V], sc[V], sh[V];
   unsigned bp = 0;  // 4 bits per channel
 #pragma unroll
-  for (int i = 0; i < V; ++i) best[i] = -INFINITY;
-  {
+  for (int i = 0; i < V; ++i) { best[i] = -INFINITY; sc[i] = 1.f; sh[i] = 0.f; }
+  if (pre.ss) {
     const float* p = pre.ss + ((img / pre.imgs_per_group) * C + cv * V) * 2;
 #pragma unroll
     for (int i = 0; i < V; i += 2) {
@@ -278,7 +274,7 @@ bn_act_maxpool_fwd_vec_x2_kernel(X2CPtr z, X2Ptr y, unsigned char* __restrict__ 
         VecIO<x2_t>::unpack(q[s_], v);
 #pragma unroll
         for (int i = 0; i < V; ++i) {
-          const float a = act_apply(fmaf(v[i], sc[i], sh[i]), pre.act);
+          const float a = pre.ss ? act_apply(fmaf(v[i], sc[i], sh[i]), pre.act) : v[i];
           if (a > best[i] || a != a) {
             best[i] = a;
             bp = (bp & ~(0xFu << (4 * i))) | ((unsigned)(r * 3 + s_) << (4 * i));
@@ -288,10 +284,25 @@ bn_act_maxpool_fwd_vec_x2_kernel(X2CPtr z, X2Ptr y, unsigned char* __restrict__ 
     }
   }
   VecIO<x2_t>::store(y + pix * C + cv * V, best);
-  uint2 pk;
-  pk.x = (bp & 0xFu) | ((bp & 0xF0u) << 4) | ((bp & 0xF00u) << 8) | ((bp & 0xF000u) << 12);
-  pk.y = ((bp >> 16) & 0xFu) | ((bp >> 12) & 0xF00u) | ((bp >> 8) & 0xF0000u) | ((bp >> 4) & 0xF000000u);
-  *reinterpret_cast<uint2*>(pos + pix * C + cv * V) = pk;
+  if (pos) {
+    uint2 pk;
+    pk.x = (bp & 0xFu) | ((bp & 0xF0u) << 4) | ((bp & 0xF00u) << 8) | ((bp & 0xF000u) << 12);
+    pk.y = ((bp >> 16) & 0xFu) | ((bp >> 12) & 0xF00u) | ((bp >> 8) & 0xF0000u) | ((bp >> 4) & 0xF000000u);
+    *reinterpret_cast<uint2*>(pos + pix * C + cv * V) = pk;
+  }
+}
+
+int launch_maxpool_rows_x2(X2CPtr z, X2Ptr y, unsigned char* pos, int IMGS, int H, int W, int C, int Ho, int Wo,
+                           LiveLimit live, PreBN pre, cudaStream_t stream) {
+  ADAMML_REQUIRE((long long)IMGS * Ho < (1LL << 31) && (long long)Wo * (C / 8) < (1LL << 31), "maxpool_x2: too large");
+  // threads of one output row, split evenly over as few blocks (<= 256 threads, whole warps) as it takes
+  const int per_row = Wo * (C / 8);
+  const int parts = (per_row + 255) / 256;
+  const int threads = (((per_row + parts - 1) / parts) + 31) / 32 * 32;
+  ADAMML_REQUIRE(parts <= 65535, "maxpool_x2: row too wide");
+  maxpool_rows_x2_kernel<<<dim3((unsigned)((long long)IMGS * Ho), (unsigned)parts), threads, 0, stream>>>(
+      z, y, pos, IMGS, H, W, C, Ho, Wo, live, pre);
+  return ADAMML_OK;
 }
 
 // gather backward from recorded positions, one thread per 2x2 input quad (rows 2m, 2m+1; cols 2n, 2n+1) and channel
@@ -604,10 +615,10 @@ int adamml_maxpool3x3s2_fwd_x2(const void* x_hi, const void* x_lo, void* y_hi, v
   ADAMML_REQUIRE(Ho == (H + 2 - 3) / 2 + 1 && Wo == (W + 2 - 3) / 2 + 1, "maxpool: bad Ho/Wo");
   ADAMML_REQUIRE(pool_vec_ok<bf16>(C, x_hi, x_lo, y_hi) && pool_vec_ok<bf16>(C, y_lo) && ((uintptr_t)pos % 8) == 0,
                  "maxpool_fwd_x2: needs C %% 8 == 0 and aligned planes");
-  const long long tv = (long long)IMGS * Ho * Wo * (C / 8);
-  maxpool_fwd_vec_x2_kernel<<<(unsigned)((tv + 255) / 256), 256, 0, stream>>>(
-      x2c(x_hi, x_lo), x2m(y_hi, y_lo), pos, IMGS, H, W, C, Ho, Wo,
-      pos ? LiveLimit{nullptr, 0} : adamml_live_limit(IMGS));
+  const int rc = launch_maxpool_rows_x2(x2c(x_hi, x_lo), x2m(y_hi, y_lo), pos, IMGS, H, W, C, Ho, Wo,
+                                        pos ? LiveLimit{nullptr, 0} : adamml_live_limit(IMGS),
+                                        PreBN{nullptr, 1, ADAMML_ACT_NONE}, stream);
+  if (rc) return rc;
   return adamml_check_launch("maxpool_fwd_x2");
 }
 
@@ -621,26 +632,9 @@ int adamml_bn_act_maxpool3x3s2_fwd_x2(const void* z_hi, const void* z_lo, const 
   ADAMML_REQUIRE(pool_vec_ok<bf16>(C, z_hi, z_lo, y_hi) && pool_vec_ok<bf16>(C, y_lo) && ((uintptr_t)pos % 8) == 0 &&
                      ((uintptr_t)scale_shift % 16) == 0,
                  "bn_act_maxpool_fwd_x2: needs C %% 8 == 0 and aligned planes");
-  const long long tv = (long long)IMGS * Ho * Wo * (C / 8);
-  static const int minb = []() { const char* e = getenv("ADAMML_B200_POOL_MINB"); return e ? atoi(e) : 3; }();
-  (void)tv;
-  ADAMML_REQUIRE((long long)IMGS * Ho < (1LL << 31) && (long long)Wo * (C / 8) < (1LL << 31), "bn_act_maxpool: too large");
-  // threads of one output row, split evenly over as few blocks (<= 256 threads, whole warps) as it takes
-  const int per_row = Wo * (C / 8);
-  const int parts = (per_row + 255) / 256;
-  const int threads = (((per_row + parts - 1) / parts) + 31) / 32 * 32;
-  ADAMML_REQUIRE(parts <= 65535, "bn_act_maxpool: row too wide");
-  const dim3 grid((unsigned)((long long)IMGS * Ho), (unsigned)parts);
-  const PreBN pre{scale_shift, imgs_per_group, act};
-  if (minb == 2)
-    bn_act_maxpool_fwd_vec_x2_kernel<2><<<grid, threads, 0, stream>>>(x2c(z_hi, z_lo), x2m(y_hi, y_lo), pos, IMGS, H,
-                                                                      W, C, Ho, Wo, pre);
-  else if (minb == 1)
-    bn_act_maxpool_fwd_vec_x2_kernel<1><<<grid, threads, 0, stream>>>(x2c(z_hi, z_lo), x2m(y_hi, y_lo), pos, IMGS, H,
-                                                                      W, C, Ho, Wo, pre);
-  else
-    bn_act_maxpool_fwd_vec_x2_kernel<3><<<grid, threads, 0, stream>>>(x2c(z_hi, z_lo), x2m(y_hi, y_lo), pos, IMGS, H,
-                                                                      W, C, Ho, Wo, pre);
+  const int rc = launch_maxpool_rows_x2(x2c(z_hi, z_lo), x2m(y_hi, y_lo), pos, IMGS, H, W, C, Ho, Wo,
+                                        LiveLimit{nullptr, 0}, PreBN{scale_shift, imgs_per_group, act}, stream);
+  if (rc) return rc;
   return adamml_check_launch("bn_act_maxpool_fwd_x2");
 }
 
