@@ -1,4 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_x2_gpu.py tests/test_eval_skip_gpu.py tests/test_fused_eval_gpu.py tests/test_kernels_gpu.py -q -x -k "pool or skip or fused or eval" 2>&1 | tail -2 | cut -c1-200
-timeout 300 python scripts/bench_pool.py 2>&1 | tail -2
+for i in 1 2 3; do timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -4 > gpurun_out/pytest_$i.log; tail -1 gpurun_out/pytest_$i.log | cut -c1-200; grep -E "^FAILED|^E " gpurun_out/pytest_$i.log | head -5 | cut -c1-300; done
+cp gpurun_out/pytest_3.log gpurun_out/r2_pytest_gpu.log
