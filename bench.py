@@ -371,6 +371,13 @@ def run_gpu_arm(a):
     torch.manual_seed(0)
     model, _ = build_model(namespace(modality, S, a.precision))
     model = model.to(dev).train()
+    # trainability modes of SURVEY 8(d): A = everything trains (headline), B = policy frozen (the reference's warm-up /
+    # main / fine-tune stages: the policy nets run forward only), C = main frozen (policy stage: the main nets run forward
+    # only).  train_adamml.py:250-253,344-345 toggle exactly these flags.
+    if a.phase == "main":
+        model.freeze_policy_net()
+    elif a.phase == "policy":
+        model.freeze_main_net()
     net = model
     sync_bn = world > 1 and not a.no_sync_bn
     use_graph = not a.no_graph
@@ -401,16 +408,21 @@ def run_gpu_arm(a):
         p_opt.zero_grad(set_to_none=True)
         opt.zero_grad(set_to_none=True)
         out, sel = net(xs)
+        # (classification always, selection loss only while the policy trains: utils/utils.py:378-381,393-398)
         if a.torch_tail:
-            loss = F.cross_entropy(out, y) + policy_loss(sel, cost_weights, 10.0, out, y)
+            loss = F.cross_entropy(out, y)
+            if model.update_policy_net:
+                loss = loss + policy_loss(sel, cost_weights, 10.0, out, y)
         else:
-            loss = loss_tail(out, y, sel, cw_dev, 10.0, True)
+            loss = loss_tail(out, y, sel, cw_dev, 10.0, bool(model.update_policy_net))
         loss.backward()
         if world > 1 and use_graph:  # DDP's gradient averaging as one flat NCCL all-reduce inside the graph
             from adamml_b200.dist_utils import allreduce_grads
-            allreduce_grads(params)
-        p_opt.step()
-        opt.step()
+            allreduce_grads([p for p in params if p.requires_grad])
+        if model.update_policy_net:
+            p_opt.step()
+        if model.update_main_net:
+            opt.step()
         return loss
 
     def barrier():
@@ -570,6 +582,8 @@ def run_gpu_arm(a):
                                f"fwd+loss+bwd+Adam(policy)+SGD(main)", "batch_per_gpu": N, "segments": S,
                    "sync_bn": sync_bn, "parallelism": f"dp{world}", "cuda_graph": use_graph,
                    "recompute_activations": bool(a.recompute), "fused_tail": not a.torch_tail,
+                   "trainable": {"all": "A: policy + main", "main": "B: policy frozen (forward only)",
+                                 "policy": "C: main frozen (forward only)"}[a.phase],
                    "l2": "inputs (1.8 GB/step) and activations exceed the 126 MB L2; no explicit flush",
                    "peak_mem_gib": round(peak_mem, 1)},
         "e2e": {"value": clips / (ms_e2e / 1e3), "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
@@ -646,6 +660,9 @@ def main():
     ap.add_argument("--recompute", action="store_true", help="do not keep the outputs of layers without residual input "
                     "for backward (rebuilt from the saved pre-BN tensors): -35 %% activation memory for one extra bf16 "
                     "BN-apply pass per such layer; lets the two-ResNet configs run at batch 72")
+    ap.add_argument("--phase", default="all", choices=["all", "main", "policy"],
+                    help="trainability mode (SURVEY 8d): all = A (headline), main = B (policy frozen), policy = C (main "
+                         "frozen)")
     ap.add_argument("--dump-calls", default=None, help="write one JSON line per C-ABI call of one step (op, ms, args)")
     a = ap.parse_args()
     if a.warmup < 3 and a.impl == "ours":

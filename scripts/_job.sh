@@ -1,4 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for i in 1 2 3; do timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -4 > gpurun_out/pytest_$i.log; tail -1 gpurun_out/pytest_$i.log | cut -c1-200; grep -E "^FAILED|^E " gpurun_out/pytest_$i.log | head -5 | cut -c1-300; done
-cp gpurun_out/pytest_3.log gpurun_out/r2_pytest_gpu.log
+for ph in main policy; do timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --phase $ph 2>&1 | tail -1 > gpurun_out/r2_bench_1gpu_phase_$ph.log; python -c "
+import json
+d=json.loads(open('gpurun_out/r2_bench_1gpu_phase_$ph.log').read()); print('$ph', d['ms_per_step'], d['value'], d['e2e']['value'], d['config']['peak_mem_gib'], d['config']['trainable'], d['roofline']['kernel'], round(d['roofline']['frac'],3))" || tail -5 gpurun_out/r2_bench_1gpu_phase_$ph.log; done
