@@ -1,7 +1,8 @@
 // Train-step tail of train_adamml() (utils/utils.py:362-400, train_adamml.py:250-257), §8 f2:
 //   * cross-entropy + 'blockdrop' policy loss (utils/utils.py:166-184) forward AND gradients in one launch,
 //   * multi-tensor SGD(momentum, weight decay) and Adam(weight decay) over ALL parameter tensors of an optimizer in one
-//     launch each (the reference's torch.optim.SGD / Adam loop over ~650 tensors each).
+//     launch each (the reference's torch.optim.SGD / Adam loop over ~650 tensors each),
+//   * clip_grad_norm_ (utils/utils.py:390-391) over all gradients as two launches without a host round trip.
 // Semantics follow torch.optim exactly (dampening 0, no Nesterov, L2 weight decay added to the gradient, Adam with bias
 // correction and eps outside the square root, no amsgrad); the step counter lives on the device so that the launches
 // capture into a CUDA graph.
@@ -67,6 +68,52 @@ adam_multi_kernel(const unsigned long long* __restrict__ table, const long long*
 }
 
 __global__ void adam_step_kernel(long long* step) { *step += 1; }
+
+// torch.nn.utils.clip_grad_norm_(parameters, max_norm) (utils/utils.py:390-391), L2 norm over ALL gradient tensors:
+//   total = sqrt(sum_t sum_i g_t[i]^2);  every gradient *= min(1, max_norm / (total + 1e-6))
+// pass 1: sum of squares (fp32 per thread, fp64 across the block and the grid); pass 2: the scaling, with the
+// coefficient computed on the device (no host round trip: the pair captures into the step's CUDA graph).
+// grads: device array [n] of gradient addresses.
+__global__ void __launch_bounds__(OPT_THREADS)
+grad_sqnorm_multi_kernel(const unsigned long long* __restrict__ grads, const long long* __restrict__ sizes,
+                         const int* __restrict__ chunk_tensor, const long long* __restrict__ chunk_start,
+                         double* __restrict__ sq) {
+  const int t = chunk_tensor[blockIdx.x];
+  const float* __restrict__ g = reinterpret_cast<const float*>(grads[t]);
+  const long long e0 = chunk_start[blockIdx.x];
+  long long e1 = e0 + OPT_CHUNK;
+  if (e1 > sizes[t]) e1 = sizes[t];
+  float acc = 0.f;
+  for (long long i = e0 + threadIdx.x; i < e1; i += OPT_THREADS) acc = fmaf(g[i], g[i], acc);
+  double d = (double)acc;
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
+  __shared__ double part[OPT_THREADS / 32];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = d;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+#pragma unroll
+    for (int w = 0; w < OPT_THREADS / 32; ++w) tot += part[w];
+    atomicAdd(sq, tot);
+  }
+}
+
+__global__ void __launch_bounds__(OPT_THREADS)
+grad_clip_multi_kernel(const unsigned long long* __restrict__ grads, const long long* __restrict__ sizes,
+                       const int* __restrict__ chunk_tensor, const long long* __restrict__ chunk_start,
+                       const double* __restrict__ sq, float max_norm, float* __restrict__ total_norm) {
+  const float total = (float)sqrt(*sq);
+  if (blockIdx.x == 0 && threadIdx.x == 0) *total_norm = total;
+  const float coef = max_norm / (total + 1e-6f);
+  if (!(coef < 1.f)) return;  // torch multiplies by clamp(coef, max=1): a no-op here
+  const int t = chunk_tensor[blockIdx.x];
+  float* __restrict__ g = reinterpret_cast<float*>(grads[t]);
+  const long long e0 = chunk_start[blockIdx.x];
+  long long e1 = e0 + OPT_CHUNK;
+  if (e1 > sizes[t]) e1 = sizes[t];
+  for (long long i = e0 + threadIdx.x; i < e1; i += OPT_THREADS) g[i] *= coef;
+}
 
 // One block: CE(logits, target) + blockdrop policy loss and their gradients.
 // logits [N][C], target [N] int64, sel [N][S][M] (0/1 decisions with straight-through gradient), cw [M].
@@ -141,6 +188,19 @@ int adamml_adam_multi(const unsigned long long* table, const long long* sizes, c
 }
 
 int adamml_opt_chunk(void) { return OPT_CHUNK; }
+
+int adamml_clip_grad_norm_multi(const unsigned long long* grads, const long long* sizes, const int* chunk_tensor,
+                                const long long* chunk_start, int n_tensors, int n_chunks, float max_norm,
+                                double* sq_scratch, float* total_norm, cudaStream_t stream) {
+  ADAMML_REQUIRE(grads && sizes && chunk_tensor && chunk_start && sq_scratch && total_norm && n_tensors > 0 &&
+                     n_chunks > 0 && max_norm >= 0.f,
+                 "clip_grad_norm_multi: bad arguments");
+  cudaMemsetAsync(sq_scratch, 0, sizeof(double), stream);
+  grad_sqnorm_multi_kernel<<<n_chunks, OPT_THREADS, 0, stream>>>(grads, sizes, chunk_tensor, chunk_start, sq_scratch);
+  grad_clip_multi_kernel<<<n_chunks, OPT_THREADS, 0, stream>>>(grads, sizes, chunk_tensor, chunk_start, sq_scratch,
+                                                               max_norm, total_norm);
+  return adamml_check_launch("clip_grad_norm_multi");
+}
 
 int adamml_loss_tail(const float* logits, const long long* target, const float* selection, const float* cost_weights,
                      float gamma, int use_policy, int N, int C, int S, int M, float* loss, float* dlogits,

@@ -8,7 +8,10 @@ parameter tensors each (utils/utils.py:362-400, train_adamml.py:250-257).  Here:
 * `FusedSGD` / `FusedAdam` — drop-in `torch.optim.Optimizer`s with torch's update rules (SGD: momentum, dampening 0,
   L2 weight decay; Adam: bias correction, eps outside the root, L2 weight decay, no amsgrad) that update every tensor
   of a parameter group in ONE multi-tensor launch.  The Adam step counter lives on the device, the pointer table is
-  copied from pinned memory, so `step()` captures into a CUDA graph.
+  copied from pinned memory, so `step()` captures into a CUDA graph;
+* `clip_grad_norm_(parameters, max_norm)` — `torch.nn.utils.clip_grad_norm_` (L2; utils/utils.py:390-391, the
+  reference's `--clip_gradient`) over all gradient tensors as two multi-tensor launches, the coefficient computed on the
+  device: no host synchronisation, capturable.
 """
 import torch
 
@@ -133,3 +136,51 @@ class FusedAdam(_FusedOptimizer):
             b1, b2 = group["betas"]
             call("adam_multi", table, sizes, ct, cs, n, nchunks, float(group["lr"]), float(b1), float(b2),
                  float(group["eps"]), float(group["weight_decay"]), group["_adamml_step"])
+
+
+_CLIP_CACHE = {}
+_CLIP_GEO = {}
+
+
+@torch.no_grad()
+def clip_grad_norm_(parameters, max_norm):
+    """torch.nn.utils.clip_grad_norm_(parameters, max_norm, norm_type=2.0) for contiguous fp32 CUDA gradients
+    (utils/utils.py:390-391).  -> total norm BEFORE clipping as a 0-dim device tensor (torch returns the same; reading it
+    is the caller's synchronisation, the clipping itself needs none)."""
+    if isinstance(parameters, torch.Tensor):
+        parameters = [parameters]
+    grads = [p.grad for p in parameters if p.grad is not None]
+    if not grads:
+        return torch.zeros((), dtype=torch.float32)
+    for g in grads:
+        if g.dtype != torch.float32 or not g.is_contiguous() or not g.is_cuda:
+            raise TypeError("fused clip_grad_norm_ takes contiguous fp32 CUDA gradients")
+    dev = grads[0].device
+    # chunk geometry: keyed by the tensor sizes, built once (an eager warm-up step) -- inside a graph capture only the
+    # pinned-memory address table below may be (re)built, exactly as in _FusedOptimizer._tables
+    skey = (dev.index,) + tuple(g.numel() for g in grads)
+    geo = _CLIP_GEO.get(skey)
+    if geo is None:
+        chunk = int(lib().cdll.adamml_opt_chunk())
+        ct, cs = [], []
+        for i, n in enumerate(skey[1:]):
+            for off in range(0, n, chunk):
+                ct.append(i)
+                cs.append(off)
+        geo = (torch.tensor(skey[1:], dtype=torch.int64, device=dev), torch.tensor(ct, dtype=torch.int32, device=dev),
+               torch.tensor(cs, dtype=torch.int64, device=dev), len(ct), torch.empty(1, dtype=torch.float64, device=dev))
+        _CLIP_GEO[skey] = geo
+    key = tuple(g.data_ptr() for g in grads)
+    ent = _CLIP_CACHE.get(key)
+    if ent is None:
+        if len(_CLIP_CACHE) > 4:  # eager steps with set_to_none re-allocate the gradients every step
+            _CLIP_CACHE.clear()
+        host = torch.tensor(key, dtype=torch.int64).pin_memory()
+        table = torch.empty_like(host, device=dev)
+        table.copy_(host, non_blocking=True)
+        ent = (table, host) + geo
+        _CLIP_CACHE[key] = ent
+    table, _, sizes, ct, cs, nchunks, scratch = ent
+    total = torch.empty((), dtype=torch.float32, device=dev)
+    call("clip_grad_norm_multi", table, sizes, ct, cs, len(grads), nchunks, float(max_norm), scratch, total)
+    return total

@@ -391,7 +391,7 @@ def run_gpu_arm(a):
         p_opt = torch.optim.Adam(model.policy_net.parameters(), 0.01, weight_decay=1e-4, capturable=use_graph)
         opt = torch.optim.SGD(model.main_net.parameters(), 0.01, momentum=0.9, weight_decay=1e-4)
     else:              # same update rules, one multi-tensor launch per optimizer (adamml_b200/optim.py, §8 f2)
-        from adamml_b200.optim import FusedAdam, FusedSGD, loss_tail
+        from adamml_b200.optim import FusedAdam, FusedSGD, clip_grad_norm_, loss_tail
         p_opt = FusedAdam(model.policy_net.parameters(), 0.01, weight_decay=1e-4)
         opt = FusedSGD(model.main_net.parameters(), 0.01, momentum=0.9, weight_decay=1e-4)
         cw_dev = torch.ones(model.num_modality, device=dev)
@@ -419,6 +419,11 @@ def run_gpu_arm(a):
         if world > 1 and use_graph:  # DDP's gradient averaging as one flat NCCL all-reduce inside the graph
             from adamml_b200.dist_utils import allreduce_grads
             allreduce_grads([p for p in params if p.requires_grad])
+        if a.clip_gradient is not None:  # utils/utils.py:390-391 (--clip_gradient, default None)
+            if a.torch_tail:
+                torch.nn.utils.clip_grad_norm_(params, a.clip_gradient)
+            else:
+                clip_grad_norm_(params, a.clip_gradient)
         if model.update_policy_net:
             p_opt.step()
         if model.update_main_net:
@@ -660,6 +665,8 @@ def main():
     ap.add_argument("--recompute", action="store_true", help="do not keep the outputs of layers without residual input "
                     "for backward (rebuilt from the saved pre-BN tensors): -35 %% activation memory for one extra bf16 "
                     "BN-apply pass per such layer; lets the two-ResNet configs run at batch 72")
+    ap.add_argument("--clip-gradient", type=float, default=None, help="clip the total gradient norm before the "
+                    "optimizer steps (the reference's --clip_gradient; default off, as in the reference)")
     ap.add_argument("--phase", default="all", choices=["all", "main", "policy"],
                     help="trainability mode (SURVEY 8d): all = A (headline), main = B (policy frozen), policy = C (main "
                          "frozen)")

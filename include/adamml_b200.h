@@ -304,6 +304,13 @@ int adamml_adam_multi(const unsigned long long* table, const long long* sizes, c
                       const long long* chunk_start, int n_tensors, int n_chunks, float lr, float beta1, float beta2,
                       float eps, float weight_decay, long long* step, cudaStream_t stream);
 int adamml_opt_chunk(void);
+/* torch.nn.utils.clip_grad_norm_(parameters, max_norm), L2 (utils/utils.py:390-391, opts.py:75 --clip_gradient): total =
+ * sqrt(sum of squares over ALL gradient tensors), every gradient *= min(1, max_norm / (total + 1e-6)).  grads = device
+ * array [n_tensors] of fp32 gradient addresses; sizes / chunk_tensor / chunk_start as above; sq_scratch fp64 [1]
+ * (overwritten), total_norm fp32 [1] receives the norm BEFORE clipping.  No host synchronisation. */
+int adamml_clip_grad_norm_multi(const unsigned long long* grads, const long long* sizes, const int* chunk_tensor,
+                                const long long* chunk_start, int n_tensors, int n_chunks, float max_norm,
+                                double* sq_scratch, float* total_norm, cudaStream_t stream);
 
 /* ---- device-side gating: inference with decision-driven skipping, no host round trip ----
  * The reference runs every main backbone on every (segment, video) pair and multiplies its logits by the policy's 0/1

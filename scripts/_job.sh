@@ -1,5 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for ph in main policy; do timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --phase $ph 2>&1 | tail -1 > gpurun_out/r2_bench_1gpu_phase_$ph.log; python -c "
-import json
-d=json.loads(open('gpurun_out/r2_bench_1gpu_phase_$ph.log').read()); print('$ph', d['ms_per_step'], d['value'], d['e2e']['value'], d['config']['peak_mem_gib'], d['config']['trainable'], d['roofline']['kernel'], round(d['roofline']['frac'],3))" || tail -5 gpurun_out/r2_bench_1gpu_phase_$ph.log; done
+timeout 600 python -m pytest tests/test_train_tail_gpu.py -q -x 2>&1 | tail -2 | cut -c1-250
+timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --clip-gradient 20 2>&1 | tail -1 | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print('clip', d['ms_per_step'], d['value'], d['gpu_launches'])"

@@ -133,3 +133,60 @@ def test_fused_tail_in_cuda_graph(cuda):
         torch.cuda.synchronize()
         assert abs(gl.item() - le) < 1e-5 * max(1.0, abs(le)), (i, gl.item(), le)
     assert torch.allclose(wa, wb, rtol=1e-5, atol=1e-6) and torch.allclose(va, vb, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("max_norm", [0.5, 5.0, 1e6])
+def test_fused_clip_grad_norm_matches_torch(cuda, max_norm):
+    """clip_grad_norm_ (utils/utils.py:390-391, --clip_gradient) as two multi-tensor launches: same total norm, same
+    clipped gradients as torch.nn.utils.clip_grad_norm_ (clipping active, marginal, inactive); parameters without a
+    gradient are skipped; the second call goes through the cached tables."""
+    from adamml_b200.optim import clip_grad_norm_
+    pa, pb = _params(cuda, 2), _params(cuda, 2)
+    g = torch.Generator().manual_seed(11)
+    for rep in range(2):
+        for i, (a, b) in enumerate(zip(pa, pb)):
+            if i == 2:
+                a.grad = b.grad = None
+                continue
+            gr = torch.randn(a.shape, generator=g).to(cuda) * (0.3 + rep)
+            if a.grad is None:
+                a.grad, b.grad = gr.clone(), gr.clone()
+            else:  # same storage as in the first round: exercises the table cache
+                a.grad.copy_(gr)
+                b.grad.copy_(gr)
+        want = torch.nn.utils.clip_grad_norm_(pa, max_norm)
+        got = clip_grad_norm_(pb, max_norm)
+        assert got.shape == want.shape and got.device == want.device
+        assert abs(got.item() - want.item()) <= 2e-6 * want.item()
+        for i, (a, b) in enumerate(zip(pa, pb)):
+            if a.grad is None:
+                assert b.grad is None
+            else:
+                assert torch.allclose(a.grad, b.grad, rtol=3e-6, atol=1e-9), (i, (a.grad - b.grad).abs().max().item())
+
+
+def test_fused_clip_grad_norm_in_cuda_graph(cuda):
+    """the clipping pair captures (device-side coefficient, pinned address table) and replays on fresh gradient values"""
+    from adamml_b200.optim import clip_grad_norm_
+    ps = _params(cuda, 4)
+    for p in ps:
+        p.grad = torch.randn_like(p)
+    clip_grad_norm_(ps, 1.0)                 # eager warm-up: chunk geometry exists before the capture
+    for p in ps:                             # new gradient storage, as zero_grad(set_to_none=True) + backward gives
+        p.grad = torch.randn_like(p)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        total = clip_grad_norm_(ps, 1.0)
+    for rep in range(2):
+        fresh = [torch.randn_like(p) * (rep + 1) for p in ps]
+        for p, f in zip(ps, fresh):
+            p.grad.copy_(f)
+        graph.replay()
+        ref = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+        for r, f in zip(ref, fresh):
+            r.grad = f.clone()
+        want = torch.nn.utils.clip_grad_norm_(ref, 1.0)
+        assert abs(total.item() - want.item()) <= 2e-6 * want.item()
+        for r, p in zip(ref, ps):
+            assert torch.allclose(r.grad, p.grad, rtol=3e-6, atol=1e-9)
