@@ -11,8 +11,8 @@ set -u
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 T=${1:-300}
-K1='test_tc_gemm_x2 and (1000 or 129 or 513) or test_tc_conv_x2 and (case0 or case3) or test_first_conv_x2 and 3-7-64 or test_tc_wgrad and case0 or bn_apply_and_stats_x2 or dwconv_fwd_x2 or test_dwconv_fwd_stats_x2 and (case0 or case3 or case6 or case9) or test_dwconv_bwd_fused and (case0 or case1 or case3 or case10 or case13) or test_tc_gemm_x2 and 40000 or pools_x2 or test_conv_bn_act_matches_unfused and case1'
-FILES="tests/test_kernels_gpu.py tests/test_x2_gpu.py tests/test_fused_eval_gpu.py"
+K1='test_tc_gemm_x2 and (1000 or 129 or 513) or test_tc_conv_x2 and (case0 or case3) or test_first_conv_x2 and 3-7-64 or test_tc_wgrad and case0 or bn_apply_and_stats_x2 or dwconv_fwd_x2 or test_dwconv_fwd_stats_x2 and (case0 or case3 or case6 or case9) or test_dwconv_bwd_fused and (case0 or case1 or case3 or case10 or case13) or test_tc_gemm_x2 and 40000 or pools_x2 or test_conv_bn_act_matches_unfused and case1 or test_bn_act_maxpool_x2 and (case0 or case1) or test_tc_conv_x2 and case4 or test_tc_gemm_x2 and 20002 or test_fused_clip_grad_norm'
+FILES="tests/test_kernels_gpu.py tests/test_x2_gpu.py tests/test_fused_eval_gpu.py tests/test_train_tail_gpu.py"
 for tool in memcheck racecheck; do
   log=gpurun_out/sanitizer_${tool}.log
   timeout $T compute-sanitizer --tool $tool --error-exitcode 9 --print-limit 10 \
