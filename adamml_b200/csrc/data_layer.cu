@@ -299,6 +299,54 @@ __global__ void transpose_dw_kernel(const float* __restrict__ src, float* __rest
   }
 }
 
+// ---- every weight operand of a model in ONE launch -------------------------------------------------------------
+// The engine re-derives its weight operands from the fp32 OIHW parameters every step (they change with every optimizer
+// step): OHWI in the compute precision for the forward pass, the rotated [Cin][R][S][Cout] operand for the data
+// gradient, tap-major depthwise weights -- one small launch per layer and kind, ~360 launches per RGB+Audio step.  This
+// kernel takes a job table instead: block b converts elements [chunk_start[b], + PACK_CHUNK) of job chunk_job[b].
+// job = 8 x int64: {src, dst, Cout, Cin, R, S, CinPad, kind}; element maps are those of pack_weight_kernel,
+// pack_weight_dgrad_kernel and transpose_dw_kernel (bit-identical results).
+constexpr int PACK_CHUNK = 4096;
+enum { PK_OHWI_F32 = 0, PK_OHWI_BF16 = 1, PK_OHWI_X2 = 2, PK_DGRAD_F32 = 3, PK_DGRAD_BF16 = 4, PK_DW = 5 };
+__global__ void __launch_bounds__(256)
+pack_weights_multi_kernel(const long long* __restrict__ jobs, const int* __restrict__ chunk_job,
+                          const long long* __restrict__ chunk_start) {
+  const long long* j = jobs + (long long)chunk_job[blockIdx.x] * 8;
+  const float* __restrict__ src = reinterpret_cast<const float*>(j[0]);
+  void* dst = reinterpret_cast<void*>(j[1]);
+  const int Cout = (int)j[2], Cin = (int)j[3], R = (int)j[4], S = (int)j[5], CinPad = (int)j[6], kind = (int)j[7];
+  long long total;
+  if (kind == PK_DW) total = (long long)Cout * 9;
+  else if (kind == PK_DGRAD_F32 || kind == PK_DGRAD_BF16) total = (long long)Cin * R * S * Cout;
+  else total = (long long)Cout * R * S * CinPad;
+  const long long e0 = chunk_start[blockIdx.x];
+  long long e1 = e0 + PACK_CHUNK;
+  if (e1 > total) e1 = total;
+  for (long long idx = e0 + threadIdx.x; idx < e1; idx += 256) {
+    if (kind == PK_DW) {  // [C][3][3] -> [9][C]
+      const int c = (int)(idx / 9), t = (int)(idx % 9);
+      reinterpret_cast<float*>(dst)[(long long)t * Cout + c] = src[idx];
+    } else if (kind == PK_DGRAD_F32 || kind == PK_DGRAD_BF16) {
+      const int co = (int)(idx % Cout);
+      const int s_ = (int)((idx / Cout) % S);
+      const int r = (int)((idx / ((long long)Cout * S)) % R);
+      const int ci = (int)(idx / ((long long)Cout * S * R));
+      const float v = src[(((long long)co * Cin + ci) * R + (R - 1 - r)) * S + (S - 1 - s_)];
+      if (kind == PK_DGRAD_F32) reinterpret_cast<float*>(dst)[idx] = v;
+      else reinterpret_cast<bf16*>(dst)[idx] = __float2bfloat16_rn(v);
+    } else {
+      const int ci = (int)(idx % CinPad);
+      const int s_ = (int)((idx / CinPad) % S);
+      const int r = (int)((idx / ((long long)CinPad * S)) % R);
+      const int co = (int)(idx / ((long long)CinPad * S * R));
+      const float v = ci < Cin ? src[(((long long)co * Cin + ci) * R + r) * S + s_] : 0.f;
+      if (kind == PK_OHWI_F32) reinterpret_cast<float*>(dst)[idx] = v;
+      else if (kind == PK_OHWI_BF16) reinterpret_cast<bf16*>(dst)[idx] = __float2bfloat16_rn(v);
+      else st_elem(W4Ptr{reinterpret_cast<bf16*>(dst), total}, idx, v);
+    }
+  }
+}
+
 template <typename TI, typename TO>
 __global__ void cast_kernel(const TI* __restrict__ src, TO* __restrict__ dst, long long total) {
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -503,6 +551,15 @@ int adamml_unpack_wgrad_stem(const float* dw_packed, float* dw_oihw, int Cout, i
   unpack_wgrad_stem_kernel<<<ew_blocks((long long)Cout * C * R * R), 256, 0, stream>>>(dw_packed, dw_oihw, Cout, C, Cs,
                                                                                         R, T);
   return adamml_check_launch("unpack_wgrad_stem");
+}
+
+int adamml_pack_chunk(void) { return PACK_CHUNK; }
+
+int adamml_pack_weights_multi(const long long* jobs, const int* chunk_job, const long long* chunk_start, int n_jobs,
+                              int n_chunks, cudaStream_t stream) {
+  ADAMML_REQUIRE(jobs && chunk_job && chunk_start && n_jobs > 0 && n_chunks > 0, "pack_weights_multi: bad arguments");
+  pack_weights_multi_kernel<<<n_chunks, 256, 0, stream>>>(jobs, chunk_job, chunk_start);
+  return adamml_check_launch("pack_weights_multi");
 }
 
 int adamml_pack_weight_dw(const float* w_c33, float* w_9c, int C, cudaStream_t stream) {

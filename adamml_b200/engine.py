@@ -56,8 +56,9 @@ def assign_bn_keys(model):
 class Exec:
     """State of one backbone pass."""
 
-    def __init__(self, dtype, training, groups, save, param_needs_grad=True, lane=0):
+    def __init__(self, dtype, training, groups, save, param_needs_grad=True, lane=0, packs=None):
         self.lane = lane  # stream / backbone index: the sync-BN peer-memory exchange keeps one flag row per lane
+        self.packs = packs  # ops.WeightPackCache of the model this pass belongs to (None: per-layer pack launches)
         # x2 precision: the FORWARD pass runs on two-plane activations (ops.X2); the tape keeps their bf16 hi planes
         # and the backward pass is the bf16 engine
         self.x2 = dtype == ops.PREC_X2
@@ -173,10 +174,10 @@ class Exec:
         if conv.groups > 1:
             if not (conv.groups == conv.in_channels == Cout and R == 3 and pad == 1):
                 return None
-            return ops.dwconv_bn_act_fwd(x, ops.pack_weight_dw(w.detach()), stride, ss, act)
+            return ops.dwconv_bn_act_fwd(x, ops.pack_weight_dw(w.detach(), cache=self.packs), stride, ss, act)
         if not (self.x2 or self.dtype == torch.bfloat16):
             return None
-        wp = ops.pack_weight(w.detach(), ops.PREC_X2 if self.x2 else self.dtype)
+        wp = ops.pack_weight(w.detach(), ops.PREC_X2 if self.x2 else self.dtype, cache=self.packs)
         return ops.conv_bn_act_fwd(x, wp, stride, pad, ss, act, res=res)
 
     def conv_bn_stats(self, x, conv, bn):
@@ -207,14 +208,14 @@ class Exec:
             fused = sums is not None
         elif depthwise:
             assert conv.groups == conv.in_channels == Cout and R == 3 and pad == 1
-            wp = ops.pack_weight_dw(w.detach())
+            wp = ops.pack_weight_dw(w.detach(), cache=self.packs)
             if self.training:
                 sums = p2p_sums if p2p is not None else torch.empty((G, Cout, 2), device=x.device, dtype=torch.float64)
                 z, fused = ops.dwconv_fwd_stats(x, wp, stride, sums, x.shape[0] // G)
             else:
                 z = ops.dwconv_fwd(x, wp, stride)
         else:
-            wp = ops.pack_weight(w.detach(), ops.PREC_X2 if self.x2 else self.dtype)
+            wp = ops.pack_weight(w.detach(), ops.PREC_X2 if self.x2 else self.dtype, cache=self.packs)
             if self.training:
                 sums = p2p_sums if p2p is not None else torch.empty((G, Cout, 2), device=x.device, dtype=torch.float64)
             rows = x.shape[0] * ((x.shape[1] + 2 * pad - R) // stride + 1) * ((x.shape[2] + 2 * pad - S) // stride + 1)
@@ -333,7 +334,7 @@ class Exec:
                 w_rot = None
                 R, S = w.shape[1], w.shape[2]
                 if ops.tc_dgrad_ok(self.dtype, w.shape[0], w.shape[3], R, S, stride):
-                    w_rot = ops.pack_weight_dgrad(conv.weight.detach(), self.dtype)
+                    w_rot = ops.pack_weight_dgrad(conv.weight.detach(), self.dtype, cache=self.packs)
                 if w_rot is not None and stride == 2 and R == 1 and S == 1 and addend is None and compact_ok:
                     # stride-2 1x1 (Bottleneck downsample): only the even pixels receive gradient -> compact GEMM,
                     # scattered by the consumer's epilogue (conv_dgrad addend_sub=2)
@@ -514,7 +515,8 @@ class BackboneFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, net, x, groups, extra, *params):
         need = bool(extra.get("_save")) and any(ctx.needs_input_grad[4:])
-        ex = Exec(net.compute_dtype, net.training, groups, save=need, lane=int(extra.get("_lane", 0)))
+        ex = Exec(net.compute_dtype, net.training, groups, save=need, lane=int(extra.get("_lane", 0)),
+                  packs=extra.get("_packs"))
         live = extra.get("_live")  # (count tensor, clip capacity): inference with device-side skipping
         if live is not None:
             assert not need and not net.training, "the device-side work limit is an inference-only feature"

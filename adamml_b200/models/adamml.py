@@ -11,6 +11,8 @@ from .joint_resnet_mobilenetv2 import joint_resnet_mobilenetv2
 from .policy_net import p_joint_mobilenet
 from .resnet import default_compute_dtype
 
+PACK_CACHE = os.environ.get("ADAMML_B200_PACK_CACHE", "1") != "0"
+
 
 class AdaMML(nn.Module):
     def __init__(self, policy_net, main_net, num_frames, num_segments, modality, rng_policy, rng_threshold,
@@ -100,6 +102,13 @@ class AdaMML(nn.Module):
             from ..engine import assign_bn_keys
             assign_bn_keys(self)
             self.__dict__["_bn_keys_done"] = True
+        # weight operands of every backbone: one multi-tensor launch here instead of ~360 per-layer ones (first pass:
+        # per-layer launches that record the jobs); ADAMML_B200_PACK_CACHE=0 keeps the per-layer launches
+        cache = self.__dict__.get("_pack_cache")
+        if cache is None and PACK_CACHE:
+            cache = self.__dict__["_pack_cache"] = ops.WeightPackCache()
+        if cache is not None:
+            cache.begin()
         p_x, m_x, S = self.data_layer(x, S)
         dev = x[0].device
         expo = noise["expo"] if noise else None
@@ -122,7 +131,7 @@ class AdaMML(nn.Module):
         # backbones are enqueued FIRST: their millisecond-scale kernels keep the device busy while the host issues the
         # hundreds of microsecond-scale launches of the policy nets (eager mode; inside a captured graph the order
         # is irrelevant)
-        outs = run_backbones_parallel(m_jobs + p_jobs)
+        outs = self._run_backbones(m_jobs + p_jobs)
         n_main = len(m_jobs)
         del p_x, m_x, p_jobs, m_jobs
         if not self.rng_policy:
@@ -130,6 +139,10 @@ class AdaMML(nn.Module):
         outs = outs[:n_main]
         logits = self.main_net(None, decisions, S, N, per_mod=outs)
         return logits, decisions.permute(2, 0, 1)
+
+    def _run_backbones(self, jobs):
+        cache = self.__dict__.get("_pack_cache")
+        return run_backbones_parallel([(n, x_, g, dict(e or {}, _packs=cache)) for n, x_, g, e in jobs])
 
     # ------------------------------------------------------------------ inference with decision-driven skipping
     def _can_skip(self):
@@ -165,7 +178,7 @@ class AdaMML(nn.Module):
             idx, count = ops.select_compact(dec, m)
             jobs.append((net, ops.gather_clips(x, idx, count, SN), 1, dict(_live=(count, SN))))
             meta.append((idx, count))
-        outs = run_backbones_parallel(jobs)
+        outs = self._run_backbones(jobs)
         per_mod = [ops.scatter_rows(y.contiguous(), idx, count, SN) for y, (idx, count) in zip(outs, meta)]
         self._sel_state = ([c for _, c in meta], SN * len(m_x))
         logits = self.main_net(None, decisions, S, N, per_mod=per_mod)
@@ -173,7 +186,7 @@ class AdaMML(nn.Module):
 
     def _forward_selected(self, p_jobs, m_x, S, N, expo, decisions):
         if decisions is None:
-            feats = run_backbones_parallel(p_jobs)
+            feats = self._run_backbones(p_jobs)
             decisions, _ = self.policy_net(None, S, N, expo=expo, feats=feats)
             del feats
         if self.skip_mode == "device":
@@ -197,7 +210,7 @@ class AdaMML(nn.Module):
                 idx = None
             jobs.append((net, x, 1, None))
             slots.append((m, idx))
-        outs = run_backbones_parallel(jobs)
+        outs = self._run_backbones(jobs)
         for (m, idx), y in zip(slots, outs):
             if idx is None:
                 per_mod[m] = y

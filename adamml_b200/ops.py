@@ -326,28 +326,148 @@ def stem_wgrad(xs, dy, Cout):
     return dw
 
 
-def pack_weight(w, dtype, cin_pad=None):
+# kinds of adamml_pack_weights_multi
+PK_OHWI_F32, PK_OHWI_BF16, PK_OHWI_X2, PK_DGRAD_F32, PK_DGRAD_BF16, PK_DW = range(6)
+
+
+class WeightPackCache:
+    """Weight operands of ONE model, refreshed by ONE launch per forward pass (adamml_pack_weights_multi).
+
+    The engine derives every weight operand from the fp32 OIHW parameter each step (OHWI in the compute precision, the
+    rotated data-gradient operand, tap-major depthwise weights): ~360 small launches per RGB+Audio training step.  With
+    a cache the FIRST step runs those per-layer launches as before and records them as jobs; from the second step on
+    `begin()` -- called by AdaMML.forward before any backbone runs -- converts all of them in one launch into one
+    persistent arena and the per-layer calls (`pack_weight(..., cache=)`) return views of it.  Entries are keyed by the
+    parameter's storage address and hold a reference to it; an operand is handed out only in the pass whose `begin()`
+    refreshed it (or that packed it itself), so a weight update between passes can never be missed.  Backbones run
+    without a cache (unimodal models, direct engine calls) keep the per-layer launches."""
+
+    class _Entry:
+        __slots__ = ("w", "out", "dims", "kind", "in_table", "wrap", "shape", "dtype", "mk")
+
+    def __init__(self):
+        self.ent = {}
+        self.epoch = 0
+        self.packed_epoch = -1
+        self.dirty = False
+        self.table = None
+        self.arena = None
+        self._retired = []  # tables / arenas a captured CUDA graph may still read
+
+    def __deepcopy__(self, memo):   # a copied / pickled model starts with an empty cache (entries are keyed by the
+        return WeightPackCache()    # ORIGINAL parameters' addresses)
+
+    def __reduce__(self):
+        return (WeightPackCache, ())
+
+    def begin(self):
+        """start of a forward pass: refresh every recorded operand from the current parameter values"""
+        self.epoch += 1
+        if not self.ent:
+            return
+        if self.dirty:
+            self._build()
+        jobs, cj, cs, n_jobs, n_chunks = self.table
+        call("pack_weights_multi", jobs, cj, cs, n_jobs, n_chunks)
+        self.packed_epoch = self.epoch
+
+    def _build(self):
+        """job table + ONE arena holding every operand (a single allocation made between two passes: persistent
+        per-layer buffers allocated in the middle of a forward pass pin the caching allocator's segments and, at
+        119 GiB of activations, send eager steps into its free-and-retry path)"""
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("WeightPackCache: a new weight operand appeared during CUDA-graph capture; run one eager "
+                               "step in the same mode before capturing")
+        chunk = int(_lib.lib().cdll.adamml_pack_chunk())
+        ents = list(self.ent.values())
+        dev = ents[0].w.device
+        offs, size = [], 0
+        for e in ents:
+            offs.append(size)
+            nbytes = torch.empty((), dtype=e.dtype).element_size()
+            for d in e.shape:
+                nbytes *= d
+            size += (nbytes + 255) // 256 * 256
+        arena = torch.empty(size, dtype=torch.uint8, device=dev)
+        rows, cj, cs = [], [], []
+        for i, (e, off) in enumerate(zip(ents, offs)):
+            n = 1
+            for d in e.shape:
+                n *= d
+            nbytes = n * torch.empty((), dtype=e.dtype).element_size()
+            e.out = arena[off:off + nbytes].view(e.dtype).view(e.shape)
+            e.wrap = e.mk(e.out) if e.mk else e.out
+            e.in_table = True
+            Cout, Cin, R, S, cin_pad = e.dims
+            rows.append([e.w.data_ptr(), e.out.data_ptr(), Cout, Cin, R, S, cin_pad, e.kind])
+            total = Cout * 9 if e.kind == PK_DW else (Cin * R * S * Cout if e.kind in (PK_DGRAD_F32, PK_DGRAD_BF16)
+                                                      else Cout * R * S * cin_pad)
+            for o in range(0, total, chunk):
+                cj.append(i)
+                cs.append(o)
+        if self.table is not None:
+            self._retired.append((self.table, self.arena))
+        self.arena = arena
+        self.table = (torch.tensor(rows, dtype=torch.int64, device=dev), torch.tensor(cj, dtype=torch.int32, device=dev),
+                      torch.tensor(cs, dtype=torch.int64, device=dev), len(rows), len(cj))
+        self.dirty = False
+
+    def get(self, w, kind, dims, shape, dtype, launch, wrap=None):
+        key = (w.data_ptr(), kind)
+        e = self.ent.get(key)
+        if e is None:
+            e = WeightPackCache._Entry()
+            e.w, e.dims, e.kind, e.in_table, e.shape, e.dtype, e.mk = w, dims, kind, False, tuple(shape), dtype, wrap
+            e.out = e.wrap = None
+            self.ent[key] = e
+            self.dirty = True
+        if e.in_table and self.packed_epoch == self.epoch:
+            return e.wrap
+        # not (yet) refreshed by begin() in this pass: an ordinary per-layer launch into a buffer of its own
+        out = torch.empty(e.shape, device=w.device, dtype=dtype)
+        launch(out)
+        return wrap(out) if wrap else out
+
+
+def pack_weight(w, dtype, cin_pad=None, cache=None):
     """OIHW fp32 parameter -> OHWI operand [Cout, R, S, cin_pad] in `dtype`."""
     _chk(w, torch.float32)
     Cout, Cin, R, S = w.shape
     cin_pad = cin_pad or Cin
     if dtype == PREC_X2:
+        def launch(out):
+            call("pack_weight_x2", w, out, Cout, Cin, R, S, cin_pad, 0)
+        if cache is not None:
+            return cache.get(w, PK_OHWI_X2, (Cout, Cin, R, S, cin_pad), (4, Cout, R, S, cin_pad), torch.bfloat16, launch,
+                             wrap=X2W)
         out = torch.empty((4, Cout, R, S, cin_pad), device=w.device, dtype=torch.bfloat16)
-        call("pack_weight_x2", w, out, Cout, Cin, R, S, cin_pad, 0)
+        launch(out)
         return X2W(out)
     if R == 1 and S == 1 and cin_pad == Cin and dtype == torch.float32:
         return w.view(Cout, 1, 1, Cin)
+
+    def launch(out):
+        call("pack_weight", w, out, Cout, Cin, R, S, cin_pad, dtype_code(dtype))
+    if cache is not None:
+        return cache.get(w, PK_OHWI_F32 if dtype == torch.float32 else PK_OHWI_BF16, (Cout, Cin, R, S, cin_pad),
+                         (Cout, R, S, cin_pad), dtype, launch)
     out = torch.empty((Cout, R, S, cin_pad), device=w.device, dtype=dtype)
-    call("pack_weight", w, out, Cout, Cin, R, S, cin_pad, dtype_code(dtype))
+    launch(out)
     return out
 
 
-def pack_weight_dgrad(w, dtype):
+def pack_weight_dgrad(w, dtype, cache=None):
     """OIHW fp32 parameter -> rotated dgrad operand [Cin, R, S, Cout] in `dtype`."""
     _chk(w, torch.float32)
     Cout, Cin, R, S = w.shape
+
+    def launch(out):
+        call("pack_weight_dgrad", w, out, Cout, Cin, R, S, dtype_code(dtype))
+    if cache is not None:
+        return cache.get(w, PK_DGRAD_F32 if dtype == torch.float32 else PK_DGRAD_BF16, (Cout, Cin, R, S, Cin),
+                         (Cin, R, S, Cout), dtype, launch)
     out = torch.empty((Cin, R, S, Cout), device=w.device, dtype=dtype)
-    call("pack_weight_dgrad", w, out, Cout, Cin, R, S, dtype_code(dtype))
+    launch(out)
     return out
 
 
@@ -587,12 +707,17 @@ def linear_wgrad(x, dy, K=None, x_ld=0, y_ld=0):
 
 
 # ---------------------------------------------------------------- depthwise
-def pack_weight_dw(w):
+def pack_weight_dw(w, cache=None):
     """nn.Conv2d(groups=C).weight [C,1,3,3] fp32 -> tap-major operand [9, C] fp32."""
     _chk(w, torch.float32)
     C = w.shape[0]
+
+    def launch(out):
+        call("pack_weight_dw", w, out, C)
+    if cache is not None:
+        return cache.get(w, PK_DW, (C, 1, 3, 3, 1), (9, C), torch.float32, launch)
     out = torch.empty((9, C), device=w.device, dtype=torch.float32)
-    call("pack_weight_dw", w, out, C)
+    launch(out)
     return out
 
 

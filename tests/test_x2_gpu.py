@@ -471,3 +471,72 @@ def test_recompute_mode_same_gradients_less_memory(cuda, mode):
     assert len(bad) <= len(res[True][2]) // 50, bad[:5]
     print(f"{mode}: tape memory {res[False][3] / 2**20:.0f} -> {res[True][3] / 2**20:.0f} MiB")
     assert res[True][3] < 0.8 * res[False][3]
+
+
+def test_weight_pack_cache_same_training_trajectory(cuda):
+    """AdaMML.forward refreshes every weight operand with ONE multi-tensor launch (ops.WeightPackCache,
+    adamml_pack_weights_multi) instead of one launch per layer and kind.  Over three SGD steps (weights change between
+    the passes): the first pass runs and records the per-layer launches, later passes launch ONE pack kernel, every
+    operand in the arena is bit-identical to the per-layer conversion of the CURRENT parameter, and the trajectory
+    matches the per-layer path (first pass to rounding noise of the statistics atomics, later passes to the run-to-run
+    divergence of the atomically accumulated weight gradients -- a stale operand would be off by tens of percent)."""
+    import copy
+    import importlib
+    from adamml_b200 import _lib, ops
+    adamml_mod = importlib.import_module("adamml_b200.models.adamml")
+    g = load_golden("adamml_rgb_sound_train")
+    case = g["case"]
+    model0, _ = build(case, cuda)
+    cfg = O.make_cfg(case["modality"], num_segments=case["S"])
+    xs, y = O.make_inputs(cfg, case["N"], case["S"], hw=case["hw"])
+    xs, y = [t.to(cuda) for t in xs], y.to(cuda)
+    noise = noise_for_model(O.draw_noise(1, cfg, case["N"], case["S"], True), cuda)
+    results = {}
+    old = adamml_mod.PACK_CACHE
+    try:
+        for on in (False, True):
+            adamml_mod.PACK_CACHE = on
+            model = copy.deepcopy(model0).train()
+            opt = torch.optim.SGD(model.parameters(), 0.05)
+            trace, packs = [], []
+            for step in range(3):
+                _lib.PROFILE = []
+                opt.zero_grad(set_to_none=True)
+                logits, dec = model(xs, noise=noise)
+                F.cross_entropy(logits, y).backward()
+                opt.step()
+                names = [n for n, *_ in _lib.PROFILE]
+                _lib.PROFILE = None
+                packs.append((sum(n in ("pack_weight", "pack_weight_x2", "pack_weight_dgrad", "pack_weight_dw")
+                                  for n in names), names.count("pack_weights_multi")))
+                trace.append((logits.detach().clone(), dec.detach().clone()))
+            results[on] = (trace, packs)
+            if on:  # the arena against the per-layer conversions of the parameters as they are NOW (after 3 updates)
+                cache = model.__dict__["_pack_cache"]
+                cache.begin()
+                kinds = set()
+                for e in cache.ent.values():
+                    assert e.in_table
+                    if e.kind == ops.PK_OHWI_X2:
+                        ref = ops.pack_weight(e.w, ops.PREC_X2).planes
+                    elif e.kind in (ops.PK_OHWI_BF16, ops.PK_OHWI_F32):
+                        ref = ops.pack_weight(e.w, e.dtype)
+                    elif e.kind in (ops.PK_DGRAD_BF16, ops.PK_DGRAD_F32):
+                        ref = ops.pack_weight_dgrad(e.w, e.dtype)
+                    else:
+                        ref = ops.pack_weight_dw(e.w)
+                    assert torch.equal(e.out.view(torch.int16 if e.out.element_size() == 2 else torch.int32),
+                                       ref.view(torch.int16 if ref.element_size() == 2 else torch.int32)), e.kind
+                    kinds.add(e.kind)
+                assert {ops.PK_OHWI_X2, ops.PK_DGRAD_BF16, ops.PK_DW} <= kinds
+    finally:
+        adamml_mod.PACK_CACHE = old
+        _lib.PROFILE = None
+    (t0, p0), (t1, p1) = results[False], results[True]
+    assert rel(t1[0][0], t0[0][0]) < 1e-5 and torch.equal(t0[0][1], t1[0][1])
+    for (l0, d0), (l1, d1) in zip(t0[1:], t1[1:]):
+        assert rel(l1, l0) < 2e-2
+    assert all(m == 0 for _, m in p0) and p0[0][0] > 50
+    assert p1[0] == (p0[0][0], 0), (p1, p0)          # first pass: per-layer launches, recorded
+    # then ONE launch per pass (+ the space-to-depth stem operands of the first convolutions, packed by stem_conv_fwd)
+    assert p1[1] == p1[2] and p1[1][1] == 1 and p1[1][0] <= 4, p1
