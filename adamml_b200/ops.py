@@ -343,7 +343,9 @@ class WeightPackCache:
     without a cache (unimodal models, direct engine calls) keep the per-layer launches."""
 
     class _Entry:
-        __slots__ = ("w", "out", "dims", "kind", "in_table", "wrap", "shape", "dtype", "mk")
+        __slots__ = ("w", "out", "dims", "kind", "in_table", "wrap", "shape", "dtype", "mk", "used")
+
+    PRUNE_EVERY = 16  # passes
 
     def __init__(self):
         self.ent = {}
@@ -352,6 +354,7 @@ class WeightPackCache:
         self.dirty = False
         self.table = None
         self.arena = None
+        self._captured = False
         self._retired = []  # tables / arenas a captured CUDA graph may still read
 
     def __deepcopy__(self, memo):   # a copied / pickled model starts with an empty cache (entries are keyed by the
@@ -365,11 +368,31 @@ class WeightPackCache:
         self.epoch += 1
         if not self.ent:
             return
+        if self.epoch % self.PRUNE_EVERY == 0 and not torch.cuda.is_current_stream_capturing():
+            # operands nobody asked for lately (parameters replaced by .to() / re-assignment, the data-gradient operands
+            # of a phase that no longer runs backward) stop being converted and release their parameter reference
+            stale = [k for k, e in self.ent.items() if e.used < self.epoch - self.PRUNE_EVERY]
+            for k in stale:
+                del self.ent[k]
+            if stale:
+                self.dirty = True
+                if not self.ent:
+                    self._retire()
+                    return
         if self.dirty:
             self._build()
+        if torch.cuda.is_current_stream_capturing():
+            self._captured = True
         jobs, cj, cs, n_jobs, n_chunks = self.table
         call("pack_weights_multi", jobs, cj, cs, n_jobs, n_chunks)
         self.packed_epoch = self.epoch
+
+    def _retire(self):
+        """drop the current table / arena -- unless a CUDA graph captured a launch that reads them"""
+        if self.table is not None and self._captured:
+            self._retired.append((self.table, self.arena))
+        self.table = self.arena = None
+        self._captured = False
 
     def _build(self):
         """job table + ONE arena holding every operand (a single allocation made between two passes: persistent
@@ -405,8 +428,7 @@ class WeightPackCache:
             for o in range(0, total, chunk):
                 cj.append(i)
                 cs.append(o)
-        if self.table is not None:
-            self._retired.append((self.table, self.arena))
+        self._retire()
         self.arena = arena
         self.table = (torch.tensor(rows, dtype=torch.int64, device=dev), torch.tensor(cj, dtype=torch.int32, device=dev),
                       torch.tensor(cs, dtype=torch.int64, device=dev), len(rows), len(cj))
@@ -421,6 +443,7 @@ class WeightPackCache:
             e.out = e.wrap = None
             self.ent[key] = e
             self.dirty = True
+        e.used = self.epoch
         if e.in_table and self.packed_epoch == self.epoch:
             return e.wrap
         # not (yet) refreshed by begin() in this pass: an ordinary per-layer launch into a buffer of its own

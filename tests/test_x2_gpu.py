@@ -529,6 +529,21 @@ def test_weight_pack_cache_same_training_trajectory(cuda):
                                        ref.view(torch.int16 if ref.element_size() == 2 else torch.int32)), e.kind
                     kinds.add(e.kind)
                 assert {ops.PK_OHWI_X2, ops.PK_DGRAD_BF16, ops.PK_DW} <= kinds
+                # operands nobody asks for any more (here: the data-gradient operands during forward-only passes) are
+                # pruned, and come back with the next backward pass
+                cache.PRUNE_EVERY = 2
+                n_all = len(cache.ent)
+                with torch.no_grad():
+                    for _ in range(6):
+                        lg, _ = model(xs, noise=noise)
+                assert 0 < len(cache.ent) < n_all
+                assert not any(e.kind in (ops.PK_DGRAD_BF16, ops.PK_DGRAD_F32) for e in cache.ent.values())
+                opt.zero_grad(set_to_none=True)
+                lg2, _ = model(xs, noise=noise)
+                assert rel(lg2, lg) < 1e-5
+                F.cross_entropy(lg2, y).backward()
+                assert any(e.kind == ops.PK_DGRAD_BF16 for e in cache.ent.values())
+                assert all(torch.isfinite(p.grad).all() for p in model.parameters() if p.grad is not None)
     finally:
         adamml_mod.PACK_CACHE = old
         _lib.PROFILE = None
