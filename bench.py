@@ -227,9 +227,11 @@ def run_reference_arm(a):
 # ------------------------------------------------------------------------------------------- GPU arm
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (ncu --set full, profiles/r1_ncu_ops_N72.txt) divided by
 # the algorithmic bytes of that launch: measured traffic == algorithmic traffic to within 1-2 % for the streaming
-# kernels, 1.2x for the weight-gradient kernel (dy is re-read per 128-row M tile).
+# kernels, 1.03x for the weight-gradient kernel (round 1: 1.2x, dy re-read per 128-row M tile).
 NCU_TRAFFIC_RATIO = {"bn_bwd_reduce": 14.014 / 13.873, "bn_bwd_apply": 18.479 / 18.498, "bn_apply": 9.205 / 9.249,
-                     "tc_gemm_bf16": 5.722 / 5.780, "tc_wgrad_bf16": 6.941 / 5.780,
+                     "tc_gemm_bf16": 5.722 / 5.780,
+                     # (weight gradient after the row-tile-fastest item order: profiles/r2_ncu_mid_shapes.txt, 3x3 64->64)
+                     "tc_wgrad_bf16": 2.375 / 2.312,
                      # round 2, profiles/r2_ncu_ops_x2_N72.txt: 9 M x 256 x 64 x2 GEMM reads its A planes 1.57x (the four
                      # column-block CTAs of a row block drift apart), 3x3 x2 conv and bn_apply_x2 move the algorithmic bytes
                      "tc_gemm_x2": (3.638 + 9.195) / 11.561, "bn_apply_x2": (18.497 + 9.216) / 27.745,

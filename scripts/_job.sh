@@ -1,6 +1,3 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1 | cut -c1-300
-timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | python -c "
-import json,sys
-d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['value'], d['e2e']['value'], d['gpu_launches'], d['clocks']['sm_mhz'])"
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:"tc_" -o gpurun_out/r2_prof_mid_after -f python scripts/ncu_mid.py > gpurun_out/ncu_mid_after.log 2>&1; tail -2 gpurun_out/ncu_mid_after.log
