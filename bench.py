@@ -314,6 +314,9 @@ def kernel_work(name, a):
     if name == "maxpool3x3s2_fwd_x2":
         I, H, W, C, Ho, Wo = a[5:11]
         return 0.0, 4.0 * float(I * H * W * C + I * Ho * Wo * C) + I * Ho * Wo * C
+    if name == "bn_act_maxpool3x3s2_fwd_x2":   # (z_hi, z_lo, ss, imgs_per_group, act, y_hi, y_lo, pos, IMGS, H, W, C, Ho, Wo)
+        I, H, W, C, Ho, Wo = a[8:14]
+        return 0.0, 4.0 * float(I * H * W * C + I * Ho * Wo * C) + I * Ho * Wo * C
     if name == "maxpool3x3s2_fwd":
         I, H, W, C, Ho, Wo, dt = a[3:10]
         return 0.0, (2 if dt == 1 else 4) * float(I * H * W * C + I * Ho * Wo * C) + I * Ho * Wo * C
